@@ -1,0 +1,446 @@
+// Temporal neighbour sampling over the device CSR.
+// HBM-bound integer / float64-compare work: binary search on the 16-byte half-edge records,
+// then a contiguous tail gather.  No tensor cores here by design.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+// ---------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+void dyg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* dyg_last_error(void) { return g_err; }
+extern "C" int dyg_abi_version(void) { return DYG_ABI_VERSION; }
+
+// ---------------------------------------------------------------- device helpers
+struct Rec {
+    double t;
+    int nbr;
+    int eid;
+};
+__device__ __forceinline__ Rec load_rec(const dyg_halfedge_t* he, int64_t i) {
+    const int4 r = __ldg(reinterpret_cast<const int4*>(he + i));
+    Rec o;
+    o.t = __hiloint2double(r.y, r.x);
+    o.nbr = r.z;
+    o.eid = r.w;
+    return o;
+}
+__device__ __forceinline__ double load_time(const dyg_halfedge_t* he, int64_t i) {
+    return __ldg(reinterpret_cast<const double*>(he + i));
+}
+// number of half-edges of [a, a+deg) with t < tq  (np.searchsorted side='left', utils/utils.py:141)
+__device__ __forceinline__ int64_t lower_bound_time(const dyg_halfedge_t* he, int64_t a, int64_t deg, double tq) {
+    int64_t lo = 0, hi = deg;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (load_time(he, a + mid) < tq) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ void node_range(const int64_t* indptr, int64_t num_nodes, int64_t v, int64_t& a, int64_t& deg) {
+    a = 0;
+    deg = 0;
+    if (v >= 0 && v < num_nodes) {
+        a = __ldg(indptr + v);
+        deg = __ldg(indptr + v + 1) - a;
+    }
+}
+
+// ---------------------------------------------------------------- CSR build
+__global__ void csr_degrees_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                   int64_t num_nodes, unsigned long long* __restrict__ deg) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = src[e], d = dst[e];
+        if (s >= 0 && s < num_nodes) atomicAdd(deg + s, 1ull);
+        if (d >= 0 && d < num_nodes) atomicAdd(deg + d, 1ull);
+    }
+}
+__global__ void csr_pack_kernel(const int64_t* __restrict__ order, const int64_t* __restrict__ src,
+                                const int64_t* __restrict__ dst, const int64_t* __restrict__ eid,
+                                const double* __restrict__ t, int64_t n_half, dyg_halfedge_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_half; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t h = order[i];
+        const int64_t e = h >> 1;
+        const int64_t nb = (h & 1) ? src[e] : dst[e];
+        const double tt = t[e];
+        int4 r;
+        r.x = __double2loint(tt);
+        r.y = __double2hiint(tt);
+        r.z = (int)nb;
+        r.w = (int)eid[e];
+        reinterpret_cast<int4*>(out)[i] = r;
+    }
+}
+__global__ void csr_tia_kernel(const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+                               double tsf, double* __restrict__ prob, double* __restrict__ cum,
+                               const double* __restrict__ prob_in) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < num_nodes; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = indptr[v], b = indptr[v + 1];
+        if (a == b) continue;
+        const double t_last = prob_in ? 0.0 : load_time(he, b - 1);
+        double c = 0.0, s = 0.0;
+        for (int64_t j = a; j < b; ++j) {
+            double p;
+            if (prob_in) {
+                p = prob_in[j];
+            } else {
+                const double e = exp(tsf * (load_time(he, j) - t_last));
+                c += e;
+                p = e / c;
+                if (isnan(p)) p = -1e10;
+                if (prob) prob[j] = p;
+            }
+            if (cum) {
+                s += exp(p);
+                cum[j] = s;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- queries
+__global__ void count_before_kernel(const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr,
+                                    int64_t num_nodes, const int64_t* __restrict__ node_ids,
+                                    const double* __restrict__ times, int64_t n, int32_t* __restrict__ cnt) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int64_t a, deg;
+    node_range(indptr, num_nodes, node_ids[q], a, deg);
+    cnt[q] = (int32_t)lower_bound_time(he, a, deg, times[q]);
+}
+
+// LANES threads cooperate on one query: every lane runs the same search (same address -> one sector
+// per probe per group), then the lanes split the k-entry tail gather and the (n,k) row writes.
+template <int LANES>
+__global__ void __launch_bounds__(256) sample_recent_kernel(
+    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+    const int64_t* __restrict__ node_ids, const double* __restrict__ times, int64_t n, int k,
+    int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid, float* __restrict__ out_t,
+    int32_t* __restrict__ cnt_out) {
+    const int lane = threadIdx.x % LANES;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
+    if (q >= n) return;
+    int64_t a, deg;
+    node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
+    const int64_t cnt = lower_bound_time(he, a, deg, __ldg(times + q));
+    if (cnt_out && lane == 0) cnt_out[q] = (int32_t)cnt;
+    const int64_t base = q * (int64_t)k;
+    for (int j = lane; j < k; j += LANES) {
+        const int64_t s = cnt - k + j;  // left padding: valid entries sit at the back (utils/utils.py:206-209)
+        int64_t nb = 0, ei = 0;
+        float tf = 0.f;
+        if (s >= 0) {
+            const Rec r = load_rec(he, a + s);
+            nb = r.nbr;
+            ei = r.eid;
+            tf = (float)r.t;
+        }
+        out_nbr[base + j] = nb;
+        out_eid[base + j] = ei;
+        out_t[base + j] = tf;
+    }
+}
+
+// One warp per query: [self, last min(cnt, L-1) neighbours, zeros...] (models/DyGFormer.py:214-242).
+__global__ void __launch_bounds__(256) first_hop_pad_kernel(
+    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+    const int64_t* __restrict__ node_ids, const double* __restrict__ times, int64_t n, int L, int row_stride,
+    int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid, float* __restrict__ out_t,
+    int32_t* __restrict__ out_len, int32_t* __restrict__ group_max, int group_size) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q >= n) return;
+    const int64_t v = __ldg(node_ids + q);
+    const double tq = __ldg(times + q);
+    int64_t a, deg;
+    node_range(indptr, num_nodes, v, a, deg);
+    const int64_t cnt = lower_bound_time(he, a, deg, tq);
+    const int m = (int)(cnt < (int64_t)(L - 1) ? cnt : (int64_t)(L - 1));
+    if (lane == 0) {
+        if (out_len) out_len[q] = m + 1;
+        if (group_max) atomicMax(group_max + q / group_size, m + 1);
+    }
+    const int64_t base = q * (int64_t)row_stride;
+    const int64_t first = a + cnt - m;
+    for (int j = lane; j < row_stride; j += 32) {
+        int64_t nb = 0, ei = 0;
+        float tf = 0.f;
+        if (j == 0) {
+            nb = v;
+            tf = (float)tq;
+        } else if (j <= m) {
+            const Rec r = load_rec(he, first + (j - 1));
+            nb = r.nbr;
+            ei = r.eid;
+            tf = (float)r.t;
+        }
+        out_nbr[base + j] = nb;
+        out_eid[base + j] = ei;
+        out_t[base + j] = tf;
+    }
+}
+
+// Gather at drawn positions, then order each row by float32 time (utils/utils.py:189-199).  Rank sort in
+// shared memory; equal times keep draw order (the reference's argsort leaves that order unspecified).
+template <int LANES>
+__global__ void sample_indexed_kernel(const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr,
+                                      const int64_t* __restrict__ node_ids, const int32_t* __restrict__ cnt,
+                                      const int64_t* __restrict__ sel, int64_t n, int k,
+                                      int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid,
+                                      float* __restrict__ out_t) {
+    extern __shared__ unsigned char smem_raw[];
+    const int groups = blockDim.x / LANES;
+    const int g = threadIdx.x / LANES;
+    const int lane = threadIdx.x % LANES;
+    float* st = reinterpret_cast<float*>(smem_raw) + (size_t)g * k;
+    int* sn = reinterpret_cast<int*>(smem_raw) + (size_t)groups * k + (size_t)g * k;
+    int* se = reinterpret_cast<int*>(smem_raw) + (size_t)2 * groups * k + (size_t)g * k;
+    const int64_t q = blockIdx.x * (int64_t)groups + g;
+    const bool valid = q < n;
+    int c = 0;
+    int64_t a = 0;
+    if (valid) {
+        c = cnt[q];
+        if (c > 0) a = __ldg(indptr + node_ids[q]);
+    }
+    const int64_t base = q * (int64_t)k;
+    if (valid && c > 0) {
+        for (int j = lane; j < k; j += LANES) {
+            int64_t s = sel[base + j];
+            s = s < 0 ? 0 : (s >= c ? c - 1 : s);
+            const Rec r = load_rec(he, a + s);
+            st[j] = (float)r.t;
+            sn[j] = r.nbr;
+            se[j] = r.eid;
+        }
+    }
+    if (LANES >= 32) __syncthreads(); else __syncwarp();
+    if (valid) {
+        for (int j = lane; j < k; j += LANES) {
+            if (c > 0) {
+                const float tj = st[j];
+                int rank = 0;
+                for (int i = 0; i < k; ++i) {
+                    const float ti = st[i];
+                    rank += (ti < tj) || (ti == tj && i < j);
+                }
+                out_nbr[base + rank] = sn[j];
+                out_eid[base + rank] = se[j];
+                out_t[base + rank] = tj;
+            } else {
+                out_nbr[base + j] = 0;
+                out_eid[base + j] = 0;
+                out_t[base + j] = 0.f;
+            }
+        }
+    }
+}
+
+__global__ void draw_uniform_kernel(const int32_t* __restrict__ cnt, const double* __restrict__ u, int64_t total, int k,
+                                    int64_t* __restrict__ sel) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = cnt[i / k];
+    int64_t s = 0;
+    if (c > 0) {
+        s = (int64_t)floor(u[i] * (double)c);
+        if (s >= c) s = c - 1;
+    }
+    sel[i] = s;
+}
+
+// searchsorted(cdf, u, 'right') on cdf[j] = cum[a+j] / cum[a+cnt-1] without materialising the cdf.
+__global__ void draw_tia_kernel(const double* __restrict__ cum, const int64_t* __restrict__ indptr,
+                                const int64_t* __restrict__ node_ids, const int32_t* __restrict__ cnt,
+                                const double* __restrict__ u, int64_t total, int k, int64_t* __restrict__ sel) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t q = i / k;
+    const int c = cnt[q];
+    int64_t s = 0;
+    if (c > 0) {
+        const int64_t a = __ldg(indptr + node_ids[q]);
+        const double tot = __ldg(cum + a + c - 1);
+        const double uu = u[i];
+        if (!(tot > 0.0)) {
+            s = (int64_t)floor(uu * (double)c);  // every weight underflowed: softmax of equal values is uniform
+        } else {
+            const double target = uu * tot;
+            int64_t lo = 0, hi = c;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(cum + a + mid) <= target) lo = mid + 1; else hi = mid;
+            }
+            s = lo;
+        }
+        if (s >= c) s = c - 1;
+    }
+    sel[i] = s;
+}
+
+// Philox4x32-10 counter RNG -> float64 uniforms with numpy's 53-bit construction ((a>>5)*2^26+(b>>6))/2^53.
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+}
+__global__ void philox_uniform_kernel(uint64_t seed, uint64_t offset, int64_t count, double* __restrict__ u) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one counter -> two doubles
+    if (2 * i >= count) return;
+    const uint64_t ctr = offset / 2 + (uint64_t)i;
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x9E3779B9u, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const double inv = 1.0 / 9007199254740992.0;
+    u[2 * i] = ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * inv;
+    if (2 * i + 1 < count) u[2 * i + 1] = ((double)(c2 >> 5) * 67108864.0 + (double)(c3 >> 6)) * inv;
+}
+
+// ---------------------------------------------------------------- C ABI
+static inline unsigned blocks_for(int64_t work, int threads, int64_t cap = (1ll << 30)) {
+    int64_t b = (work + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (unsigned)b;
+}
+
+extern "C" int dyg_csr_degrees(const int64_t* src, const int64_t* dst, int64_t E, int64_t num_nodes, int64_t* deg,
+                               dyg_stream_t stream) {
+    DYG_CHECK_ARG(E >= 0 && num_nodes > 0, "dyg_csr_degrees: bad sizes");
+    if (E == 0) return 0;
+    csr_degrees_kernel<<<blocks_for(E, 256, 148 * 32), 256, 0, as_stream(stream)>>>(
+        src, dst, E, num_nodes, reinterpret_cast<unsigned long long*>(deg));
+    DYG_LAUNCH_CHECK("dyg_csr_degrees");
+    return 0;
+}
+
+extern "C" int dyg_csr_pack(const int64_t* order, const int64_t* src, const int64_t* dst, const int64_t* eid,
+                            const double* t, int64_t n_half, dyg_halfedge_t* out, dyg_stream_t stream) {
+    DYG_CHECK_ARG(n_half >= 0, "dyg_csr_pack: bad size");
+    DYG_CHECK_ARG(aligned16(out), "dyg_csr_pack: out must be 16-byte aligned");
+    if (n_half == 0) return 0;
+    csr_pack_kernel<<<blocks_for(n_half, 256, 148 * 32), 256, 0, as_stream(stream)>>>(order, src, dst, eid, t, n_half, out);
+    DYG_LAUNCH_CHECK("dyg_csr_pack");
+    return 0;
+}
+
+extern "C" int dyg_csr_tia_tables(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, double tsf,
+                                  double* prob, double* cum, dyg_stream_t stream) {
+    DYG_CHECK_ARG(num_nodes > 0, "dyg_csr_tia_tables: bad size");
+    csr_tia_kernel<<<blocks_for(num_nodes, 128, 148 * 16), 128, 0, as_stream(stream)>>>(he, indptr, num_nodes, tsf, prob, cum, nullptr);
+    DYG_LAUNCH_CHECK("dyg_csr_tia_tables");
+    return 0;
+}
+
+extern "C" int dyg_csr_tia_cum(const double* prob, const int64_t* indptr, int64_t num_nodes, double* cum,
+                               dyg_stream_t stream) {
+    DYG_CHECK_ARG(num_nodes > 0 && prob && cum, "dyg_csr_tia_cum: bad args");
+    csr_tia_kernel<<<blocks_for(num_nodes, 128, 148 * 16), 128, 0, as_stream(stream)>>>(nullptr, indptr, num_nodes, 0.0, nullptr, cum, prob);
+    DYG_LAUNCH_CHECK("dyg_csr_tia_cum");
+    return 0;
+}
+
+extern "C" int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
+                                const int64_t* node_ids, const double* times, int64_t n, int32_t* cnt,
+                                dyg_stream_t stream) {
+    DYG_CHECK_ARG(n >= 0, "dyg_count_before: bad size");
+    if (n == 0) return 0;
+    count_before_kernel<<<blocks_for(n, 128), 128, 0, as_stream(stream)>>>(he, indptr, num_nodes, node_ids, times, n, cnt);
+    DYG_LAUNCH_CHECK("dyg_count_before");
+    return 0;
+}
+
+extern "C" int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
+                                 const int64_t* node_ids, const double* times, int64_t n, int k, int64_t* out_nbr,
+                                 int64_t* out_eid, float* out_t, int32_t* cnt, dyg_stream_t stream) {
+    DYG_CHECK_ARG(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    DYG_CHECK_ARG(n >= 0, "dyg_sample_recent: bad size");
+    if (n == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+#define LAUNCH_RECENT(L) \
+    sample_recent_kernel<L><<<blocks_for(n * L, 256), 256, 0, s>>>(he, indptr, num_nodes, node_ids, times, n, k, out_nbr, out_eid, out_t, cnt)
+    if (k <= 4) LAUNCH_RECENT(2);
+    else if (k <= 12) LAUNCH_RECENT(4);
+    else if (k <= 32) LAUNCH_RECENT(8);
+    else if (k <= 96) LAUNCH_RECENT(16);
+    else LAUNCH_RECENT(32);
+#undef LAUNCH_RECENT
+    DYG_LAUNCH_CHECK("dyg_sample_recent");
+    return 0;
+}
+
+extern "C" int dyg_sample_indexed(const dyg_halfedge_t* he, const int64_t* indptr, const int64_t* node_ids,
+                                  const int32_t* cnt, const int64_t* sel, int64_t n, int k, int64_t* out_nbr,
+                                  int64_t* out_eid, float* out_t, dyg_stream_t stream) {
+    DYG_CHECK_ARG(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    DYG_CHECK_ARG((size_t)k * 12 <= 40 * 1024, "dyg_sample_indexed: num_neighbors %d too large (max 3413)", k);
+    if (n == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    if (k <= 32) {
+        const int lanes = 8, threads = 256, groups = threads / lanes;
+        sample_indexed_kernel<8><<<blocks_for(n, groups), threads, (size_t)groups * k * 12, s>>>(
+            he, indptr, node_ids, cnt, sel, n, k, out_nbr, out_eid, out_t);
+    } else {
+        int groups = (int)((40 * 1024) / ((size_t)k * 12));
+        if (groups > 8) groups = 8;
+        if (groups < 1) groups = 1;
+        sample_indexed_kernel<32><<<blocks_for(n, groups), groups * 32, (size_t)groups * k * 12, s>>>(
+            he, indptr, node_ids, cnt, sel, n, k, out_nbr, out_eid, out_t);
+    }
+    DYG_LAUNCH_CHECK("dyg_sample_indexed");
+    return 0;
+}
+
+extern "C" int dyg_draw_uniform(const int32_t* cnt, const double* u, int64_t n, int k, int64_t* sel, dyg_stream_t stream) {
+    DYG_CHECK_ARG(k > 0 && n >= 0, "dyg_draw_uniform: bad sizes");
+    if (n == 0) return 0;
+    draw_uniform_kernel<<<blocks_for(n * k, 256), 256, 0, as_stream(stream)>>>(cnt, u, n * k, k, sel);
+    DYG_LAUNCH_CHECK("dyg_draw_uniform");
+    return 0;
+}
+
+extern "C" int dyg_draw_tia(const double* cum, const int64_t* indptr, const int64_t* node_ids, const int32_t* cnt,
+                            const double* u, int64_t n, int k, int64_t* sel, dyg_stream_t stream) {
+    DYG_CHECK_ARG(k > 0 && n >= 0, "dyg_draw_tia: bad sizes");
+    if (n == 0) return 0;
+    draw_tia_kernel<<<blocks_for(n * k, 256), 256, 0, as_stream(stream)>>>(cum, indptr, node_ids, cnt, u, n * k, k, sel);
+    DYG_LAUNCH_CHECK("dyg_draw_tia");
+    return 0;
+}
+
+extern "C" int dyg_philox_uniform(uint64_t seed, uint64_t offset, int64_t count, double* u, dyg_stream_t stream) {
+    DYG_CHECK_ARG(count >= 0 && (offset % 2) == 0, "dyg_philox_uniform: offset must be even");
+    if (count == 0) return 0;
+    philox_uniform_kernel<<<blocks_for((count + 1) / 2, 256), 256, 0, as_stream(stream)>>>(seed, offset, count, u);
+    DYG_LAUNCH_CHECK("dyg_philox_uniform");
+    return 0;
+}
+
+extern "C" int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
+                                 const int64_t* node_ids, const double* times, int64_t n, int L, int row_stride,
+                                 int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* out_len,
+                                 int32_t* group_max, int group_size, dyg_stream_t stream) {
+    DYG_CHECK_ARG(L - 1 > 0, "Maximal number of neighbors for each node should be greater than 1!");
+    DYG_CHECK_ARG(row_stride >= L, "dyg_first_hop_pad: row_stride %d < max_input_sequence_length %d", row_stride, L);
+    DYG_CHECK_ARG(!group_max || group_size > 0, "dyg_first_hop_pad: group_size must be positive");
+    if (n == 0) return 0;
+    first_hop_pad_kernel<<<blocks_for(n * 32, 256), 256, 0, as_stream(stream)>>>(
+        he, indptr, num_nodes, node_ids, times, n, L, row_stride, out_nbr, out_eid, out_t, out_len, group_max,
+        group_size > 0 ? group_size : 1);
+    DYG_LAUNCH_CHECK("dyg_first_hop_pad");
+    return 0;
+}

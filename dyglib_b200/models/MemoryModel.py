@@ -1,0 +1,340 @@
+"""Drop-in for the reference's ``MemoryModel`` (TGN / DyRep / JODIE, ``models/MemoryModel.py``).
+
+The python dict-of-lists message store, the per-call loop over all nodes and the full-table clone of the
+reference become flat device tables (see csrc/memory.cu): persisted memory, an incrementally maintained
+look-ahead view (what ``get_updated_memories`` would return for every node), and the last raw message of
+every node.  Per positive batch only the batch's <= 2B new messages go through the GRU; results are
+identical to recomputing all pending nodes each call because a pending node's inputs cannot change before
+its message is consumed.  This holds for fixed weights (eval); training would need the recompute path.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native, ops
+from ..ops import _p, _stream
+from ..utils.utils import NeighborSampler, _as_dev
+from .modules import TimeEncoder, MergeLayer, MultiHeadAttention, _eval_only
+from ._temporal import temporal_conv, zero_time_features
+
+
+class MessageAggregator(nn.Module):
+    """``MessageAggregator`` (``models/MemoryModel.py:267-300``): keep the last message of every node."""
+
+    def __init__(self):
+        super().__init__()
+
+    def aggregate_messages(self, node_ids: np.ndarray, node_raw_messages: dict):
+        """Compat API over the reference's dict-of-lists format (host bookkeeping only; the fused model path
+        selects last messages on the device with dyg_tgn_select_last)."""
+        unique_node_ids = np.unique(node_ids)
+        msgs, ts, ids = [], [], []
+        for v in unique_node_ids:
+            lst = node_raw_messages.get(v, []) if isinstance(node_raw_messages, dict) else node_raw_messages[v]
+            if len(lst) > 0:
+                ids.append(v)
+                msgs.append(lst[-1][0])
+                ts.append(lst[-1][1])
+        return (np.array(ids), torch.stack(msgs, dim=0) if msgs else torch.Tensor([]), np.array(ts))
+
+
+class MemoryBank(nn.Module):
+
+    def __init__(self, num_nodes: int, memory_dim: int, message_dim: int = 0):
+        """``MemoryBank`` (``models/MemoryModel.py:304-422``); ``node_memories`` and ``node_last_updated_times`` are
+        non-grad Parameters so they land in the state_dict like the reference's."""
+        super().__init__()
+        self.num_nodes = num_nodes
+        self.memory_dim = memory_dim
+        self.message_dim = message_dim
+        self.node_memories = nn.Parameter(torch.zeros((num_nodes, memory_dim)), requires_grad=False)
+        self.node_last_updated_times = nn.Parameter(torch.zeros(num_nodes), requires_grad=False)
+        self._state = None
+
+    def _ensure(self):
+        dev = self.node_memories.device
+        if self._state is None or self._state['mem_view'].device != dev:
+            N, D = self.num_nodes, self.memory_dim
+            self._state = dict(
+                mem_view=self.node_memories.data.clone(),
+                lu_view=self.node_last_updated_times.data.clone(),
+                pending=torch.zeros(N, dtype=torch.uint8, device=dev),
+                winner=torch.full((N,), -1, dtype=torch.int32, device=dev),
+                msg_store=torch.zeros((N, max(self.message_dim, 1)), dtype=torch.float32, device=dev),
+                msg_time=torch.zeros(N, dtype=torch.float64, device=dev),
+                flag=torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._state
+
+    def __init_memory_bank__(self):
+        """``__init_memory_bank__`` (``models/MemoryModel.py:325-332``)."""
+        self.node_memories.data.zero_()
+        self.node_last_updated_times.data.zero_()
+        self._state = None
+        self._ensure()
+
+    def get_memories(self, node_ids):
+        ids = _as_dev(node_ids, torch.int64, self.node_memories.device)
+        return ops.gather_rows(self.node_memories.data, ids)
+
+    def set_memories(self, node_ids, updated_node_memories: torch.Tensor):
+        ids = _as_dev(node_ids, torch.int64, self.node_memories.device)
+        self.node_memories.data[ids] = updated_node_memories
+        st = self._ensure()
+        st['mem_view'][ids] = updated_node_memories
+
+    def get_node_last_updated_times(self, unique_node_ids):
+        ids = _as_dev(unique_node_ids, torch.int64, self.node_memories.device)
+        return self.node_last_updated_times.data[ids]
+
+    @property
+    def node_raw_messages(self):
+        """The pending messages in the reference's format {node_id: [(message, time)]} (export for checkpoints,
+        ``utils/EarlyStopping.py:73-86``)."""
+        st = self._ensure()
+        out = defaultdict(list)
+        for v in torch.nonzero(st['pending']).reshape(-1).tolist():
+            out[v].append((st['msg_store'][v].clone(), np.float64(st['msg_time'][v].item())))
+        return out
+
+    def backup_memory_bank(self):
+        """``backup_memory_bank`` (``models/MemoryModel.py:351-360``): flat device copies."""
+        st = self._ensure()
+        return (self.node_memories.data.clone(), self.node_last_updated_times.data.clone(),
+                {k: v.clone() for k, v in st.items()})
+
+    def reload_memory_bank(self, backup_memory_bank: tuple):
+        """``reload_memory_bank`` (``models/MemoryModel.py:362-372``)."""
+        self.node_memories.data = backup_memory_bank[0].clone()
+        self.node_last_updated_times.data = backup_memory_bank[1].clone()
+        self._state = {k: v.clone() for k, v in backup_memory_bank[2].items()}
+
+    def detach_memory_bank(self):
+        """``detach_memory_bank`` (``models/MemoryModel.py:374-387``): nothing carries gradients here."""
+        self.node_memories.detach_()
+
+    def extra_repr(self):
+        return 'num_nodes={}, memory_dim={}'.format(self.node_memories.shape[0], self.node_memories.shape[1])
+
+
+class MemoryUpdater(nn.Module):
+    """``MemoryUpdater`` (``models/MemoryModel.py:425-487``); subclasses own the recurrent cell's parameters."""
+
+    def __init__(self, memory_bank: MemoryBank):
+        super().__init__()
+        self.memory_bank = memory_bank
+
+
+class GRUMemoryUpdater(MemoryUpdater):
+
+    def __init__(self, memory_bank: MemoryBank, message_dim: int, memory_dim: int):
+        super().__init__(memory_bank)
+        self.memory_updater = nn.GRUCell(input_size=message_dim, hidden_size=memory_dim)
+        self.gates = 3
+
+
+class RNNMemoryUpdater(MemoryUpdater):
+
+    def __init__(self, memory_bank: MemoryBank, message_dim: int, memory_dim: int):
+        super().__init__(memory_bank)
+        self.memory_updater = nn.RNNCell(input_size=message_dim, hidden_size=memory_dim)
+        self.gates = 1
+
+
+class TimeProjectionEmbedding(nn.Module):
+
+    def __init__(self, memory_dim: int, dropout: float):
+        """``TimeProjectionEmbedding`` (``models/MemoryModel.py:519-545``)."""
+        super().__init__()
+        self.memory_dim = memory_dim
+        self.dropout = nn.Dropout(dropout)
+        self.linear_layer = nn.Linear(1, self.memory_dim)
+
+
+class GraphAttentionEmbedding(nn.Module):
+
+    def __init__(self, node_raw_features: torch.Tensor, edge_raw_features: torch.Tensor, neighbor_sampler: NeighborSampler,
+                 time_encoder: TimeEncoder, node_feat_dim: int, edge_feat_dim: int, time_feat_dim: int,
+                 num_layers: int = 2, num_heads: int = 2, dropout: float = 0.1):
+        """``GraphAttentionEmbedding`` (``models/MemoryModel.py:548-586``)."""
+        super().__init__()
+        self.node_raw_features = node_raw_features
+        self.edge_raw_features = edge_raw_features
+        self.neighbor_sampler = neighbor_sampler
+        self.time_encoder = time_encoder
+        self.node_feat_dim = node_feat_dim
+        self.edge_feat_dim = edge_feat_dim
+        self.time_feat_dim = time_feat_dim
+        self.num_layers = num_layers
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.temporal_conv_layers = nn.ModuleList([
+            MultiHeadAttention(node_feat_dim, edge_feat_dim, time_feat_dim, num_heads, dropout) for _ in range(num_layers)])
+        self.merge_layers = nn.ModuleList([
+            MergeLayer(node_feat_dim + time_feat_dim, node_feat_dim, node_feat_dim, node_feat_dim) for _ in range(num_layers)])
+
+    def compute_node_temporal_embeddings(self, node_memories: torch.Tensor, node_ids, node_interact_times,
+                                         current_layer_num: int, num_neighbors: int = 20):
+        """``compute_node_temporal_embeddings`` (``models/MemoryModel.py:588-664``): layer-0 features are
+        memory + raw features; neighbours' layer-0 rows are gathered inside the attention kernel."""
+        assert current_layer_num >= 0
+        dev = self.node_raw_features.device
+        ids = _as_dev(node_ids, torch.int64, dev)
+        tq = _as_dev(node_interact_times, torch.float64, dev)
+        t0 = zero_time_features(self.time_encoder, dev)
+        return self._embed(node_memories, ids, tq, current_layer_num, num_neighbors, t0)
+
+    def _embed(self, mem, ids, tq, layer, k, t0):
+        feat = ops.gather_rows(self.node_raw_features, ids, table2=mem)
+        if layer == 0:
+            return feat
+        conv = feat if layer == 1 else self._embed(mem, ids, tq, layer - 1, k, t0)
+        nbr, eid, nt = self.neighbor_sampler.get_historical_neighbors_device(ids, tq, k)
+        nbr_dense = None
+        if layer > 1:
+            nbr_dense = self._embed(mem, nbr.reshape(-1), nt.reshape(-1).double(), layer - 1, k, t0)
+        return temporal_conv(self.temporal_conv_layers[layer - 1], self.merge_layers[layer - 1], self.time_encoder, t0,
+                             conv, feat, self.node_raw_features, mem, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k)
+
+
+class MemoryModel(torch.nn.Module):
+
+    def __init__(self, node_raw_features: np.ndarray, edge_raw_features: np.ndarray, neighbor_sampler: NeighborSampler,
+                 time_feat_dim: int, model_name: str = 'TGN', num_layers: int = 2, num_heads: int = 2, dropout: float = 0.1,
+                 src_node_mean_time_shift: float = 0.0, src_node_std_time_shift: float = 1.0, dst_node_mean_time_shift_dst: float = 0.0,
+                 dst_node_std_time_shift: float = 1.0, device: str = 'cuda'):
+        """Same arguments as ``MemoryModel.__init__`` (``models/MemoryModel.py:12-85``)."""
+        super().__init__()
+        self.node_raw_features = torch.from_numpy(node_raw_features.astype(np.float32)).to(device).contiguous()
+        self.edge_raw_features = torch.from_numpy(edge_raw_features.astype(np.float32)).to(device).contiguous()
+        self.node_feat_dim = self.node_raw_features.shape[1]
+        self.edge_feat_dim = self.edge_raw_features.shape[1]
+        self.time_feat_dim = time_feat_dim
+        self.num_layers = num_layers
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.device = device
+        self.src_node_mean_time_shift = src_node_mean_time_shift
+        self.src_node_std_time_shift = src_node_std_time_shift
+        self.dst_node_mean_time_shift_dst = dst_node_mean_time_shift_dst
+        self.dst_node_std_time_shift = dst_node_std_time_shift
+        self.model_name = model_name
+        self.num_nodes = self.node_raw_features.shape[0]
+        self.memory_dim = self.node_feat_dim
+        self.message_dim = self.memory_dim + self.memory_dim + self.time_feat_dim + self.edge_feat_dim
+        self.time_encoder = TimeEncoder(time_dim=time_feat_dim)
+        self.message_aggregator = MessageAggregator()
+        self.memory_bank = MemoryBank(num_nodes=self.num_nodes, memory_dim=self.memory_dim, message_dim=self.message_dim)
+        if self.model_name == 'TGN':
+            self.memory_updater = GRUMemoryUpdater(self.memory_bank, self.message_dim, self.memory_dim)
+        elif self.model_name in ['DyRep', 'JODIE']:
+            self.memory_updater = RNNMemoryUpdater(self.memory_bank, self.message_dim, self.memory_dim)
+        else:
+            raise ValueError(f'Not implemented error for model_name {self.model_name}!')
+        if self.model_name == 'JODIE':
+            self.embedding_module = TimeProjectionEmbedding(memory_dim=self.memory_dim, dropout=self.dropout)
+        else:
+            self.embedding_module = GraphAttentionEmbedding(self.node_raw_features, self.edge_raw_features, neighbor_sampler,
+                                                            self.time_encoder, self.node_feat_dim, self.edge_feat_dim,
+                                                            self.time_feat_dim, self.num_layers, self.num_heads, self.dropout)
+        self.check_time_order = True
+        self.to(device)
+
+    def compute_src_dst_node_temporal_embeddings(self, src_node_ids: np.ndarray, dst_node_ids: np.ndarray, node_interact_times: np.ndarray,
+                                                 edge_ids: np.ndarray, edges_are_positive: bool = True, num_neighbors: int = 20):
+        """``compute_src_dst_node_temporal_embeddings`` (``models/MemoryModel.py:87-168``)."""
+        _eval_only(self)
+        lib = _native.load()
+        dev = self.node_raw_features.device
+        bank = self.memory_bank
+        st = bank._ensure()
+        D, T, E = self.memory_dim, self.time_feat_dim, self.edge_feat_dim
+        src = _as_dev(src_node_ids, torch.int64, dev)
+        dst = _as_dev(dst_node_ids, torch.int64, dev)
+        tq = _as_dev(node_interact_times, torch.float64, dev)
+        B = src.numel()
+        node_ids = torch.cat([src, dst])
+        tq2 = torch.cat([tq, tq])
+        mem_view, lu_view = st['mem_view'], st['lu_view']   # == get_updated_memories(all nodes) (:108-109)
+        if self.model_name == 'JODIE':
+            ll = self.embedding_module.linear_layer
+            emb = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
+            wv, bv = ll.weight.detach().reshape(-1), ll.bias.detach()
+            for ids, off, mean, std in ((src, 0, self.src_node_mean_time_shift, self.src_node_std_time_shift),
+                                        (dst, B, self.dst_node_mean_time_shift_dst, self.dst_node_std_time_shift)):
+                _native.check(lib.dyg_jodie_project(_p(mem_view), D, _p(lu_view), _p(ids), _p(tq), B, D, float(mean), float(std),
+                                                    _p(wv), _p(bv), _p(emb[off:off + B]), D, _stream()))
+                ops._count()
+        else:
+            emb = self.embedding_module.compute_node_temporal_embeddings(mem_view, node_ids, tq2, self.num_layers, num_neighbors)
+        src_emb, dst_emb = emb[:B], emb[B:]
+        if self.model_name == 'DyRep':
+            # DyRep returns the look-ahead memories computed before this batch's update (:163-166)
+            out = ops.gather_rows(mem_view, node_ids)
+            ret = (out[:B], out[B:])
+        else:
+            ret = (src_emb, dst_emb)
+        if edges_are_positive:
+            assert edge_ids is not None
+            eid = _as_dev(edge_ids, torch.int64, dev)
+            mem, lu = bank.node_memories.data, bank.node_last_updated_times.data
+            if self.check_time_order:
+                _native.check(lib.dyg_tgn_check_time(_p(node_ids), 2 * B, _p(lu), _p(lu_view), _p(st['pending']), _p(st['flag']), _stream()))
+                ops._count()
+            # update_memories + clear_node_raw_messages for the batch's nodes (:142-145)
+            _native.check(lib.dyg_tgn_persist(_p(node_ids), 2 * B, _p(mem), _p(mem_view), _p(lu), _p(lu_view), _p(st['pending']), D, _stream()))
+            ops._count(2)
+            # new raw messages, src role then dst role (:148-161); last message per node wins
+            _native.check(lib.dyg_tgn_select_last(_p(src), _p(dst), B, _p(st['winner']), _stream()))
+            other = torch.cat([dst_emb, src_emb]).contiguous() if self.model_name == 'DyRep' else None
+            w, b = self.time_encoder.wb()
+            msg = torch.empty((2 * B, self.message_dim), dtype=torch.float32, device=dev)
+            _native.check(lib.dyg_tgn_build_messages(_p(src), _p(dst), _p(tq), _p(eid), B, _p(mem), _p(lu), D, _p(other), D,
+                                                     _p(self.edge_raw_features), self.edge_raw_features.stride(0), E,
+                                                     _p(w), _p(b), T, _p(msg), self.message_dim, _stream()))
+            cell = self.memory_updater.memory_updater
+            G = self.memory_updater.gates
+            gi = ops.linear([ops.seg_rows(msg)], 2 * B, cell.weight_ih.detach(), cell.bias_ih.detach())
+            gh = ops.linear([ops.seg_rows(mem, D, node_ids)], 2 * B, cell.weight_hh.detach(), cell.bias_hh.detach())
+            _native.check(lib.dyg_tgn_cell_commit(_p(gi), _p(gh), G, _p(src), _p(dst), _p(tq), B, _p(st['winner']), _p(mem),
+                                                  _p(mem_view), _p(lu_view), _p(st['pending']), D, _p(msg), self.message_dim,
+                                                  self.message_dim, _p(st['msg_store']), _p(st['msg_time']), _stream()))
+            ops._count(3)
+        return ret
+
+    def assert_time_order(self):
+        """Raises if any update went backwards in time (the reference asserts per call, ``:448-449``; here the
+        device flag is read on demand to avoid a host sync per batch)."""
+        assert int(self.memory_bank._ensure()['flag'].item()) == 0, 'Trying to update memory to time in the past!'
+
+    def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):
+        """``set_neighbor_sampler`` (``models/MemoryModel.py:253-263``)."""
+        assert self.model_name in ['TGN', 'DyRep'], f'Neighbor sampler is not defined in model {self.model_name}!'
+        self.embedding_module.neighbor_sampler = neighbor_sampler
+        if self.embedding_module.neighbor_sampler.sample_neighbor_strategy in ['uniform', 'time_interval_aware']:
+            assert self.embedding_module.neighbor_sampler.seed is not None
+            self.embedding_module.neighbor_sampler.reset_random_state()
+
+
+def compute_src_dst_node_time_shifts(src_node_ids: np.ndarray, dst_node_ids: np.ndarray, node_interact_times: np.ndarray):
+    """``compute_src_dst_node_time_shifts`` (``models/MemoryModel.py:667-698``): mean / std of the gaps between
+    consecutive interactions of each src (resp. dst) node, first gap measured from time 0.  Host preprocessing,
+    vectorised with a stable sort instead of the reference's python dict loop."""
+    def shifts(ids, t):
+        order = np.argsort(ids, kind='stable')
+        si, st = ids[order], t[order]
+        prev = np.empty_like(st)
+        prev[1:] = st[:-1]
+        first = np.ones(len(si), dtype=bool)
+        first[1:] = si[1:] != si[:-1]
+        prev[first] = 0
+        out = np.empty_like(st)
+        out[order] = st - prev
+        return out
+    t = np.asarray(node_interact_times, dtype=np.float64)
+    s = shifts(np.asarray(src_node_ids), t)
+    d = shifts(np.asarray(dst_node_ids), t)
+    return np.mean(s), np.std(s), np.mean(d), np.std(d)

@@ -1,0 +1,48 @@
+"""Fused temporal graph-convolution layer shared by TGAT and the TGN/DyRep embedding module.
+
+One layer = reference steps ``models/TGAT.py:116-134`` / ``models/MemoryModel.py:644-662``:
+time-encode deltas, gather edge rows, MultiHeadAttention, MergeLayer.  Here:
+  GEMM  q~   = conv W_qk[:, :F]^T + (W_qk[:, F:] cos(b))          (n, H*Dk)
+  K5    s    = dyg_temporal_attend (gather + time enc + softmax)   (n, H*Dk)   <- HBM-bound part
+  GEMM  o    = s W_vr^T + residual_fc.bias                          (n, Dq)
+  LN    y    = LayerNorm(o + [conv | cos(b)])
+  GEMM  out  = fc2(relu(fc1([y | root_feat])))                      (n, F)
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+def zero_time_features(time_encoder, device):
+    """cos(b): the time encoding of a zero interval, a per-forward constant (``models/TGAT.py:82``)."""
+    w, b = time_encoder.wb()
+    return ops.time_encode(torch.zeros(1, dtype=torch.float32, device=device), w, b).reshape(-1)
+
+
+def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node_tab2, nbr_ids, nbr_dense,
+                  edge_tab, nbr_eids, tq, nbr_t, k):
+    """conv, root_feat: (n, F) dense; neighbours either lazily gathered from node_tab (+node_tab2) by nbr_ids
+    (layer 1) or dense (n*k, F) rows ``nbr_dense`` (deeper layers).  tq float64 (n,), nbr_t float32 (n,k)."""
+    n = conv.shape[0]
+    F_, E_, T_ = attn.node_feat_dim, attn.edge_feat_dim, attn.time_feat_dim
+    H = attn.num_heads
+    wqk, wvr = attn.folded()
+    w, b = time_encoder.wb()
+    # constant part of the query: W_qk[:, F:] @ cos(b)
+    cq = ops.linear([ops.seg_rows(t0.reshape(1, T_))], 1, wqk[:, F_:], ldw=wqk.stride(0)).reshape(-1)
+    qk = ops.linear([ops.seg_rows(conv)], n, wqk[:, :F_], bias=cq, ldw=wqk.stride(0))
+    flat_ids = nbr_ids.reshape(-1)
+    if nbr_dense is None:
+        s, _ = ops.temporal_attend(qk, n, k, H, node_tab, flat_ids, F_, edge_tab, nbr_eids.reshape(-1), E_, T_, flat_ids,
+                                   node_tab2=node_tab2, t_query=tq, t_nbr=nbr_t.reshape(-1), w=w, b=b)
+    else:
+        s, _ = ops.temporal_attend(qk, n, k, H, nbr_dense, None, F_, edge_tab, nbr_eids.reshape(-1), E_, T_, flat_ids,
+                                   t_query=tq, t_nbr=nbr_t.reshape(-1), w=w, b=b)
+    o = ops.linear([ops.seg_rows(s)], n, wvr, attn.residual_fc.bias.detach())
+    y = ops.layernorm(o, attn.layer_norm.weight.detach(), attn.layer_norm.bias.detach(), r1=conv, F1=F_, rconst=t0,
+                      eps=attn.layer_norm.eps)
+    h = ops.linear([ops.seg_rows(y), ops.seg_rows(root_feat)], n, merge.fc1.weight.detach(), merge.fc1.bias.detach(),
+                   act=ops.ACT_RELU)
+    return ops.linear([ops.seg_rows(h)], n, merge.fc2.weight.detach(), merge.fc2.bias.detach())

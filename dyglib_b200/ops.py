@@ -1,0 +1,215 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dygb200.h).
+
+torch is used for device memory and streams only; every computation below is one call into
+libdygb200.so on the current CUDA stream.  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import Seg
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3
+
+# number of kernels this process launched through the library (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _lib():
+    return _native.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('dyglib_b200 kernels need CUDA tensors: there is no CPU fallback')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: dyglib_b200 has no CPU path')
+    if t.dtype != dtype:
+        raise TypeError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+    return t
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# optional per-launch timing (bench.py roofline pass): PROFILE = [] enables it; each entry is
+# (kernel name, start event, end event, algorithmic flops, algorithmic bytes)
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.e0, self.e1, self.flops, self.nbytes))
+        return False
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('dyglib_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+
+
+# ------------------------------------------------------------------ segments for dyg_linear
+def seg_rows(table, width=None, idx=None, group=1, table2=None, idx2=None):
+    """A gathered / dense row segment: width columns from table[idx] (+ table2[idx2])."""
+    s = Seg()
+    s.kind = 0
+    s.width = int(width if width is not None else table.shape[-1])
+    s.group = int(group)
+    s.ld = int(table.stride(-2)) if table.dim() >= 2 else s.width
+    s.ptr = _p(table).value
+    s.idx = _p(idx).value if idx is not None else None
+    if table2 is not None:
+        s.ptr2 = _p(table2).value
+        s.ld2 = int(table2.stride(-2))
+        s.idx2 = _p(idx2).value if idx2 is not None else None
+    s._keep = (table, idx, table2, idx2)
+    return s
+
+
+def seg_time(dt, w, b, mask_ids=None, group=1, t_query=None, tq_div=1):
+    """A time-encoding segment: cos(fma(dt, w, b)), zero where mask_ids == 0.  With ``t_query`` (float64, one
+    per ``tq_div`` sub-rows) ``dt`` holds float32 neighbour times and the delta is formed in the kernel."""
+    s = Seg()
+    s.kind = 1
+    s.width = int(w.numel())
+    s.group = int(group)
+    s.dt = _p(dt).value
+    s.w = _p(w).value
+    s.b = _p(b).value
+    s.mask_ids = _p(mask_ids).value if mask_ids is not None else None
+    if t_query is not None:
+        s.t_query = _p(t_query).value
+        s.tq_div = int(tq_div)
+    s._keep = (dt, w, b, mask_ids, t_query)
+    return s
+
+
+def linear(segs, M, weight, bias=None, residual=None, act=ACT_NONE, out=None, out_cols=None,
+           c_group=0, c_group_stride=0, c_offset=0, ldw=None):
+    """out[row(m), :N] = act(A @ weight[:N, :K].T + bias + residual[row(m)])."""
+    N = weight.shape[0]
+    K = sum(s.width * s.group for s in segs)
+    if ldw is None:
+        ldw = weight.stride(0)
+    if out is None:
+        out = torch.empty((M, N), device=weight.device, dtype=torch.float32)
+    arr = (Seg * len(segs))(*segs)
+    ldc = out.stride(-2)
+    ldr = residual.stride(-2) if residual is not None else 0
+    with _Timed('linear_kernel', 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+        _native.check(_lib().dyg_linear(arr, len(segs), _p(weight), int(ldw), _p(bias), _p(residual), int(ldr),
+                                        _p(out), int(ldc), int(M), int(N), int(act), int(c_group), int(c_group_stride),
+                                        int(c_offset), _stream()))
+    _count()
+    return out
+
+
+def layernorm(x, gamma, beta, r1=None, F1=0, rconst=None, eps=1e-5, out=None):
+    M, D = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _native.check(_lib().dyg_layernorm(_p(x), x.stride(0), _p(r1), r1.stride(0) if r1 is not None else 0,
+                                       int(F1 if (r1 is not None or rconst is not None) else D), _p(rconst),
+                                       _p(gamma), _p(beta), float(eps), _p(out), out.stride(0), int(M), int(D), _stream()))
+    _count()
+    return out
+
+
+def gather_rows(table, idx, table2=None, out=None):
+    M = idx.numel()
+    D = table.shape[1]
+    if out is None:
+        out = torch.empty((M, D), device=table.device, dtype=torch.float32)
+    _native.check(_lib().dyg_gather_rows(_p(table), table.stride(0), _p(table2),
+                                         table2.stride(0) if table2 is not None else 0, _p(idx), int(M), int(D),
+                                         _p(out), out.stride(0), _stream()))
+    _count()
+    return out
+
+
+def time_encode(dt, w, b, out=None):
+    n = dt.numel()
+    T = w.numel()
+    if out is None:
+        out = torch.empty((n, T), device=dt.device, dtype=torch.float32)
+    _native.check(_lib().dyg_time_encode(_p(dt), int(n), _p(w), _p(b), int(T), _p(out), _stream()))
+    _count()
+    return out
+
+
+def temporal_attend(qk, n, k, H, node_tab, node_idx, F, edge_tab, edge_idx, E, T, mask_ids, node_tab2=None,
+                    time_feat=None, t_query=None, t_nbr=None, w=None, b=None, want_scores=False):
+    Dk = F + E + T
+    out = torch.empty((n, H * Dk), device=qk.device, dtype=torch.float32)
+    scores = torch.empty((n, H, k), device=qk.device, dtype=torch.float32) if want_scores else None
+    rows = 4.0 * (F * (2 if node_tab2 is not None else 1) + E + (T if time_feat is not None else 0))
+    with _Timed('temporal_attend_kernel', 4.0 * n * k * H * Dk, n * (k * (rows + 28.0) + 8.0 * H * Dk)):
+        _native.check(_lib().dyg_temporal_attend(
+            _p(qk), qk.stride(0), int(n), int(k), int(H), _p(node_tab), node_tab.stride(-2), _p(node_tab2),
+            node_tab2.stride(-2) if node_tab2 is not None else 0, _p(node_idx), int(F), _p(edge_tab), edge_tab.stride(-2),
+            _p(edge_idx), int(E), _p(time_feat), _p(t_query), _p(t_nbr), _p(w), _p(b), int(T), _p(mask_ids),
+            _p(out), out.stride(0), _p(scores), _stream()))
+    _count()
+    return out, scores
+
+
+def seq_attention(qkv, B, S, H, hd, out=None):
+    if out is None:
+        out = torch.empty((B * S, H * hd), device=qkv.device, dtype=torch.float32)
+    with _Timed('seq_attention_kernel', 4.0 * B * H * S * S * hd, 16.0 * B * S * H * hd):
+        _native.check(_lib().dyg_seq_attention(_p(qkv), qkv.stride(-2), int(B), int(S), int(H), int(hd), _p(out),
+                                               out.stride(-2), _stream()))
+    _count()
+    return out
+
+
+def mean_tokens(x, B, S, D, tok0, cnt, out=None):
+    if out is None:
+        out = torch.empty((B, D), device=x.device, dtype=torch.float32)
+    _native.check(_lib().dyg_mean_tokens(_p(x), int(B), int(S), int(D), int(tok0), int(cnt), _p(out), out.stride(0), _stream()))
+    _count()
+    return out
+
+
+def cooc_count(src_ids, dst_ids, want_float=True, want_int=False):
+    """src_ids (B,Ls), dst_ids (B,Ld) int64 device tensors."""
+    B, Ls = src_ids.shape
+    Ld = dst_ids.shape[1]
+    dev = src_ids.device
+    fs = torch.empty((B, Ls, 2), device=dev, dtype=torch.float32) if want_float else None
+    fd = torch.empty((B, Ld, 2), device=dev, dtype=torch.float32) if want_float else None
+    cs = torch.empty((2, B, Ls), device=dev, dtype=torch.int64) if want_int else None
+    cd = torch.empty((2, B, Ld), device=dev, dtype=torch.int64) if want_int else None
+    _native.check(_lib().dyg_cooc_count(_p(src_ids), src_ids.stride(0), _p(dst_ids), dst_ids.stride(0), int(B), int(Ls),
+                                        int(Ld), _p(fs), _p(fd), _p(cs), _p(cd), _stream()))
+    _count()
+    return fs, fd, cs, cd

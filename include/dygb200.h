@@ -1,0 +1,203 @@
+/*
+ * dygb200.h -- C ABI of libdygb200.so: B200 (sm_100a) kernels for DyGLib's temporal
+ * neighbour-aggregation path.
+ *
+ * Boundary rules:
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *   - no allocation and no host synchronisation inside; the caller owns every buffer;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, non-zero = error, text via dyg_last_error() (thread-local);
+ *   - ids / edge ids are int64 and sampled times float32 at this boundary because that is
+ *     what the reference's numpy API returns (utils/utils.py:161-167).
+ *
+ * The reference has no FFI of its own (it is pure Python); each entry point names the
+ * reference Python symbol it replaces.  INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef DYGB200_H
+#define DYGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYG_ABI_VERSION 1
+
+typedef void* dyg_stream_t; /* cudaStream_t */
+
+/* One directed half of an interaction as stored in the device CSR (16 bytes, one LDG.128).
+ * Node v owns half-edges [indptr[v], indptr[v+1]) sorted by t (stable), exactly the order of
+ * NeighborSampler.nodes_neighbor_{ids,edge_ids,times}[v] (utils/utils.py:96-103). */
+typedef struct {
+    double t;
+    int32_t nbr;
+    int32_t eid;
+} dyg_halfedge_t;
+
+const char* dyg_last_error(void);
+int dyg_abi_version(void);
+
+/* ---- a1: CSR construction (get_neighbor_sampler + NeighborSampler.__init__, utils/utils.py:283-302, 73-110) ---- */
+
+/* deg[v] += number of half-edges owned by v.  deg must be zeroed by the caller (num_nodes entries). */
+int dyg_csr_degrees(const int64_t* src, const int64_t* dst, int64_t num_events, int64_t num_nodes,
+                    int64_t* deg, dyg_stream_t stream);
+/* order[i] = index of the i-th half-edge in CSR order; half-edge h = 2*e + side (side 0: owner src[e],
+ * neighbour dst[e]; side 1: owner dst[e], neighbour src[e]).  Packs the 16-byte records. */
+int dyg_csr_pack(const int64_t* order, const int64_t* src, const int64_t* dst, const int64_t* eid,
+                 const double* t, int64_t num_half_edges, dyg_halfedge_t* out, dyg_stream_t stream);
+/* time_interval_aware tables (compute_sampled_probabilities, utils/utils.py:112-128), one thread per node,
+ * sequential float64 like numpy: prob[j] = e_j / cumsum(e)_j (NaN -> -1e10), e_j = exp(tsf*(t_j - t_last));
+ * cum[j] = sum_{l<=j} exp(prob[l]) (prefix table used by the device CDF search). Either output may be NULL. */
+int dyg_csr_tia_tables(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, double time_scaling_factor,
+                       double* prob, double* cum, dyg_stream_t stream);
+/* cum from a given prob table (used when prob was computed on the host for bit-exactness). */
+int dyg_csr_tia_cum(const double* prob, const int64_t* indptr, int64_t num_nodes, double* cum, dyg_stream_t stream);
+
+/* ---- a2: find_neighbors_before (utils/utils.py:130-147): cnt[q] = #{j : t_j < times[q]} ---- */
+int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
+                     const int64_t* node_ids, const double* times, int64_t n, int32_t* cnt, dyg_stream_t stream);
+
+/* ---- a3: get_historical_neighbors, strategy 'recent' (utils/utils.py:149-175, 200-209) ----
+ * last min(cnt,k) entries, left-padded with zeros. out_* are (n,k) row-major. cnt may be NULL. */
+int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
+                      const int64_t* node_ids, const double* times, int64_t n, int k,
+                      int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* cnt, dyg_stream_t stream);
+
+/* ---- a4/a5: 'uniform' and 'time_interval_aware' (utils/utils.py:176-199) ----
+ * Gather at caller-supplied positions sel[q*k+j] in [0,cnt[q]) (the replayed RandomState draws), then
+ * re-sort each row by float32 time (ties keep draw order).  Rows with cnt[q]==0 are all zero. */
+int dyg_sample_indexed(const dyg_halfedge_t* he, const int64_t* indptr, const int64_t* node_ids,
+                       const int32_t* cnt, const int64_t* sel, int64_t n, int k,
+                       int64_t* out_nbr, int64_t* out_eid, float* out_t, dyg_stream_t stream);
+/* Device draws.  u is (n*k) float64 in [0,1) (RandomState.random_sample replay, or any stream).
+ * uniform: sel = floor(u*cnt) (throughput mode; NOT the reference's rejection-sampled stream).
+ * tia:     sel = searchsorted(cum[:cnt]/cum[cnt-1], u, 'right') using the prefix table (utils/utils.py:183-187). */
+int dyg_draw_uniform(const int32_t* cnt, const double* u, int64_t n, int k, int64_t* sel, dyg_stream_t stream);
+int dyg_draw_tia(const double* cum, const int64_t* indptr, const int64_t* node_ids, const int32_t* cnt,
+                 const double* u, int64_t n, int k, int64_t* sel, dyg_stream_t stream);
+/* Counter-based uniforms for the sharded throughput mode (labelled non-parity): u[i] from (seed, offset+i). */
+int dyg_philox_uniform(uint64_t seed, uint64_t offset, int64_t count, double* u, dyg_stream_t stream);
+
+/* ---- a7 + a12: get_all_first_hop_neighbors + DyGFormer.pad_sequences (utils/utils.py:254-273,
+ * models/DyGFormer.py:196-245) ----  row q = [node_ids[q], last min(cnt,L-1) neighbours..., 0...] over
+ * row_stride columns (row_stride >= L); out_t[q,0] = (float)times[q]; out_len[q] = min(cnt,L-1)+1.
+ * group_max[q / group_size] = max over the group of out_len (atomicMax; caller zeroes it; may be NULL). */
+int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
+                      const int64_t* node_ids, const double* times, int64_t n, int max_input_sequence_length,
+                      int row_stride, int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* out_len,
+                      int32_t* group_max, int group_size, dyg_stream_t stream);
+
+/* ---- a13: NeighborCooccurrenceEncoder.count_nodes_appearances (models/DyGFormer.py:337-393) ----
+ * out_src (B,Ls,2), out_dst (B,Ld,2) float32 counts [in src row, in dst row], zero where id==0.
+ * cnt_src (2,B,Ls) / cnt_dst (2,B,Ld) int64 hold the same counts as planes [in src row | in dst row], the
+ * row indices of the count-LUT gather in the fused DyGFormer path; any output may be NULL. */
+int dyg_cooc_count(const int64_t* src_ids, int ld_src, const int64_t* dst_ids, int ld_dst, int64_t B, int Ls, int Ld,
+                   float* out_src, float* out_dst, int64_t* cnt_src, int64_t* cnt_dst, dyg_stream_t stream);
+
+/* ---- a8: TimeEncoder.forward (models/modules.py:27-39): out[i,c] = cos(fma(dt[i], w[c], b[c])) ---- */
+int dyg_time_encode(const float* dt, int64_t n, const float* w, const float* b, int T, float* out, dyg_stream_t stream);
+
+/* ---- dense contractions with fused gathers (nn.Linear call sites of models/modules.py:155-199,65-67;
+ * models/DyGFormer.py:148-157,442-461; nn.GRUCell of models/MemoryModel.py:501) ----
+ * A row m is the concatenation of up to DYG_MAX_SEGS segments; segment s contributes width*group columns:
+ *   column (p*width + c) = ptr[idx[m*group+p]*ld + c] (+ ptr2[idx2[m*group+p]*ld2 + c])        kind 0
+ *                        = mask_ids[m*group+p]==0 ? 0 : cos(fma(dt[m*group+p], w[c], b[c]))      kind 1
+ *                          (with t_query set, dt[] holds float32 neighbour times and the delta is formed here)
+ * idx NULL = identity; idx2 NULL = idx.  C[row(m), :N] = act(A W^T + bias + residual[row(m)]),
+ * row(m) = c_group>0 ? (m / c_group)*c_group_stride + m % c_group + c_offset : m. */
+#define DYG_MAX_SEGS 4
+#define DYG_ACT_NONE 0
+#define DYG_ACT_RELU 1
+#define DYG_ACT_GELU 2
+#define DYG_ACT_SIGMOID 3 /* link probability: model[1](...).sigmoid(), train_link_prediction.py:243-244 */
+typedef struct {
+    int32_t kind;
+    int32_t width;
+    int32_t group;
+    int32_t ld;
+    int32_t ld2;
+    int32_t tq_div;          /* kind 1 with t_query: sub-row r belongs to query r / tq_div */
+    const float* ptr;
+    const int64_t* idx;
+    const float* ptr2;
+    const int64_t* idx2;
+    const float* dt;
+    const int64_t* mask_ids;
+    const float* w;
+    const float* b;
+    const double* t_query;   /* kind 1: if set, dt = (float)(t_query[r / tq_div] - (double)dt[r]) (models/DyGFormer.py:263) */
+} dyg_seg_t;
+
+int dyg_linear(const dyg_seg_t* segs_host, int nseg, const float* W, int ldw, const float* bias,
+               const float* residual, int ldr, float* C, int ldc, int64_t M, int N, int act,
+               int c_group, int c_group_stride, int c_offset, dyg_stream_t stream);
+
+/* y = LayerNorm(x + r) * gamma + beta over D columns; r row = [r1 row (F1 cols) | rconst (D-F1 cols)];
+ * r1/rconst may be NULL (models/modules.py:199, models/DyGFormer.py:452,458). */
+int dyg_layernorm(const float* x, int ldx, const float* r1, int ldr1, int F1, const float* rconst,
+                  const float* gamma, const float* beta, float eps, float* y, int ldy, int64_t M, int D,
+                  dyg_stream_t stream);
+
+/* out[m,:] = tab[idx[m],:] (+ tab2[idx[m],:]) -- the advanced-index gathers of models/TGAT.py:84,
+ * models/MemoryModel.py:609 (memory + raw features). */
+int dyg_gather_rows(const float* tab, int ld, const float* tab2, int ld2, const int64_t* idx, int64_t M, int D,
+                    float* out, int ldo, dyg_stream_t stream);
+
+/* ---- a9: MultiHeadAttention.forward core (models/modules.py:157-193), folded form ----
+ * For root i, head h:  score_j = qk[i,h,:] . x_ij ; masked (mask_ids==0) -> -1e10 ; a = softmax_j ;
+ * out_s[i,h,:] = sum_j a_j x_ij, with x_ij = [node row | edge row | time enc] built on the fly:
+ *   node row  = node_tab[r]  (+ node_tab2[r]),  r = node_idx ? node_idx[i*k+j] : i*k+j
+ *   edge row  = edge_tab[e],                    e = edge_idx ? edge_idx[i*k+j] : i*k+j
+ *   time enc  = time_feat ? time_feat[i*k+j,:] : cos(fma((float)(t_query[i]-(double)t_nbr[i*k+j]), w, b))
+ * qk already holds scaling * W_k,h^T W_q,h [x_i | cos(b)] (H*Dk floats per root, Dk = F+E+T). */
+int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H,
+                        const float* node_tab, int ld_node, const float* node_tab2, int ld_node2,
+                        const int64_t* node_idx, int F,
+                        const float* edge_tab, int ld_edge, const int64_t* edge_idx, int E,
+                        const float* time_feat, const double* t_query, const float* t_nbr,
+                        const float* w, const float* b, int T,
+                        const int64_t* mask_ids, float* out_s, int lds, float* out_scores, dyg_stream_t stream);
+
+/* ---- a16: nn.MultiheadAttention core inside DyGFormer's TransformerEncoder (models/DyGFormer.py:454) ----
+ * qkv (B,S,3*H*hd) packed [q|k|v]; out (B,S,H*hd) = softmax(q k^T / sqrt(hd)) v per head; no mask. */
+int dyg_seq_attention(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, float* out, int ldo,
+                      dyg_stream_t stream);
+/* out[b,:] = mean over tokens [tok0, tok0+cnt) of x[b,:,:] (models/DyGFormer.py:185-187). */
+int dyg_mean_tokens(const float* x, int64_t B, int S, int D, int tok0, int cnt, float* out, int ldo, dyg_stream_t stream);
+
+/* ---- a17-a19: TGN memory path (models/MemoryModel.py:139-161, 212-251, 275-300, 435-487) ---- */
+/* persist look-ahead state of the batch's nodes: memory[v]=mem_view[v], last_update[v]=lu_view[v], pending[v]=0. */
+int dyg_tgn_persist(const int64_t* node_ids, int64_t n, float* memory, const float* mem_view, float* last_update,
+                    const float* lu_view, uint8_t* pending, int D, dyg_stream_t stream);
+/* winner[v] = max over candidates c in [0,2B) owned by v of c (c<B: src role of event c; c>=B: dst role of
+ * event c-B) == the message the reference's list order leaves last (src-role appends, then dst-role appends). */
+int dyg_tgn_select_last(const int64_t* src, const int64_t* dst, int64_t B, int32_t* winner, dyg_stream_t stream);
+/* msg[c,:] = [memory[owner] | other_feat | cos(fma((float)t - last_update[owner], w, b)) | edge_tab[eid]],
+ * other_feat = other_emb ? other_emb[c] : memory[other]  (DyRep passes embeddings). msg is (2B, 2D+T+E). */
+int dyg_tgn_build_messages(const int64_t* src, const int64_t* dst, const double* t, const int64_t* eid, int64_t B,
+                           const float* memory, const float* last_update, int D, const float* other_emb, int ld_other,
+                           const float* edge_tab, int ld_edge, int E, const float* w, const float* b, int T,
+                           float* msg, int ldm, dyg_stream_t stream);
+/* GRU / RNN cell epilogue + commit for winning candidates: gi=(2B,G*D) input gates incl. bias_ih, gh=(2B,G*D)
+ * hidden gates incl. bias_hh (G=3 GRU: r,z,n order of nn.GRUCell; G=1 tanh RNNCell).
+ * mem_view[v]=h', lu_view[v]=(float)t, pending[v]=1, msg_store[v]=msg[c], msg_time[v]=t, winner[v] reset to -1. */
+int dyg_tgn_cell_commit(const float* gi, const float* gh, int G, const int64_t* src, const int64_t* dst,
+                        const double* t, int64_t B, int32_t* winner, const float* memory, float* mem_view,
+                        float* lu_view, uint8_t* pending, int D, const float* msg, int ldm, int msg_dim,
+                        float* msg_store, double* msg_time, dyg_stream_t stream);
+/* reference's "Trying to update memory to time in the past" assert (models/MemoryModel.py:448-449):
+ * flag[0] set to 1 if any last_update[v] > (float)msg_time for pending v in node_ids. */
+int dyg_tgn_check_time(const int64_t* node_ids, int64_t n, const float* last_update, const float* lu_view,
+                       const uint8_t* pending, int32_t* flag, dyg_stream_t stream);
+
+/* JODIE TimeProjectionEmbedding (models/MemoryModel.py:534-545) fused with the time-shift normalisation
+ * (models/MemoryModel.py:114-118): out[m,:] = mem[ids[m],:] * (1 + ((t[m]-lu[ids[m]]-mean)/std) * w + b). */
+int dyg_jodie_project(const float* mem, int ld, const float* lu, const int64_t* ids, const double* t, int64_t M, int D,
+                      float mean, float stdv, const float* w, const float* b, float* out, int ldo, dyg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYGB200_H */

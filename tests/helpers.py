@@ -1,0 +1,188 @@
+"""Shared test fixtures: small seeded graphs, deterministic weights, batch iteration."""
+import numpy as np
+import torch
+
+from dyglib_b200.synthetic import make_graph
+
+
+def small_graph(seed=7, E=3000, nu=60, ni=25, tmax=200000.0, F=172):
+    return make_graph(E, nu, ni, tmax, seed, feat_dim=F)
+
+
+def deterministic_state_dict(template: dict, seed: int = 0) -> dict:
+    """Weights that depend only on (key, shape, seed), so the reference (build container), the oracle and the
+    CUDA modules (GPU box) can be given identical parameters without shipping checkpoints."""
+    import zlib
+    out = {}
+    for key in sorted(template.keys()):
+        shape = tuple(template[key].shape)
+        # shared modules appear under two prefixes in the reference's state_dict; give aliases one value
+        canon = key.replace('embedding_module.time_encoder', 'time_encoder').replace('memory_updater.memory_bank', 'memory_bank')
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(canon.encode()))
+        if 'node_memories' in key or 'node_last_updated_times' in key:
+            v = torch.zeros(shape)
+        elif key.endswith('time_encoder.w.weight'):
+            v = template[key].detach().clone().float().cpu()          # keep the fixed 1/10^linspace init
+        elif key.endswith('time_encoder.w.bias'):
+            v = 0.1 * torch.randn(shape, generator=g)                 # non-zero bias exercises the fp32 FMA
+        elif ('norm' in key) and key.endswith('weight'):
+            v = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) >= 2:
+            v = torch.randn(shape, generator=g) / np.sqrt(shape[-1])
+        else:
+            v = 0.1 * torch.randn(shape, generator=g)
+        out[key] = v.float()
+    return out
+
+
+def batches(g, start, nb, B, seed=0):
+    rng = np.random.RandomState(seed)
+    uniq = np.unique(g.dst_node_ids)
+    for b in range(nb):
+        sl = slice(start + b * B, start + (b + 1) * B)
+        neg = uniq[rng.randint(0, len(uniq), B)]
+        yield g.src_node_ids[sl], g.dst_node_ids[sl], g.node_interact_times[sl], g.edge_ids[sl], neg
+
+
+def make_queries(g, n, rng, with_f32=False):
+    e = rng.integers(0, g.num_interactions, n)
+    side = rng.integers(0, 2, n).astype(bool)
+    nodes = np.where(side, g.src_node_ids[e], g.dst_node_ids[e])
+    times = g.node_interact_times[e].copy()
+    nodes[: n // 20] = 0
+    times[n // 20: n // 10] += 0.5
+    if with_f32:
+        times = times.astype(np.float32)
+    return nodes, times
+
+
+# ---------------------------------------------------------------------------------------------
+# Case runners shared by the oracle-vs-golden (CPU) and CUDA-vs-oracle / CUDA-vs-golden (GPU) tests.
+# `make_sampler(graph, strategy, seed, tsf)` returns an object with the reference's sampler API.
+def run_sampler_cases(make_sampler, pad_fn, cooc_fn):
+    g = small_graph(seed=7)
+    out = {}
+    for strategy, seed in (('recent', None), ('uniform', 3), ('time_interval_aware', 3)):
+        s = make_sampler(g, strategy, seed, 1e-5)
+        rng = np.random.default_rng(0)
+        for k, f32 in ((20, False), (3, True), (1, False)):
+            nodes, times = make_queries(g, 400, rng, f32)
+            a, b, c = s.get_historical_neighbors(nodes, times, k)
+            out[f'{strategy}_k{k}_nbr'], out[f'{strategy}_k{k}_eid'], out[f'{strategy}_k{k}_t'] = a, b, c
+    s = make_sampler(g, 'recent', None, 0.0)
+    rng = np.random.default_rng(5)
+    nodes, times = make_queries(g, 100, rng)
+    ln, le, lt = s.get_multi_hop_neighbors(2, nodes, times, 3)
+    for h in range(2):
+        out[f'multihop_{h}_nbr'], out[f'multihop_{h}_eid'], out[f'multihop_{h}_t'] = ln[h], le[h], lt[h]
+    rng = np.random.default_rng(1)
+    n1, t1 = make_queries(g, 200, rng)
+    n2, _ = make_queries(g, 200, rng)
+    pads = []
+    for nodes in (n1, n2):
+        a = s.get_all_first_hop_neighbors(nodes, t1)
+        out.setdefault('firsthop_len', np.array([len(x) for x in a[0]]))
+        pads.append(pad_fn(s, g, nodes, t1, a, 4, 32))
+    for i, p in enumerate(pads):
+        out[f'pad{i}_nbr'], out[f'pad{i}_eid'], out[f'pad{i}_t'] = p
+    out['cooc_src'], out['cooc_dst'] = cooc_fn(pads[0][0], pads[1][0])
+    return out
+
+
+def run_model_cases(make_tgat, make_dygformer, make_memory, which=('tgat', 'dygformer', 'TGN', 'DyRep', 'JODIE')):
+    """make_*(graph, ...) return objects exposing compute_src_dst_node_temporal_embeddings; outputs as numpy."""
+    out = {}
+
+    def np_(x):
+        return x.detach().cpu().numpy()
+    with torch.no_grad():
+        if 'tgat' in which:
+            g = small_graph(seed=11)
+            m = make_tgat(g, 1)
+            for bi, (src, dst, t, _, neg) in enumerate(batches(g, 2000, 2, 40)):
+                for tag, d in (('pos', dst), ('neg', neg)):
+                    a, b = m.compute_src_dst_node_temporal_embeddings(src, d, t, 20)
+                    out[f'tgat_{bi}_{tag}_src'], out[f'tgat_{bi}_{tag}_dst'] = np_(a), np_(b)
+        if 'dygformer' in which:
+            g = small_graph(seed=12)
+            for P, L in ((2, 16), (1, 8), (4, 32)):
+                m = make_dygformer(g, P, L, 2)
+                for bi, (src, dst, t, _, neg) in enumerate(batches(g, 1000, 2, 50)):
+                    for tag, d in (('pos', dst), ('neg', neg)):
+                        a, b = m.compute_src_dst_node_temporal_embeddings(src, d, t)
+                        out[f'dygformer_P{P}_L{L}_{bi}_{tag}_src'], out[f'dygformer_P{P}_L{L}_{bi}_{tag}_dst'] = np_(a), np_(b)
+        g = small_graph(seed=13)
+        for name in ('TGN', 'DyRep', 'JODIE'):
+            if name not in which:
+                continue
+            m, mem_fn = make_memory(g, name, 3)
+            for bi, (src, dst, t, eid, neg) in enumerate(batches(g, 0, 12, 30)):
+                ra = m.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, 10)
+                rb = m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+                if bi >= 9:
+                    out[f'{name}_{bi}_neg_src'], out[f'{name}_{bi}_neg_dst'] = np_(ra[0]), np_(ra[1])
+                    out[f'{name}_{bi}_pos_src'], out[f'{name}_{bi}_pos_dst'] = np_(rb[0]), np_(rb[1])
+            mem, lu = mem_fn(m)
+            out[f'{name}_memory'], out[f'{name}_last_update'] = np_(mem), np_(lu)
+    return out
+
+
+def templates():
+    """state_dict templates (keys / shapes) from the CUDA package's parameter containers, built on CPU."""
+    from dyglib_b200.models.TGAT import TGAT
+    from dyglib_b200.models.DyGFormer import DyGFormer
+    from dyglib_b200.models.MemoryModel import MemoryModel
+    return TGAT, DyGFormer, MemoryModel
+
+
+def oracle_factories():
+    from oracle.sampler import OracleSampler
+    from oracle.models import OracleTGAT, OracleDyGFormer, OracleMemoryModel
+    TGAT, DyGFormer, MemoryModel = templates()
+
+    def sampler(g, strategy='recent', seed=None, tsf=0.0):
+        return OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, strategy, tsf, seed)
+
+    def tgat(g, wseed):
+        sd = deterministic_state_dict(TGAT(g.node_raw_features, g.edge_raw_features, None, 100, 2, 2, 0.1, 'cpu').state_dict(), wseed)
+        return OracleTGAT(sd, g.node_raw_features, g.edge_raw_features, sampler(g), 2, 2)
+
+    def dygformer(g, P, L, wseed):
+        sd = deterministic_state_dict(DyGFormer(g.node_raw_features, g.edge_raw_features, None, 100, 50, P, 2, 2, 0.1, L, 'cpu').state_dict(), wseed)
+        return OracleDyGFormer(sd, g.node_raw_features, g.edge_raw_features, sampler(g), 50, P, 2, 2, L)
+
+    def memory(g, name, wseed):
+        sd = deterministic_state_dict(MemoryModel(g.node_raw_features, g.edge_raw_features, None, 100, name, 1, 2, 0.1, device='cpu').state_dict(), wseed)
+        m = OracleMemoryModel(sd, g.node_raw_features, g.edge_raw_features, sampler(g), name, 1, 2, 3.0, 50.0, 5.0, 70.0)
+        return m, (lambda mm: (mm.memory, mm.last_update))
+    return sampler, tgat, dygformer, memory
+
+
+def cuda_factories():
+    from dyglib_b200.utils.utils import get_neighbor_sampler
+    TGAT, DyGFormer, MemoryModel = templates()
+
+    def sampler(g, strategy='recent', seed=None, tsf=0.0):
+        return get_neighbor_sampler(g, strategy, time_scaling_factor=tsf, seed=seed)
+
+    def tgat(g, wseed):
+        m = TGAT(g.node_raw_features, g.edge_raw_features, sampler(g), 100, 2, 2, 0.1, 'cuda').eval()
+        m.load_state_dict(deterministic_state_dict(m.state_dict(), wseed))
+        return m
+
+    def dygformer(g, P, L, wseed):
+        m = DyGFormer(g.node_raw_features, g.edge_raw_features, sampler(g), 100, 50, P, 2, 2, 0.1, L, 'cuda').eval()
+        m.load_state_dict(deterministic_state_dict(m.state_dict(), wseed))
+        return m
+
+    def memory(g, name, wseed):
+        m = MemoryModel(g.node_raw_features, g.edge_raw_features, sampler(g), 100, name, 1, 2, 0.1, 3.0, 50.0, 5.0, 70.0, 'cuda').eval()
+        m.load_state_dict(deterministic_state_dict(m.state_dict(), wseed))
+        m.memory_bank.__init_memory_bank__()
+        return m, (lambda mm: (mm.memory_bank.node_memories.data, mm.memory_bank.node_last_updated_times.data))
+    return sampler, tgat, dygformer, memory
+
+
+def load_golden(name):
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)))

@@ -1,0 +1,230 @@
+"""GPU parity: device sampler / pad / co-occurrence kernels vs the oracle and the reference's golden vectors.
+Integer, index and time outputs must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (run_sampler_cases, oracle_factories, cuda_factories, load_golden, small_graph, make_queries)
+from dyglib_b200.synthetic import make_graph, make_config_graph
+from oracle.sampler import OracleSampler, pad_sequences, count_nodes_appearances
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda_pad(s, g, nodes, times, lists, P, L):
+    pn, pe, pt, ln, _ = s.get_all_first_hop_neighbors_device(nodes, times, L, P)
+    Lp = (int(ln.max().item()) + P - 1) // P * P
+    return pn[:, :Lp].cpu().numpy(), pe[:, :Lp].cpu().numpy(), pt[:, :Lp].cpu().numpy()
+
+
+def cuda_cooc(a, b):
+    from dyglib_b200.models.DyGFormer import NeighborCooccurrenceEncoder
+    enc = NeighborCooccurrenceEncoder(50, 'cuda').to('cuda')
+    x, y = enc.count_nodes_appearances(a, b)
+    return x.cpu().numpy(), y.cpu().numpy()
+
+
+def assert_same(got, want):
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].dtype == want[k].dtype, (k, got[k].dtype, want[k].dtype)
+        assert got[k].shape == want[k].shape, k
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_sampler_cases_match_golden_and_oracle():
+    csampler = cuda_factories()[0]
+    got = run_sampler_cases(csampler, cuda_pad, cuda_cooc)
+    assert_same(got, load_golden('sampler.npz'))
+    osampler = oracle_factories()[0]
+    want = run_sampler_cases(osampler, lambda s, g, n, t, lists, P, L: pad_sequences(n, t, lists[0], lists[1], lists[2], P, L),
+                             count_nodes_appearances)
+    assert_same(got, want)
+
+
+def _pair(g, strategy='recent', seed=None, tsf=0.0, **kw):
+    from dyglib_b200.utils.utils import get_neighbor_sampler
+    return (get_neighbor_sampler(g, strategy, tsf, seed, **kw),
+            OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, strategy, tsf, seed))
+
+
+def _check(c, o, nodes, times, k):
+    a = c.get_historical_neighbors(nodes, times, k)
+    b = o.get_historical_neighbors(nodes, times, k)
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+
+
+@pytest.mark.parametrize('k', [1, 2, 5, 10, 20, 33, 64, 130])
+def test_recent_all_lane_widths(k):
+    g = small_graph(seed=21, E=6000, nu=30, ni=10)
+    c, o = _pair(g)
+    rng = np.random.default_rng(k)
+    nodes, times = make_queries(g, 700, rng)
+    _check(c, o, nodes, times, k)
+
+
+def test_recent_edge_cases():
+    """zero history, deg < k, query time equal to an event time (strict <), float32-rounded times > 2^24,
+    node 0, duplicate timestamps, self loops, unsorted input."""
+    rng = np.random.default_rng(3)
+    E = 4000
+    src = rng.integers(1, 40, E)
+    dst = rng.integers(1, 40, E)                       # non-bipartite, self loops occur
+    t = np.sort(rng.integers(1, 500, E)).astype(np.float64) + 1.0e8   # many duplicates, > 2^24
+    g = make_graph(16, 4, 4, 100, 0, with_features=False)
+    g.src_node_ids, g.dst_node_ids, g.node_interact_times = src, dst, t
+    g.edge_ids = np.arange(1, E + 1)
+    g.num_nodes = 40
+    c, o = _pair(g)
+    nodes = rng.integers(0, 40, 3000)
+    times = t[rng.integers(0, E, 3000)]
+    times[:500] = times[:500].astype(np.float32)        # hop-2 style float32-rounded query times
+    times[500:600] = 0.0                                 # before everything
+    times[600:700] = 1e12                                # after everything
+    for k in (20, 4):
+        _check(c, o, nodes, times, k)
+        _check(c, o, nodes, times.astype(np.float32), k)
+    # unsorted input order: both must stable-sort by time per node
+    perm = rng.permutation(E)
+    g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids = src[perm], dst[perm], t[perm], g.edge_ids[perm]
+    c, o = _pair(g)
+    _check(c, o, nodes, times, 7)
+
+
+def test_adj_list_constructor_matches():
+    from dyglib_b200.utils.utils import NeighborSampler
+    g = small_graph(seed=5, E=1500)
+    adj = [[] for _ in range(g.num_nodes)]
+    for s, d, e, t in zip(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times):
+        adj[s].append((d, e, t))
+        adj[d].append((s, e, t))
+    c = NeighborSampler(adj, 'recent')
+    o = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
+    nodes, times = make_queries(g, 500, np.random.default_rng(0))
+    _check(c, o, nodes, times, 20)
+    nb, ei, tt, _ = c.find_neighbors_before(int(nodes[100]), float(times[100]))
+    a, i = o.count_before(nodes[100], times[100])
+    assert np.array_equal(nb, o.nbr[a:a + i]) and np.array_equal(ei, o.eid[a:a + i]) and np.array_equal(tt, o.t[a:a + i])
+
+
+@pytest.mark.parametrize('strategy', ['uniform', 'time_interval_aware'])
+def test_random_strategies_replay_stream_across_calls(strategy):
+    """The RNG stream is consumed in call order, also across recursion-style repeated calls."""
+    g = small_graph(seed=31, E=5000, nu=50, ni=20)
+    c, o = _pair(g, strategy, seed=11, tsf=2e-5)
+    rng = np.random.default_rng(9)
+    for k in (20, 5):
+        nodes, times = make_queries(g, 300, rng)
+        _check(c, o, nodes, times, k)
+    c.reset_random_state()
+    o.reset_random_state()
+    nodes, times = make_queries(g, 200, rng)
+    a = c.get_multi_hop_neighbors(2, nodes, times, 4)
+    b = o.get_multi_hop_neighbors(2, nodes, times, 4)
+    for la, lb in zip(a, b):
+        for x, y in zip(la, lb):
+            assert np.array_equal(x, y)
+
+
+def test_tia_device_table_mismatch_rate():
+    """Device prefix-CDF draw fed with the replayed random_sample stream: indices equal the reference's unless a
+    uniform lands within float32-softmax rounding of a CDF boundary (expected rate <~ 1e-6 per draw)."""
+    g = small_graph(seed=41, E=8000, nu=40, ni=15)
+    c, o = _pair(g, 'time_interval_aware', seed=5, tsf=1e-5)
+    from dyglib_b200 import _native
+    from dyglib_b200.ops import _p, _stream
+    rng = np.random.default_rng(2)
+    nodes, times = make_queries(g, 3000, rng)
+    k = 20
+    want = o.get_historical_neighbors(nodes, times, k)
+    ids, tq = c._queries(nodes, times)
+    cnt = c.count_before_device(ids, tq)
+    cnt_h = cnt.cpu().numpy()
+    rs = np.random.RandomState(5)
+    u = np.zeros((len(nodes), k))
+    for q in np.nonzero(cnt_h)[0]:
+        u[q] = rs.random_sample(k)
+    u_d = torch.from_numpy(u).cuda()
+    sel = torch.empty((len(nodes), k), dtype=torch.int64, device='cuda')
+    _native.check(_native.load().dyg_draw_tia(_p(c.tia_cum), _p(c.indptr), _p(ids), _p(cnt), _p(u_d), len(nodes), k, _p(sel), _stream()))
+    out = [torch.empty((len(nodes), k), dtype=d, device='cuda') for d in (torch.int64, torch.int64, torch.float32)]
+    _native.check(_native.load().dyg_sample_indexed(_p(c.halfedges), _p(c.indptr), _p(ids), _p(cnt), _p(sel), len(nodes), k,
+                                                    _p(out[0]), _p(out[1]), _p(out[2]), _stream()))
+    mism = float((out[1].cpu().numpy() != want[1]).mean())
+    assert mism <= 1e-4, mism
+
+
+def test_philox_mode_draws_valid_history():
+    g = small_graph(seed=51, E=5000)
+    from dyglib_b200.utils.utils import get_neighbor_sampler
+    for strategy in ('uniform', 'time_interval_aware'):
+        c = get_neighbor_sampler(g, strategy, 1e-5, seed=7, rng='philox')
+        nodes, times = make_queries(g, 2000, np.random.default_rng(4))
+        nb, ei, tt = c.get_historical_neighbors(nodes, times, 20)
+        has = nb[:, 0] != 0
+        assert has.any()
+        assert (np.diff(tt[has], axis=1) >= 0).all()                      # rows re-sorted by time
+        assert (tt[has] < times[has, None].astype(np.float32) + 1).all()  # only history
+        # every sampled edge id is a real interaction of that node
+        e = ei[has].reshape(-1)
+        owner = np.repeat(nodes[has], 20)
+        assert ((g.src_node_ids[e - 1] == owner) | (g.dst_node_ids[e - 1] == owner)).all()
+
+
+def test_large_random_recent_and_firsthop():
+    """>= 1e5 random queries on a wikipedia-sized graph against the oracle."""
+    g = make_config_graph('dygformer_wiki', with_features=False)
+    c, o = _pair(g)
+    rng = np.random.default_rng(0)
+    nodes, times = make_queries(g, 100_000, rng)
+    _check(c, o, nodes, times, 20)
+    nodes, times = nodes[:3000], times[:3000]
+    for P, L in ((2, 64), (16, 512)):
+        lists = o.get_all_first_hop_neighbors(nodes, times)
+        want = pad_sequences(nodes, times, lists[0], lists[1], lists[2], P, L)
+        got = cuda_pad(c, g, nodes, times, None, P, L)
+        for x, y in zip(got, want):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+    ln, le, lt = c.get_all_first_hop_neighbors(nodes[:50], times[:50])
+    ol = o.get_all_first_hop_neighbors(nodes[:50], times[:50])
+    for i in range(50):
+        assert np.array_equal(ln[i], ol[0][i]) and np.array_equal(le[i], ol[1][i]) and np.array_equal(lt[i], ol[2][i])
+
+
+@pytest.mark.parametrize('Ls,Ld', [(64, 64), (512, 512), (8, 40), (1, 1)])
+def test_cooc_counts_exact(Ls, Ld):
+    rng = np.random.default_rng(Ls + Ld)
+    B = 37
+    s = rng.integers(0, 12, (B, Ls))      # few distinct ids -> many collisions, zeros = padding
+    d = rng.integers(0, 12, (B, Ld))
+    s[0] = 0
+    d[1] = 0
+    want = count_nodes_appearances(s, d)
+    got = cuda_cooc(s, d)
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y)
+
+
+def test_full_size_properties():
+    """BASELINE-size (1.29 M events, LastFM-shaped) properties that need no oracle: sortedness, strictness,
+    left padding, idempotence, agreement between count_before and the sampled tail."""
+    g = make_config_graph('dygformer_lastfm', with_features=False)
+    from dyglib_b200.utils.utils import get_neighbor_sampler
+    c = get_neighbor_sampler(g, 'recent')
+    rng = np.random.default_rng(1)
+    e = rng.integers(0, g.num_interactions, 1 << 18)
+    nodes = np.where(rng.integers(0, 2, len(e)) == 1, g.src_node_ids[e], g.dst_node_ids[e])
+    times = g.node_interact_times[e]
+    nb, ei, tt = c.get_historical_neighbors(nodes, times, 20)
+    nb2, ei2, tt2 = c.get_historical_neighbors(nodes, times, 20)
+    assert np.array_equal(nb, nb2) and np.array_equal(ei, ei2) and np.array_equal(tt, tt2)
+    valid = nb != 0
+    assert (np.diff(valid.astype(np.int8), axis=1) >= 0).all()           # zeros only on the left
+    assert (np.diff(np.where(valid, tt, -np.inf), axis=1) >= 0).all()    # ascending times
+    assert (g.node_interact_times[ei[valid] - 1] < np.repeat(times[:, None], 20, 1)[valid]).all()   # strict history
+    ids, tq = c._queries(nodes, times)
+    cnt = c.count_before_device(ids, tq).cpu().numpy()
+    assert np.array_equal(np.minimum(cnt, 20), valid.sum(1))
+    deg = np.bincount(np.concatenate([g.src_node_ids, g.dst_node_ids]), minlength=g.num_nodes)
+    assert (cnt <= deg[nodes]).all()

@@ -1,0 +1,28 @@
+"""CPU: the oracle reproduces the golden vectors the unmodified reference produced (scripts/make_golden.py)."""
+import numpy as np
+import pytest
+
+from helpers import run_sampler_cases, run_model_cases, oracle_factories, load_golden
+from oracle.sampler import pad_sequences, count_nodes_appearances
+
+
+def test_oracle_sampler_matches_golden():
+    sampler, _, _, _ = oracle_factories()
+    got = run_sampler_cases(lambda g, st, seed, tsf: sampler(g, st, seed, tsf),
+                            lambda s, g, nodes, times, lists, P, L: pad_sequences(nodes, times, lists[0], lists[1], lists[2], P, L),
+                            count_nodes_appearances)
+    gold = load_golden('sampler.npz')
+    assert set(got) == set(gold)
+    for k in gold:
+        assert got[k].dtype == gold[k].dtype, k
+        assert np.array_equal(got[k], gold[k]), k
+
+
+@pytest.mark.parametrize('which', ['tgat', 'dygformer', 'TGN', 'DyRep', 'JODIE'])
+def test_oracle_models_match_golden(which):
+    _, tgat, dygformer, memory = oracle_factories()
+    got = run_model_cases(tgat, dygformer, memory, which=(which,))
+    gold = load_golden('models.npz')
+    assert len(got) > 0
+    for k in got:
+        np.testing.assert_allclose(got[k], gold[k], rtol=1e-4, atol=1e-5, err_msg=k)
