@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Benchmark of the temporal neighbour-aggregation hot path (contract: see DESIGN.md section "Measurement").
+"""Benchmark of the temporal neighbour-aggregation hot path (contract: DESIGN.md section "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
@@ -9,11 +9,15 @@ A step = one pass of the hot path over `--batches-per-step` reference batches of
 keeps its own padding unit): negative draw (host, precomputed like the reference's seeded sampler) ->
 first-hop search + pad -> co-occurrence -> patch projections -> 2 transformer layers -> link scores for
 the positive and the negative pair of every event.
+
+Other workloads (parity-test configs of BASELINE.json, reported in profiles/ and DESIGN.md, not the headline):
+    tgat_myket, tgn_reddit, dygformer_lastfm, sampler_sweep
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -30,12 +34,6 @@ sys.path.insert(0, ROOT)
 from dyglib_b200.synthetic import make_config_graph  # noqa: E402
 
 REF_BATCH = 200
-WORKLOADS = {
-    'dygformer_wiki': dict(graph='dygformer_wiki', model='DyGFormer', P=2, L=64),
-    'dygformer_lastfm': dict(graph='dygformer_lastfm', model='DyGFormer', P=16, L=512),
-    'tgat_myket': dict(graph='tgat_myket', model='TGAT', k=20, layers=2),
-    'tgn_reddit': dict(graph='tgn_reddit', model='TGN', k=10, layers=1),
-}
 
 
 def peaks():
@@ -84,15 +82,17 @@ class ClockSampler:
 
 
 def dist_env():
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    return rank, world, local
+    return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
 
 
-# ------------------------------------------------------------------------------------------------ workload data
+def shard_batches(step, G, world, rank, nb):
+    """Reference batches of one step for one rank: whole batches, round-robin over ranks (weak scaling)."""
+    return [((step * G + j) * world + rank) % nb for j in range(G)]
+
+
 class Stream:
-    """Chronological reference batches of the evaluation region (last 15 % of events) with seeded negatives."""
+    """Chronological reference batches with seeded random negatives (the reference's `random` negative mode,
+    utils/utils.py:378-390, drawn once on the host before timing)."""
 
     def __init__(self, g, batch=REF_BATCH, region=0.15, seed=2, start=None):
         E = g.num_interactions
@@ -108,108 +108,248 @@ class Stream:
         idx = np.concatenate([np.arange(self.start + b * self.batch, self.start + (b + 1) * self.batch) for b in batch_ids])
         nidx = np.concatenate([np.arange(b * self.batch, (b + 1) * self.batch) for b in batch_ids])
         g = self.g
-        return g.src_node_ids[idx], g.dst_node_ids[idx], self.neg[nidx], g.node_interact_times[idx], g.edge_ids[idx]
+        return (g.src_node_ids[idx], g.dst_node_ids[idx], self.neg[nidx], g.node_interact_times[idx], g.edge_ids[idx])
 
 
-def build_dygformer(g, wl, device):
-    from dyglib_b200.utils.utils import get_neighbor_sampler, set_random_seed
-    from dyglib_b200.models.DyGFormer import DyGFormer
-    from dyglib_b200.models.modules import MergeLayer
-    set_random_seed(0)
-    t0 = time.perf_counter()
-    sampler = get_neighbor_sampler(g, 'recent', device=device)
-    torch.cuda.synchronize()
-    build_s = time.perf_counter() - t0
-    model = DyGFormer(g.node_raw_features, g.edge_raw_features, sampler, 100, 50, wl['P'], 2, 2, 0.1, wl['L'], device).eval()
-    pred = MergeLayer(172, 172, 172, 1).to(device).eval()
-    return sampler, model, pred, build_s
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """One BASELINE.json config: GPU step through the package's public API + the oracle (CPU port) step."""
+    name = ''
+    dominant_bound = 'tensor'
+    sequential = False        # TGN: batches form a dependency chain -> replicas only across GPUs
+    default_G = 32
+    cpu_batches = 12
+
+    def describe(self):
+        raise NotImplementedError
+
+    def build(self, dev):
+        raise NotImplementedError
+
+    def step(self, src, dst, neg, t, eid):
+        raise NotImplementedError
+
+    def oracle(self):
+        raise NotImplementedError
 
 
-def dygformer_step(model, pred, src, dst, neg, t):
-    """pos and neg pairs of every event; every reference batch is its own padding unit for pos and for neg."""
+def _predict(pred, a, b):
     from dyglib_b200 import ops
-    s2, d2, t2 = torch.cat([src, src]), torch.cat([dst, neg]), torch.cat([t, t])
-    es, ed = model.compute_src_dst_node_temporal_embeddings(s2, d2, t2, batch_size=REF_BATCH)
-    h = ops.linear([ops.seg_rows(es), ops.seg_rows(ed)], es.shape[0], pred.fc1.weight.detach(), pred.fc1.bias.detach(), act=ops.ACT_RELU)
+    h = ops.linear([ops.seg_rows(a), ops.seg_rows(b)], a.shape[0], pred.fc1.weight.detach(), pred.fc1.bias.detach(), act=ops.ACT_RELU)
     return ops.linear([ops.seg_rows(h)], h.shape[0], pred.fc2.weight.detach(), pred.fc2.bias.detach(), act=ops.ACT_SIGMOID)
 
 
-# ------------------------------------------------------------------------------------------------ CPU oracle arm
-def oracle_dygformer(g, wl, state_dict, pred_sd):
-    from oracle.sampler import OracleSampler
-    from oracle.models import OracleDyGFormer, merge_layer
-    samp = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
-    m = OracleDyGFormer(state_dict, g.node_raw_features, g.edge_raw_features, samp, 50, wl['P'], 2, 2, wl['L'])
+class DyGFormerWL(Workload):
+    def __init__(self, graph, P, L):
+        self.name, self.P, self.L = graph, P, L
+        self.cpu_batches = 12 if L <= 64 else 3
+        self.default_G = 32 if L <= 64 else 8
 
-    def step(src, dst, neg, t):
-        out = []
-        with torch.no_grad():
-            for d in (dst, neg):
-                a, b = m.compute_src_dst_node_temporal_embeddings(src, d, t)
-                out.append(torch.sigmoid(merge_layer(pred_sd, '', a, b)))
-        return out
-    return step
+    def describe(self):
+        return f'{self.name} (DyGFormer P={self.P} L={self.L}, recent first-hop history, batch 200, pos+neg pairs)'
+
+    def build(self, dev):
+        from dyglib_b200.utils.utils import get_neighbor_sampler, set_random_seed
+        from dyglib_b200.models.DyGFormer import DyGFormer
+        from dyglib_b200.models.modules import MergeLayer
+        self.g = g = make_config_graph(self.name)
+        set_random_seed(0)
+        t0 = time.perf_counter()
+        self.sampler = get_neighbor_sampler(g, 'recent', device=dev)
+        torch.cuda.synchronize()
+        self.build_s = time.perf_counter() - t0
+        self.model = DyGFormer(g.node_raw_features, g.edge_raw_features, self.sampler, 100, 50, self.P, 2, 2, 0.1, self.L, dev).eval()
+        self.pred = MergeLayer(172, 172, 172, 1).to(dev).eval()
+        self.stream = Stream(g)
+
+    def step(self, src, dst, neg, t, eid):
+        # pos and neg pairs of every event; every reference batch is its own padding unit for pos and for neg
+        s2, d2, t2 = torch.cat([src, src]), torch.cat([dst, neg]), torch.cat([t, t])
+        es, ed = self.model.compute_src_dst_node_temporal_embeddings(s2, d2, t2, batch_size=REF_BATCH)
+        return _predict(self.pred, es, ed)
+
+    def oracle(self):
+        from oracle.sampler import OracleSampler
+        from oracle.models import OracleDyGFormer, merge_layer
+        g = self.g
+        sd = {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+        psd = {k: v.detach().cpu() for k, v in self.pred.state_dict().items()}
+        samp = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
+        m = OracleDyGFormer(sd, g.node_raw_features, g.edge_raw_features, samp, 50, self.P, 2, 2, self.L)
+
+        def step(src, dst, neg, t, eid):
+            out = []
+            with torch.no_grad():
+                for d in (dst, neg):
+                    a, b = m.compute_src_dst_node_temporal_embeddings(src, d, t)
+                    out.append(torch.sigmoid(merge_layer(psd, '', a, b)))
+            return torch.cat(out)
+        return step
 
 
-def cpu_state_dicts(wl, g):
-    """Reference-default initialised weights under seed 0, built on CPU from the package's parameter containers."""
-    from dyglib_b200.utils.utils import set_random_seed
-    from dyglib_b200.models.DyGFormer import DyGFormer
-    from dyglib_b200.models.modules import MergeLayer
-    set_random_seed(0)
-    m = DyGFormer(g.node_raw_features[:2], g.edge_raw_features[:2], None, 100, 50, wl['P'], 2, 2, 0.1, wl['L'], 'cpu')
-    p = MergeLayer(172, 172, 172, 1)
-    return ({k: v.detach().clone() for k, v in m.state_dict().items()}, {k: v.detach().clone() for k, v in p.state_dict().items()})
+class TGATWL(Workload):
+    name = 'tgat_myket'
+    dominant_bound = 'hbm'
+    default_G = 8
+    cpu_batches = 2
+
+    def describe(self):
+        return 'tgat_myket (TGAT 2 layers, 20 recent neighbours, batch 200, pos+neg pairs; src embedding shared by both pairs)'
+
+    def build(self, dev):
+        from dyglib_b200.utils.utils import get_neighbor_sampler, set_random_seed
+        from dyglib_b200.models.TGAT import TGAT
+        from dyglib_b200.models.modules import MergeLayer
+        self.g = g = make_config_graph(self.name)
+        set_random_seed(0)
+        t0 = time.perf_counter()
+        self.sampler = get_neighbor_sampler(g, 'recent', device=dev)
+        torch.cuda.synchronize()
+        self.build_s = time.perf_counter() - t0
+        self.model = TGAT(g.node_raw_features, g.edge_raw_features, self.sampler, 100, 2, 2, 0.1, dev).eval()
+        self.pred = MergeLayer(172, 172, 172, 1).to(dev).eval()
+        self.stream = Stream(g)
+
+    def step(self, src, dst, neg, t, eid):
+        n = src.numel()
+        emb = self.model.compute_node_temporal_embeddings(torch.cat([src, dst, neg]), torch.cat([t, t, t]), 2, 20)
+        es = torch.cat([emb[:n], emb[:n]])
+        return _predict(self.pred, es, emb[n:])
+
+    def oracle(self):
+        from oracle.sampler import OracleSampler
+        from oracle.models import OracleTGAT, merge_layer
+        g = self.g
+        sd = {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+        psd = {k: v.detach().cpu() for k, v in self.pred.state_dict().items()}
+        samp = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
+        m = OracleTGAT(sd, g.node_raw_features, g.edge_raw_features, samp, 2, 2)
+
+        def step(src, dst, neg, t, eid):
+            out = []
+            with torch.no_grad():
+                for d in (dst, neg):       # the reference recomputes the src embedding for the negative pair
+                    a, b = m.compute_src_dst_node_temporal_embeddings(src, d, t, 20)
+                    out.append(torch.sigmoid(merge_layer(psd, '', a, b)))
+            return torch.cat(out)
+        return step
 
 
-def time_cpu(step, stream, n_batches, warm=1):
-    for b in range(warm):
-        step(*stream.rows([b])[:4])
-    t0 = time.perf_counter()
-    for b in range(warm, warm + n_batches):
-        step(*stream.rows([b])[:4])
-    return n_batches * stream.batch / (time.perf_counter() - t0)
+class TGNWL(Workload):
+    name = 'tgn_reddit'
+    dominant_bound = 'hbm'
+    sequential = True
+    default_G = 1
+    cpu_batches = 12
+
+    def describe(self):
+        return 'tgn_reddit (TGN 1 layer, 10 recent neighbours, last-message + GRU memory, batch 200 sequential, neg then pos call)'
+
+    def build(self, dev):
+        from dyglib_b200.utils.utils import get_neighbor_sampler, set_random_seed
+        from dyglib_b200.models.MemoryModel import MemoryModel
+        from dyglib_b200.models.modules import MergeLayer
+        self.g = g = make_config_graph(self.name)
+        set_random_seed(0)
+        t0 = time.perf_counter()
+        self.sampler = get_neighbor_sampler(g, 'recent', device=dev)
+        torch.cuda.synchronize()
+        self.build_s = time.perf_counter() - t0
+        self.model = MemoryModel(g.node_raw_features, g.edge_raw_features, self.sampler, 100, 'TGN', 1, 2, 0.1, device=dev).eval()
+        self.model.memory_bank.__init_memory_bank__()
+        self.pred = MergeLayer(172, 172, 172, 1).to(dev).eval()
+        self.stream = Stream(g, start=0, region=1.0)
+
+    def step(self, src, dst, neg, t, eid):
+        a, b = self.model.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, 10)
+        c, d = self.model.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+        return _predict(self.pred, torch.cat([c, a]), torch.cat([d, b]))
+
+    def oracle(self):
+        from oracle.sampler import OracleSampler
+        from oracle.models import OracleMemoryModel, merge_layer
+        g = self.g
+        sd = {k: v.detach().cpu() for k, v in self.model.state_dict().items()}
+        for k in sd:
+            if 'node_memories' in k or 'node_last_updated_times' in k:
+                sd[k] = torch.zeros_like(sd[k])
+        psd = {k: v.detach().cpu() for k, v in self.pred.state_dict().items()}
+        samp = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
+        m = OracleMemoryModel(sd, g.node_raw_features, g.edge_raw_features, samp, 'TGN', 1, 2)
+
+        def step(src, dst, neg, t, eid):
+            with torch.no_grad():
+                a, b = m.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, 10)
+                c, d = m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+                return torch.sigmoid(merge_layer(psd, '', torch.cat([c, a]), torch.cat([d, b])))
+        return step
 
 
-def run_reference(args, wl_name, wl):
+def make_workload(name):
+    if name == 'dygformer_wiki':
+        return DyGFormerWL('dygformer_wiki', 2, 64)
+    if name == 'dygformer_lastfm':
+        return DyGFormerWL('dygformer_lastfm', 16, 512)
+    if name == 'tgat_myket':
+        return TGATWL()
+    if name == 'tgn_reddit':
+        return TGNWL()
+    raise ValueError(name)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU arm: the oracle port of the reference path with all host threads, on the same config / metric."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    g = make_config_graph(wl['graph'])
-    sd, psd = cpu_state_dicts(wl, g)
-    stream = Stream(g)
-    step = oracle_dygformer(g, wl, sd, psd)
-    per_step = 2                                           # bounded sample: 2 reference batches per step
-    for w in range(args.warmup):
-        step(*stream.rows([w % stream.nb])[:4])
-    times = []
-    b = args.warmup
+    wl = make_workload(args.workload)
+    # weights: same constructors / seed as the GPU arm, built on CPU
+    from dyglib_b200.utils.utils import set_random_seed
+    set_random_seed(0)
+    wl.g = g = make_config_graph(wl.name)
+    from dyglib_b200.models.modules import MergeLayer
+    if isinstance(wl, DyGFormerWL):
+        from dyglib_b200.models.DyGFormer import DyGFormer
+        wl.model = DyGFormer(g.node_raw_features, g.edge_raw_features, None, 100, 50, wl.P, 2, 2, 0.1, wl.L, 'cpu')
+        wl.stream = Stream(g)
+    elif isinstance(wl, TGATWL):
+        from dyglib_b200.models.TGAT import TGAT
+        wl.model = TGAT(g.node_raw_features, g.edge_raw_features, None, 100, 2, 2, 0.1, 'cpu')
+        wl.stream = Stream(g)
+    else:
+        from dyglib_b200.models.MemoryModel import MemoryModel
+        wl.model = MemoryModel(g.node_raw_features, g.edge_raw_features, None, 100, 'TGN', 1, 2, 0.1, device='cpu')
+        wl.stream = Stream(g, start=0, region=1.0)
+    wl.pred = MergeLayer(172, 172, 172, 1)
+    step = wl.oracle()
+    per_step = 1 if isinstance(wl, TGATWL) else 2          # bounded sample per step
+    b = 0
+    for _ in range(args.warmup):
+        step(*wl.stream.rows([b % wl.stream.nb]))
+        b += 1
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        t0 = time.perf_counter()
         for _ in range(per_step):
-            step(*stream.rows([b % stream.nb])[:4])
+            step(*wl.stream.rows([b % wl.stream.nb]))
             b += 1
-        times.append(time.perf_counter() - t0)
-    total = sum(times)
+    total = time.perf_counter() - t0
     value = args.steps * per_step * REF_BATCH / total
     cores = torch.get_num_threads()
-    line = {
+    print(json.dumps({
         'impl': 'reference', 'metric': 'link-pred events/sec', 'value': value, 'unit': 'events/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f"{wl_name} (DyGFormer P={wl['P']} L={wl['L']}, recent first-hop history, batch 200, pos+neg pairs)"},
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': wl.describe()},
         'cpu_baseline': {'value': value, 'unit': 'events/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{per_step} reference batches of 200 events per step, oracle/ (torch-CPU port of the reference path; '
-                                   f'python sampler single-core, torch ops {cores} threads)'},
+                         'sample': f'{per_step} reference batch(es) of 200 events per step; oracle/ = torch-CPU port of the reference '
+                                   f'path (python sampler loop single-core, torch ops {cores} threads)'},
         'e2e': {'value': value, 'unit': 'events/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
-    print(json.dumps(line))
+        'gpu_launches': 0}))
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args, wl_name, wl):
+def run_ours(args):
     rank, world, local = dist_env()
     import torch.distributed as dist
     if world > 1:
@@ -220,18 +360,25 @@ def run_ours(args, wl_name, wl):
     dev = torch.device('cuda', torch.cuda.current_device())
     from dyglib_b200 import ops
     pk = peaks()
-    g = make_config_graph(wl['graph'])
-    sampler, model, pred, build_s = build_dygformer(g, wl, dev)
-    stream = Stream(g)
-    G = args.batches_per_step
+    wl = make_workload(args.workload)
+    wl.build(dev)
+    stream = wl.stream
+    G = args.batches_per_step or wl.default_G
     K, W = args.steps, args.warmup
+    if wl.sequential:
+        # dependency chain through the memory: every rank runs an independent replica of the same stream
+        batches_of = lambda i: [i % stream.nb]   # noqa: E731
+    else:
+        batches_of = lambda i: shard_batches(i, G, world, rank, stream.nb)   # noqa: E731
 
-    def step_batches(i):
-        # reference batches are sharded round-robin over ranks (whole batches: the padding unit must stay intact)
-        return [((i * G + j) * world + rank) % stream.nb for j in range(G)]
+    def reset():
+        if wl.sequential:
+            wl.model.memory_bank.__init_memory_bank__()
 
-    host_steps = [stream.rows(step_batches(i)) for i in range(W + K)]
-    dev_steps = [tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in hs[:4]) for hs in host_steps]
+    total_steps = 3 * (W + K) if wl.sequential else (W + K)
+    host_steps = [stream.rows(batches_of(i)) for i in range(total_steps)]
+    to_dev = lambda hs: tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in hs)   # noqa: E731
+    dev_steps = [to_dev(hs) for hs in host_steps]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -239,57 +386,59 @@ def run_ours(args, wl_name, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
-        # ---------------- device-resident timing
-        for i in range(W):
-            dygformer_step(model, pred, *dev_steps[i])
-        barrier()
-        clocks = ClockSampler(torch.cuda.current_device())
-        launches0 = ops.launch_count
+    def timed(run_step, first):
         evs = []
-        for i in range(W, W + K):
-            flush.zero_()                                     # L2 flush between timed iterations (outside the events)
+        for i in range(first, first + K):
+            flush.zero_()                                  # L2 flush between timed iterations (outside the events)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            scores = dygformer_step(model, pred, *dev_steps[i])
+            out = run_step(i)
             e1.record()
             evs.append((e0, e1))
         barrier()
+        return sum(a.elapsed_time(b) for a, b in evs), out
+
+    with torch.no_grad():
+        # ---------------- device-resident inputs
+        reset()
+        for i in range(W):
+            wl.step(*dev_steps[i])
+        barrier()
+        clocks = ClockSampler(torch.cuda.current_device())
+        launches0 = ops.launch_count
+        total_ms, scores = timed(lambda i: wl.step(*dev_steps[i]), W)
         launches = ops.launch_count - launches0
         clk = clocks.stop()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        # ---------------- end to end: host buffers in, host scores out, copies inside the timed region
-        pinned = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in hs[:4]) for hs in host_steps]
-        out_host = torch.empty((2 * G * REF_BATCH, 1), dtype=torch.float32).pin_memory()
-        for i in range(W):
-            sc = dygformer_step(model, pred, *[a.to(dev, non_blocking=True) for a in pinned[i]])
+        # ---------------- end to end: pinned host buffers in, host scores out, copies inside the timed region
+        pinned = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in hs) for hs in host_steps]
+        out_host = torch.empty(tuple(scores.shape), dtype=torch.float32).pin_memory()
+        base = (W + K) if wl.sequential else 0
+
+        def e2e_step(i):
+            sc = wl.step(*[a.to(dev, non_blocking=True) for a in pinned[i]])
             out_host.copy_(sc, non_blocking=True)
+            return sc
+        for i in range(base, base + W):
+            e2e_step(i)
         barrier()
-        e2e_evs = []
-        for i in range(W, W + K):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            sc = dygformer_step(model, pred, *[a.to(dev, non_blocking=True) for a in pinned[i]])
-            out_host.copy_(sc, non_blocking=True)
-            e1.record()
-            e2e_evs.append((e0, e1))
-        barrier()
-        e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+        e2e_ms, _ = timed(e2e_step, base + W)
         h2d = sum(a.numel() * a.element_size() for a in pinned[0])
         d2h = out_host.numel() * 4
-        # ---------------- roofline pass: same steps, every launch bracketed by CUDA events on its stream
+        # ---------------- roofline pass: same steps again, every launch bracketed by CUDA events on its stream
+        base = 2 * (W + K) if wl.sequential else 0
+        for i in range(base, base + W):
+            wl.step(*dev_steps[i])
         ops.PROFILE = []
-        for i in range(W, W + K):
+        for i in range(base + W, base + W + K):
             flush.zero_()
-            dygformer_step(model, pred, *dev_steps[i])
+            wl.step(*dev_steps[i])
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
     if world > 1:
         tt = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = tt.tolist()
-        # final score gather over NCCL (outside the timed region; verifies every rank produced scores)
+        # final score gather over NCCL (outside the timed region)
         gathered = torch.empty((world,) + tuple(scores.shape), device=dev, dtype=scores.dtype)
         dist.all_gather_into_tensor(gathered, scores.contiguous())
         checksum = float(gathered.double().sum().item())
@@ -302,46 +451,194 @@ def run_ours(args, wl_name, wl):
         d[1] += fl
         d[2] += by
         d[3] += 1
-    events_total = K * G * REF_BATCH * world
+    events_per_step = (1 if wl.sequential else G) * REF_BATCH
+    events_total = K * events_per_step * world
     value = events_total / (total_ms * 1e-3)
-    top = max(per_kernel.items(), key=lambda kv: kv[1][0])
-    name, (ms, fl, by, cnt) = top
-    achieved = fl / (ms * 1e-3) / 1e12
-    roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' (bf16 sustained)',
-                'launches': cnt, 'avg_launch_us': 1e3 * ms / cnt,
-                'share_of_step': ms / max(sum(v[0] for v in per_kernel.values()), 1e-9),
-                'note': 'fp32 FFMA tiles in round 1 (tcgen05 path not yet wired); flops = sum 2*M*N*K over launches'}
+    name, (ms, fl, by, cnt) = max(per_kernel.items(), key=lambda kv: kv[1][0])
+    share = ms / max(sum(v[0] for v in per_kernel.values()), 1e-9)
+    if name == 'linear_kernel':
+        achieved = fl / (ms * 1e-3) / 1e12
+        roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+                    'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' (bf16 sustained)',
+                    'note': 'algorithmic flops = sum of 2*M*N*K over the launches'}
+    else:
+        achieved = by / (ms * 1e-3) / 1e9
+        roofline = {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
+                    'frac': achieved / pk['hbm'], 'traffic': None, 'peak_source': pk['source'],
+                    'note': 'algorithmic bytes = gathered rows + indices + query/result vectors per launch'}
+    roofline.update({'launches': cnt, 'avg_launch_us': 1e3 * ms / cnt, 'share_of_timed_kernels': share})
     line = {
         'metric': 'link-pred events/sec', 'value': value, 'unit': 'events/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': f"{wl_name} (DyGFormer P={wl['P']} L={wl['L']}, recent first-hop history, batch 200, pos+neg pairs)",
-                   'events_per_step_per_gpu': G * REF_BATCH, 'reference_batch': REF_BATCH,
-                   'sharding': 'whole reference batches round-robin over ranks; CSR + feature tables replicated',
-                   'l2': 'flushed between timed steps (256 MiB write)', 'csr_build_s': round(build_s, 4)},
+        'config': {'workload': wl.describe(), 'events_per_step_per_gpu': events_per_step, 'reference_batch': REF_BATCH,
+                   'sharding': ('replicas only (memory dependency chain)' if wl.sequential else
+                                'whole reference batches round-robin over ranks; CSR + feature tables replicated'),
+                   'l2': 'flushed between timed steps (256 MiB write)', 'csr_build_s': round(wl.build_s, 4)},
         'roofline': roofline,
         'e2e': {'value': events_total / (e2e_ms * 1e-3), 'unit': 'events/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': launches,
-        'clocks': clk,
+        'gpu_launches': launches, 'clocks': clk,
         'kernels': {k: {'ms': round(v[0], 3), 'launches': v[3], 'tflops': round(v[1] / max(v[0], 1e-9) / 1e9, 3),
                         'alg_gbs': round(v[2] / max(v[0], 1e-9) / 1e6, 1)} for k, v in per_kernel.items()},
         'score_checksum': checksum,
     }
     if rank == 0 and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-        psd = {k: v.detach().cpu() for k, v in pred.state_dict().items()}
-        ostep = oracle_dygformer(g, wl, sd, psd)
-        nb = args.cpu_batches
-        v = time_cpu(ostep, stream, nb)
+        ostep = wl.oracle()
+        nb = args.cpu_batches or wl.cpu_batches
+        first = 0 if wl.sequential else batches_of(W)[0]
+        reset()
+        # parity of the first batch, then the timed CPU sample (1 warm-up + nb batches)
+        hs = stream.rows([first])
+        want = ostep(*hs)
+        got = wl.step(*to_dev(hs)).cpu()
+        line['parity_max_abs_err'] = float((want - got).abs().max())
+        t0 = time.perf_counter()
+        for b in range(1, 1 + nb):
+            ostep(*stream.rows([(first + b) % stream.nb]))
+        v = nb * REF_BATCH / (time.perf_counter() - t0)
         line['cpu_baseline'] = {'value': v, 'unit': 'events/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                                 'sample': f'{nb} reference batches of 200 events (pos+neg), oracle/ torch-CPU port, after 1 warm-up batch'}
-        # sanity: the CPU port and the GPU path agree on the first timed batch
-        hs = stream.rows(step_batches(W)[:1])
-        want = torch.cat(ostep(*hs[:4]))
-        got = dygformer_step(model, pred, *[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in hs[:4]]).cpu()
-        line['parity_max_abs_err'] = float((want - got).abs().max())
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ sampler sweep
+def device_power_law_graph(E, nu, ni, seed, dev):
+    """Config 5 (SURVEY.md 8(d)): 1e8-event power-law bipartite stream, strictly increasing integer times;
+    generated on the device (the host generator would take minutes at this size)."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+
+    def zipf(n_items, alpha, size):
+        cdf = torch.cumsum(torch.arange(1, n_items + 1, device=dev, dtype=torch.float64) ** (-alpha), 0)
+        cdf /= cdf[-1].clone()
+        out = torch.empty(size, dtype=torch.int64, device=dev)
+        for s in range(0, size, 1 << 25):
+            u = torch.rand(min(1 << 25, size - s), generator=gen, device=dev, dtype=torch.float64)
+            out[s:s + u.numel()] = torch.searchsorted(cdf, u, right=True).clamp_(max=n_items - 1)
+        return out
+    pu = torch.randperm(nu, generator=gen, device=dev)
+    pi = torch.randperm(ni, generator=gen, device=dev)
+    src = 1 + pu[zipf(nu, 0.8, E)]
+    dst = 1 + nu + pi[zipf(ni, 1.0, E)]
+    t = torch.cumsum(torch.randint(1, 4, (E,), generator=gen, device=dev), 0).double()
+    eid = torch.arange(1, E + 1, device=dev)
+    return src, dst, eid, t, nu + ni + 1
+
+
+def run_sampler_sweep(args):
+    rank, world, local = dist_env()
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    from dyglib_b200 import ops, _native
+    from dyglib_b200.ops import _p, _stream
+    from dyglib_b200.utils.utils import NeighborSampler
+    pk = peaks()
+    E, Q, k = args.events, args.queries, 20
+    nu, ni = max(8, int(E * 0.08)), max(4, int(E * 0.02))
+    src, dst, eid, t, num_nodes = device_power_law_graph(E, nu, ni, 5, dev)
+    t0 = time.perf_counter()
+    samplers = {}
+    for strat in ('recent', 'uniform', 'time_interval_aware'):
+        if strat == 'recent':
+            samplers[strat] = NeighborSampler(None, strat, 1e-6, 0, dev, 'philox', 'device', _edges=(src, dst, eid, t, num_nodes, True))
+            torch.cuda.synchronize()
+            build_s = time.perf_counter() - t0
+        else:   # share the CSR, add the tia tables once
+            s = object.__new__(NeighborSampler)
+            s.__dict__.update(samplers['recent'].__dict__)
+            s.sample_neighbor_strategy = strat
+            if strat == 'time_interval_aware':
+                s.time_scaling_factor = 1e-6
+                s._build_tia('device')
+            samplers[strat] = s
+    # queries: event uniform in the last 30 %, endpoint by coin flip, time = event time; contiguous shard per rank
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    qe = torch.randint(int(E * 0.7), E, (Q * world,), generator=gen, device=dev)
+    coin = torch.rand(Q * world, generator=gen, device=dev) < 0.5
+    nodes_all = torch.where(coin, src[qe], dst[qe])
+    times_all = t[qe]
+    nodes = nodes_all[rank * Q:(rank + 1) * Q].contiguous()
+    times = times_all[rank * Q:(rank + 1) * Q].contiguous()
+    del src, dst, eid, qe, coin
+    base = samplers['recent']
+    cnt = base.count_before_device(nodes, times).double()
+    deg = (base.indptr[nodes + 1] - base.indptr[nodes]).double()
+    m = torch.clamp(cnt, max=k)
+    log_deg = torch.ceil(torch.log2(deg + 1))
+    log_cnt = torch.ceil(torch.log2(cnt + 1))
+    alg = {'recent': float((32 + 8 * log_deg + 16 * m + 20 * k).sum()),
+           'uniform': float((32 + 8 * log_deg + 16 * torch.clamp(cnt, max=1) * k + 20 * k).sum()),
+           'time_interval_aware': float((32 + 8 * log_deg + 16 * torch.clamp(cnt, max=1) * k + 8 * k * log_cnt + 20 * k).sum())}
+    res = {}
+    K, W = args.steps, max(args.warmup, 3)
+    for strat, s in samplers.items():
+        for _ in range(W):
+            s.get_historical_neighbors_device(nodes, times, k)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(torch.cuda.current_device()) if strat == 'recent' else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            out = s.get_historical_neighbors_device(nodes, times, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if clocks is not None:
+            clk = clocks.stop()
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        gbs = alg[strat] * K / (ms * 1e-3) / 1e9
+        res[strat] = {'queries_per_s': Q * world * K / (ms * 1e-3), 'ms_per_launch': ms / K, 'alg_bytes_per_query': alg[strat] / Q,
+                      'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / pk['hbm'],
+                      'checksum': int(out[1].sum().item())}
+    line = {'metric': 'sampler queries/s', 'value': res['recent']['queries_per_s'], 'unit': 'queries/s', 'n_gpus': world,
+            'steps': K, 'warmup': W, 'ms_per_step': res['recent']['ms_per_launch'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64 compare / int32 ids', 'data': 'synthetic',
+            'config': {'workload': f'sampler_sweep: {E} events, {num_nodes} nodes power-law, {Q} queries per GPU in the last 30 %, k={k}',
+                       'csr_build_s': round(build_s, 3), 'csr_bytes': int(base.halfedges.numel() * 8 + base.indptr.numel() * 8),
+                       'l2': 'CSR (>= 3 GB at 1e8 events) and outputs far exceed L2', 'random_strategies': 'philox (throughput mode, non-parity)'},
+            'roofline': {'kernel': 'sample_recent_kernel', 'bound': 'hbm', 'achieved': res['recent']['achieved_gbs'], 'peak': pk['hbm'],
+                         'unit': 'GB/s', 'frac': res['recent']['frac_of_hbm_peak'], 'traffic': None, 'peak_source': pk['source']},
+            'strategies': res, 'gpu_launches': K * 3, 'clocks': clk}
+    if rank == 0 and world == 1 and args.cpu_queries > 0:
+        # CPU baseline: the oracle's per-query loop (port of utils/utils.py:149-214) over arrays installed from the device CSR
+        from oracle.sampler import OracleSampler
+        o = object.__new__(OracleSampler)
+        rec = base.halfedges[:base.num_half_edges].cpu().numpy()
+        o.t = np.ascontiguousarray(rec[:, 0])
+        ints = np.ascontiguousarray(rec[:, 1]).view(np.int32).reshape(-1, 2)
+        o.nbr, o.eid = ints[:, 0].astype(np.int64), ints[:, 1].astype(np.int64)
+        o.indptr = base.indptr.cpu().numpy()
+        o.num_nodes, o.seed = num_nodes, 0
+        nq = args.cpu_queries
+        hn, ht = nodes[:nq].cpu().numpy(), times[:nq].cpu().numpy()
+        cpu = {}
+        for strat in ('recent', 'uniform', 'time_interval_aware'):
+            o.sample_neighbor_strategy = strat
+            o.random_state = np.random.RandomState(0)
+            if strat == 'time_interval_aware':
+                o.prob = samplers[strat].tia_prob[:base.num_half_edges].cpu().numpy()
+            n_ = nq if strat != 'time_interval_aware' else max(100, nq // 20)
+            t1 = time.perf_counter()
+            got = o.get_historical_neighbors(hn[:n_], ht[:n_], k)
+            cpu[strat] = n_ / (time.perf_counter() - t1)
+            if strat == 'recent':
+                dv = samplers['recent'].get_historical_neighbors_device(nodes[:n_], times[:n_], k)
+                line['parity_recent_bit_exact'] = bool(all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(got, dv)))
+        line['cpu_baseline'] = {'value': cpu['recent'], 'unit': 'queries/s', 'cores': 1, 'kind': 'port',
+                                'sample': f'{nq} queries (tia: {max(100, nq // 20)}), oracle per-query python loop', 'strategies': cpu}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -354,16 +651,23 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='dygformer_wiki', choices=['dygformer_wiki', 'dygformer_lastfm'])
-    ap.add_argument('--batches-per-step', type=int, default=32)
-    ap.add_argument('--cpu-batches', type=int, default=12)
+    ap.add_argument('--workload', default='dygformer_wiki',
+                    choices=['dygformer_wiki', 'dygformer_lastfm', 'tgat_myket', 'tgn_reddit', 'sampler_sweep'])
+    ap.add_argument('--batches-per-step', type=int, default=0)
+    ap.add_argument('--cpu-batches', type=int, default=0)
+    ap.add_argument('--events', type=int, default=100_000_000)
+    ap.add_argument('--queries', type=int, default=1 << 24)
+    ap.add_argument('--cpu-queries', type=int, default=20000)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
-    wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
-        run_reference(args, args.workload, wl)
+        if args.workload == 'sampler_sweep':
+            args.workload = 'dygformer_wiki'
+        run_reference(args)
+    elif args.workload == 'sampler_sweep':
+        run_sampler_sweep(args)
     else:
-        run_ours(args, args.workload, wl)
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
 
 
 if __name__ == '__main__':

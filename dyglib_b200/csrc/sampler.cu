@@ -310,6 +310,89 @@ __global__ void philox_uniform_kernel(uint64_t seed, uint64_t offset, int64_t co
     if (2 * i + 1 < count) u[2 * i + 1] = ((double)(c2 >> 5) * 67108864.0 + (double)(c3 >> 6)) * inv;
 }
 
+// Fused throughput path for the random strategies: search + counter-based draw + gather + time re-sort in one
+// kernel (no (n,k) uniforms / positions round trip through HBM).  Draw (q, j) uses Philox counter
+// offset + q*k + j, so results do not depend on the launch shape or on how queries are sharded over GPUs.
+__device__ __forceinline__ double philox_u01(uint64_t seed, uint64_t ctr) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x9E3779B9u, c3 = 0;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+template <int LANES, bool TIA>
+__global__ void __launch_bounds__(256) sample_random_kernel(
+    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+    const double* __restrict__ cum, const int64_t* __restrict__ node_ids, const double* __restrict__ times,
+    int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid,
+    float* __restrict__ out_t) {
+    extern __shared__ unsigned char smem_raw[];
+    const int groups = blockDim.x / LANES;
+    const int g = threadIdx.x / LANES;
+    const int lane = threadIdx.x % LANES;
+    float* st = reinterpret_cast<float*>(smem_raw) + (size_t)g * k;
+    int* sn = reinterpret_cast<int*>(smem_raw) + (size_t)groups * k + (size_t)g * k;
+    int* se = reinterpret_cast<int*>(smem_raw) + (size_t)2 * groups * k + (size_t)g * k;
+    const int64_t q = blockIdx.x * (int64_t)groups + g;
+    const bool valid = q < n;
+    int64_t a = 0, cnt = 0;
+    if (valid) {
+        int64_t deg;
+        node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
+        cnt = lower_bound_time(he, a, deg, __ldg(times + q));
+    }
+    const int64_t base = q * (int64_t)k;
+    if (valid && cnt > 0) {
+        double tot = 0.0;
+        if (TIA) tot = __ldg(cum + a + cnt - 1);
+        for (int j = lane; j < k; j += LANES) {
+            const double u = philox_u01(seed, offset + (uint64_t)(base + j));
+            int64_t s;
+            if (TIA && tot > 0.0) {
+                const double target = u * tot;
+                int64_t lo = 0, hi = cnt;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (__ldg(cum + a + mid) <= target) lo = mid + 1; else hi = mid;
+                }
+                s = lo;
+            } else {
+                s = (int64_t)floor(u * (double)cnt);
+            }
+            if (s >= cnt) s = cnt - 1;
+            const Rec r = load_rec(he, a + s);
+            st[j] = (float)r.t;
+            sn[j] = r.nbr;
+            se[j] = r.eid;
+        }
+    }
+    if (LANES >= 32) __syncthreads(); else __syncwarp();
+    if (valid) {
+        for (int j = lane; j < k; j += LANES) {
+            if (cnt > 0) {
+                const float tj = st[j];
+                int rank = 0;
+                for (int i = 0; i < k; ++i) {
+                    const float ti = st[i];
+                    rank += (ti < tj) || (ti == tj && i < j);
+                }
+                out_nbr[base + rank] = sn[j];
+                out_eid[base + rank] = se[j];
+                out_t[base + rank] = tj;
+            } else {
+                out_nbr[base + j] = 0;
+                out_eid[base + j] = 0;
+                out_t[base + j] = 0.f;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- C ABI
 static inline unsigned blocks_for(int64_t work, int threads, int64_t cap = (1ll << 30)) {
     int64_t b = (work + threads - 1) / threads;
@@ -442,5 +525,29 @@ extern "C" int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr
         he, indptr, num_nodes, node_ids, times, n, L, row_stride, out_nbr, out_eid, out_t, out_len, group_max,
         group_size > 0 ? group_size : 1);
     DYG_LAUNCH_CHECK("dyg_first_hop_pad");
+    return 0;
+}
+
+extern "C" int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* cum,
+                                 const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed,
+                                 uint64_t offset, int64_t* out_nbr, int64_t* out_eid, float* out_t, dyg_stream_t stream) {
+    DYG_CHECK_ARG(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
+    DYG_CHECK_ARG((size_t)k * 12 <= 40 * 1024, "dyg_sample_random: num_neighbors %d too large (max 3413)", k);
+    if (n == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    if (k <= 32) {
+        const int threads = 256, groups = threads / 8;
+        const size_t smem = (size_t)groups * k * 12;
+        if (cum) sample_random_kernel<8, true><<<blocks_for(n, groups), threads, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
+        else sample_random_kernel<8, false><<<blocks_for(n, groups), threads, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
+    } else {
+        int groups = (int)((40 * 1024) / ((size_t)k * 12));
+        if (groups > 8) groups = 8;
+        if (groups < 1) groups = 1;
+        const size_t smem = (size_t)groups * k * 12;
+        if (cum) sample_random_kernel<32, true><<<blocks_for(n, groups), groups * 32, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
+        else sample_random_kernel<32, false><<<blocks_for(n, groups), groups * 32, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
+    }
+    DYG_LAUNCH_CHECK("dyg_sample_random");
     return 0;
 }

@@ -244,6 +244,16 @@ class NeighborSampler:
                                                 _p(out_n), _p(out_e), _p(out_t), None, _stream()))
             ops._count()
             return out_n, out_e, out_t
+        if self.rng == 'philox':
+            # throughput mode: one fused kernel, counter-based draws (not the reference's RandomState stream)
+            off = self._philox_offset
+            _native.check(lib.dyg_sample_random(_p(self.halfedges), _p(self.indptr), self.num_nodes,
+                                                _p(self.tia_cum) if strat == 'time_interval_aware' else None,
+                                                _p(ids), _p(tq), n, k, int(self.seed or 0), int(off),
+                                                _p(out_n), _p(out_e), _p(out_t), _stream()))
+            self._philox_offset = off + n * k
+            ops._count()
+            return out_n, out_e, out_t
         cnt = self.count_before_device(ids, tq)
         sel = self._draw(ids, cnt, n, k)
         _native.check(lib.dyg_sample_indexed(_p(self.halfedges), _p(self.indptr), _p(ids), _p(cnt), _p(sel), n, k,

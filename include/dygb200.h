@@ -79,6 +79,11 @@ int dyg_draw_tia(const double* cum, const int64_t* indptr, const int64_t* node_i
                  const double* u, int64_t n, int k, int64_t* sel, dyg_stream_t stream);
 /* Counter-based uniforms for the sharded throughput mode (labelled non-parity): u[i] from (seed, offset+i). */
 int dyg_philox_uniform(uint64_t seed, uint64_t offset, int64_t count, double* u, dyg_stream_t stream);
+/* Fused throughput path (labelled non-parity): search + Philox draw (counter offset + q*k + j) + gather + time
+ * re-sort in one kernel.  cum == NULL: uniform (floor(u*cnt)); cum != NULL: time_interval_aware prefix-CDF search. */
+int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* cum,
+                      const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed, uint64_t offset,
+                      int64_t* out_nbr, int64_t* out_eid, float* out_t, dyg_stream_t stream);
 
 /* ---- a7 + a12: get_all_first_hop_neighbors + DyGFormer.pad_sequences (utils/utils.py:254-273,
  * models/DyGFormer.py:196-245) ----  row q = [node_ids[q], last min(cnt,L-1) neighbours..., 0...] over

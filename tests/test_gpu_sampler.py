@@ -221,7 +221,7 @@ def test_full_size_properties():
     assert np.array_equal(nb, nb2) and np.array_equal(ei, ei2) and np.array_equal(tt, tt2)
     valid = nb != 0
     assert (np.diff(valid.astype(np.int8), axis=1) >= 0).all()           # zeros only on the left
-    assert (np.diff(np.where(valid, tt, -np.inf), axis=1) >= 0).all()    # ascending times
+    assert (np.diff(np.where(valid, tt, np.float32(-1.0)), axis=1) >= 0).all()   # ascending times
     assert (g.node_interact_times[ei[valid] - 1] < np.repeat(times[:, None], 20, 1)[valid]).all()   # strict history
     ids, tq = c._queries(nodes, times)
     cnt = c.count_before_device(ids, tq).cpu().numpy()
