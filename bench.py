@@ -456,7 +456,7 @@ def run_ours(args):
     value = events_total / (total_ms * 1e-3)
     name, (ms, fl, by, cnt) = max(per_kernel.items(), key=lambda kv: kv[1][0])
     share = ms / max(sum(v[0] for v in per_kernel.values()), 1e-9)
-    if name == 'linear_kernel':
+    if name in ('linear_kernel', 'linear_tc_kernel', 'gemm_bf16x3_kernel'):
         achieved = fl / (ms * 1e-3) / 1e12
         roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
                     'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' (bf16 sustained)',
@@ -632,7 +632,20 @@ def run_sampler_sweep(args):
                 o.prob = samplers[strat].tia_prob[:base.num_half_edges].cpu().numpy()
             n_ = nq if strat != 'time_interval_aware' else max(100, nq // 20)
             t1 = time.perf_counter()
-            got = o.get_historical_neighbors(hn[:n_], ht[:n_], k)
+            if strat == 'time_interval_aware':
+                # RandomState.choice(p=float32 softmax) raises "probabilities do not sum to 1" on hubs with millions of
+                # neighbours (utils/utils.py:183-187 has the same limit): such queries are counted, not timed
+                done = raised = 0
+                for q in range(n_):
+                    try:
+                        o.get_historical_neighbors(hn[q:q + 1], ht[q:q + 1], k)
+                        done += 1
+                    except ValueError:
+                        raised += 1
+                line['cpu_tia_reference_raises'] = raised
+                n_ = max(done, 1)
+            else:
+                got = o.get_historical_neighbors(hn[:n_], ht[:n_], k)
             cpu[strat] = n_ / (time.perf_counter() - t1)
             if strat == 'recent':
                 dv = samplers['recent'].get_historical_neighbors_device(nodes[:n_], times[:n_], k)

@@ -95,6 +95,8 @@ SIGNATURES = {
     'dyg_cooc_count': [c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     'dyg_time_encode': [c_p, c_l, c_p, c_p, c_i, c_p, c_p],
     'dyg_linear': [ctypes.POINTER(Seg), c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
+    'dyg_linear_tc_tile': [c_i],
+    'dyg_linear_tc': [ctypes.POINTER(Seg), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
     'dyg_layernorm': [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_l, c_i, c_p],
     'dyg_gather_rows': [c_p, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p],
     'dyg_temporal_attend': [c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i,

@@ -173,7 +173,7 @@ class DyGFormer(nn.Module):
         w, b = (time_encoder or self.time_encoder).wb()
         T = self.time_feat_dim
         eye = torch.eye(T, dtype=torch.float32, device=dev)
-        tf = ops.linear([ops.seg_time(pt.reshape(-1), w, b, mask_ids=pn.reshape(-1), t_query=tq, tq_div=Lp)], B * Lp, eye)
+        tf = ops.linear([ops.seg_time(pt.reshape(-1), w, b, mask_ids=pn.reshape(-1), t_query=tq, tq_div=Lp)], B * Lp, eye, tc=False)
         return nf, ef, tf.reshape(B, Lp, T)
 
     def get_patches(self, padded_nodes_neighbor_node_raw_features, padded_nodes_edge_raw_features,

@@ -113,8 +113,47 @@ def seg_time(dt, w, b, mask_ids=None, group=1, t_query=None, tq_div=1):
     return s
 
 
+# tensor-core dispatch: rows at or above this use dyg_linear_tc (tcgen05 BF16x3); 0 disables it
+TC_MIN_ROWS = 512
+_tc_weights = {}
+
+
+def _split_weight(weight, K, ldw):
+    """bf16 hi / mid copies of weight[:, :K], zero padded to (n_pad, k_pad); cached per weight version."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), int(ldw), int(K))
+    ent = _tc_weights.get(key)
+    if ent is None:
+        N = weight.shape[0]
+        nt = _lib().dyg_linear_tc_tile(int(N))
+        n_pad = (N + nt - 1) // nt * nt
+        k_pad = (K + 63) // 64 * 64
+        w = torch.as_strided(weight, (N, K), (int(ldw), 1)).float()
+        hi = w.to(torch.bfloat16)
+        mid = (w - hi.float()).to(torch.bfloat16)
+        wh = torch.zeros((n_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
+        wm = torch.zeros((n_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
+        wh[:N, :K] = hi
+        wm[:N, :K] = mid
+        if len(_tc_weights) > 256:
+            _tc_weights.clear()
+        ent = _tc_weights[key] = (wh, wm, n_pad, k_pad, weight)
+    return ent
+
+
+def _tc_ok(segs):
+    for s in segs:
+        if s.width % 4:
+            return False
+        if s.kind == 0:
+            if s.ld % 4 or (s.ptr or 0) % 16 or (s.ptr2 and (s.ld2 % 4 or s.ptr2 % 16)):
+                return False
+        elif (s.w or 0) % 16 or (s.b or 0) % 16:
+            return False
+    return True
+
+
 def linear(segs, M, weight, bias=None, residual=None, act=ACT_NONE, out=None, out_cols=None,
-           c_group=0, c_group_stride=0, c_offset=0, ldw=None):
+           c_group=0, c_group_stride=0, c_offset=0, ldw=None, tc=None):
     """out[row(m), :N] = act(A @ weight[:N, :K].T + bias + residual[row(m)])."""
     N = weight.shape[0]
     K = sum(s.width * s.group for s in segs)
@@ -125,6 +164,15 @@ def linear(segs, M, weight, bias=None, residual=None, act=ACT_NONE, out=None, ou
     arr = (Seg * len(segs))(*segs)
     ldc = out.stride(-2)
     ldr = residual.stride(-2) if residual is not None else 0
+    use_tc = (TC_MIN_ROWS > 0 and M >= TC_MIN_ROWS) if tc is None else tc
+    if use_tc and _tc_ok(segs):
+        wh, wm, n_pad, k_pad, _ = _split_weight(weight, K, ldw)
+        with _Timed('linear_tc_kernel', 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
+            _native.check(_lib().dyg_linear_tc(arr, len(segs), _p(wh), _p(wm), int(k_pad), int(n_pad), _p(bias), _p(residual),
+                                               int(ldr), _p(out), int(ldc), int(M), int(N), int(act), int(c_group),
+                                               int(c_group_stride), int(c_offset), _stream()))
+        _count()
+        return out
     with _Timed('linear_kernel', 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)):
         _native.check(_lib().dyg_linear(arr, len(segs), _p(weight), int(ldw), _p(bias), _p(residual), int(ldr),
                                         _p(out), int(ldc), int(M), int(N), int(act), int(c_group), int(c_group_stride),

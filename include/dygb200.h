@@ -139,6 +139,15 @@ int dyg_linear(const dyg_seg_t* segs_host, int nseg, const float* W, int ldw, co
                const float* residual, int ldr, float* C, int ldc, int64_t M, int N, int act,
                int c_group, int c_group_stride, int c_offset, dyg_stream_t stream);
 
+/* Tensor-core variant (tcgen05, BF16x3: x = hi + mid, three bf16 MMAs, fp32 accumulation in TMEM; ~1e-5 relative).
+ * W_hi / W_mid: bf16 (n_pad, ldwp) row-major copies of hi = bf16(W), mid = bf16(W - hi), zero padded so that
+ * ldwp % 64 == 0, ldwp >= K and n_pad >= ceil(N / tile) * tile with tile = dyg_linear_tc_tile(N).
+ * Same A-segment, epilogue and row-mapping semantics as dyg_linear; every segment width must be a multiple of 4. */
+int dyg_linear_tc_tile(int N);
+int dyg_linear_tc(const dyg_seg_t* segs_host, int nseg, const void* W_hi, const void* W_mid, int ldwp, int n_pad,
+                  const float* bias, const float* residual, int ldr, float* C, int ldc, int64_t M, int N, int act,
+                  int c_group, int c_group_stride, int c_offset, dyg_stream_t stream);
+
 /* y = LayerNorm(x + r) * gamma + beta over D columns; r row = [r1 row (F1 cols) | rconst (D-F1 cols)];
  * r1/rconst may be NULL (models/modules.py:199, models/DyGFormer.py:452,458). */
 int dyg_layernorm(const float* x, int ldx, const float* r1, int ldr1, int F1, const float* rconst,
