@@ -97,6 +97,9 @@ SIGNATURES = {
     'dyg_linear': [ctypes.POINTER(Seg), c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
     'dyg_linear_tc_tile': [c_i],
     'dyg_linear_tc': [ctypes.POINTER(Seg), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
+    'dyg_gemm_bf16x3': [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_p],
+    'dyg_split_bf16': [c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p],
+    'dyg_layernorm_split': [c_p, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_p],
     'dyg_layernorm': [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_l, c_i, c_p],
     'dyg_gather_rows': [c_p, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p],
     'dyg_temporal_attend': [c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i,

@@ -1,0 +1,599 @@
+// dyg_gemm_bf16x3: the dense contractions of DyGFormer's transformer (models/DyGFormer.py:442-461, 190-192) on tcgen05.
+//
+//   C[m, :N] = act(A W^T + bias + residual[m])      A (M,K), W (N,K), both handed over as BF16x3 operand pairs
+//
+// Precision: every fp32 value x travels as x = hi + mid, hi = bf16(x), mid = bf16(x - hi) (two bf16 planes, the same
+// 4 bytes per element as fp32).  The product is A_hi W_hi + A_hi W_mid + A_mid W_hi with fp32 accumulation in TMEM;
+// the dropped terms are O(2^-16) relative per product.  Producing kernels (LayerNorm, attention, the previous GEMM's
+// epilogue) write the planes, so operands reach shared memory by TMA with no thread touching them.
+//
+// Structure: persistent, one CTA per SM, 192 threads.
+//   warp 0     TMA producer: per 32-wide k block one stage = A_hi | A_mid (128 rows) + W_hi | W_mid (NT rows), 64-byte
+//              rows in SWIZZLE_64B layout, landing on the stage's full mbarrier (expect_tx)
+//   warp 1     TMEM allocation (512 columns = two accumulator buffers) + single-thread tcgen05.mma issue (M=128, N=NT,
+//              K=16, kind::f16 bf16 -> fp32); tcgen05.commit frees the stage / publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias / residual / activation -> 32-byte vector stores
+//              of the fp32 result and / or its bf16 hi|mid planes; overlaps the next tile's MMAs (double-buffered TMEM)
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int G_BM = 128;            // rows per tile == TMEM lanes
+constexpr int G_BK = 32;             // bf16 elements per stage along K == one 64-byte swizzle row
+constexpr int G_THREADS = 192;
+constexpr int G_A_PLANE = G_BM * 64; // bytes of one A plane per stage
+constexpr int G_MAX_STAGES = 8;
+constexpr int G_TMEM_COLS = 512;
+constexpr int G_BUF_COLS = 256;      // accumulator buffer stride in TMEM columns
+
+struct GemmArgs {
+    const float* bias;
+    const float* residual;
+    float* C;
+    __nv_bfloat16* Chi;
+    __nv_bfloat16* Cmid;
+    int64_t M;
+    int64_t m_tiles;
+    int ldr, ldc, ldcs;
+    int N, K, act;
+    int NS;        // columns owned by one n tile (multiple of 16)
+    int NT;        // MMA N of one n tile (== NS)
+    int n_tiles;
+    int stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "GW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GW_DONE;\n\t"
+        "bra GW_LOOP;\n\t"
+        "GW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), LBO (unused for swizzled K-major, canonical 1) in [16,30), SBO = 512 B between 8-row groups in [32,46),
+// version 1 in [46,48), layout type 4 (SWIZZLE_64B) in [61,64).
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor, kind::f16: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major A and B,
+// N >> 3 in [17,23), M >> 4 in [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == DYG_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == DYG_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    if (act == DYG_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+    return v;
+}
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& mid) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 am = __float2bfloat16_rn(a - __bfloat162float(ah)), bm = __float2bfloat16_rn(b - __bfloat162float(bh));
+    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+    mid = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
+}
+__device__ __forceinline__ void st_v8(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+                 "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_v4(void* p, const uint32_t* r) {
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah,
+                                                                   const __grid_constant__ CUtensorMap map_am,
+                                                                   const __grid_constant__ CUtensorMap map_wh,
+                                                                   const __grid_constant__ CUtensorMap map_wm, const GemmArgs g) {
+    extern __shared__ __align__(1024) unsigned char gemm_smem[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~(uintptr_t)1023);
+    const int w_plane = g.NT * 64;
+    const int stage_bytes = 2 * G_A_PLANE + 2 * w_plane;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)g.stages * stage_bytes);
+    uint64_t* full_bar = bars;                            // [stages]
+    uint64_t* empty_bar = bars + G_MAX_STAGES;            // [stages]
+    uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES;        // [2]
+    uint64_t* tempty_bar = bars + 2 * G_MAX_STAGES + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 4);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nkb = (g.K + G_BK - 1) / G_BK;
+    const int64_t total = g.m_tiles * g.n_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar + b, 1);
+            mbar_init(tempty_bar + b, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ah)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_am)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wm)) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+                const int m0 = (int)(w / g.n_tiles) * G_BM;
+                const int n0 = (int)(w % g.n_tiles) * g.NS;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(empty_bar + s, ph ^ 1u);
+                    unsigned char* st = base + (size_t)s * stage_bytes;
+                    mbar_expect_tx(full_bar + s, (uint32_t)stage_bytes);
+                    tma_load_2d(&map_ah, full_bar + s, st, kb * G_BK, m0);
+                    tma_load_2d(&map_am, full_bar + s, st + G_A_PLANE, kb * G_BK, m0);
+                    tma_load_2d(&map_wh, full_bar + s, st + 2 * G_A_PLANE, kb * G_BK, n0);
+                    tma_load_2d(&map_wm, full_bar + s, st + 2 * G_A_PLANE + w_plane, kb * G_BK, n0);
+                    if (++s == g.stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = make_idesc(g.NT);
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t bph = (uint32_t)((it >> 1) & 1);
+            mbar_wait(tempty_bar + buf, bph ^ 1u);                      // epilogue drained this accumulator buffer
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * G_BUF_COLS);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar + s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_h = smem_u32(base + (size_t)s * stage_bytes), a_m = a_h + G_A_PLANE;
+                    const uint32_t b_h = a_h + 2 * G_A_PLANE, b_m = b_h + (uint32_t)w_plane;
+                    const int krem = g.K - kb * G_BK;
+                    const int nk16 = krem >= G_BK ? G_BK / 16 : (krem + 15) / 16;
+                    for (int kk = 0; kk < nk16; ++kk) {
+                        const uint32_t o = (uint32_t)kk * 32u;            // 16 bf16 = 32 bytes inside the swizzle row
+                        const uint64_t dah = make_desc_sw64(a_h + o), dam = make_desc_sw64(a_m + o);
+                        const uint64_t dbh = make_desc_sw64(b_h + o), dbm = make_desc_sw64(b_m + o);
+                        umma_bf16(tacc, dah, dbh, idesc, (kb | kk) != 0);
+                        umma_bf16(tacc, dah, dbm, idesc, 1);
+                        umma_bf16(tacc, dam, dbh, idesc, 1);
+                    }
+                    umma_commit(empty_bar + s);                            // stage reusable once these MMAs retire
+                    if (kb == nkb - 1) umma_commit(tfull_bar + buf);       // accumulator complete
+                }
+                __syncwarp();
+                if (++s == g.stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                                      // TMEM lane quarter this warp may read
+        const int row = quarter * 32 + lane;
+        const bool c_v8 = g.C && ((g.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 31u) == 0);
+        const bool c_v4 = g.C && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+        const bool s_v8 = g.Chi && ((g.ldcs & 15) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 31u) == 0);
+        const bool s_v4 = g.Chi && ((g.ldcs & 7) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 15u) == 0);
+        const bool r_v4 = g.residual && ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0);
+        const bool b_v4 = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+        int it = 0;
+        for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t bph = (uint32_t)((it >> 1) & 1);
+            const int64_t m = (w / g.n_tiles) * G_BM + row;
+            const int n0 = (int)(w % g.n_tiles) * g.NS;
+            const int ncols = min(g.NS, g.N - n0);
+            const bool rowok = m < g.M;
+            mbar_wait(tfull_bar + buf, bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
+            for (int col = 0; col < ncols; col += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t)col, r);
+                if (rowok) {
+                const int n = n0 + col;
+                const int valid = min(16, ncols - col);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (valid == 16) {
+                    if (g.bias) {
+                        if (b_v4) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += __ldg(g.bias + n + j);
+                        }
+                    }
+                    if (g.residual) {
+                        const float* rp = g.residual + m * g.ldr + n;
+                        if (r_v4) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] += rp[j];
+                        }
+                    }
+                    if (g.act != DYG_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], g.act);
+                    }
+                    if (g.C) {
+                        float* dst = g.C + m * g.ldc + n;
+                        uint32_t o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(v[j]);
+                        if (c_v8) {
+                            st_v8(dst, o);
+                            st_v8(dst + 8, o + 8);
+                        } else if (c_v4) {
+                            st_v4(dst, o); st_v4(dst + 4, o + 4); st_v4(dst + 8, o + 8); st_v4(dst + 12, o + 12);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) dst[j] = v[j];
+                        }
+                    }
+                    if (g.Chi) {
+                        uint32_t hi[8], mid[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) split_pack(v[2 * j], v[2 * j + 1], hi[j], mid[j]);
+                        __nv_bfloat16* dh = g.Chi + m * g.ldcs + n;
+                        __nv_bfloat16* dm = g.Cmid + m * g.ldcs + n;
+                        if (s_v8) {
+                            st_v8(dh, hi);
+                            st_v8(dm, mid);
+                        } else if (s_v4) {
+                            st_v4(dh, hi); st_v4(dh + 8, hi + 4);
+                            st_v4(dm, mid); st_v4(dm + 8, mid + 4);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                *reinterpret_cast<uint32_t*>(dh + 2 * j) = hi[j];
+                                *reinterpret_cast<uint32_t*>(dm + 2 * j) = mid[j];
+                            }
+                        }
+                    }
+                } else {
+                    // ragged last chunk of the row (N not a multiple of 16)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j >= valid) break;
+                        float x = v[j];
+                        if (g.bias) x += __ldg(g.bias + n + j);
+                        if (g.residual) x += g.residual[m * g.ldr + n + j];
+                        x = act_apply(x, g.act);
+                        if (g.C) g.C[m * g.ldc + n + j] = x;
+                        if (g.Chi) {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                            g.Chi[m * g.ldcs + n + j] = h;
+                            g.Cmid[m * g.ldcs + n + j] = __float2bfloat16_rn(x - __bfloat162float(h));
+                        }
+                    }
+                }
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty_bar + buf);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G_TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ tensor maps (driver entry point fetched at run time:
+// the library links against cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ k.rows;
+        h = h * 1000003u ^ k.cols;
+        h = h * 1000003u ^ k.ld;
+        h = h * 1000003u ^ k.box_rows;
+        return h;
+    }
+};
+
+// (rows, cols) bf16 row-major with leading dimension ld elements; box = box_rows x 32 columns, SWIZZLE_64B, OOB -> 0.
+// Encoding depends only on the key, so maps are cached (a descriptor holds the address, not the data).
+bool get_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, rows, cols, ld, box_rows};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return true;
+    }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        dyg_set_error("dyg_gemm_bf16x3: cuTensorMapEncodeTiled is not available from the driver");
+        return false;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)G_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dyg_set_error("dyg_gemm_bf16x3: cuTensorMapEncodeTiled failed (%d) for %llu x %llu, ld %llu, box %u", (int)r,
+                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return false;
+    }
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return true;
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 hi | mid planes
+__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, int64_t M, int D, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ mid, int ld) {
+    const int64_t pairs = (int64_t)(D + 1) / 2;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= M * pairs) return;
+    const int64_t m = i / pairs;
+    const int c = (int)(i - m * pairs) * 2;
+    const float a = x[m * ldx + c];
+    const float b = (c + 1 < D) ? x[m * ldx + c + 1] : 0.f;
+    uint32_t h, l;
+    split_pack(a, b, h, l);
+    if (c + 1 < D && ((ld & 1) == 0)) {
+        *reinterpret_cast<uint32_t*>(hi + m * ld + c) = h;
+        *reinterpret_cast<uint32_t*>(mid + m * ld + c) = l;
+    } else {
+        hi[m * ld + c] = __ushort_as_bfloat16((unsigned short)(h & 0xFFFF));
+        mid[m * ld + c] = __ushort_as_bfloat16((unsigned short)(l & 0xFFFF));
+        if (c + 1 < D) {
+            hi[m * ld + c + 1] = __ushort_as_bfloat16((unsigned short)(h >> 16));
+            mid[m * ld + c + 1] = __ushort_as_bfloat16((unsigned short)(l >> 16));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm -> bf16 hi | mid planes
+// One warp per row; lane l owns column pairs (2l, 2l+1), (2l+64, 2l+65), ...; two-pass mean / biased variance like
+// torch.nn.functional.layer_norm; the fp32 result is split on the way out (and optionally also stored as fp32).
+template <int MAXP>
+__global__ void layernorm_split_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, float* __restrict__ y, int ldy,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid, int ld, int64_t M, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (m >= M) return;
+    float2 v[MAXP];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int c = 2 * lane + 64 * i;
+        float2 t = make_float2(0.f, 0.f);
+        if (c < D) t = *reinterpret_cast<const float2*>(x + m * ldx + c);
+        v[i] = t;
+        sum += t.x + t.y;
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int c = 2 * lane + 64 * i;
+        if (c < D) {
+            const float dx = v[i].x - mean, dy = v[i].y - mean;
+            sq += dx * dx + dy * dy;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int c = 2 * lane + 64 * i;
+        if (c < D) {
+            const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma + c));
+            const float2 bt = __ldg(reinterpret_cast<const float2*>(beta + c));
+            const float a = (v[i].x - mean) * rstd * gm.x + bt.x;
+            const float b = (v[i].y - mean) * rstd * gm.y + bt.y;
+            if (y) *reinterpret_cast<float2*>(y + m * ldy + c) = make_float2(a, b);
+            uint32_t h, l;
+            split_pack(a, b, h, l);
+            *reinterpret_cast<uint32_t*>(hi + m * ld + c) = h;
+            *reinterpret_cast<uint32_t*>(mid + m * ld + c) = l;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, const void* W_hi, const void* W_mid, int ldw,
+                               const float* bias, const float* residual, int ldr, float* C, int ldc, void* C_hi, void* C_mid,
+                               int ldcs, int64_t M, int N, int K, int act, dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && N > 0 && K > 0, "dyg_gemm_bf16x3: bad sizes");
+    DYG_CHECK_ARG(M < ((int64_t)1 << 31) - G_BM, "dyg_gemm_bf16x3: M too large");
+    DYG_CHECK_ARG(act >= DYG_ACT_NONE && act <= DYG_ACT_SIGMOID, "dyg_gemm_bf16x3: unknown activation %d", act);
+    DYG_CHECK_ARG(A_hi && A_mid && W_hi && W_mid, "dyg_gemm_bf16x3: operand planes must not be NULL");
+    DYG_CHECK_ARG(aligned16(A_hi) && aligned16(A_mid) && aligned16(W_hi) && aligned16(W_mid),
+                  "dyg_gemm_bf16x3: operand planes must be 16-byte aligned");
+    DYG_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && lda >= K && ldw >= K,
+                  "dyg_gemm_bf16x3: lda=%d / ldw=%d must be multiples of 8 and >= K=%d", lda, ldw, K);
+    DYG_CHECK_ARG(C || (C_hi && C_mid), "dyg_gemm_bf16x3: no output given");
+    DYG_CHECK_ARG((C_hi == nullptr) == (C_mid == nullptr), "dyg_gemm_bf16x3: C_hi and C_mid go together");
+    DYG_CHECK_ARG(!C_hi || (ldcs % 2) == 0, "dyg_gemm_bf16x3: ldcs must be even");
+    if (M == 0) return 0;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.bias = bias; g.residual = residual; g.ldr = ldr;
+    g.C = C; g.ldc = ldc;
+    g.Chi = reinterpret_cast<__nv_bfloat16*>(C_hi); g.Cmid = reinterpret_cast<__nv_bfloat16*>(C_mid); g.ldcs = ldcs;
+    g.M = M; g.N = N; g.K = K; g.act = act;
+    g.m_tiles = (M + G_BM - 1) / G_BM;
+    g.n_tiles = (N + 207) / 208;                                   // <= 208 columns per tile: two tiles' accumulators fit TMEM
+    g.NS = ((N + g.n_tiles - 1) / g.n_tiles + 15) / 16 * 16;       // tile starts stay 32-byte aligned in fp32 and in bf16 rows
+    g.NT = g.NS;
+    const int stage_bytes = 2 * G_A_PLANE + 2 * g.NT * 64;
+    const int max_smem = 227 * 1024;
+    g.stages = (max_smem - 1024 - 256) / stage_bytes;
+    if (g.stages > G_MAX_STAGES) g.stages = G_MAX_STAGES;
+    DYG_CHECK_ARG(g.stages >= 2, "dyg_gemm_bf16x3: tile does not fit shared memory");
+    const size_t smem = (size_t)g.stages * stage_bytes + 1024 + 256;
+    CUtensorMap mah, mam, mwh, mwm;
+    if (!get_map(A_hi, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mah)) return 1;
+    if (!get_map(A_mid, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mam)) return 1;
+    if (!get_map(W_hi, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)g.NT, &mwh)) return 1;
+    if (!get_map(W_mid, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)g.NT, &mwm)) return 1;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            dyg_set_error("dyg_gemm_bf16x3: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return 1;
+        }
+        configured = smem;
+    }
+    const int64_t total = g.m_tiles * g.n_tiles;
+    const int grid = (int)(total < dyg_num_sms() ? total : dyg_num_sms());
+    gemm_bf16x3_kernel<<<grid, G_THREADS, smem, as_stream(stream)>>>(mah, mam, mwh, mwm, g);
+    DYG_LAUNCH_CHECK("dyg_gemm_bf16x3");
+    return 0;
+}
+
+extern "C" int dyg_split_bf16(const float* x, int ldx, int64_t M, int D, void* hi, void* mid, int ld, dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && D > 0 && ld >= D && ldx >= D, "dyg_split_bf16: bad sizes");
+    DYG_CHECK_ARG(x && hi && mid, "dyg_split_bf16: NULL pointer");
+    if (M == 0) return 0;
+    const int64_t n = M * ((D + 1) / 2);
+    split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, M, D, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                             reinterpret_cast<__nv_bfloat16*>(mid), ld);
+    DYG_LAUNCH_CHECK("dyg_split_bf16");
+    return 0;
+}
+
+extern "C" int dyg_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, float eps, float* y, int ldy,
+                                   void* hi, void* mid, int ld, int64_t M, int D, dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && D > 0 && D <= 1024 && (D % 2) == 0, "dyg_layernorm_split: D=%d unsupported (even, max 1024)", D);
+    DYG_CHECK_ARG((ldx % 2) == 0 && (ld % 2) == 0 && (!y || (ldy % 2) == 0), "dyg_layernorm_split: leading dims must be even");
+    DYG_CHECK_ARG(x && hi && mid && gamma && beta, "dyg_layernorm_split: NULL pointer");
+    DYG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(beta) & 7u) == 0 && (!y || (reinterpret_cast<uintptr_t>(y) & 7u) == 0),
+                  "dyg_layernorm_split: fp32 pointers must be 8-byte aligned");
+    if (M == 0) return 0;
+    const unsigned blocks = (unsigned)((M * 32 + 255) / 256);
+    cudaStream_t s = as_stream(stream);
+    __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+    __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(mid);
+    if (D <= 256) layernorm_split_kernel<4><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, h, l, ld, M, D);
+    else if (D <= 512) layernorm_split_kernel<8><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, h, l, ld, M, D);
+    else layernorm_split_kernel<16><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, h, l, ld, M, D);
+    DYG_LAUNCH_CHECK("dyg_layernorm_split");
+    return 0;
+}

@@ -94,13 +94,14 @@ class TransformerEncoder(nn.Module):
         mha = self.multi_head_attention
         n0, n1 = self.norm_layers
         l0, l1 = self.linear_layers
-        y = ops.layernorm(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
-        qkv = ops.linear([ops.seg_rows(y)], B * S, mha.in_proj_weight.detach(), mha.in_proj_bias.detach())
-        a = ops.seq_attention(qkv, B, S, self.num_heads, D // self.num_heads)
-        x1 = ops.linear([ops.seg_rows(a)], B * S, mha.out_proj.weight.detach(), mha.out_proj.bias.detach(), residual=x)
-        y = ops.layernorm(x1, n1.weight.detach(), n1.bias.detach(), eps=n1.eps)
-        h = ops.linear([ops.seg_rows(y)], B * S, l0.weight.detach(), l0.bias.detach(), act=ops.ACT_GELU)
-        out = ops.linear([ops.seg_rows(h)], B * S, l1.weight.detach(), l1.bias.detach(), residual=x1)
+        # every dense contraction runs on tcgen05 from BF16x3 operand planes (ops.gemm); the residual stream stays fp32
+        y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
+        qkv = ops.gemm(y, mha.in_proj_weight, mha.in_proj_bias.detach())
+        a = ops.split_bf16(ops.seq_attention(qkv, B, S, self.num_heads, D // self.num_heads))
+        x1 = ops.gemm(a, mha.out_proj.weight, mha.out_proj.bias.detach(), residual=x)
+        y = ops.layernorm_split(x1, n1.weight.detach(), n1.bias.detach(), eps=n1.eps)
+        h = ops.gemm(y, l0.weight, l0.bias.detach(), act=ops.ACT_GELU, want='split')
+        out = ops.gemm(h, l1.weight, l1.bias.detach(), residual=x1)
         return out.reshape(B, S, D)
 
 
@@ -270,14 +271,15 @@ class DyGFormer(nn.Module):
                  self._cooc_weight(), pl['neighbor_co_occurrence'].bias),
             )
             for ch, (seg, wt, bias) in enumerate(chans):
-                ops.linear([seg], M, wt, bias.detach(), out=X[:, ch * C:(ch + 1) * C], c_group=ntok, c_group_stride=S, c_offset=off)
+                ops.linear([seg], M, wt, bias.detach(), out=X[:, ch * C:(ch + 1) * C], c_group=ntok, c_group_stride=S, c_offset=off,
+                           tc=True)   # same kernel for every batch size: a row's result never depends on its batch
         x = X.reshape(B, S, D)
         for tr in self.transformers:
             x = tr(x)
         means = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
         ops.mean_tokens(x, B, S, D, 0, ns, out=means[:B])
         ops.mean_tokens(x, B, S, D, ns, nd, out=means[B:])
-        out = ops.linear([ops.seg_rows(means)], 2 * B, self.output_layer.weight.detach(), self.output_layer.bias.detach())
+        out = ops.gemm(ops.split_bf16(means), self.output_layer.weight, self.output_layer.bias.detach())
         return out[:B], out[B:]
 
     def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):

@@ -181,6 +181,106 @@ def linear(segs, M, weight, bias=None, residual=None, act=ACT_NONE, out=None, ou
     return out
 
 
+# ------------------------------------------------------------------ BF16x3 operand pairs + TMA / tcgen05 GEMM
+class Split:
+    """A fp32 matrix (rows, cols) carried as bf16 planes hi | mid: ``planes`` is a (2, rows, ld) bf16 tensor,
+    ld a multiple of 16 so every row starts on a 32-byte boundary (vector stores, TMA strides)."""
+    __slots__ = ('planes', 'rows', 'cols')
+
+    def __init__(self, planes, rows, cols):
+        self.planes, self.rows, self.cols = planes, rows, cols
+
+    @property
+    def ld(self):
+        return self.planes.shape[2]
+
+    @property
+    def hi(self):
+        return self.planes[0]
+
+    @property
+    def mid(self):
+        return self.planes[1]
+
+    def float(self):
+        return (self.planes[0].float() + self.planes[1].float())[:, :self.cols]
+
+
+def empty_split(rows, cols, device):
+    ld = (cols + 15) // 16 * 16
+    return Split(torch.empty((2, rows, ld), dtype=torch.bfloat16, device=device), rows, cols)
+
+
+def split_bf16(x, out=None):
+    """hi | mid planes of a fp32 matrix (last dimension contiguous)."""
+    M, D = x.shape
+    if out is None:
+        out = empty_split(M, D, x.device)
+    _native.check(_lib().dyg_split_bf16(_p(x), int(x.stride(0)), int(M), int(D), _p(out.hi), _p(out.mid), int(out.ld), _stream()))
+    _count()
+    return out
+
+
+_split_weights = {}
+
+
+def split_weight(weight):
+    """Cached BF16x3 planes of a (N, K) fp32 weight (re-split when the parameter changes)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
+    ent = _split_weights.get(key)
+    if ent is None:
+        if len(_split_weights) > 256:
+            _split_weights.clear()
+        w = weight.detach()
+        if w.stride(-1) != 1:
+            w = w.contiguous()
+        ent = _split_weights[key] = (split_bf16(w.float()), weight)
+    return ent[0]
+
+
+def gemm(a, weight, bias=None, residual=None, act=ACT_NONE, out=None, out_split=None, want='f32'):
+    """act(a @ weight.T + bias + residual) on tcgen05 (dyg_gemm_bf16x3).  ``a``: Split; ``weight``: fp32 (N, K) parameter
+    (split once and cached) or a Split.  ``want``: 'f32' -> fp32 tensor, 'split' -> Split, 'both' -> (fp32, Split)."""
+    w = weight if isinstance(weight, Split) else split_weight(weight)
+    M, K, N = a.rows, a.cols, w.rows
+    if w.cols != K:
+        raise ValueError(f'gemm: A has {K} columns, W has {w.cols}')
+    dev = a.planes.device
+    if want in ('f32', 'both') and out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if want in ('split', 'both') and out_split is None:
+        out_split = empty_split(M, N, dev)
+    if want == 'f32':
+        out_split = None
+    if want == 'split':
+        out = None
+    with _Timed('gemm_bf16x3_kernel', 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N) * (2 if want == 'both' else 1)):
+        _native.check(_lib().dyg_gemm_bf16x3(
+            _p(a.hi), _p(a.mid), int(a.ld), _p(w.hi), _p(w.mid), int(w.ld), _p(bias), _p(residual),
+            int(residual.stride(0)) if residual is not None else 0, _p(out), int(out.stride(0)) if out is not None else 0,
+            _p(out_split.hi) if out_split is not None else None, _p(out_split.mid) if out_split is not None else None,
+            int(out_split.ld) if out_split is not None else 0, int(M), int(N), int(K), int(act), _stream()))
+    _count()
+    if want == 'f32':
+        return out
+    if want == 'split':
+        return out_split
+    return out, out_split
+
+
+def layernorm_split(x, gamma, beta, eps=1e-5, out=None, y=None):
+    """LayerNorm(x) as a Split (and optionally also as fp32 ``y``)."""
+    M, D = x.shape
+    if out is None:
+        out = empty_split(M, D, x.device)
+    with _Timed('layernorm_split_kernel', 8.0 * M * D, 8.0 * M * D):
+        _native.check(_lib().dyg_layernorm_split(_p(x), int(x.stride(0)), _p(gamma), _p(beta), float(eps), _p(y),
+                                                 int(y.stride(0)) if y is not None else 0, _p(out.hi), _p(out.mid), int(out.ld),
+                                                 int(M), int(D), _stream()))
+    _count()
+    return out
+
+
 def layernorm(x, gamma, beta, r1=None, F1=0, rconst=None, eps=1e-5, out=None):
     M, D = x.shape
     if out is None:

@@ -148,6 +148,22 @@ int dyg_linear_tc(const dyg_seg_t* segs_host, int nseg, const void* W_hi, const 
                   const float* bias, const float* residual, int ldr, float* C, int ldc, int64_t M, int N, int act,
                   int c_group, int c_group_stride, int c_offset, dyg_stream_t stream);
 
+/* ---- a16 on tensor cores: DyGFormer's transformer / output GEMMs (models/DyGFormer.py:442-461, 190-192) ----
+ * BF16x3 operand pairs: a float x is carried as hi = bf16(x), mid = bf16(x - hi) in two bf16 planes of identical layout.
+ * dyg_gemm_bf16x3: C[m,:N] = act(A W^T + bias + residual[m]),  A (M,K) planes with leading dimension lda, W (N,K) planes
+ * with leading dimension ldw (elements; multiples of 8, planes 16-byte aligned); operands are fetched by TMA, the
+ * product runs as three tcgen05 bf16 MMAs with fp32 accumulation in TMEM (~1e-5 relative).  Outputs: C (M,ldc) fp32
+ * and / or the bf16 planes C_hi | C_mid (M,ldcs) of the same fp32 result (either may be NULL, not both). */
+int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, const void* W_hi, const void* W_mid, int ldw,
+                    const float* bias, const float* residual, int ldr, float* C, int ldc, void* C_hi, void* C_mid,
+                    int ldcs, int64_t M, int N, int K, int act, dyg_stream_t stream);
+/* hi | mid planes (M,ld) of a fp32 matrix x (M,ldx), D columns. */
+int dyg_split_bf16(const float* x, int ldx, int64_t M, int D, void* hi, void* mid, int ld, dyg_stream_t stream);
+/* LayerNorm(x) * gamma + beta over D (even) columns written as hi | mid planes (and as fp32 y when y != NULL)
+ * (norm_layers of models/DyGFormer.py:452,458 feeding the next GEMM). */
+int dyg_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, float eps, float* y, int ldy,
+                        void* hi, void* mid, int ld, int64_t M, int D, dyg_stream_t stream);
+
 /* y = LayerNorm(x + r) * gamma + beta over D columns; r row = [r1 row (F1 cols) | rconst (D-F1 cols)];
  * r1/rconst may be NULL (models/modules.py:199, models/DyGFormer.py:452,458). */
 int dyg_layernorm(const float* x, int ldx, const float* r1, int ldr1, int F1, const float* rconst,

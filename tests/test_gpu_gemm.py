@@ -1,0 +1,95 @@
+"""GPU: dyg_gemm_bf16x3 (TMA + tcgen05, BF16x3 operand planes), dyg_split_bf16 and dyg_layernorm_split against
+float64 torch references of the same inputs."""
+import numpy as np
+import pytest
+import torch
+
+from dyglib_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, want):
+    return float((got.double() - want).abs().max() / want.abs().max().clamp_min(1e-30))
+
+
+# (M, N, K): DyGFormer's transformer / output shapes, ragged M, N and K tails, single tiles, many tiles per CTA
+SHAPES = [(128, 16, 32), (1, 8, 8), (129, 50, 172), (1000, 200, 200), (4096, 600, 200), (777, 800, 200), (640, 200, 800),
+          (513, 172, 200), (300, 516, 616), (260, 272, 444), (40000, 200, 200), (25600, 800, 200), (256, 1, 176),
+          (148 * 128 * 2 + 5, 208, 72)]
+
+
+def test_split_roundtrip():
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.randn(333, 200, device='cuda', generator=g) * 37.0
+    s = ops.split_bf16(x)
+    assert s.planes.shape == (2, 333, 208) and s.planes.dtype == torch.bfloat16
+    hi = x.to(torch.bfloat16)
+    mid = (x - hi.float()).to(torch.bfloat16)
+    assert torch.equal(s.hi[:, :200], hi) and torch.equal(s.mid[:, :200], mid)
+    assert rel_err(s.float(), x.double()) < 2e-5
+    y = torch.randn(7, 5, device='cuda', generator=g)          # odd width, strided input
+    big = torch.zeros(7, 9, device='cuda')
+    big[:, :5] = y
+    s = ops.split_bf16(big[:, :5])
+    assert rel_err(s.float(), y.double()) < 2e-5
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+def test_gemm_vs_float64(M, N, K):
+    g = torch.Generator(device='cuda').manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, device='cuda', generator=g)
+    w = torch.randn(N, K, device='cuda', generator=g) / np.sqrt(K)
+    b = torch.randn(N, device='cuda', generator=g)
+    r = torch.randn(M, N, device='cuda', generator=g)
+    sa = ops.split_bf16(a)
+    base = a.double() @ w.double().t()
+    got = ops.gemm(sa, w)
+    assert rel_err(got, base) < 3e-5, rel_err(got, base)
+    want = base + b.double() + r.double()
+    got, gs = ops.gemm(sa, w, b, residual=r, want='both')
+    assert rel_err(got, want) < 3e-5
+    assert rel_err(gs.float(), want) < 5e-5
+    hi = got.to(torch.bfloat16)
+    assert torch.equal(gs.hi[:, :N], hi) and torch.equal(gs.mid[:, :N], (got - hi.float()).to(torch.bfloat16))
+    for act, fn in ((ops.ACT_RELU, torch.relu), (ops.ACT_GELU, torch.nn.functional.gelu), (ops.ACT_SIGMOID, torch.sigmoid)):
+        gs = ops.gemm(sa, w, b, act=act, want='split')
+        assert rel_err(gs.float(), fn(base + b.double())) < 5e-5
+
+
+def test_gemm_chain_keeps_fp32_accuracy():
+    """FFN shape chain 200 -> 800 (GELU, planes only) -> 200 (+ residual): errors stay at the 1e-5 level."""
+    g = torch.Generator(device='cuda').manual_seed(5)
+    M = 6400
+    x = torch.randn(M, 200, device='cuda', generator=g)
+    w0 = torch.randn(800, 200, device='cuda', generator=g) / np.sqrt(200)
+    b0 = torch.randn(800, device='cuda', generator=g)
+    w1 = torch.randn(200, 800, device='cuda', generator=g) / np.sqrt(800)
+    b1 = torch.randn(200, device='cuda', generator=g)
+    h = ops.gemm(ops.split_bf16(x), w0, b0, act=ops.ACT_GELU, want='split')
+    out = ops.gemm(h, w1, b1, residual=x)
+    want = torch.nn.functional.gelu(x.double() @ w0.double().t() + b0.double()) @ w1.double().t() + b1.double() + x.double()
+    assert rel_err(out, want) < 5e-5
+
+
+def test_gemm_row_independent_of_batch():
+    """A row's result does not depend on how many rows share the launch (grouped == per-batch results)."""
+    g = torch.Generator(device='cuda').manual_seed(9)
+    a = torch.randn(1000, 200, device='cuda', generator=g)
+    w = torch.randn(600, 200, device='cuda', generator=g)
+    full = ops.gemm(ops.split_bf16(a), w)
+    part = ops.gemm(ops.split_bf16(a[300:437].contiguous()), w)
+    assert torch.equal(full[300:437], part)
+
+
+@pytest.mark.parametrize('M,D', [(1, 200), (1000, 200), (77, 64), (300, 444), (50, 800)])
+def test_layernorm_split(M, D):
+    g = torch.Generator(device='cuda').manual_seed(M + D)
+    x = torch.randn(M, D, device='cuda', generator=g) * 3 + 1
+    gm = torch.randn(D, device='cuda', generator=g)
+    bt = torch.randn(D, device='cuda', generator=g)
+    y = torch.empty_like(x)
+    s = ops.layernorm_split(x, gm, bt, eps=1e-5, y=y)
+    want = torch.nn.functional.layer_norm(x.double(), (D,), gm.double(), bt.double(), 1e-5)
+    assert rel_err(y, want) < 1e-5
+    assert rel_err(s.float(), want) < 3e-5
