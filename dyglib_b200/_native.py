@@ -105,6 +105,7 @@ SIGNATURES = {
     'dyg_temporal_attend': [c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i,
                             c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p],
     'dyg_seq_attention': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p],
+    'dyg_seq_attention_tc': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
     'dyg_mean_tokens': [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_tgn_persist': [c_p, c_l, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     'dyg_tgn_select_last': [c_p, c_p, c_l, c_p, c_p],

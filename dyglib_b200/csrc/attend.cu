@@ -276,3 +276,230 @@ extern "C" int dyg_seq_attention(const float* qkv, int ld_qkv, int64_t B, int S,
     DYG_LAUNCH_CHECK("dyg_seq_attention");
     return 0;
 }
+
+// ------------------------------------------------------------------ DyGFormer sequence attention on tensor cores
+// softmax(q k^T / sqrt(hd)) v for S <= 128 tokens, head_dim <= 128 (DyGFormer: S <= 64, hd = 100).  One CTA per
+// (pair, head); K and V rows of the head are split into bf16 hi | mid on the way into shared memory; every warp owns
+// 16-query blocks and runs both products as BF16x3 (hi*hi + hi*mid + mid*hi, fp32 accumulate) with register-resident
+// m16n8k16 fragments: scores -> softmax in the accumulator layout -> probabilities reused in place as the A operand
+// of P V (V read with ldmatrix.trans).  ~1e-5 relative, like the tcgen05 GEMMs around it.  The two products are 5 % of
+// the transformer's flops on 64-token tiles; the dense projections run on tcgen05 (gemm_tc.cu).
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ void sa_split(float a, float b, uint32_t& hi, uint32_t& mid) {
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 am = __float2bfloat16_rn(a - __bfloat162float(ah)), bm = __float2bfloat16_rn(b - __bfloat162float(bh));
+    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+    mid = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
+}
+__device__ __forceinline__ void sa_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void sa_ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+
+// NKT: 8-key tiles (S <= 8*NKT, even), KDT: 16-wide head-dim steps (hd <= 16*KDT)
+template <int NKT, int KDT>
+__global__ void __launch_bounds__(128) seq_attention_mma_kernel(const float* __restrict__ qkv, int ld_qkv, int S, int H, int hd,
+                                                                float* __restrict__ out, int ldo, __nv_bfloat16* __restrict__ ohi,
+                                                                __nv_bfloat16* __restrict__ omid, int ldos) {
+    constexpr int SK = NKT * 8, KD = KDT * 16, KS = KD + 8;   // KS/2 = 4 (mod 8): conflict-free fragment loads
+    extern __shared__ __align__(16) unsigned char sa_smem[];
+    __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(sa_smem);
+    __nv_bfloat16* Km = Kh + SK * KS;
+    __nv_bfloat16* Vh = Km + SK * KS;
+    __nv_bfloat16* Vm = Vh + SK * KS;
+    const int64_t b = blockIdx.x / H;
+    const int h = blockIdx.x % H;
+    const int D = H * hd;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const float* base = qkv + b * (int64_t)S * ld_qkv;
+    for (int idx = tid; idx < SK * (KD / 2); idx += 128) {
+        const int j = idx / (KD / 2), d = (idx - j * (KD / 2)) * 2;
+        float2 kv = make_float2(0.f, 0.f), vv = kv;
+        if (j < S && d < hd) {
+            const float* rowp = base + (int64_t)j * ld_qkv + h * hd + d;
+            kv = *reinterpret_cast<const float2*>(rowp + D);
+            vv = *reinterpret_cast<const float2*>(rowp + 2 * D);
+        }
+        uint32_t hi, mid;
+        sa_split(kv.x, kv.y, hi, mid);
+        *reinterpret_cast<uint32_t*>(Kh + j * KS + d) = hi;
+        *reinterpret_cast<uint32_t*>(Km + j * KS + d) = mid;
+        sa_split(vv.x, vv.y, hi, mid);
+        *reinterpret_cast<uint32_t*>(Vh + j * KS + d) = hi;
+        *reinterpret_cast<uint32_t*>(Vm + j * KS + d) = mid;
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)hd);
+    for (int rb = warp; rb * 16 < S; rb += 4) {
+        const int r0 = rb * 16 + g, r1 = r0 + 8;
+        const float* q0 = base + (int64_t)min(r0, S - 1) * ld_qkv + h * hd;
+        const float* q1 = base + (int64_t)min(r1, S - 1) * ld_qkv + h * hd;
+        float sc[NKT][4];
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KDT; ++ks) {
+            const int d0 = ks * 16 + 2 * t, d1 = d0 + 8;
+            const float2 z = make_float2(0.f, 0.f);
+            const float2 q00 = d0 < hd ? *reinterpret_cast<const float2*>(q0 + d0) : z;
+            const float2 q10 = d0 < hd ? *reinterpret_cast<const float2*>(q1 + d0) : z;
+            const float2 q01 = d1 < hd ? *reinterpret_cast<const float2*>(q0 + d1) : z;
+            const float2 q11 = d1 < hd ? *reinterpret_cast<const float2*>(q1 + d1) : z;
+            uint32_t ah[4], am[4];
+            sa_split(q00.x, q00.y, ah[0], am[0]);
+            sa_split(q10.x, q10.y, ah[1], am[1]);
+            sa_split(q01.x, q01.y, ah[2], am[2]);
+            sa_split(q11.x, q11.y, ah[3], am[3]);
+#pragma unroll
+            for (int nt = 0; nt < NKT; ++nt) {
+                const int off = (nt * 8 + g) * KS + ks * 16 + 2 * t;
+                const uint32_t b0h = *reinterpret_cast<const uint32_t*>(Kh + off), b1h = *reinterpret_cast<const uint32_t*>(Kh + off + 8);
+                const uint32_t b0m = *reinterpret_cast<const uint32_t*>(Km + off), b1m = *reinterpret_cast<const uint32_t*>(Km + off + 8);
+                sa_mma(sc[nt], ah, b0h, b1h);
+                sa_mma(sc[nt], ah, b0m, b1m);
+                sa_mma(sc[nt], am, b0h, b1h);
+            }
+        }
+        // softmax over the keys: rows r0 (c0,c1) and r1 (c2,c3); the four lanes of a quad share a row
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) {
+            const int key = nt * 8 + 2 * t;
+            sc[nt][0] = key < S ? sc[nt][0] * scale : -INFINITY;
+            sc[nt][1] = key + 1 < S ? sc[nt][1] * scale : -INFINITY;
+            sc[nt][2] = key < S ? sc[nt][2] * scale : -INFINITY;
+            sc[nt][3] = key + 1 < S ? sc[nt][3] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) {
+            sc[nt][0] = expf(sc[nt][0] - mx0);
+            sc[nt][1] = expf(sc[nt][1] - mx0);
+            sc[nt][2] = expf(sc[nt][2] - mx1);
+            sc[nt][3] = expf(sc[nt][3] - mx1);
+            sum0 += sc[nt][0] + sc[nt][1];
+            sum1 += sc[nt][2] + sc[nt][3];
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        // P V: the score accumulators of two adjacent key tiles are exactly one A fragment (16 queries x 16 keys)
+        float o[2 * KDT][4];
+#pragma unroll
+        for (int dt = 0; dt < 2 * KDT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < NKT / 2; ++kk) {
+            uint32_t ph[4], pm[4];
+            sa_split(sc[2 * kk][0], sc[2 * kk][1], ph[0], pm[0]);
+            sa_split(sc[2 * kk][2], sc[2 * kk][3], ph[1], pm[1]);
+            sa_split(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pm[2]);
+            sa_split(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pm[3]);
+            const int voff = (kk * 16 + (lane & 15)) * KS;
+#pragma unroll
+            for (int dt = 0; dt < 2 * KDT; ++dt) {
+                uint32_t b0h, b1h, b0m, b1m;
+                sa_ldmatrix_x2_trans(b0h, b1h, Vh + voff + dt * 8);
+                sa_ldmatrix_x2_trans(b0m, b1m, Vm + voff + dt * 8);
+                sa_mma(o[dt], ph, b0h, b1h);
+                sa_mma(o[dt], ph, b0m, b1m);
+                sa_mma(o[dt], pm, b0h, b1h);
+            }
+        }
+        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+#pragma unroll
+        for (int dt = 0; dt < 2 * KDT; ++dt) {
+            const int d = dt * 8 + 2 * t;
+            if (d >= hd) continue;
+            const float a0 = o[dt][0] * inv0, a1 = o[dt][1] * inv0, c0 = o[dt][2] * inv1, c1 = o[dt][3] * inv1;
+            if (r0 < S) {
+                const int64_t row = b * S + r0;
+                if (out) *reinterpret_cast<float2*>(out + row * ldo + h * hd + d) = make_float2(a0, a1);
+                if (ohi) {
+                    uint32_t hi, mid;
+                    sa_split(a0, a1, hi, mid);
+                    *reinterpret_cast<uint32_t*>(ohi + row * ldos + h * hd + d) = hi;
+                    *reinterpret_cast<uint32_t*>(omid + row * ldos + h * hd + d) = mid;
+                }
+            }
+            if (r1 < S) {
+                const int64_t row = b * S + r1;
+                if (out) *reinterpret_cast<float2*>(out + row * ldo + h * hd + d) = make_float2(c0, c1);
+                if (ohi) {
+                    uint32_t hi, mid;
+                    sa_split(c0, c1, hi, mid);
+                    *reinterpret_cast<uint32_t*>(ohi + row * ldos + h * hd + d) = hi;
+                    *reinterpret_cast<uint32_t*>(omid + row * ldos + h * hd + d) = mid;
+                }
+            }
+        }
+    }
+}
+
+template <int NKT, int KDT>
+int launch_seq_mma(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, float* out, int ldo, void* ohi, void* omid,
+                   int ldos, cudaStream_t s) {
+    const size_t smem = (size_t)4 * (NKT * 8) * (KDT * 16 + 8) * sizeof(__nv_bfloat16);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(seq_attention_mma_kernel<NKT, KDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            dyg_set_error("dyg_seq_attention_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return 1;
+        }
+        configured = true;
+    }
+    seq_attention_mma_kernel<NKT, KDT><<<(unsigned)(B * H), 128, smem, s>>>(qkv, ld_qkv, S, H, hd, out, ldo,
+                                                                           reinterpret_cast<__nv_bfloat16*>(ohi),
+                                                                           reinterpret_cast<__nv_bfloat16*>(omid), ldos);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int dyg_seq_attention_tc(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, float* out, int ldo,
+                                    void* out_hi, void* out_mid, int ldos, dyg_stream_t stream) {
+    DYG_CHECK_ARG(B >= 0 && S > 0 && H > 0 && hd > 0, "dyg_seq_attention_tc: bad sizes");
+    DYG_CHECK_ARG(S <= 128 && hd <= 128 && (hd % 2) == 0, "dyg_seq_attention_tc: S=%d (max 128), head_dim=%d (even, max 128) unsupported", S, hd);
+    DYG_CHECK_ARG((ld_qkv % 2) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 7u) == 0, "dyg_seq_attention_tc: qkv must be 8-byte aligned with an even leading dimension");
+    DYG_CHECK_ARG(out || (out_hi && out_mid), "dyg_seq_attention_tc: no output given");
+    DYG_CHECK_ARG((out_hi == nullptr) == (out_mid == nullptr), "dyg_seq_attention_tc: out_hi and out_mid go together");
+    DYG_CHECK_ARG(!out || ((ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(out) & 7u) == 0), "dyg_seq_attention_tc: out must be 8-byte aligned, ldo even");
+    DYG_CHECK_ARG(!out_hi || (ldos % 2) == 0, "dyg_seq_attention_tc: ldos must be even");
+    DYG_CHECK_ARG(B * H < ((int64_t)1 << 31), "dyg_seq_attention_tc: too many (pair, head) tiles");
+    if (B == 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    int rc;
+#define SA_GO(NKT, KDT) rc = launch_seq_mma<NKT, KDT>(qkv, ld_qkv, B, S, H, hd, out, ldo, out_hi, out_mid, ldos, s)
+#define SA_KD(NKT)                     \
+    do {                               \
+        if (hd <= 32) SA_GO(NKT, 2);   \
+        else if (hd <= 64) SA_GO(NKT, 4); \
+        else if (hd <= 112) SA_GO(NKT, 7); \
+        else SA_GO(NKT, 8);            \
+    } while (0)
+    if (S <= 32) SA_KD(4);
+    else if (S <= 64) SA_KD(8);
+    else SA_KD(16);
+#undef SA_KD
+#undef SA_GO
+    if (rc != 0) return rc;
+    DYG_LAUNCH_CHECK("dyg_seq_attention_tc");
+    return 0;
+}

@@ -97,7 +97,11 @@ class TransformerEncoder(nn.Module):
         # every dense contraction runs on tcgen05 from BF16x3 operand planes (ops.gemm); the residual stream stays fp32
         y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
         qkv = ops.gemm(y, mha.in_proj_weight, mha.in_proj_bias.detach())
-        a = ops.split_bf16(ops.seq_attention(qkv, B, S, self.num_heads, D // self.num_heads))
+        hd = D // self.num_heads
+        if S <= 128 and hd <= 128 and hd % 2 == 0:
+            a = ops.seq_attention_tc(qkv, B, S, self.num_heads, hd, want='split')
+        else:
+            a = ops.split_bf16(ops.seq_attention(qkv, B, S, self.num_heads, hd))
         x1 = ops.gemm(a, mha.out_proj.weight, mha.out_proj.bias.detach(), residual=x)
         y = ops.layernorm_split(x1, n1.weight.detach(), n1.bias.detach(), eps=n1.eps)
         h = ops.gemm(y, l0.weight, l0.bias.detach(), act=ops.ACT_GELU, want='split')

@@ -340,6 +340,20 @@ def seq_attention(qkv, B, S, H, hd, out=None):
     return out
 
 
+def seq_attention_tc(qkv, B, S, H, hd, want='split'):
+    """Tensor-core sequence attention (S <= 128, even hd <= 128).  want: 'f32' | 'split' | 'both'."""
+    dev = qkv.device
+    out = torch.empty((B * S, H * hd), device=dev, dtype=torch.float32) if want in ('f32', 'both') else None
+    sp = empty_split(B * S, H * hd, dev) if want in ('split', 'both') else None
+    with _Timed('seq_attention_mma_kernel', 4.0 * B * H * S * S * hd, 16.0 * B * S * H * hd):
+        _native.check(_lib().dyg_seq_attention_tc(_p(qkv), qkv.stride(-2), int(B), int(S), int(H), int(hd), _p(out),
+                                                  out.stride(-2) if out is not None else 0,
+                                                  _p(sp.hi) if sp is not None else None, _p(sp.mid) if sp is not None else None,
+                                                  int(sp.ld) if sp is not None else 0, _stream()))
+    _count()
+    return out if want == 'f32' else sp if want == 'split' else (out, sp)
+
+
 def mean_tokens(x, B, S, D, tok0, cnt, out=None):
     if out is None:
         out = torch.empty((B, D), device=x.device, dtype=torch.float32)

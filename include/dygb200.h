@@ -194,6 +194,10 @@ int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H,
  * qkv (B,S,3*H*hd) packed [q|k|v]; out (B,S,H*hd) = softmax(q k^T / sqrt(hd)) v per head; no mask. */
 int dyg_seq_attention(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, float* out, int ldo,
                       dyg_stream_t stream);
+/* Tensor-core variant for S <= 128, even hd <= 128: both products as BF16x3 m16n8k16 MMAs with fp32 accumulation
+ * (~1e-5 relative); writes fp32 out (B*S, ldo) and / or the bf16 hi | mid planes (B*S, ldos) that feed dyg_gemm_bf16x3. */
+int dyg_seq_attention_tc(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, float* out, int ldo,
+                         void* out_hi, void* out_mid, int ldos, dyg_stream_t stream);
 /* out[b,:] = mean over tokens [tok0, tok0+cnt) of x[b,:,:] (models/DyGFormer.py:185-187). */
 int dyg_mean_tokens(const float* x, int64_t B, int S, int D, int tok0, int cnt, float* out, int ldo, dyg_stream_t stream);
 

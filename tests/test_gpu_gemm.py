@@ -93,3 +93,19 @@ def test_layernorm_split(M, D):
     want = torch.nn.functional.layer_norm(x.double(), (D,), gm.double(), bt.double(), 1e-5)
     assert rel_err(y, want) < 1e-5
     assert rel_err(s.float(), want) < 3e-5
+
+
+@pytest.mark.parametrize('B,S,H,hd', [(3, 64, 2, 100), (5, 20, 2, 100), (2, 7, 1, 32), (4, 100, 2, 64), (2, 128, 2, 128),
+                                       (300, 64, 2, 100), (3, 33, 2, 50), (2, 2, 2, 100)])
+def test_seq_attention_tc(B, S, H, hd):
+    g = torch.Generator(device='cuda').manual_seed(B + S + hd)
+    D = H * hd
+    qkv = torch.randn(B * S, 3 * D, device='cuda', generator=g) * 1.5
+    out, sp = ops.seq_attention_tc(qkv, B, S, H, hd, want='both')
+    q, k, v = (qkv.double()[:, i * D:(i + 1) * D].reshape(B, S, H, hd).transpose(1, 2) for i in range(3))
+    a = torch.softmax(q @ k.transpose(-1, -2) / np.sqrt(hd), dim=-1)
+    want = (a @ v).transpose(1, 2).reshape(B * S, D)
+    assert rel_err(out, want) < 3e-5, rel_err(out, want)
+    assert rel_err(sp.float(), want) < 5e-5
+    old = ops.seq_attention(qkv, B, S, H, hd)
+    assert rel_err(old, want) < 1e-5
