@@ -7,12 +7,12 @@
 // the dropped terms are O(2^-16) relative per product.  Producing kernels (LayerNorm, attention, the previous GEMM's
 // epilogue) write the planes, so operands reach shared memory by TMA with no thread touching them.
 //
-// Structure: persistent, one CTA per SM, 192 threads.
+// Structure: persistent, one CTA per SM, 320 threads.
 //   warp 0     TMA producer: per 32-wide k block one stage = A_hi | A_mid (128 rows) + W_hi | W_mid (NT rows), 64-byte
 //              rows in SWIZZLE_64B layout, landing on the stage's full mbarrier (expect_tx)
 //   warp 1     TMEM allocation (512 columns = two accumulator buffers) + single-thread tcgen05.mma issue (M=128, N=NT,
 //              K=16, kind::f16 bf16 -> fp32); tcgen05.commit frees the stage / publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias / residual / activation -> 32-byte vector stores
+//   warps 2-9  epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias / residual / activation -> 32-byte vector stores
 //              of the fp32 result and / or its bf16 hi|mid planes; overlaps the next tile's MMAs (double-buffered TMEM)
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -28,7 +28,8 @@ namespace {
 
 constexpr int G_BM = 128;            // rows per tile == TMEM lanes
 constexpr int G_BK = 32;             // bf16 elements per stage along K == one 64-byte swizzle row
-constexpr int G_THREADS = 192;
+constexpr int G_EPI_WARPS = 8;         // two warps per TMEM lane quarter, interleaved over 16-column chunks
+constexpr int G_THREADS = 64 + 32 * G_EPI_WARPS;
 constexpr int G_A_PLANE = G_BM * 64; // bytes of one A plane per stage
 constexpr int G_MAX_STAGES = 8;
 constexpr int G_TMEM_COLS = 512;
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar + b, 1);
-            mbar_init(tempty_bar + b, 128);
+            mbar_init(tempty_bar + b, 32 * G_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp & 3;                                      // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
+        const int chunk0 = (warp - 2) >> 2;                                // which of the interleaved chunk sets is this warp's
         const bool c_v8 = g.C && ((g.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 31u) == 0);
         const bool c_v4 = g.C && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
         const bool s_v8 = g.Chi && ((g.ldcs & 15) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 31u) == 0);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
             mbar_wait(tfull_bar + buf, bph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
-            for (int col = 0; col < ncols; col += 16) {
+            for (int col = 16 * chunk0; col < ncols; col += 16 * (G_EPI_WARPS / 4)) {
                 uint32_t r[16];
                 tmem_ld16(taddr + (uint32_t)col, r);
                 if (rowok) {
