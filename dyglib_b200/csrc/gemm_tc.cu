@@ -7,11 +7,12 @@
 // the dropped terms are O(2^-16) relative per product.  Producing kernels (LayerNorm, attention, the previous GEMM's
 // epilogue) write the planes, so operands reach shared memory by TMA with no thread touching them.
 //
-// Structure: persistent, one CTA per SM, 320 threads.
-//   warp 0     TMA producer: per 32-wide k block one stage = A_hi | A_mid (128 rows) + W_hi | W_mid (NT rows), 64-byte
-//              rows in SWIZZLE_64B layout, landing on the stage's full mbarrier (expect_tx)
-//   warp 1     TMEM allocation (512 columns = two accumulator buffers) + single-thread tcgen05.mma issue (M=128, N=NT,
-//              K=16, kind::f16 bf16 -> fp32); tcgen05.commit frees the stage / publishes the accumulator
+// Structure: persistent CTA pairs (cluster of 2, tcgen05 cta_group::2), one CTA per SM, 320 threads each.
+//   warp 0     TMA producer: per 32-wide k block A_hi | A_mid (this CTA's 128 rows) + W_hi | W_mid (this CTA's half of
+//              the NT rows), 64-byte rows in SWIZZLE_64B layout, counted on the leader's full mbarrier (expect_tx)
+//   warp 1     TMEM allocation (512 columns = two accumulator buffers); in the leader CTA one thread issues the
+//              tcgen05.mma (M=256 over the pair, N=NT, K=16, kind::f16 bf16 -> fp32); tcgen05.commit (multicast to both
+//              CTAs) frees the stage / publishes the accumulator
 //   warps 2-9  epilogue: tcgen05.ld (32 lanes x 16 columns) -> bias / residual / activation -> 32-byte vector stores
 //              of the fp32 result and / or its bf16 hi|mid planes; overlaps the next tile's MMAs (double-buffered TMEM)
 #include <cuda.h>
@@ -49,15 +50,14 @@ struct GemmArgs {
     int NT;        // MMA N of one n tile (== NS)
     int n_tiles;
     int stages;
+    int resident;  // 1: A super tile stays in shared memory across the n tiles (K <= 224)
+    int64_t m_super;   // 256-row super tiles (one per CTA pair and round)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -73,12 +73,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "GW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 
 // K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
 // [0,14), LBO (unused for swizzled K-major, canonical 1) in [16,30), SBO = 512 B between 8-row groups in [32,46),
@@ -91,20 +85,6 @@ __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)4 << 61;
     return d;
-}
-// cute::UMMA::InstrDescriptor, kind::f16: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major A and B,
-// N >> 3 in [17,23), M >> 4 in [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(G_BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -136,41 +116,201 @@ __device__ __forceinline__ void st_v4(void* p, const uint32_t* r) {
     asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the CTA pair's leader is the even rank: clearing the peer bit of a shared::cluster address names the leader's copy
+constexpr uint32_t G_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & G_PEER_MASK) : "memory");
+}
+// TMA load whose bytes are counted on the LEADER CTA's mbarrier (both CTAs of the pair feed one MMA)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & G_PEER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+// One accumulator tile -> global memory: this thread owns TMEM lane `row` (output row m), this warp the 16-column
+// chunks chunk0, chunk0 + step, ...  Warp-collective (tcgen05.ld): every lane runs the loop, stores are masked.
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int64_t m, int n0, int ncols, int chunk0, int step) {
+    const bool rowok = m < g.M;
+    const bool c_v8 = g.C && ((g.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 31u) == 0);
+    const bool c_v4 = g.C && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
+    const bool s_v8 = g.Chi && ((g.ldcs & 15) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 31u) == 0);
+    const bool s_v4 = g.Chi && ((g.ldcs & 7) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 15u) == 0);
+    const bool r_v4 = g.residual && ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0);
+    const bool b_v4 = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+    for (int col = 16 * chunk0; col < ncols; col += 16 * step) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)col, r);
+        if (rowok) {
+            const int n = n0 + col;
+            const int valid = min(16, ncols - col);
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            if (valid == 16) {
+                if (g.bias) {
+                    if (b_v4) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += __ldg(g.bias + n + j);
+                    }
+                }
+                if (g.residual) {
+                    const float* rp = g.residual + m * g.ldr + n;
+                    if (r_v4) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                            v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += rp[j];
+                    }
+                }
+                if (g.act != DYG_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], g.act);
+                }
+                if (g.C) {
+                    float* dst = g.C + m * g.ldc + n;
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(v[j]);
+                    if (c_v8) {
+                        st_v8(dst, o);
+                        st_v8(dst + 8, o + 8);
+                    } else if (c_v4) {
+                        st_v4(dst, o); st_v4(dst + 4, o + 4); st_v4(dst + 8, o + 8); st_v4(dst + 12, o + 12);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dst[j] = v[j];
+                    }
+                }
+                if (g.Chi) {
+                    uint32_t hi[8], mid[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) split_pack(v[2 * j], v[2 * j + 1], hi[j], mid[j]);
+                    __nv_bfloat16* dh = g.Chi + m * g.ldcs + n;
+                    __nv_bfloat16* dm = g.Cmid + m * g.ldcs + n;
+                    if (s_v8) {
+                        st_v8(dh, hi);
+                        st_v8(dm, mid);
+                    } else if (s_v4) {
+                        st_v4(dh, hi); st_v4(dh + 8, hi + 4);
+                        st_v4(dm, mid); st_v4(dm + 8, mid + 4);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            *reinterpret_cast<uint32_t*>(dh + 2 * j) = hi[j];
+                            *reinterpret_cast<uint32_t*>(dm + 2 * j) = mid[j];
+                        }
+                    }
+                }
+            } else {
+                // ragged last chunk of the row (N not a multiple of 16)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (j >= valid) break;
+                    float x = v[j];
+                    if (g.bias) x += __ldg(g.bias + n + j);
+                    if (g.residual) x += g.residual[m * g.ldr + n + j];
+                    x = act_apply(x, g.act);
+                    if (g.C) g.C[m * g.ldc + n + j] = x;
+                    if (g.Chi) {
+                        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+                        g.Chi[m * g.ldcs + n + j] = h;
+                        g.Cmid[m * g.ldcs + n + j] = __float2bfloat16_rn(x - __bfloat162float(h));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Work decomposition: a CTA PAIR (cluster of 2, cta_group::2) owns 256-row super tiles; CTA r of the pair holds rows
+// [256 ms + 128 r, +128) of A and rows [n0 + r NT/2, + NT/2) of W, the leader's thread issues M=256 MMAs that read both
+// CTAs' shared memory and write each CTA's own TMEM.  Each W byte read from L2 thus serves 256 output rows.
+// Two operand schedules:
+//   resident (K <= 224, several n tiles): the pair keeps its A super tile in shared memory across the n tiles (per k
+//             block slots with their own full / empty barriers, so the next super tile streams in behind the last n
+//             tile's MMAs) and rings only W;
+//   streamed: A and W blocks travel together through the ring.
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah,
                                                                    const __grid_constant__ CUtensorMap map_am,
                                                                    const __grid_constant__ CUtensorMap map_wh,
                                                                    const __grid_constant__ CUtensorMap map_wm, const GemmArgs g) {
     extern __shared__ __align__(1024) unsigned char gemm_smem[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem) + 1023) & ~(uintptr_t)1023);
-    const int w_plane = g.NT * 64;
-    const int stage_bytes = 2 * G_A_PLANE + 2 * w_plane;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)g.stages * stage_bytes);
-    uint64_t* full_bar = bars;                            // [stages]
-    uint64_t* empty_bar = bars + G_MAX_STAGES;            // [stages]
-    uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES;        // [2]
-    uint64_t* tempty_bar = bars + 2 * G_MAX_STAGES + 2;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 4);
+    const int nkb = (g.K + G_BK - 1) / G_BK;
+    const bool resident = g.resident != 0;
+    const int w_plane = (g.NT / 2) * 64;                       // this CTA's half of the W tile, one plane, one k block
+    const int a_stage = 2 * G_A_PLANE;
+    const int stage_bytes = (resident ? 0 : a_stage) + 2 * w_plane;
+    unsigned char* a_res = base;                               // resident mode: nkb slots of [A_hi | A_mid]
+    unsigned char* ring = base + (resident ? (size_t)nkb * a_stage : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * stage_bytes);
+    uint64_t* full_bar = bars;                                 // [stages]   leader: ring stage landed (both CTAs' bytes)
+    uint64_t* empty_bar = bars + G_MAX_STAGES;                 // [stages]   both:   ring stage consumed
+    uint64_t* afull_bar = bars + 2 * G_MAX_STAGES;             // [7]        leader: resident A slot landed
+    uint64_t* aempty_bar = bars + 2 * G_MAX_STAGES + 8;        // [7]        both:   resident A slot consumed by the last n tile
+    uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES + 16;        // [2]        both:   accumulator buffer complete
+    uint64_t* tempty_bar = bars + 2 * G_MAX_STAGES + 18;       // [2]        leader: accumulator buffer drained by both epilogues
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 20);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int nkb = (g.K + G_BK - 1) / G_BK;
-    const int64_t total = g.m_tiles * g.n_tiles;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(full_bar + s, 1);
             mbar_init(empty_bar + s, 1);
         }
+        for (int k = 0; k < 8; ++k) {
+            mbar_init(afull_bar + k, 1);
+            mbar_init(aempty_bar + k, 1);
+        }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar + b, 1);
-            mbar_init(tempty_bar + b, 32 * G_EPI_WARPS);
+            mbar_init(tempty_bar + b, 2 * G_EPI_WARPS);        // one arrival per epilogue warp of either CTA
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G_TMEM_COLS)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G_TMEM_COLS)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ah)) : "memory");
@@ -179,195 +319,119 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wm)) : "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();                                         // barriers + TMEM of BOTH CTAs are ready
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ TMA producer (one thread in each CTA)
         if (lane == 0) {
             int s = 0;
-            uint32_t ph = 0;
-            for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-                const int m0 = (int)(w / g.n_tiles) * G_BM;
-                const int n0 = (int)(w % g.n_tiles) * g.NS;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(empty_bar + s, ph ^ 1u);
-                    unsigned char* st = base + (size_t)s * stage_bytes;
-                    mbar_expect_tx(full_bar + s, (uint32_t)stage_bytes);
-                    tma_load_2d(&map_ah, full_bar + s, st, kb * G_BK, m0);
-                    tma_load_2d(&map_am, full_bar + s, st + G_A_PLANE, kb * G_BK, m0);
-                    tma_load_2d(&map_wh, full_bar + s, st + 2 * G_A_PLANE, kb * G_BK, n0);
-                    tma_load_2d(&map_wm, full_bar + s, st + 2 * G_A_PLANE + w_plane, kb * G_BK, n0);
-                    if (++s == g.stages) {
-                        s = 0;
-                        ph ^= 1u;
+            uint32_t ph = 0, aph = 0;
+            for (int64_t ms = pair; ms < g.m_super; ms += npairs, aph ^= 1u) {
+                const int m0 = (int)ms * 2 * G_BM + (int)rank * G_BM;
+                for (int nt = 0; nt < g.n_tiles; ++nt) {
+                    const int n0 = nt * g.NS + (int)rank * (g.NT / 2);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (resident && nt == 0) {
+                            mbar_wait(aempty_bar + kb, aph ^ 1u);
+                            if (leader) mbar_expect_tx(afull_bar + kb, 2u * (uint32_t)a_stage);
+                            unsigned char* as = a_res + (size_t)kb * a_stage;
+                            tma_load_2d_pair(&map_ah, afull_bar + kb, as, kb * G_BK, m0);
+                            tma_load_2d_pair(&map_am, afull_bar + kb, as + G_A_PLANE, kb * G_BK, m0);
+                        }
+                        mbar_wait(empty_bar + s, ph ^ 1u);
+                        if (leader) mbar_expect_tx(full_bar + s, 2u * (uint32_t)stage_bytes);
+                        unsigned char* st = ring + (size_t)s * stage_bytes;
+                        if (!resident) {
+                            tma_load_2d_pair(&map_ah, full_bar + s, st, kb * G_BK, m0);
+                            tma_load_2d_pair(&map_am, full_bar + s, st + G_A_PLANE, kb * G_BK, m0);
+                            st += a_stage;
+                        }
+                        tma_load_2d_pair(&map_wh, full_bar + s, st, kb * G_BK, n0);
+                        tma_load_2d_pair(&map_wm, full_bar + s, st + w_plane, kb * G_BK, n0);
+                        if (++s == g.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = make_idesc(g.NT);
-        int s = 0;
-        uint32_t ph = 0;
-        int it = 0;
-        for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t bph = (uint32_t)((it >> 1) & 1);
-            mbar_wait(tempty_bar + buf, bph ^ 1u);                      // epilogue drained this accumulator buffer
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tacc = tmem_base + (uint32_t)(buf * G_BUF_COLS);
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(full_bar + s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t a_h = smem_u32(base + (size_t)s * stage_bytes), a_m = a_h + G_A_PLANE;
-                    const uint32_t b_h = a_h + 2 * G_A_PLANE, b_m = b_h + (uint32_t)w_plane;
-                    const int krem = g.K - kb * G_BK;
-                    const int nk16 = krem >= G_BK ? G_BK / 16 : (krem + 15) / 16;
-                    for (int kk = 0; kk < nk16; ++kk) {
-                        const uint32_t o = (uint32_t)kk * 32u;            // 16 bf16 = 32 bytes inside the swizzle row
-                        const uint64_t dah = make_desc_sw64(a_h + o), dam = make_desc_sw64(a_m + o);
-                        const uint64_t dbh = make_desc_sw64(b_h + o), dbm = make_desc_sw64(b_m + o);
-                        umma_bf16(tacc, dah, dbh, idesc, (kb | kk) != 0);
-                        umma_bf16(tacc, dah, dbm, idesc, 1);
-                        umma_bf16(tacc, dam, dbh, idesc, 1);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            // cute::UMMA::InstrDescriptor, kind::f16: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major A and B,
+            // N >> 3 in [17,23), M >> 4 in [24,29) with M = 256 rows over the CTA pair
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((uint32_t)((2 * G_BM) >> 4) << 24);
+            int s = 0;
+            uint32_t ph = 0, aph = 0;
+            int it = 0;
+            for (int64_t ms = pair; ms < g.m_super; ms += npairs, aph ^= 1u) {
+                for (int nt = 0; nt < g.n_tiles; ++nt, ++it) {
+                    const int buf = it & 1;
+                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(tempty_bar + buf, bph ^ 1u);              // both epilogues drained this accumulator buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * G_BUF_COLS);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (resident && nt == 0) mbar_wait(afull_bar + kb, aph);
+                        mbar_wait(full_bar + s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (lane == 0) {
+                            unsigned char* st = ring + (size_t)s * stage_bytes;
+                            const uint32_t a_h = smem_u32(resident ? a_res + (size_t)kb * a_stage : st), a_m = a_h + G_A_PLANE;
+                            const uint32_t b_h = smem_u32(st) + (resident ? 0u : (uint32_t)a_stage), b_m = b_h + (uint32_t)w_plane;
+                            const int krem = g.K - kb * G_BK;
+                            const int nk16 = krem >= G_BK ? G_BK / 16 : (krem + 15) / 16;
+                            for (int kk = 0; kk < nk16; ++kk) {
+                                const uint32_t o = (uint32_t)kk * 32u;        // 16 bf16 = 32 bytes inside the swizzle row
+                                const uint64_t dah = make_desc_sw64(a_h + o), dam = make_desc_sw64(a_m + o);
+                                const uint64_t dbh = make_desc_sw64(b_h + o), dbm = make_desc_sw64(b_m + o);
+                                umma_bf16_pair(tacc, dah, dbh, idesc, (kb | kk) != 0);
+                                umma_bf16_pair(tacc, dah, dbm, idesc, 1);
+                                umma_bf16_pair(tacc, dam, dbh, idesc, 1);
+                            }
+                            umma_commit_pair(empty_bar + s);                                   // ring stage reusable in both CTAs
+                            if (resident && nt == g.n_tiles - 1) umma_commit_pair(aempty_bar + kb);   // A slot free for the next super tile
+                            if (kb == nkb - 1) umma_commit_pair(tfull_bar + buf);              // accumulator complete in both CTAs
+                        }
+                        __syncwarp();
+                        if (++s == g.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
-                    umma_commit(empty_bar + s);                            // stage reusable once these MMAs retire
-                    if (kb == nkb - 1) umma_commit(tfull_bar + buf);       // accumulator complete
-                }
-                __syncwarp();
-                if (++s == g.stages) {
-                    s = 0;
-                    ph ^= 1u;
                 }
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
         const int quarter = warp & 3;                                      // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
-        const int chunk0 = (warp - 2) >> 2;                                // which of the interleaved chunk sets is this warp's
-        const bool c_v8 = g.C && ((g.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 31u) == 0);
-        const bool c_v4 = g.C && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15u) == 0);
-        const bool s_v8 = g.Chi && ((g.ldcs & 15) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 31u) == 0);
-        const bool s_v4 = g.Chi && ((g.ldcs & 7) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 15u) == 0);
-        const bool r_v4 = g.residual && ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0);
-        const bool b_v4 = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+        const int chunk0 = (warp - 2) >> 2;
         int it = 0;
-        for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t bph = (uint32_t)((it >> 1) & 1);
-            const int64_t m = (w / g.n_tiles) * G_BM + row;
-            const int n0 = (int)(w % g.n_tiles) * g.NS;
-            const int ncols = min(g.NS, g.N - n0);
-            const bool rowok = m < g.M;
-            mbar_wait(tfull_bar + buf, bph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
-            for (int col = 16 * chunk0; col < ncols; col += 16 * (G_EPI_WARPS / 4)) {
-                uint32_t r[16];
-                tmem_ld16(taddr + (uint32_t)col, r);
-                if (rowok) {
-                const int n = n0 + col;
-                const int valid = min(16, ncols - col);
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                if (valid == 16) {
-                    if (g.bias) {
-                        if (b_v4) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += __ldg(g.bias + n + j);
-                        }
-                    }
-                    if (g.residual) {
-                        const float* rp = g.residual + m * g.ldr + n;
-                        if (r_v4) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-                                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] += rp[j];
-                        }
-                    }
-                    if (g.act != DYG_ACT_NONE) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], g.act);
-                    }
-                    if (g.C) {
-                        float* dst = g.C + m * g.ldc + n;
-                        uint32_t o[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(v[j]);
-                        if (c_v8) {
-                            st_v8(dst, o);
-                            st_v8(dst + 8, o + 8);
-                        } else if (c_v4) {
-                            st_v4(dst, o); st_v4(dst + 4, o + 4); st_v4(dst + 8, o + 8); st_v4(dst + 12, o + 12);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) dst[j] = v[j];
-                        }
-                    }
-                    if (g.Chi) {
-                        uint32_t hi[8], mid[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) split_pack(v[2 * j], v[2 * j + 1], hi[j], mid[j]);
-                        __nv_bfloat16* dh = g.Chi + m * g.ldcs + n;
-                        __nv_bfloat16* dm = g.Cmid + m * g.ldcs + n;
-                        if (s_v8) {
-                            st_v8(dh, hi);
-                            st_v8(dm, mid);
-                        } else if (s_v4) {
-                            st_v4(dh, hi); st_v4(dh + 8, hi + 4);
-                            st_v4(dm, mid); st_v4(dm + 8, mid + 4);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                *reinterpret_cast<uint32_t*>(dh + 2 * j) = hi[j];
-                                *reinterpret_cast<uint32_t*>(dm + 2 * j) = mid[j];
-                            }
-                        }
-                    }
-                } else {
-                    // ragged last chunk of the row (N not a multiple of 16)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j >= valid) break;
-                        float x = v[j];
-                        if (g.bias) x += __ldg(g.bias + n + j);
-                        if (g.residual) x += g.residual[m * g.ldr + n + j];
-                        x = act_apply(x, g.act);
-                        if (g.C) g.C[m * g.ldc + n + j] = x;
-                        if (g.Chi) {
-                            const __nv_bfloat16 h = __float2bfloat16_rn(x);
-                            g.Chi[m * g.ldcs + n + j] = h;
-                            g.Cmid[m * g.ldcs + n + j] = __float2bfloat16_rn(x - __bfloat162float(h));
-                        }
-                    }
-                }
-                }
+        for (int64_t ms = pair; ms < g.m_super; ms += npairs) {
+            const int64_t m = ms * 2 * G_BM + (int64_t)rank * G_BM + row;
+            for (int nt = 0; nt < g.n_tiles; ++nt, ++it) {
+                const int buf = it & 1;
+                const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                const int n0 = nt * g.NS;
+                const int ncols = min(g.NS, g.N - n0);
+                mbar_wait(tfull_bar + buf, bph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
+                epilogue_tile(g, taddr, m, n0, ncols, chunk0, G_EPI_WARPS / 4);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tempty_bar + buf);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    cluster_sync_all();                                         // no CTA leaves while its peer may still touch its smem / barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G_TMEM_COLS) : "memory");
     }
 }
 
@@ -539,20 +603,25 @@ extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, con
     g.Chi = reinterpret_cast<__nv_bfloat16*>(C_hi); g.Cmid = reinterpret_cast<__nv_bfloat16*>(C_mid); g.ldcs = ldcs;
     g.M = M; g.N = N; g.K = K; g.act = act;
     g.m_tiles = (M + G_BM - 1) / G_BM;
+    g.m_super = (M + 2 * G_BM - 1) / (2 * G_BM);
     g.n_tiles = (N + 207) / 208;                                   // <= 208 columns per tile: two tiles' accumulators fit TMEM
     g.NS = ((N + g.n_tiles - 1) / g.n_tiles + 15) / 16 * 16;       // tile starts stay 32-byte aligned in fp32 and in bf16 rows
     g.NT = g.NS;
-    const int stage_bytes = 2 * G_A_PLANE + 2 * g.NT * 64;
+    const int nkb = (K + G_BK - 1) / G_BK;
+    g.resident = (nkb <= 7 && g.n_tiles > 1) ? 1 : 0;
+    const int w_stage = 2 * (g.NT / 2) * 64;
+    const int stage_bytes = (g.resident ? 0 : 2 * G_A_PLANE) + w_stage;
+    const int fixed = (g.resident ? nkb * 2 * G_A_PLANE : 0) + 1024 + 512;
     const int max_smem = 227 * 1024;
-    g.stages = (max_smem - 1024 - 256) / stage_bytes;
+    g.stages = (max_smem - fixed) / stage_bytes;
     if (g.stages > G_MAX_STAGES) g.stages = G_MAX_STAGES;
     DYG_CHECK_ARG(g.stages >= 2, "dyg_gemm_bf16x3: tile does not fit shared memory");
-    const size_t smem = (size_t)g.stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)g.stages * stage_bytes + fixed;
     CUtensorMap mah, mam, mwh, mwm;
     if (!get_map(A_hi, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mah)) return 1;
     if (!get_map(A_mid, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mam)) return 1;
-    if (!get_map(W_hi, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)g.NT, &mwh)) return 1;
-    if (!get_map(W_mid, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)g.NT, &mwm)) return 1;
+    if (!get_map(W_hi, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwh)) return 1;
+    if (!get_map(W_mid, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwm)) return 1;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -562,9 +631,26 @@ extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, con
         }
         configured = smem;
     }
-    const int64_t total = g.m_tiles * g.n_tiles;
-    const int grid = (int)(total < dyg_num_sms() ? total : dyg_num_sms());
-    gemm_bf16x3_kernel<<<grid, G_THREADS, smem, as_stream(stream)>>>(mah, mam, mwh, mwm, g);
+    const int max_pairs = dyg_num_sms() / 2;
+    const int pairs = (int)(g.m_super < max_pairs ? g.m_super : max_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(G_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16x3_kernel, mah, mam, mwh, mwm, g);
+    if (le != cudaSuccess) {
+        dyg_set_error("dyg_gemm_bf16x3: launch failed: %s", cudaGetErrorString(le));
+        return 1;
+    }
     DYG_LAUNCH_CHECK("dyg_gemm_bf16x3");
     return 0;
 }
