@@ -78,6 +78,12 @@ class Seg(ctypes.Structure):
                 ('dt', c_p), ('mask_ids', c_p), ('w', c_p), ('b', c_p), ('t_query', c_p)]
 
 
+class ProjSide(ctypes.Structure):
+    """dyg_proj_side_t (include/dygb200.h)."""
+    _fields_ = [('ids', c_p), ('eids', c_p), ('t_nbr', c_p), ('cnt_a', c_p), ('cnt_b', c_p),
+                ('tokens', ctypes.c_int64), ('ntok', ctypes.c_int32), ('tok_off', ctypes.c_int32)]
+
+
 # name -> argtypes, exactly the prototypes of include/dygb200.h (tests check the symbol list against the header)
 SIGNATURES = {
     'dyg_csr_degrees': [c_p, c_p, c_l, c_l, c_p, c_p],
@@ -100,6 +106,9 @@ SIGNATURES = {
     'dyg_gemm_bf16x3': [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_p],
     'dyg_split_bf16': [c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p],
     'dyg_layernorm_split': [c_p, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_p],
+    'dyg_patch_project_stages': [c_i, c_i, c_i, c_i, c_i, c_p],
+    'dyg_patch_project': [ctypes.POINTER(ProjSide), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p,
+                          c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_layernorm': [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_l, c_i, c_p],
     'dyg_gather_rows': [c_p, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p],
     'dyg_temporal_attend': [c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i,

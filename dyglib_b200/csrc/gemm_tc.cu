@@ -23,7 +23,7 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -54,68 +54,12 @@ struct GemmArgs {
     int64_t m_super;   // 256-row super tiles (one per CTA pair and round)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "GW_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra GW_DONE;\n\t"
-        "bra GW_LOOP;\n\t"
-        "GW_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-
-// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
-// [0,14), LBO (unused for swizzled K-major, canonical 1) in [16,30), SBO = 512 B between 8-row groups in [32,46),
-// version 1 in [46,48), layout type 4 (SWIZZLE_64B) in [61,64).
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == DYG_ACT_RELU) return fmaxf(v, 0.f);
     if (act == DYG_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
     if (act == DYG_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
 }
-__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& mid) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 am = __float2bfloat16_rn(a - __bfloat162float(ah)), bm = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    mid = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
-}
-__device__ __forceinline__ void st_v8(void* p, const uint32_t* r) {
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
-                 "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ void st_v4(void* p, const uint32_t* r) {
-    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-}
-
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -435,77 +379,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
     }
 }
 
-// ------------------------------------------------------------------ tensor maps (driver entry point fetched at run time:
-// the library links against cudart only)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    return fn;
-}
-
-struct MapKey {
-    const void* ptr;
-    uint64_t rows, cols, ld;
-    uint32_t box_rows;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
-};
-struct MapKeyHash {
-    size_t operator()(const MapKey& k) const {
-        size_t h = reinterpret_cast<size_t>(k.ptr);
-        h = h * 1000003u ^ k.rows;
-        h = h * 1000003u ^ k.cols;
-        h = h * 1000003u ^ k.ld;
-        h = h * 1000003u ^ k.box_rows;
-        return h;
-    }
-};
-
-// (rows, cols) bf16 row-major with leading dimension ld elements; box = box_rows x 32 columns, SWIZZLE_64B, OOB -> 0.
-// Encoding depends only on the key, so maps are cached (a descriptor holds the address, not the data).
-bool get_map(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
-    static std::mutex mu;
-    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-    const MapKey key{ptr, rows, cols, ld, box_rows};
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) {
-        *out = it->second;
-        return true;
-    }
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) {
-        dyg_set_error("dyg_gemm_bf16x3: cuTensorMapEncodeTiled is not available from the driver");
-        return false;
-    }
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)G_BK, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUtensorMap m;
-    const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        dyg_set_error("dyg_gemm_bf16x3: cuTensorMapEncodeTiled failed (%d) for %llu x %llu, ld %llu, box %u", (int)r,
-                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
-        return false;
-    }
-    if (cache.size() > 4096) cache.clear();
-    cache.emplace(key, m);
-    *out = m;
-    return true;
-}
-
 // ------------------------------------------------------------------ fp32 -> bf16 hi | mid planes
 __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, int64_t M, int D, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ mid, int ld) {
@@ -581,6 +454,82 @@ __global__ void layernorm_split_kernel(const float* __restrict__ x, int ldx, con
 
 }  // namespace
 
+namespace {
+
+// ------------------------------------------------------------------ tensor maps (driver entry point fetched at run time:
+// the library links against cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.ptr);
+        h = h * 1000003u ^ k.rows;
+        h = h * 1000003u ^ k.cols;
+        h = h * 1000003u ^ k.ld;
+        h = h * 1000003u ^ k.box_rows;
+        return h;
+    }
+};
+
+// (rows, cols) bf16 row-major with leading dimension ld elements; box = box_rows x 32 columns, SWIZZLE_64B, OOB -> 0.
+// Encoding depends only on the key, so maps are cached (a descriptor holds the address, not the data).
+}  // namespace
+
+bool dyg_tensor_map_bf16(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+    const MapKey key{ptr, rows, cols, ld, box_rows};
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return true;
+    }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        dyg_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return false;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)G_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        dyg_set_error("cuTensorMapEncodeTiled failed (%d) for %llu x %llu, ld %llu, box %u", (int)r,
+                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return false;
+    }
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+    *out = m;
+    return true;
+}
+
+
 extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, const void* W_hi, const void* W_mid, int ldw,
                                const float* bias, const float* residual, int ldr, float* C, int ldc, void* C_hi, void* C_mid,
                                int ldcs, int64_t M, int N, int K, int act, dyg_stream_t stream) {
@@ -618,10 +567,10 @@ extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, con
     DYG_CHECK_ARG(g.stages >= 2, "dyg_gemm_bf16x3: tile does not fit shared memory");
     const size_t smem = (size_t)g.stages * stage_bytes + fixed;
     CUtensorMap mah, mam, mwh, mwm;
-    if (!get_map(A_hi, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mah)) return 1;
-    if (!get_map(A_mid, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mam)) return 1;
-    if (!get_map(W_hi, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwh)) return 1;
-    if (!get_map(W_mid, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwm)) return 1;
+    if (!dyg_tensor_map_bf16(A_hi, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mah)) return 1;
+    if (!dyg_tensor_map_bf16(A_mid, (uint64_t)M, (uint64_t)K, (uint64_t)lda, G_BM, &mam)) return 1;
+    if (!dyg_tensor_map_bf16(W_hi, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwh)) return 1;
+    if (!dyg_tensor_map_bf16(W_mid, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwm)) return 1;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

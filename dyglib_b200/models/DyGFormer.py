@@ -144,6 +144,9 @@ class DyGFormer(nn.Module):
         self.output_layer = nn.Linear(self.num_channels * self.channel_embedding_dim, self.node_feat_dim, bias=True)
         self._cooc_w_key = None
         self._cooc_w = None
+        self._planes = None
+        self._proj_key = None
+        self._proj_ops = None
         self.to(device)
 
     # ------------------------------------------------------------------ reference-compatible pieces
@@ -264,6 +267,32 @@ class DyGFormer(nn.Module):
         w, b = self.time_encoder.wb()
         X = torch.empty((B * S, D), dtype=torch.float32, device=dev)
         pl = self.projection_layer
+        if C <= 64 and C % 2 == 0:
+            # one fused gather + time-encode + patch-projection kernel over both sides (dyg_patch_project)
+            node_pl, edge_pl = self._table_planes()
+            lut_pl, packed, bias = self._projection_operands(lut)
+            sides = [(s_pn, s_pe, s_pt, cs[0], cs[1], ns, 0), (d_pn, d_pe, d_pt, cd[0], cd[1], nd, ns)]
+            ops.patch_project(sides, node_pl, self.node_feat_dim, edge_pl, self.edge_feat_dim, lut_pl,
+                              self.neighbor_co_occurrence_feat_dim, tq, w, b, packed, bias, P, C, S, X)
+        else:
+            self._project_unfused(X, tq, s_pn, s_pe, s_pt, cs, d_pn, d_pe, d_pt, cd, lut, w, b)
+        x = X.reshape(B, S, D)
+        for tr in self.transformers:
+            x = tr(x)
+        means = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
+        ops.mean_tokens(x, B, S, D, 0, ns, out=means[:B])
+        ops.mean_tokens(x, B, S, D, ns, nd, out=means[B:])
+        out = ops.gemm(ops.split_bf16(means), self.output_layer.weight, self.output_layer.bias.detach())
+        return out[:B], out[B:]
+
+    def _project_unfused(self, X, tq, s_pn, s_pe, s_pt, cs, d_pn, d_pe, d_pt, cd, lut, w, b):
+        """Channel-by-channel gather-GEMMs (dyg_linear_tc) for channel widths the fused kernel does not take."""
+        P, C = self.patch_size, self.channel_embedding_dim
+        B = tq.numel()
+        Ls, Ld = s_pn.shape[1], d_pn.shape[1]
+        ns, nd = Ls // P, Ld // P
+        S = ns + nd
+        pl = self.projection_layer
         for pn, pe, pt, cnt, Lp, ntok, off in ((s_pn, s_pe, s_pt, cs, Ls, ns, 0), (d_pn, d_pe, d_pt, cd, Ld, nd, ns)):
             M = B * ntok
             ids_flat = pn.reshape(-1)
@@ -277,14 +306,26 @@ class DyGFormer(nn.Module):
             for ch, (seg, wt, bias) in enumerate(chans):
                 ops.linear([seg], M, wt, bias.detach(), out=X[:, ch * C:(ch + 1) * C], c_group=ntok, c_group_stride=S, c_offset=off,
                            tc=True)   # same kernel for every batch size: a row's result never depends on its batch
-        x = X.reshape(B, S, D)
-        for tr in self.transformers:
-            x = tr(x)
-        means = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
-        ops.mean_tokens(x, B, S, D, 0, ns, out=means[:B])
-        ops.mean_tokens(x, B, S, D, ns, nd, out=means[B:])
-        out = ops.gemm(ops.split_bf16(means), self.output_layer.weight, self.output_layer.bias.detach())
-        return out[:B], out[B:]
+
+    def _table_planes(self):
+        """BF16x3 operand planes of the (constant) node / edge feature tables, built on first use."""
+        if self._planes is None:
+            self._planes = (ops.table_planes(self.node_raw_features), ops.table_planes(self.edge_raw_features))
+        return self._planes
+
+    def _projection_operands(self, lut):
+        """(LUT planes, packed projection weights, concatenated bias), rebuilt when a parameter changes."""
+        pl = self.projection_layer
+        ps = [pl[k].weight for k in ('node', 'edge', 'time', 'neighbor_co_occurrence')] + \
+             [pl[k].bias for k in ('node', 'edge', 'time', 'neighbor_co_occurrence')]
+        key = (lut.data_ptr(), tuple(lut.shape)) + tuple((q.data_ptr(), q._version) for q in ps)
+        if key != self._proj_key:
+            C = self.neighbor_co_occurrence_feat_dim
+            lut_pl = ops.table_planes(lut[:, :C])
+            packed = ops.pack_patch_weights(ps[0], ps[1], ps[2], ps[3], self.patch_size)
+            bias = torch.cat([q.detach().float() for q in ps[4:]]).contiguous()
+            self._proj_ops, self._proj_key = (lut_pl, packed, bias, lut), key
+        return self._proj_ops[:3]
 
     def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):
         """``set_neighbor_sampler`` (``models/DyGFormer.py:308-317``)."""

@@ -268,6 +268,72 @@ def gemm(a, weight, bias=None, residual=None, act=ACT_NONE, out=None, out_split=
     return out, out_split
 
 
+def table_planes(table):
+    """BF16x3 operand planes of a fp32 feature table, rows padded with zeros to a multiple of 16 columns (the layout
+    dyg_patch_project gathers from)."""
+    t = table.detach().float().contiguous()
+    out = empty_split(t.shape[0], t.shape[1], t.device)
+    out.planes.zero_()
+    return split_bf16(t, out)
+
+
+def patch_project_stage_blocks(F_node, F_edge, T, F_lut, P):
+    """(number of stages, 32-column blocks per (type, p)) of dyg_patch_project for these widths."""
+    nblk = (ctypes.c_int32 * 5)()
+    nst = _lib().dyg_patch_project_stages(int(F_node), int(F_edge), int(T), int(F_lut), int(P), nblk)
+    return nst, list(nblk)
+
+
+def pack_patch_weights(w_node, w_edge, w_time, w_cooc, P):
+    """Packed BF16x3 weight planes (2, 64, 32*stages) for dyg_patch_project: stage s = (type, p, block) owns columns
+    [32 s, 32 s + 32) holding W_type[:, p*F + 32*block : p*F + min(F, 32*block + 32)] (zero elsewhere); the two
+    co-occurrence LUT gathers (count in src row, count in dst row) both use the co-occurrence weight."""
+    C = w_node.shape[0]
+    ws = [w_node, w_edge, w_time, w_cooc, w_cooc]
+    Fs = [w.shape[1] // P for w in ws]
+    nst, nblk = patch_project_stage_blocks(Fs[0], Fs[1], Fs[2], Fs[3], P)
+    dev = w_node.device
+    packed = torch.zeros((64, nst * 32), dtype=torch.float32, device=dev)
+    s = 0
+    for ty in range(5):
+        w, F = ws[ty].detach().float(), Fs[ty]
+        for p in range(P):
+            for blk in range(nblk[ty]):
+                lo, hi = blk * 32, min(F, blk * 32 + 32)
+                if hi > lo:
+                    packed[:C, s * 32:s * 32 + hi - lo] = w[:, p * F + lo:p * F + hi]
+                s += 1
+    assert s == nst
+    return split_bf16(packed)
+
+
+def patch_project(sides, node_planes, F_node, edge_planes, F_edge, lut_planes, F_lut, t_query, tw, tb, packed_w, bias, P, C, S, X):
+    """dyg_patch_project.  ``sides``: list of (ids, eids, t_nbr, cnt_a, cnt_b, ntok, tok_off) with (B, Lp) device tensors."""
+    arr = (_native.ProjSide * len(sides))()
+    keep = []
+    rows = 0
+    for i, (ids, eids, tn, ca, cb, ntok, off) in enumerate(sides):
+        B = ids.shape[0]
+        for t_, dt_ in ((ids, torch.int64), (eids, torch.int64), (tn, torch.float32), (ca, torch.int64), (cb, torch.int64)):
+            _chk(t_, dt_, 'patch_project side array')
+        arr[i].ids, arr[i].eids, arr[i].t_nbr = _p(ids).value, _p(eids).value, _p(tn).value
+        arr[i].cnt_a, arr[i].cnt_b = _p(ca).value, _p(cb).value
+        arr[i].tokens, arr[i].ntok, arr[i].tok_off = int(B * ntok), int(ntok), int(off)
+        rows += B * ntok
+        keep.append((ids, eids, tn, ca, cb))
+    T = tw.numel()
+    K = P * (F_node + F_edge + T + 2 * F_lut)
+    with _Timed('patch_project_kernel', 2.0 * rows * C * K, rows * (P * (2.0 * 4 * (F_node + F_edge) + 8.0 * F_lut + 28.0) + 16.0 * C)):
+        _native.check(_lib().dyg_patch_project(
+            arr, len(sides), _p(node_planes.hi), _p(node_planes.mid), int(node_planes.ld), int(F_node),
+            _p(edge_planes.hi), _p(edge_planes.mid), int(edge_planes.ld), int(F_edge),
+            _p(lut_planes.hi), _p(lut_planes.mid), int(lut_planes.ld), int(F_lut), _p(t_query), _p(tw), _p(tb), int(T),
+            _p(packed_w.hi), _p(packed_w.mid), int(packed_w.ld), _p(bias), int(P), int(C), int(S), _p(X), int(X.stride(0)),
+            _stream()))
+    _count()
+    return X
+
+
 def layernorm_split(x, gamma, beta, eps=1e-5, out=None, y=None):
     """LayerNorm(x) as a Split (and optionally also as fp32 ``y``)."""
     M, D = x.shape

@@ -164,6 +164,36 @@ int dyg_split_bf16(const float* x, int ldx, int64_t M, int D, void* hi, void* mi
 int dyg_layernorm_split(const float* x, int ldx, const float* gamma, const float* beta, float eps, float* y, int ldy,
                         void* hi, void* mid, int ld, int64_t M, int D, dyg_stream_t stream);
 
+/* ---- a15 + first half of a16: get_features + get_patches + the four channel projections, fused
+ * (models/DyGFormer.py:247-306, 148-174) ----
+ * One side = the padded sequences of the src (or dst) nodes of a batch: B rows of Lp = ntok*P positions.  Token m covers
+ * positions q = m*P .. m*P+P-1 (row-major over (B, Lp)); it is written to row (m / ntok)*S + tok_off + m % ntok of X
+ * (B*S, ldx), columns [ch*C, (ch+1)*C) for channel ch = node, edge, time, co-occurrence:
+ *   X = bias_ch + sum_p W_ch[:, p*F_ch:(p+1)*F_ch] feat_ch(q),
+ *   feat = node_tab[ids[q]], edge_tab[eids[q]], (ids[q]==0 ? 0 : cos(fma((float)(t_query[m/ntok] - (double)t_nbr[q]), tw, tb))),
+ *          lut[cnt_a[q]] + lut[cnt_b[q]]   (lut[c] = the co-occurrence MLP at count c, models/DyGFormer.py:409-411).
+ * Tables are BF16x3 operand planes (hi | mid, see dyg_split_bf16) with ld % 8 == 0 and ld >= roundup(F, 16), padding
+ * columns zero.  W_hi | W_mid: (64, ldw) planes of the packed weights: stage s (dyg_patch_project_stages enumerates
+ * them: for type in node, edge, time, lut(cnt_a), lut(cnt_b): for p: for 32-column block) owns columns [32 s, 32 s + 32),
+ * rows >= C and columns past the block's valid width zero. */
+typedef struct {
+    const int64_t* ids;    /* (B, Lp) padded neighbour ids */
+    const int64_t* eids;   /* (B, Lp) padded edge ids */
+    const float* t_nbr;    /* (B, Lp) padded neighbour times */
+    const int64_t* cnt_a;  /* (B, Lp) appearances in the src sequence */
+    const int64_t* cnt_b;  /* (B, Lp) appearances in the dst sequence */
+    int64_t tokens;        /* B * ntok */
+    int32_t ntok;          /* Lp / P */
+    int32_t tok_off;       /* first token of this side inside a pair's S tokens */
+} dyg_proj_side_t;
+/* number of stages for the given widths; nblk5 (may be NULL) receives the 32-column blocks per (type, p). */
+int dyg_patch_project_stages(int F_node, int F_edge, int T, int F_lut, int P, int32_t* nblk5);
+int dyg_patch_project(const dyg_proj_side_t* sides_host, int nsides, const void* node_hi, const void* node_mid, int ld_node,
+                      int F_node, const void* edge_hi, const void* edge_mid, int ld_edge, int F_edge, const void* lut_hi,
+                      const void* lut_mid, int ld_lut, int F_lut, const double* t_query, const float* tw, const float* tb,
+                      int T, const void* W_hi, const void* W_mid, int ldw, const float* bias, int P, int C, int S, float* X,
+                      int ldx, dyg_stream_t stream);
+
 /* y = LayerNorm(x + r) * gamma + beta over D columns; r row = [r1 row (F1 cols) | rconst (D-F1 cols)];
  * r1/rconst may be NULL (models/modules.py:199, models/DyGFormer.py:452,458). */
 int dyg_layernorm(const float* x, int ldx, const float* r1, int ldr1, int F1, const float* rconst,

@@ -22,7 +22,14 @@ def _ids(x):
 
 def time_encode(sd, prefix, dt):
     """``TimeEncoder.forward`` (``models/modules.py:27-39``): cos(Linear(1->T)(dt)); dt (n, L) f32."""
-    return torch.cos(F.linear(dt.unsqueeze(2), sd[prefix + 'w.weight'], sd[prefix + 'w.bias']))
+    # nn.Linear(1, T) on the reference's CPU path evaluates each output as ONE fp32 fused multiply-add (SURVEY.md A.3:
+    # 400 000 / 400 000 matches against fma, 20 % mismatches against mul-then-add).  Whether torch's CPU kernels fuse
+    # depends on the host, so the oracle states the FMA explicitly: the fp32 x fp32 product is exact in float64, one
+    # float64 add, one rounding to fp32 (double rounding can differ from a true FMA only in ~1e-8 of the cases).
+    w = sd[prefix + 'w.weight'].reshape(-1).double()
+    b = sd[prefix + 'w.bias'].double()
+    arg = (dt.double().unsqueeze(-1) * w + b).float()
+    return torch.cos(arg)
 
 
 def temporal_attention(sd, prefix, node_features, node_time_features, nbr_features, nbr_time_features,

@@ -109,3 +109,50 @@ def test_seq_attention_tc(B, S, H, hd):
     assert rel_err(sp.float(), want) < 5e-5
     old = ops.seq_attention(qkv, B, S, H, hd)
     assert rel_err(old, want) < 1e-5
+
+
+@pytest.mark.parametrize('P,B,ns,nd', [(2, 37, 8, 5), (1, 9, 32, 32), (16, 11, 3, 2), (2, 200, 32, 32), (4, 3, 1, 1)])
+def test_patch_project_vs_float64(P, B, ns, nd):
+    """Fused gather + time encoding + patching + four channel projections against the explicit float64 formula."""
+    g = torch.Generator(device='cuda').manual_seed(100 * P + B)
+    F, T, C = 172, 100, 50
+    N, E, maxc = 400, 900, 40
+    node = torch.randn(N, F, device='cuda', generator=g)
+    edge = torch.randn(E, F, device='cuda', generator=g)
+    node[0] = 0
+    edge[0] = 0
+    lut = torch.randn(maxc + 1, C, device='cuda', generator=g)
+    tw = (1.0 / 10 ** torch.linspace(0, 9, T, device='cuda')).float().contiguous()
+    tb = (0.1 * torch.randn(T, device='cuda', generator=g)).contiguous()
+    ws = [torch.randn(C, P * w, device='cuda', generator=g) / np.sqrt(P * w) for w in (F, F, T, C)]
+    bias = torch.randn(4 * C, device='cuda', generator=g)
+    tq = 2e5 + torch.rand(B, device='cuda', generator=g, dtype=torch.float64) * 1e5
+    S = ns + nd
+    X = torch.full((B * S, 4 * C), float('nan'), device='cuda')
+    sides, want = [], torch.zeros(B, S, 4 * C, dtype=torch.float64, device='cuda')
+    for ntok, off in ((ns, 0), (nd, ns)):
+        Lp = ntok * P
+        ids = torch.randint(0, N, (B, Lp), device='cuda', generator=g)
+        ids[:, Lp // 2:][torch.rand(B, Lp - Lp // 2, device='cuda', generator=g) < 0.5] = 0
+        eids = torch.randint(0, E, (B, Lp), device='cuda', generator=g)
+        tn = (torch.rand(B, Lp, device='cuda', generator=g) * 2e5).float()
+        ca = torch.randint(0, maxc + 1, (B, Lp), device='cuda', generator=g)
+        cb = torch.randint(0, maxc + 1, (B, Lp), device='cuda', generator=g)
+        sides.append((ids, eids, tn, ca, cb, ntok, off))
+        dt = (tq[:, None] - tn.double()).float()
+        te = torch.cos(torch.addcmul(tb[None, None, :], dt[:, :, None], tw[None, None, :]).double())   # fp32 fma argument
+        te = te * (ids != 0).double()[:, :, None]
+        feats = [node[ids].double(), edge[eids].double(), te, (lut[ca] + lut[cb]).double()]
+        for ch, (f, w) in enumerate(zip(feats, ws)):
+            patches = f.reshape(B, ntok, P * f.shape[-1])
+            want[:, off:off + ntok, ch * C:(ch + 1) * C] = patches @ w.double().t() + bias[ch * C:(ch + 1) * C].double()
+    packed = ops.pack_patch_weights(ws[0], ws[1], ws[2], ws[3], P)
+    ops.patch_project(sides, ops.table_planes(node), F, ops.table_planes(edge), F, ops.table_planes(lut), C, tq, tw, tb, packed,
+                      bias, P, C, S, X)
+    got = X.reshape(B, S, 4 * C)
+    assert not torch.isnan(got).any()
+    # node / edge / co-occurrence channels are pure BF16x3 contractions
+    for ch in (0, 1, 3):
+        assert rel_err(got[..., ch * C:(ch + 1) * C], want[..., ch * C:(ch + 1) * C]) < 5e-5, ch
+    # time channel: torch's fp32 addcmul may round the argument differently from a single FMA (arguments reach 3e5 rad)
+    assert rel_err(got[..., 2 * C:3 * C], want[..., 2 * C:3 * C]) < 5e-3
