@@ -107,7 +107,7 @@ SIGNATURES = {
     'dyg_split_bf16': [c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p],
     'dyg_layernorm_split': [c_p, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_p],
     'dyg_patch_project_stages': [c_i, c_i, c_i, c_i, c_i, c_p],
-    'dyg_patch_project': [ctypes.POINTER(ProjSide), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p,
+    'dyg_patch_project': [ctypes.POINTER(ProjSide), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p,
                           c_i, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_layernorm': [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_l, c_i, c_p],
     'dyg_gather_rows': [c_p, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p],

@@ -18,6 +18,7 @@
 //   warp 9     TMEM allocation + single-thread tcgen05.mma issue (M=128, N=64, K=16, BF16x3 = three MMAs per k step)
 // Two CTAs per SM (96 KB of shared memory, 256 TMEM columns each): one CTA's epilogue overlaps the other's gathers.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -33,6 +34,7 @@ constexpr int PP_NT = 64;                 // accumulator columns per channel (C 
 constexpr int PP_W_PLANE = PP_NT * 64;    // 4 KB
 constexpr int PP_STAGE_BYTES = 2 * PP_A_PLANE + 2 * PP_W_PLANE;
 constexpr int PP_TMEM_COLS = 4 * PP_NT;
+constexpr int PP_MAX_STAGES = 512;        // stage table in shared memory (patch_size 16 needs 320)
 
 struct ProjArgs {
     dyg_proj_side_t side[2];
@@ -50,10 +52,12 @@ struct ProjArgs {
     float* X;
     int ldx;
     int64_t tiles0;                   // tiles of side 0 (side 1 tiles follow)
+    int dbg;
+    int zero_rows;                    // bit u: row 0 of table u is all zero (padding id): skip its gather
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -77,9 +81,8 @@ __device__ __forceinline__ void umma_commit_cta(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct StageInfo {
+struct StageInfo {     // 16 bytes: one LDS.128 per stage
     int ty, p, blk, nk16;
-    bool first_of_unit;
 };
 __device__ __forceinline__ StageInfo decode_stage(const ProjArgs& a, int s) {
     StageInfo si;
@@ -93,7 +96,6 @@ __device__ __forceinline__ StageInfo decode_stage(const ProjArgs& a, int s) {
     si.blk = local - si.p * a.nblk[ty];
     const int rem16 = (a.w16[ty] - si.blk * 32) >> 4;
     si.nk16 = rem16 >= 2 ? 2 : rem16;
-    si.first_of_unit = si.blk == 0;
     return si;
 }
 
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
     uint64_t* empty_bar = bars + PP_STAGES;       // [PP_STAGES]  one tcgen05.commit
     uint64_t* acc_bar = bars + 2 * PP_STAGES;     // accumulators complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PP_STAGES + 1);
+    StageInfo* stage_tab = reinterpret_cast<StageInfo*>(bars + 2 * PP_STAGES + 2);   // [nst]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
     const int64_t m0 = ((int64_t)blockIdx.x - (sd ? a.tiles0 : 0)) * PP_BM;
     const int nst = a.base[5];
 
+    for (int s = tid; s < nst; s += PP_THREADS) stage_tab[s] = decode_stage(a, s);
     if (tid == 0) {
         for (int s = 0; s < PP_STAGES; ++s) {
             mbar_init(full_bar + s, PP_PRODUCERS + 1);
@@ -151,8 +155,8 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
         for (int s = 0; s < nst; ++s) {
             const int slot = s % PP_STAGES;
             const uint32_t ph = (uint32_t)((s / PP_STAGES) & 1);
-            const StageInfo si = decode_stage(a, s);
-            if (si.first_of_unit) {
+            const StageInfo si = stage_tab[s];
+            if (si.blk == 0) {
                 const int64_t q = m * a.P + si.p;
                 if (!valid) {
                     idx = 0;
@@ -176,10 +180,24 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
                 const __nv_bfloat16* src = (half ? a.tab_mid[si.ty] : a.tab_hi[si.ty]) + idx * a.ld[si.ty] + si.blk * 32;
                 const uint32_t dst = smem_u32(st + half * PP_A_PLANE) + row_off;
                 const int nchunk = si.nk16 * 2;
+                if (idx == 0 && ((a.zero_rows >> si.ty) & 1)) {
+                    // padded position of a table whose row 0 is zero: no memory traffic (and no L2 hot spot on that row)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < nchunk) cp_async16(dst + (((uint32_t)c ^ swz) << 4), src + c * 8);
-                cp_async_arrive_noinc(full_bar + slot);
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nchunk) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst + (((uint32_t)c ^ swz) << 4)), "r"(0u) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nchunk && !(a.dbg & 4)) cp_async16(dst + (((uint32_t)c ^ swz) << 4), src + c * 8);
+                }
+                if (a.dbg & 2) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_cta(full_bar + slot);
+                } else {
+                    cp_async_arrive_noinc(full_bar + slot);
+                }
             } else {
                 if (half < si.nk16) {
                     const int c0 = si.blk * 32 + half * 16;
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
                     for (int j = 0; j < 8; ++j) {
                         const int c = c0 + 2 * j;
                         float v0 = 0.f, v1 = 0.f;
-                        if (!masked) {
+                        if (!masked && !(a.dbg & 1)) {
                             if (c < a.T) v0 = dyg_time_enc(dt, __ldg(a.tw + c), __ldg(a.tb + c));
                             if (c + 1 < a.T) v1 = dyg_time_enc(dt, __ldg(a.tw + c + 1), __ldg(a.tb + c + 1));
                         }
@@ -256,8 +274,8 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
         for (int s = 0; s < nst; ++s) {
             const int slot = s % PP_STAGES;
             const uint32_t ph = (uint32_t)((s / PP_STAGES) & 1);
-            const StageInfo si = decode_stage(a, s);
-            mbar_wait(full_bar + slot, ph);
+            const StageInfo si = stage_tab[s];
+            mbar_wait_poll(full_bar + slot, ph);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // cp.async / st.shared data -> async proxy
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
@@ -311,7 +329,7 @@ extern "C" int dyg_patch_project_stages(int F_node, int F_edge, int T, int F_lut
 
 extern "C" int dyg_patch_project(const dyg_proj_side_t* sides_host, int nsides, const void* node_hi, const void* node_mid,
                                  int ld_node, int F_node, const void* edge_hi, const void* edge_mid, int ld_edge, int F_edge,
-                                 const void* lut_hi, const void* lut_mid, int ld_lut, int F_lut, const double* t_query,
+                                 const void* lut_hi, const void* lut_mid, int ld_lut, int F_lut, int zero_rows, const double* t_query,
                                  const float* tw, const float* tb, int T, const void* W_hi, const void* W_mid, int ldw,
                                  const float* bias, int P, int C, int S, float* X, int ldx, dyg_stream_t stream) {
     DYG_CHECK_ARG(nsides == 1 || nsides == 2, "dyg_patch_project: nsides=%d (1 or 2)", nsides);
@@ -350,18 +368,21 @@ extern "C" int dyg_patch_project(const dyg_proj_side_t* sides_host, int nsides, 
     DYG_CHECK_ARG(tiles < ((int64_t)1 << 31), "dyg_patch_project: too many tiles");
     a.t_query = t_query; a.tw = tw; a.tb = tb; a.T = T; a.P = P; a.C = C; a.S = S;
     a.bias = bias; a.X = X; a.ldx = ldx;
+    a.zero_rows = zero_rows & 3;
+    { const char* e = getenv("DYG_PP_DBG"); a.dbg = e ? atoi(e) : 0; }
     CUtensorMap mwh, mwm;
     if (!dyg_tensor_map_bf16(W_hi, PP_NT, (uint64_t)nst * 32, (uint64_t)ldw, PP_NT, &mwh)) return 1;
     if (!dyg_tensor_map_bf16(W_mid, PP_NT, (uint64_t)nst * 32, (uint64_t)ldw, PP_NT, &mwm)) return 1;
-    const size_t smem = (size_t)PP_STAGES * PP_STAGE_BYTES + 1024 + 128;
-    static bool configured = false;
-    if (!configured) {
+    DYG_CHECK_ARG(nst <= PP_MAX_STAGES, "dyg_patch_project: %d stages exceed the stage table (%d)", nst, PP_MAX_STAGES);
+    const size_t smem = (size_t)PP_STAGES * PP_STAGE_BYTES + 1024 + 128 + (size_t)nst * sizeof(StageInfo);
+    static size_t configured = 0;
+    if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(patch_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             dyg_set_error("dyg_patch_project: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
             return 1;
         }
-        configured = true;
+        configured = smem;
     }
     patch_project_kernel<<<(unsigned)tiles, PP_THREADS, smem, as_stream(stream)>>>(mwh, mwm, a);
     DYG_LAUNCH_CHECK("dyg_patch_project");

@@ -66,4 +66,17 @@ __device__ __forceinline__ void st_v4(void* p, const uint32_t* r) {
     asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 
+// Polling wait (mbarrier.test_wait never suspends the warp).  For barriers whose last arrival comes from
+// cp.async.mbarrier.arrive.noinc: a warp suspended in try_wait was observed to sleep until the try_wait time limit
+// instead of being woken by that asynchronous arrival (~10 us per stage on B200), so the dedicated MMA warp polls.
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "GP_LOOP:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra GP_DONE;\n\t"
+        "bra GP_LOOP;\n\t"
+        "GP_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
 }  // namespace

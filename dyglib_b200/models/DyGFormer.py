@@ -269,11 +269,11 @@ class DyGFormer(nn.Module):
         pl = self.projection_layer
         if C <= 64 and C % 2 == 0:
             # one fused gather + time-encode + patch-projection kernel over both sides (dyg_patch_project)
-            node_pl, edge_pl = self._table_planes()
+            node_pl, edge_pl, zero_rows = self._table_planes()
             lut_pl, packed, bias = self._projection_operands(lut)
             sides = [(s_pn, s_pe, s_pt, cs[0], cs[1], ns, 0), (d_pn, d_pe, d_pt, cd[0], cd[1], nd, ns)]
             ops.patch_project(sides, node_pl, self.node_feat_dim, edge_pl, self.edge_feat_dim, lut_pl,
-                              self.neighbor_co_occurrence_feat_dim, tq, w, b, packed, bias, P, C, S, X)
+                              self.neighbor_co_occurrence_feat_dim, tq, w, b, packed, bias, P, C, S, X, zero_rows=zero_rows)
         else:
             self._project_unfused(X, tq, s_pn, s_pe, s_pt, cs, d_pn, d_pe, d_pt, cd, lut, w, b)
         x = X.reshape(B, S, D)
@@ -310,7 +310,8 @@ class DyGFormer(nn.Module):
     def _table_planes(self):
         """BF16x3 operand planes of the (constant) node / edge feature tables, built on first use."""
         if self._planes is None:
-            self._planes = (ops.table_planes(self.node_raw_features), ops.table_planes(self.edge_raw_features))
+            zero = int(bool((self.node_raw_features[0] == 0).all())) | (int(bool((self.edge_raw_features[0] == 0).all())) << 1)
+            self._planes = (ops.table_planes(self.node_raw_features), ops.table_planes(self.edge_raw_features), zero)
         return self._planes
 
     def _projection_operands(self, lut):

@@ -307,8 +307,10 @@ def pack_patch_weights(w_node, w_edge, w_time, w_cooc, P):
     return split_bf16(packed)
 
 
-def patch_project(sides, node_planes, F_node, edge_planes, F_edge, lut_planes, F_lut, t_query, tw, tb, packed_w, bias, P, C, S, X):
-    """dyg_patch_project.  ``sides``: list of (ids, eids, t_nbr, cnt_a, cnt_b, ntok, tok_off) with (B, Lp) device tensors."""
+def patch_project(sides, node_planes, F_node, edge_planes, F_edge, lut_planes, F_lut, t_query, tw, tb, packed_w, bias, P, C, S, X,
+                  zero_rows=0):
+    """dyg_patch_project.  ``sides``: list of (ids, eids, t_nbr, cnt_a, cnt_b, ntok, tok_off) with (B, Lp) device tensors.
+    ``zero_rows``: bit 0 / 1 = row 0 of the node / edge table is all zero (padded positions skip the gather)."""
     arr = (_native.ProjSide * len(sides))()
     keep = []
     rows = 0
@@ -327,7 +329,7 @@ def patch_project(sides, node_planes, F_node, edge_planes, F_edge, lut_planes, F
         _native.check(_lib().dyg_patch_project(
             arr, len(sides), _p(node_planes.hi), _p(node_planes.mid), int(node_planes.ld), int(F_node),
             _p(edge_planes.hi), _p(edge_planes.mid), int(edge_planes.ld), int(F_edge),
-            _p(lut_planes.hi), _p(lut_planes.mid), int(lut_planes.ld), int(F_lut), _p(t_query), _p(tw), _p(tb), int(T),
+            _p(lut_planes.hi), _p(lut_planes.mid), int(lut_planes.ld), int(F_lut), int(zero_rows), _p(t_query), _p(tw), _p(tb), int(T),
             _p(packed_w.hi), _p(packed_w.mid), int(packed_w.ld), _p(bias), int(P), int(C), int(S), _p(X), int(X.stride(0)),
             _stream()))
     _count()

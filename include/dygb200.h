@@ -175,7 +175,8 @@ int dyg_layernorm_split(const float* x, int ldx, const float* gamma, const float
  * Tables are BF16x3 operand planes (hi | mid, see dyg_split_bf16) with ld % 8 == 0 and ld >= roundup(F, 16), padding
  * columns zero.  W_hi | W_mid: (64, ldw) planes of the packed weights: stage s (dyg_patch_project_stages enumerates
  * them: for type in node, edge, time, lut(cnt_a), lut(cnt_b): for p: for 32-column block) owns columns [32 s, 32 s + 32),
- * rows >= C and columns past the block's valid width zero. */
+ * rows >= C and columns past the block's valid width zero.  zero_rows: bit 0 / bit 1 set when row 0 of the node / edge
+ * table (the padding id) is all zero, so padded positions need no gather. */
 typedef struct {
     const int64_t* ids;    /* (B, Lp) padded neighbour ids */
     const int64_t* eids;   /* (B, Lp) padded edge ids */
@@ -190,7 +191,7 @@ typedef struct {
 int dyg_patch_project_stages(int F_node, int F_edge, int T, int F_lut, int P, int32_t* nblk5);
 int dyg_patch_project(const dyg_proj_side_t* sides_host, int nsides, const void* node_hi, const void* node_mid, int ld_node,
                       int F_node, const void* edge_hi, const void* edge_mid, int ld_edge, int F_edge, const void* lut_hi,
-                      const void* lut_mid, int ld_lut, int F_lut, const double* t_query, const float* tw, const float* tb,
+                      const void* lut_mid, int ld_lut, int F_lut, int zero_rows, const double* t_query, const float* tw, const float* tb,
                       int T, const void* W_hi, const void* W_mid, int ldw, const float* bias, int P, int C, int S, float* X,
                       int ldx, dyg_stream_t stream);
 

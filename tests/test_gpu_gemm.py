@@ -148,7 +148,7 @@ def test_patch_project_vs_float64(P, B, ns, nd):
             want[:, off:off + ntok, ch * C:(ch + 1) * C] = patches @ w.double().t() + bias[ch * C:(ch + 1) * C].double()
     packed = ops.pack_patch_weights(ws[0], ws[1], ws[2], ws[3], P)
     ops.patch_project(sides, ops.table_planes(node), F, ops.table_planes(edge), F, ops.table_planes(lut), C, tq, tw, tb, packed,
-                      bias, P, C, S, X)
+                      bias, P, C, S, X, zero_rows=3 if P != 4 else 0)
     got = X.reshape(B, S, 4 * C)
     assert not torch.isnan(got).any()
     # node / edge / co-occurrence channels are pure BF16x3 contractions
