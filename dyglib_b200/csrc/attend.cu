@@ -322,21 +322,38 @@ __global__ void __launch_bounds__(128) seq_attention_mma_kernel(const float* __r
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const float* base = qkv + b * (int64_t)S * ld_qkv;
-    for (int idx = tid; idx < SK * (KD / 2); idx += 128) {
-        const int j = idx / (KD / 2), d = (idx - j * (KD / 2)) * 2;
-        float2 kv = make_float2(0.f, 0.f), vv = kv;
-        if (j < S && d < hd) {
-            const float* rowp = base + (int64_t)j * ld_qkv + h * hd + d;
-            kv = *reinterpret_cast<const float2*>(rowp + D);
-            vv = *reinterpret_cast<const float2*>(rowp + 2 * D);
+    // stage K and V: all loads of a round are issued before the first conversion (the loop is DRAM-latency bound otherwise)
+    constexpr int TOT = SK * (KD / 2);
+    constexpr int U = 14;
+#pragma unroll 1
+    for (int it0 = 0; it0 < TOT; it0 += 128 * U) {
+        float2 kv[U], vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = it0 + u * 128 + tid;
+            const int j = idx / (KD / 2), d = (idx - j * (KD / 2)) * 2;
+            kv[u] = make_float2(0.f, 0.f);
+            vv[u] = kv[u];
+            if (idx < TOT && j < S && d < hd) {
+                const float* rowp = base + (int64_t)j * ld_qkv + h * hd + d;
+                kv[u] = *reinterpret_cast<const float2*>(rowp + D);
+                vv[u] = *reinterpret_cast<const float2*>(rowp + 2 * D);
+            }
         }
-        uint32_t hi, mid;
-        sa_split(kv.x, kv.y, hi, mid);
-        *reinterpret_cast<uint32_t*>(Kh + j * KS + d) = hi;
-        *reinterpret_cast<uint32_t*>(Km + j * KS + d) = mid;
-        sa_split(vv.x, vv.y, hi, mid);
-        *reinterpret_cast<uint32_t*>(Vh + j * KS + d) = hi;
-        *reinterpret_cast<uint32_t*>(Vm + j * KS + d) = mid;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = it0 + u * 128 + tid;
+            if (idx < TOT) {
+                const int j = idx / (KD / 2), d = (idx - j * (KD / 2)) * 2;
+                uint32_t hi, mid;
+                sa_split(kv[u].x, kv[u].y, hi, mid);
+                *reinterpret_cast<uint32_t*>(Kh + j * KS + d) = hi;
+                *reinterpret_cast<uint32_t*>(Km + j * KS + d) = mid;
+                sa_split(vv[u].x, vv[u].y, hi, mid);
+                *reinterpret_cast<uint32_t*>(Vh + j * KS + d) = hi;
+                *reinterpret_cast<uint32_t*>(Vm + j * KS + d) = mid;
+            }
+        }
     }
     __syncthreads();
     const float scale = rsqrtf((float)hd);

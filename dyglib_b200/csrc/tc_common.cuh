@@ -51,11 +51,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// x = hi + mid (+ dropped low part): hi = bf16(x), mid = bf16(x - hi); two values per call, packed {first: low half}
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& mid) {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 am = __float2bfloat16_rn(a - __bfloat162float(ah)), bm = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    mid = (uint32_t)__bfloat16_as_ushort(am) | ((uint32_t)__bfloat16_as_ushort(bm) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // one cvt.rn.bf16x2.f32
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 m = __floats2bfloat162_rn(a - ah, b - bh);
+    mid = *reinterpret_cast<const uint32_t*>(&m);
 }
 __device__ __forceinline__ void st_v8(void* p, const uint32_t* r) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
