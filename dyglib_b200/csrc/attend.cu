@@ -71,14 +71,19 @@ __global__ void __launch_bounds__(128, 3) temporal_attend_kernel(
             for (int r = 0; r < R; ++r) {
                 const int c = r * 32 + lane;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                // row 0 is the padding id: every padded neighbour of every root reads it, so it is kept in L1 (__ldg)
+                // instead of hammering one L2 slice; real rows are read once and bypass L1
                 if (c < F4) {
-                    v = ldg_stream(reinterpret_cast<const float4*>(node_tab + rn * ld_node) + c);
+                    const float4* np = reinterpret_cast<const float4*>(node_tab + rn * ld_node) + c;
+                    v = rn == 0 ? __ldg(np) : ldg_stream(np);
                     if (node_tab2) {
-                        const float4 u = ldg_stream(reinterpret_cast<const float4*>(node_tab2 + rn * ld_node2) + c);
+                        const float4* np2 = reinterpret_cast<const float4*>(node_tab2 + rn * ld_node2) + c;
+                        const float4 u = rn == 0 ? __ldg(np2) : ldg_stream(np2);
                         v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
                     }
                 } else if (c < F4 + E4) {
-                    v = ldg_stream(reinterpret_cast<const float4*>(edge_tab + re * ld_edge) + (c - F4));
+                    const float4* ep = reinterpret_cast<const float4*>(edge_tab + re * ld_edge) + (c - F4);
+                    v = re == 0 ? __ldg(ep) : ldg_stream(ep);
                 } else if (c < D4) {
                     if (time_feat) {
                         v = ldg_stream(reinterpret_cast<const float4*>(time_feat + (base + j0 + jj) * (int64_t)(T4 * 4)) + (c - F4 - E4));

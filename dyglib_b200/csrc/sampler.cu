@@ -52,6 +52,48 @@ __device__ __forceinline__ void node_range(const int64_t* indptr, int64_t num_no
     }
 }
 
+// Cooperative (LANES+1)-ary version of lower_bound_time: the LANES lanes of a query group probe LANES evenly spaced
+// records per round (independent loads, one round trip), a ballot counts how many are < tq, and the range shrinks by
+// LANES+1; ranges of <= LANES records are finished with one coalesced read.  ceil(log_{LANES+1} deg) dependent round
+// trips instead of ceil(log_2 deg).  EVERY lane of the warp must call it (groups without a query pass deg = 0).
+template <int LANES>
+__device__ __forceinline__ int64_t lower_bound_time_coop(const dyg_halfedge_t* he, int64_t a, int64_t deg, double tq, int lane) {
+    const unsigned gshift = ((threadIdx.x & 31) / LANES) * LANES;
+    const unsigned gmask = LANES >= 32 ? 0xffffffffu : ((1u << LANES) - 1u);
+    int64_t lo = 0, hi = deg;   // answer in [lo, hi]: records below lo are < tq, records from hi on are >= tq
+    while (true) {
+        const int64_t len = hi - lo;
+        const bool active = len > 0;
+        if (!__any_sync(0xffffffffu, active)) break;
+        const bool tail = len <= LANES;
+        int64_t p = lo;
+        bool inb = false;
+        if (active) {
+            if (tail) {
+                p = lo + lane;
+                inb = lane < len;
+            } else {
+                p = lo + ((int64_t)(lane + 1) * len) / (LANES + 1);
+                inb = true;
+            }
+        }
+        const bool pred = inb && (load_time(he, a + p) < tq);
+        const int c = __popc((__ballot_sync(0xffffffffu, pred) >> gshift) & gmask);   // sorted -> the true lanes are a prefix
+        if (active) {
+            if (tail) {
+                lo += c;
+                hi = lo;
+            } else {
+                const int64_t nlo = c > 0 ? lo + ((int64_t)c * len) / (LANES + 1) + 1 : lo;
+                const int64_t nhi = c < LANES ? lo + ((int64_t)(c + 1) * len) / (LANES + 1) : hi;
+                lo = nlo;
+                hi = nhi;
+            }
+        }
+    }
+    return lo;
+}
+
 // ---------------------------------------------------------------- CSR build
 __global__ void csr_degrees_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
                                    int64_t num_nodes, unsigned long long* __restrict__ deg) {
@@ -115,7 +157,7 @@ __global__ void count_before_kernel(const dyg_halfedge_t* __restrict__ he, const
     cnt[q] = (int32_t)lower_bound_time(he, a, deg, times[q]);
 }
 
-// LANES threads cooperate on one query: every lane runs the same search (same address -> one sector
+// LANES threads cooperate on one query: (LANES+1)-ary search (lower_bound_time_coop),
 // per probe per group), then the lanes split the k-entry tail gather and the (n,k) row writes.
 template <int LANES>
 __global__ void __launch_bounds__(256) sample_recent_kernel(
@@ -125,10 +167,15 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(
     int32_t* __restrict__ cnt_out) {
     const int lane = threadIdx.x % LANES;
     const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
-    if (q >= n) return;
-    int64_t a, deg;
-    node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
-    const int64_t cnt = lower_bound_time(he, a, deg, __ldg(times + q));
+    const bool valid = q < n;
+    int64_t a = 0, deg = 0;
+    double tq = 0.0;
+    if (valid) {
+        node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
+        tq = __ldg(times + q);
+    }
+    const int64_t cnt = lower_bound_time_coop<LANES>(he, a, deg, tq, lane);
+    if (!valid) return;
     if (cnt_out && lane == 0) cnt_out[q] = (int32_t)cnt;
     const int64_t base = q * (int64_t)k;
     for (int j = lane; j < k; j += LANES) {
@@ -155,12 +202,12 @@ __global__ void __launch_bounds__(256) first_hop_pad_kernel(
     int32_t* __restrict__ out_len, int32_t* __restrict__ group_max, int group_size) {
     const int lane = threadIdx.x & 31;
     const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (q >= n) return;
+    if (q >= n) return;                       // warp-uniform: one warp per query
     const int64_t v = __ldg(node_ids + q);
     const double tq = __ldg(times + q);
     int64_t a, deg;
     node_range(indptr, num_nodes, v, a, deg);
-    const int64_t cnt = lower_bound_time(he, a, deg, tq);
+    const int64_t cnt = lower_bound_time_coop<32>(he, a, deg, tq, lane);
     const int m = (int)(cnt < (int64_t)(L - 1) ? cnt : (int64_t)(L - 1));
     if (lane == 0) {
         if (out_len) out_len[q] = m + 1;
@@ -341,10 +388,14 @@ __global__ void __launch_bounds__(256) sample_random_kernel(
     const int64_t q = blockIdx.x * (int64_t)groups + g;
     const bool valid = q < n;
     int64_t a = 0, cnt = 0;
-    if (valid) {
-        int64_t deg;
-        node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
-        cnt = lower_bound_time(he, a, deg, __ldg(times + q));
+    {
+        int64_t deg = 0;
+        double tq = 0.0;
+        if (valid) {
+            node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
+            tq = __ldg(times + q);
+        }
+        cnt = lower_bound_time_coop<LANES>(he, a, deg, tq, lane);
     }
     const int64_t base = q * (int64_t)k;
     if (valid && cnt > 0) {

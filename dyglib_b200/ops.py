@@ -115,6 +115,8 @@ def seg_time(dt, w, b, mask_ids=None, group=1, t_query=None, tq_div=1):
 
 # tensor-core dispatch: rows at or above this use dyg_linear_tc (tcgen05 BF16x3); 0 disables it
 TC_MIN_ROWS = 512
+# dense (un-gathered) contractions with at least this many rows go to dyg_gemm_bf16x3 (TMA + tcgen05 CTA pairs)
+GEMM_MIN_ROWS = 2048
 _tc_weights = {}
 
 
@@ -164,6 +166,16 @@ def linear(segs, M, weight, bias=None, residual=None, act=ACT_NONE, out=None, ou
     arr = (Seg * len(segs))(*segs)
     ldc = out.stride(-2)
     ldr = residual.stride(-2) if residual is not None else 0
+    if tc is None and GEMM_MIN_ROWS > 0 and M >= GEMM_MIN_ROWS and c_group == 0 and K % 2 == 0 and \
+            all(sg.kind == 0 and not sg.idx and not sg.ptr2 and sg.group == 1 and sg.width % 2 == 0 for sg in segs):
+        # large dense contraction: BF16x3 operand planes + TMA / tcgen05 CTA-pair GEMM (dyg_gemm_bf16x3)
+        a = empty_split(M, K, weight.device)
+        col = 0
+        for sg in segs:
+            split_bf16(sg._keep[0][:, :sg.width], out=a, col=col)
+            col += sg.width
+        w = weight if (weight.shape[1] == K and weight.stride(0) == ldw) else torch.as_strided(weight, (N, K), (int(ldw), 1))
+        return gemm(a, w, bias, residual=residual, act=act, out=out)
     use_tc = (TC_MIN_ROWS > 0 and M >= TC_MIN_ROWS) if tc is None else tc
     if use_tc and _tc_ok(segs):
         wh, wm, n_pad, k_pad, _ = _split_weight(weight, K, ldw)
@@ -211,12 +223,17 @@ def empty_split(rows, cols, device):
     return Split(torch.empty((2, rows, ld), dtype=torch.bfloat16, device=device), rows, cols)
 
 
-def split_bf16(x, out=None):
-    """hi | mid planes of a fp32 matrix (last dimension contiguous)."""
+def split_bf16(x, out=None, col=0):
+    """hi | mid planes of a fp32 matrix (last dimension contiguous); with ``out`` / ``col`` the planes are written into
+    the column window [col, col + D) of an existing Split (concatenation without a copy)."""
     M, D = x.shape
     if out is None:
         out = empty_split(M, D, x.device)
-    _native.check(_lib().dyg_split_bf16(_p(x), int(x.stride(0)), int(M), int(D), _p(out.hi), _p(out.mid), int(out.ld), _stream()))
+    hi, mid = out.hi, out.mid
+    if col:
+        hi, mid = hi[:, col:], mid[:, col:]
+    _native.check(_lib().dyg_split_bf16(_p(x), int(x.stride(0)), int(M), int(D), ctypes.c_void_p(hi.data_ptr()),
+                                        ctypes.c_void_p(mid.data_ptr()), int(out.ld), _stream()))
     _count()
     return out
 
