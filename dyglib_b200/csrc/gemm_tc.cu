@@ -116,6 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
     const bool s_v8 = g.Chi && ((g.ldcs & 15) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 31u) == 0);
     const bool s_v4 = g.Chi && ((g.ldcs & 7) == 0) && (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 15u) == 0);
     const bool r_v4 = g.residual && ((g.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0);
+    const bool r_v8 = g.residual && ((g.ldr & 7) == 0) && ((reinterpret_cast<uintptr_t>(g.residual) & 31u) == 0);
     const bool b_v4 = g.bias && ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
     for (int col = 16 * chunk0; col < ncols; col += 16 * step) {
         uint32_t r[16];
@@ -141,7 +142,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
                 }
                 if (g.residual) {
                     const float* rp = g.residual + m * g.ldr + n;
-                    if (r_v4) {
+                    if (r_v8) {
+                        // one full 32-byte sector per lane and instruction: row-strided accesses cost one L1 wavefront
+                        // per sector, so 256-bit loads halve the epilogue's load wavefronts
+                        float q[16];
+                        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=f"(q[0]), "=f"(q[1]), "=f"(q[2]), "=f"(q[3]), "=f"(q[4]), "=f"(q[5]), "=f"(q[6]), "=f"(q[7])
+                                     : "l"(rp));
+                        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=f"(q[8]), "=f"(q[9]), "=f"(q[10]), "=f"(q[11]), "=f"(q[12]), "=f"(q[13]), "=f"(q[14]), "=f"(q[15])
+                                     : "l"(rp + 8));
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += q[j];
+                    } else if (r_v4) {
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
                             const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
@@ -375,6 +388,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
                 const uint32_t bph = (uint32_t)((it >> 1) & 1);
                 const int n0 = nt * g.NS;
                 const int ncols = min(g.NS, g.N - n0);
+                if (g.residual && chunk0 == 0 && m < g.M) {
+                    // this tile's MMAs are still running: pull its residual rows into L2 now, so the synchronous row
+                    // reads of the epilogue see L2 latency instead of one DRAM round trip per 16-column chunk
+                    const char* rp = reinterpret_cast<const char*>(g.residual + m * g.ldr + n0);
+                    for (int b = 0; b < ncols * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+                }
                 mbar_wait(tfull_bar + buf, bph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);

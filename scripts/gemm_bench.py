@@ -25,3 +25,7 @@ bench('out', 200, 200, res=True)
 bench('ffn1', 800, 200, act=ops.ACT_GELU, want='split')
 bench('ffn1n', 800, 200, want='split')
 bench('ffn2', 200, 800, res=True)
+bench('outnr', 200, 200)
+bench('outsp', 200, 200, want='split')
+bench('k32', 200, 32)
+bench('n208', 208, 208)
