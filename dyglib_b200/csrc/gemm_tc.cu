@@ -107,6 +107,23 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                  : "memory");
 }
 
+// Warp-uniform issue: the whole (converged) warp runs the descriptor arithmetic, so the operands live in uniform registers,
+// and elect.sync predicates the instruction itself onto one lane.  Issuing from inside `if (lane == 0)` instead makes the
+// compiler move every operand with R2UR inside a divergence (ELECT / BRA.U.ANY) loop: ~15 extra instructions per MMA.
+__device__ __forceinline__ void umma_bf16_pair_e(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_e(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+
 // One accumulator tile -> global memory: this thread owns TMEM lane `row` (output row m), this warp the 16-column
 // chunks chunk0, chunk0 + step, ...  Warp-collective (tcgen05.ld): every lane runs the loop, stores are masked.
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr, int64_t m, int n0, int ncols, int chunk0, int step) {
@@ -348,25 +365,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
                         if (resident && nt == 0) mbar_wait(afull_bar + kb, aph);
                         mbar_wait(full_bar + s, ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (lane == 0) {
+                        {
                             unsigned char* st = ring + (size_t)s * stage_bytes;
-                            const uint32_t a_h = smem_u32(resident ? a_res + (size_t)kb * a_stage : st), a_m = a_h + G_A_PLANE;
-                            const uint32_t b_h = smem_u32(st) + (resident ? 0u : (uint32_t)a_stage), b_m = b_h + (uint32_t)w_plane;
+                            const uint64_t dah0 = make_desc_sw64(smem_u32(resident ? a_res + (size_t)kb * a_stage : st));
+                            const uint64_t dam0 = dah0 + (uint64_t)(G_A_PLANE >> 4);
+                            const uint64_t dbh0 = make_desc_sw64(smem_u32(st) + (resident ? 0u : (uint32_t)a_stage));
+                            const uint64_t dbm0 = dbh0 + (uint64_t)(w_plane >> 4);
                             const int krem = g.K - kb * G_BK;
-                            const int nk16 = krem >= G_BK ? G_BK / 16 : (krem + 15) / 16;
-                            for (int kk = 0; kk < nk16; ++kk) {
-                                const uint32_t o = (uint32_t)kk * 32u;        // 16 bf16 = 32 bytes inside the swizzle row
-                                const uint64_t dah = make_desc_sw64(a_h + o), dam = make_desc_sw64(a_m + o);
-                                const uint64_t dbh = make_desc_sw64(b_h + o), dbm = make_desc_sw64(b_m + o);
-                                umma_bf16_pair(tacc, dah, dbh, idesc, (kb | kk) != 0);
-                                umma_bf16_pair(tacc, dah, dbm, idesc, 1);
-                                umma_bf16_pair(tacc, dam, dbh, idesc, 1);
+#pragma unroll
+                            for (int kk = 0; kk < G_BK / 16; ++kk) {
+                                if (kk * 16 < krem) {
+                                    const uint64_t o = (uint64_t)(kk * 2);        // 16 bf16 = 32 bytes inside the swizzle row, >> 4
+                                    umma_bf16_pair_e(tacc, dah0 + o, dbh0 + o, idesc, (kb | kk) != 0);
+                                    umma_bf16_pair_e(tacc, dah0 + o, dbm0 + o, idesc, 1);
+                                    umma_bf16_pair_e(tacc, dam0 + o, dbh0 + o, idesc, 1);
+                                }
                             }
-                            umma_commit_pair(empty_bar + s);                                   // ring stage reusable in both CTAs
-                            if (resident && nt == g.n_tiles - 1) umma_commit_pair(aempty_bar + kb);   // A slot free for the next super tile
-                            if (kb == nkb - 1) umma_commit_pair(tfull_bar + buf);              // accumulator complete in both CTAs
+                            umma_commit_pair_e(empty_bar + s);                                   // ring stage reusable in both CTAs
+                            if (resident && nt == g.n_tiles - 1) umma_commit_pair_e(aempty_bar + kb);   // A slot free for the next super tile
+                            if (kb == nkb - 1) umma_commit_pair_e(tfull_bar + buf);              // accumulator complete in both CTAs
                         }
-                        __syncwarp();
                         if (++s == g.stages) {
                             s = 0;
                             ph ^= 1u;
@@ -406,6 +424,381 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                         // no CTA leaves while its peer may still touch its smem / barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G_TMEM_COLS) : "memory");
+    }
+}
+
+
+// ====================================================================================================================
+// dyg_ln_ffn_bf16x3: out = x + W2 gelu(W1 LayerNorm(x) + b1) + b2 — the feed-forward half of DyGFormer's transformer block
+// (models/DyGFormer.py:456-461) as ONE kernel: the 4D-wide hidden activation never leaves the SM.
+//
+// Per CTA pair and 256-row super tile:
+//   LN warps   LayerNorm of the pair's rows straight into the resident A operand (BF16x3 planes, SWIZZLE_64B k blocks):
+//              row statistics are taken while the previous tile still computes, the normalised rows are written as soon
+//              as the MMA warp releases A; the same warps run the final epilogue (+ b2 + x -> global)
+//   per macro chunk of 128 hidden columns (7 for 800, the last one ragged):
+//     GEMM1    acc1[mc&1] (TMEM, 128 cols) = LN(x) W1[mc]^T     (M=256, N=128, K=200: 13 k16 steps x 3 MMAs; W1 streamed
+//              per 32-wide k block through a 3-stage TMA ring)
+//     per 32-column sub chunk:
+//       EPI1   8 warps: tcgen05.ld -> + b1 -> GELU -> bf16 hi|mid -> h[.] in shared memory as the next A operand (3 buffers)
+//       GEMM2  acc2 (TMEM, 208 cols) += h[.] W2[:, sub]^T        (M=256, N=208, K=32: 2 x 3 MMAs; W2 through a 3-stage ring)
+//   GEMM1 of macro chunk mc+1 is issued before the GEMM2s of mc, so the tensor pipe works while the GELU of mc runs.
+// MMAs are sized so that each one is worth its issue cost (a first version with N=32 GEMM1s was bound by the issuing
+// thread).  Barriers consumed by the leader's MMA warp live in the leader CTA (remote arrivals from the peer), barriers
+// released by tcgen05.commit are multicast to both CTAs.
+constexpr int F_SUB = 32;                 // hidden columns per sub chunk (K of one GEMM2 step)
+constexpr int F_MC = 128;                 // hidden columns per macro chunk (N of GEMM1)
+constexpr int F_KB1 = 7;                  // k blocks of GEMM1 (K <= 224)
+constexpr int F_W1_PLANE = (F_MC / 2) * 64;
+constexpr int F_W1_STAGE = 2 * F_W1_PLANE;   // one k block of this CTA's half of a macro chunk, hi | mid
+constexpr int F_S1 = 3, F_S2 = 3, F_HB = 3;
+constexpr int F_EPI_WARPS = 8, F_LN_WARPS = 4;
+constexpr int F_THREADS = 64 + 32 * (F_EPI_WARPS + F_LN_WARPS);
+constexpr int F_ACC1_COL = 256;           // acc2 at TMEM columns [0, 208), acc1 buffers at 256 and 384
+
+struct FfnArgs {
+    const float* x;        // (M, ldx) fp32 residual stream
+    const float* gamma;
+    const float* beta;
+    const float* b1;
+    const float* b2;
+    float* out;            // (M, ldo)
+    int64_t M;
+    int64_t m_super;
+    int ldx, ldo;
+    int D;                 // model width (K of GEMM1, N of GEMM2), <= 208, even
+    int Dff;               // hidden width, multiple of 32
+    int NT2;               // MMA N of GEMM2 (D rounded up to 16)
+    float eps;
+};
+
+__global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __grid_constant__ CUtensorMap map_w1h,
+                                                                     const __grid_constant__ CUtensorMap map_w1m,
+                                                                     const __grid_constant__ CUtensorMap map_w2h,
+                                                                     const __grid_constant__ CUtensorMap map_w2m, const FfnArgs f) {
+    extern __shared__ __align__(1024) unsigned char ffn_smem[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ffn_smem) + 1023) & ~(uintptr_t)1023);
+    const int a_stage = 2 * G_A_PLANE;                         // one k block of A (or one h buffer): hi | mid
+    const int w2_plane = (f.NT2 / 2) * 64;
+    const int w2_stage = 2 * w2_plane;
+    unsigned char* a_res = base;                               // [F_KB1] k blocks of LN(x)
+    unsigned char* h_buf = a_res + F_KB1 * a_stage;            // [F_HB] hidden sub chunks
+    unsigned char* w1_ring = h_buf + F_HB * a_stage;           // [F_S1]
+    unsigned char* w2_ring = w1_ring + F_S1 * F_W1_STAGE;      // [F_S2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w2_ring + F_S2 * w2_stage);
+    uint64_t* w1_full = bars;              // [3] leader
+    uint64_t* w1_empty = bars + 3;         // [3] both
+    uint64_t* w2_full = bars + 6;          // [3] leader
+    uint64_t* w2_empty = bars + 9;         // [3] both
+    uint64_t* h_full = bars + 12;          // [3] leader: h[b] written by both CTAs' EPI1 warps
+    uint64_t* h_empty = bars + 15;         // [3] both:   GEMM2 finished reading h[b]
+    uint64_t* acc1_full = bars + 18;       // [2] both
+    uint64_t* acc1_empty = bars + 20;      // [2] leader: both CTAs' EPI1 warps drained acc1[b]
+    uint64_t* a_full = bars + 22;          //     leader: LN(x) of the tile written by both CTAs
+    uint64_t* a_free = bars + 23;          //     both:   last GEMM1 of the tile retired
+    uint64_t* acc2_full = bars + 24;       //     both
+    uint64_t* acc2_empty = bars + 25;      //     leader: final epilogue (EPI warps of both CTAs) drained acc2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int nmacro = (f.Dff + F_MC - 1) / F_MC;
+    const int nkb1 = (f.D + G_BK - 1) / G_BK;
+
+    // zero the A region once: the K padding columns (D .. 32*nkb1) are never written again
+    for (int i = tid; i < F_KB1 * a_stage / 16; i += F_THREADS) reinterpret_cast<uint4*>(a_res)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int s = 0; s < 3; ++s) {
+            mbar_init(w1_full + s, 1); mbar_init(w1_empty + s, 1);
+            mbar_init(w2_full + s, 1); mbar_init(w2_empty + s, 1);
+            mbar_init(h_full + s, 2 * F_EPI_WARPS); mbar_init(h_empty + s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(acc1_full + s, 1);
+            mbar_init(acc1_empty + s, 2 * F_EPI_WARPS);
+        }
+        mbar_init(a_full, 2 * F_LN_WARPS);
+        mbar_init(a_free, 1);
+        mbar_init(acc2_full, 1);
+        mbar_init(acc2_empty, 2 * F_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w1h)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w1m)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w2h)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w2m)) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the zero fill above must be visible to the MMAs
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer: W1 k blocks and W2 sub chunks
+        if (lane == 0) {
+            int s1 = 0, s2 = 0;
+            uint32_t p1 = 0, p2 = 0;
+            auto load_w1 = [&](int mc) {
+                const int nmc = min(F_MC, f.Dff - mc * F_MC);
+                const int row = mc * F_MC + (int)rank * (nmc / 2);
+                for (int kb = 0; kb < nkb1; ++kb) {
+                    mbar_wait(w1_empty + s1, p1 ^ 1u);
+                    if (leader) mbar_expect_tx(w1_full + s1, 2u * F_W1_STAGE);
+                    unsigned char* d1 = w1_ring + s1 * F_W1_STAGE;
+                    tma_load_2d_pair(&map_w1h, w1_full + s1, d1, kb * G_BK, row);
+                    tma_load_2d_pair(&map_w1m, w1_full + s1, d1 + F_W1_PLANE, kb * G_BK, row);
+                    if (++s1 == F_S1) { s1 = 0; p1 ^= 1u; }
+                }
+            };
+            for (int64_t ms = pair; ms < f.m_super; ms += npairs) {
+                load_w1(0);
+                for (int mc = 0; mc < nmacro; ++mc) {
+                    if (mc + 1 < nmacro) load_w1(mc + 1);                  // same order as the MMA warp consumes them
+                    const int nsub = min(F_MC, f.Dff - mc * F_MC) / F_SUB;
+                    for (int sub = 0; sub < nsub; ++sub) {
+                        mbar_wait(w2_empty + s2, p2 ^ 1u);
+                        if (leader) mbar_expect_tx(w2_full + s2, 2u * (uint32_t)w2_stage);
+                        unsigned char* d2 = w2_ring + s2 * w2_stage;
+                        const int row2 = (int)rank * (f.NT2 / 2);
+                        tma_load_2d_pair(&map_w2h, w2_full + s2, d2, mc * F_MC + sub * F_SUB, row2);
+                        tma_load_2d_pair(&map_w2m, w2_full + s2, d2 + w2_plane, mc * F_MC + sub * F_SUB, row2);
+                        if (++s2 == F_S2) { s2 = 0; p2 ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, elected issue)
+        if (leader) {
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(f.NT2 >> 3) << 17) | ((uint32_t)((2 * G_BM) >> 4) << 24);
+            const uint64_t ad_h = make_desc_sw64(smem_u32(a_res)), ad_m = ad_h + (uint64_t)(G_A_PLANE >> 4);
+            int s1 = 0, s2 = 0;
+            uint32_t p1 = 0, p2 = 0;
+            int64_t gm = 0;      // global macro chunk counter: acc1 buffer gm & 1
+            int64_t gs = 0;      // global sub chunk counter:   h buffer gs % F_HB
+            int it = 0;
+            auto gemm1 = [&](int64_t g1, int mc) {
+                const int pb = (int)(g1 & 1);
+                const int nmc = min(F_MC, f.Dff - mc * F_MC);
+                const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nmc >> 3) << 17) | ((uint32_t)((2 * G_BM) >> 4) << 24);
+                mbar_wait(acc1_empty + pb, (uint32_t)(((g1 >> 1) & 1) ^ 1));          // EPI1 drained the previous user of acc1[pb]
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)(F_ACC1_COL + F_MC * pb);
+                for (int kb = 0; kb < nkb1; ++kb) {
+                    mbar_wait(w1_full + s1, p1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t wd_h = make_desc_sw64(smem_u32(w1_ring + s1 * F_W1_STAGE)), wd_m = wd_h + (uint64_t)(F_W1_PLANE >> 4);
+                    const uint64_t ao = (uint64_t)((kb * a_stage) >> 4);
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        if (kb * G_BK + kk * 16 < f.D) {                               // this k16 step holds valid columns
+                            const uint64_t o = (uint64_t)(kk * 2);
+                            umma_bf16_pair_e(tacc, ad_h + ao + o, wd_h + o, idesc1, (kb | kk) != 0);
+                            umma_bf16_pair_e(tacc, ad_h + ao + o, wd_m + o, idesc1, 1);
+                            umma_bf16_pair_e(tacc, ad_m + ao + o, wd_h + o, idesc1, 1);
+                        }
+                    }
+                    umma_commit_pair_e(w1_empty + s1);
+                    if (++s1 == F_S1) { s1 = 0; p1 ^= 1u; }
+                }
+                umma_commit_pair_e(acc1_full + pb);
+            };
+            for (int64_t ms = pair; ms < f.m_super; ms += npairs, ++it) {
+                mbar_wait(a_full, (uint32_t)(it & 1));                                // LN(x) of this tile is in shared memory (both CTAs)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                gemm1(gm, 0);
+                if (nmacro == 1) umma_commit_pair_e(a_free);
+                for (int mc = 0; mc < nmacro; ++mc, ++gm) {
+                    if (mc + 1 < nmacro) {
+                        gemm1(gm + 1, mc + 1);
+                        if (mc + 2 == nmacro) umma_commit_pair_e(a_free);             // A may be overwritten once the GEMM1s retire
+                    }
+                    const int nsub = min(F_MC, f.Dff - mc * F_MC) / F_SUB;
+                    for (int sub = 0; sub < nsub; ++sub, ++gs) {
+                        const int hb = (int)(gs % F_HB);
+                        if (mc == 0 && sub == 0) mbar_wait(acc2_empty, (uint32_t)((it & 1) ^ 1));   // previous tile's final epilogue done
+                        mbar_wait(h_full + hb, (uint32_t)((gs / F_HB) & 1));          // GELU(sub chunk) is in h[hb] in both CTAs
+                        mbar_wait(w2_full + s2, p2);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t hd_h = make_desc_sw64(smem_u32(h_buf + hb * a_stage)), hd_m = hd_h + (uint64_t)(G_A_PLANE >> 4);
+                        const uint64_t vd_h = make_desc_sw64(smem_u32(w2_ring + s2 * w2_stage)), vd_m = vd_h + (uint64_t)(w2_plane >> 4);
+#pragma unroll
+                        for (int kk = 0; kk < F_SUB / 16; ++kk) {
+                            const uint64_t o = (uint64_t)(kk * 2);                    // 32 bytes >> 4
+                            umma_bf16_pair_e(tmem_base, hd_h + o, vd_h + o, idesc2, (mc | sub | kk) != 0);
+                            umma_bf16_pair_e(tmem_base, hd_h + o, vd_m + o, idesc2, 1);
+                            umma_bf16_pair_e(tmem_base, hd_m + o, vd_h + o, idesc2, 1);
+                        }
+                        umma_commit_pair_e(w2_empty + s2);
+                        umma_commit_pair_e(h_empty + hb);
+                        if (mc == nmacro - 1 && sub == nsub - 1) umma_commit_pair_e(acc2_full);
+                        if (++s2 == F_S2) { s2 = 0; p2 ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp < 2 + F_EPI_WARPS) {
+        // ------------------------------------------------------------------ EPI1: bias + GELU + split of every hidden sub chunk
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;                                  // TMEM lane == tile row
+        const int halfc = (warp - 2) >> 2;                                  // which 16 of the sub chunk's 32 columns
+        const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+        const uint32_t swz = (uint32_t)((r >> 1) & 3);
+        const uint32_t c16 = (uint32_t)halfc * 2u;
+        int64_t gm = 0, gs = 0;
+        int it = 0;
+        GemmArgs eg;
+        eg.bias = f.b2; eg.residual = f.x; eg.C = f.out; eg.Chi = nullptr; eg.Cmid = nullptr;
+        eg.M = f.M; eg.ldr = f.ldx; eg.ldc = f.ldo; eg.ldcs = 0; eg.N = f.D; eg.K = 0; eg.act = DYG_ACT_NONE;
+        for (int64_t ms = pair; ms < f.m_super; ms += npairs, ++it) {
+            for (int mc = 0; mc < nmacro; ++mc, ++gm) {
+                const int pb = (int)(gm & 1);
+                const int nsub = min(F_MC, f.Dff - mc * F_MC) / F_SUB;
+                mbar_wait(acc1_full + pb, (uint32_t)((gm >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int sub = 0; sub < nsub; ++sub, ++gs) {
+                    const int hb = (int)(gs % F_HB);
+                    uint32_t rr[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(F_ACC1_COL + F_MC * pb + sub * F_SUB + 16 * halfc), rr);
+                    const float* bp = f.b1 + mc * F_MC + sub * F_SUB + 16 * halfc;
+                    uint32_t hi[8], mid[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float2 b2v = __ldg(reinterpret_cast<const float2*>(bp + 2 * j));
+                        const float v0 = act_apply(__uint_as_float(rr[2 * j]) + b2v.x, DYG_ACT_GELU);
+                        const float v1 = act_apply(__uint_as_float(rr[2 * j + 1]) + b2v.y, DYG_ACT_GELU);
+                        split_pack(v0, v1, hi[j], mid[j]);
+                    }
+                    mbar_wait(h_empty + hb, (uint32_t)(((gs / F_HB) & 1) ^ 1));       // GEMM2 of sub chunk gs-3 no longer reads h[hb]
+                    unsigned char* rowp = h_buf + hb * a_stage + row_off;
+                    *reinterpret_cast<uint4*>(rowp + ((c16 ^ swz) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(rowp + (((c16 + 1) ^ swz) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4*>(rowp + G_A_PLANE + ((c16 ^ swz) << 4)) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
+                    *reinterpret_cast<uint4*>(rowp + G_A_PLANE + (((c16 + 1) ^ swz) << 4)) = make_uint4(mid[4], mid[5], mid[6], mid[7]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(h_full + hb);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(acc1_empty + pb);
+            }
+            // final epilogue of the tile: these warps are idle until the next tile's first GEMM1 retires, the LN warps are
+            // busy writing the next A operand
+            mbar_wait(acc2_full, (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            epilogue_tile(eg, tmem_base + ((uint32_t)(quarter * 32) << 16), ms * 2 * G_BM + (int64_t)rank * G_BM + r, 0, f.D, halfc, 2);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(acc2_empty);
+        }
+    } else {
+        // ------------------------------------------------------------------ LN warps: LayerNorm -> resident A operand
+        const int quarter = warp & 3;
+        const int r0 = quarter * 32;                                        // this warp's 32 rows of the CTA's 128
+        constexpr int RB = 8;                                               // statistics: rows per batch (32 float2 loads in flight per lane)
+        constexpr int WB = 4;                                               // write pass: rows per batch, two batches in flight
+        int it = 0;
+        auto load_rows = [&](float2 (&v)[WB][4], int64_t mrow0) {
+#pragma unroll
+            for (int i = 0; i < WB; ++i) {
+                const int64_t m = mrow0 + i;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = 2 * lane + 64 * j;
+                    v[i][j] = (m < f.M && c < f.D) ? *reinterpret_cast<const float2*>(f.x + m * f.ldx + c) : make_float2(0.f, 0.f);
+                }
+            }
+        };
+        for (int64_t ms = pair; ms < f.m_super; ms += npairs, ++it) {
+            const int64_t m0 = ms * 2 * G_BM + (int64_t)rank * G_BM;
+            // pass 1: row statistics (lane i keeps mean / rstd of row r0 + i) while the previous tile computes; the rows
+            // also land in L2 for pass 2
+            float my_mean = 0.f, my_rstd = 0.f;
+            for (int i0 = 0; i0 < 32; i0 += RB) {
+                float2 v[RB][4];
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                    const int64_t m = m0 + r0 + i0 + i;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 2 * lane + 64 * j;
+                        v[i][j] = (m < f.M && c < f.D) ? *reinterpret_cast<const float2*>(f.x + m * f.ldx + c) : make_float2(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                    float sum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sum += v[i][j].x + v[i][j].y;
+                    const float mean = warp_sum(sum) / (float)f.D;
+                    float sq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (2 * lane + 64 * j < f.D) {
+                            const float dx = v[i][j].x - mean, dy = v[i][j].y - mean;
+                            sq += dx * dx + dy * dy;
+                        }
+                    }
+                    const float rstd = rsqrtf(warp_sum(sq) / (float)f.D + f.eps);
+                    if (lane == i0 + i) { my_mean = mean; my_rstd = rstd; }
+                }
+            }
+            // pass 2: the first rows are re-read (L2) before A is released, later batches are loaded one batch ahead of the
+            // batch being normalised and written, so only one load latency is exposed after the release
+            float2 va[WB][4], vb[WB][4];
+            load_rows(va, m0 + r0);
+            mbar_wait(a_free, (uint32_t)((it & 1) ^ 1));                     // last GEMM1 of the previous tile retired
+            auto write_rows = [&](float2 (&v)[WB][4], int i0) {
+#pragma unroll
+                for (int i = 0; i < WB; ++i) {
+                    const int r = r0 + i0 + i;
+                    const float mean = __shfl_sync(0xffffffffu, my_mean, i0 + i), rstd = __shfl_sync(0xffffffffu, my_rstd, i0 + i);
+                    const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+                    const uint32_t swz = (uint32_t)((r >> 1) & 3);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = 2 * lane + 64 * j;
+                        if (c < f.D) {
+                            const float2 gmm = __ldg(reinterpret_cast<const float2*>(f.gamma + c));
+                            const float2 bt = __ldg(reinterpret_cast<const float2*>(f.beta + c));
+                            const float y0 = (v[i][j].x - mean) * rstd * gmm.x + bt.x, y1 = (v[i][j].y - mean) * rstd * gmm.y + bt.y;
+                            uint32_t h, l;
+                            split_pack(y0, y1, h, l);
+                            const int kb = c >> 5, cc = c & 31;
+                            unsigned char* p = a_res + kb * a_stage + row_off + ((((uint32_t)cc >> 3) ^ swz) << 4) + (cc & 7) * 2;
+                            *reinterpret_cast<uint32_t*>(p) = h;
+                            *reinterpret_cast<uint32_t*>(p + G_A_PLANE) = l;
+                        }
+                    }
+                }
+            };
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 2 * WB) {
+                load_rows(vb, m0 + r0 + i0 + WB);
+                write_rows(va, i0);
+                if (i0 + 2 * WB < 32) load_rows(va, m0 + r0 + i0 + 2 * WB);
+                write_rows(vb, i0 + WB);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(a_full);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G_TMEM_COLS) : "memory");
     }
@@ -664,5 +1057,63 @@ extern "C" int dyg_layernorm_split(const float* x, int ldx, const float* gamma, 
     else if (D <= 512) layernorm_split_kernel<8><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, h, l, ld, M, D);
     else layernorm_split_kernel<16><<<blocks, 256, 0, s>>>(x, ldx, gamma, beta, eps, y, ldy, h, l, ld, M, D);
     DYG_LAUNCH_CHECK("dyg_layernorm_split");
+    return 0;
+}
+
+extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W1_hi,
+                                 const void* W1_mid, int ldw1, const float* b1, const void* W2_hi, const void* W2_mid, int ldw2,
+                                 const float* b2, float* out, int ldo, int64_t M, int D, int Dff, dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && D > 0 && Dff > 0, "dyg_ln_ffn_bf16x3: bad sizes");
+    DYG_CHECK_ARG(D <= 208 && (D % 2) == 0, "dyg_ln_ffn_bf16x3: model width %d unsupported (even, <= 208)", D);
+    DYG_CHECK_ARG((Dff % F_SUB) == 0, "dyg_ln_ffn_bf16x3: hidden width %d must be a multiple of %d", Dff, F_SUB);
+    DYG_CHECK_ARG(x && gamma && beta && W1_hi && W1_mid && b1 && W2_hi && W2_mid && b2 && out, "dyg_ln_ffn_bf16x3: NULL pointer");
+    DYG_CHECK_ARG((ldx % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(beta) & 7u) == 0 && (reinterpret_cast<uintptr_t>(b1) & 7u) == 0,
+                  "dyg_ln_ffn_bf16x3: fp32 inputs must be 8-byte aligned with even leading dimensions");
+    DYG_CHECK_ARG((ldw1 % 8) == 0 && ldw1 >= D && (ldw2 % 8) == 0 && ldw2 >= Dff && aligned16(W1_hi) && aligned16(W1_mid) &&
+                      aligned16(W2_hi) && aligned16(W2_mid),
+                  "dyg_ln_ffn_bf16x3: weight planes must be 16-byte aligned with leading dimensions that are multiples of 8");
+    DYG_CHECK_ARG(M < ((int64_t)1 << 31) - 2 * G_BM, "dyg_ln_ffn_bf16x3: M too large");
+    if (M == 0) return 0;
+    FfnArgs f;
+    memset(&f, 0, sizeof(f));
+    f.x = x; f.gamma = gamma; f.beta = beta; f.b1 = b1; f.b2 = b2; f.out = out;
+    f.M = M; f.m_super = (M + 2 * G_BM - 1) / (2 * G_BM);
+    f.ldx = ldx; f.ldo = ldo; f.D = D; f.Dff = Dff; f.NT2 = (D + 15) / 16 * 16; f.eps = eps;
+    CUtensorMap m1h, m1m, m2h, m2m;
+    if (!dyg_tensor_map_bf16(W1_hi, (uint64_t)Dff, (uint64_t)D, (uint64_t)ldw1, F_MC / 2, &m1h)) return 1;
+    if (!dyg_tensor_map_bf16(W1_mid, (uint64_t)Dff, (uint64_t)D, (uint64_t)ldw1, F_MC / 2, &m1m)) return 1;
+    if (!dyg_tensor_map_bf16(W2_hi, (uint64_t)D, (uint64_t)Dff, (uint64_t)ldw2, (uint32_t)(f.NT2 / 2), &m2h)) return 1;
+    if (!dyg_tensor_map_bf16(W2_mid, (uint64_t)D, (uint64_t)Dff, (uint64_t)ldw2, (uint32_t)(f.NT2 / 2), &m2m)) return 1;
+    const size_t smem = (size_t)(F_KB1 + F_HB) * 2 * G_A_PLANE + (size_t)F_S1 * F_W1_STAGE + (size_t)F_S2 * 2 * (f.NT2 / 2) * 64 + 1024 + 512;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(ln_ffn_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            dyg_set_error("dyg_ln_ffn_bf16x3: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return 1;
+        }
+        configured = smem;
+    }
+    const int max_pairs = dyg_num_sms() / 2;
+    const int pairs = (int)(f.m_super < max_pairs ? f.m_super : max_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, ln_ffn_bf16x3_kernel, m1h, m1m, m2h, m2m, f);
+    if (le != cudaSuccess) {
+        dyg_set_error("dyg_ln_ffn_bf16x3: launch failed: %s", cudaGetErrorString(le));
+        return 1;
+    }
     return 0;
 }

@@ -51,6 +51,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // x = hi + mid (+ dropped low part): hi = bf16(x), mid = bf16(x - hi); two values per call, packed {first: low half}
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& mid) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // one cvt.rn.bf16x2.f32

@@ -19,6 +19,12 @@ from ..utils.utils import NeighborSampler, _as_dev
 from .modules import TimeEncoder, _eval_only
 
 
+import os
+
+# LayerNorm + feed-forward as one kernel (dyg_ln_ffn_bf16x3); DYG_FUSED_FFN=0 selects the three-kernel path
+FUSED_FFN = os.environ.get('DYG_FUSED_FFN', '1') != '0'
+
+
 class NeighborCooccurrenceEncoder(nn.Module):
 
     def __init__(self, neighbor_co_occurrence_feat_dim: int, device: str = 'cuda'):
@@ -103,9 +109,13 @@ class TransformerEncoder(nn.Module):
         else:
             a = ops.split_bf16(ops.seq_attention(qkv, B, S, self.num_heads, hd))
         x1 = ops.gemm(a, mha.out_proj.weight, mha.out_proj.bias.detach(), residual=x)
-        y = ops.layernorm_split(x1, n1.weight.detach(), n1.bias.detach(), eps=n1.eps)
-        h = ops.gemm(y, l0.weight, l0.bias.detach(), act=ops.ACT_GELU, want='split')
-        out = ops.gemm(h, l1.weight, l1.bias.detach(), residual=x1)
+        if FUSED_FFN and ops.ffn_fusable(D, l0.weight.shape[0]):
+            # LayerNorm + FFN in one kernel: the normalised rows and the 4D hidden activation stay on the SM
+            out = ops.ln_ffn(x1, n1.weight.detach(), n1.bias.detach(), n1.eps, l0.weight, l0.bias.detach(), l1.weight, l1.bias.detach())
+        else:
+            y = ops.layernorm_split(x1, n1.weight.detach(), n1.bias.detach(), eps=n1.eps)
+            h = ops.gemm(y, l0.weight, l0.bias.detach(), act=ops.ACT_GELU, want='split')
+            out = ops.gemm(h, l1.weight, l1.bias.detach(), residual=x1)
         return out.reshape(B, S, D)
 
 

@@ -353,6 +353,25 @@ def patch_project(sides, node_planes, F_node, edge_planes, F_edge, lut_planes, F
     return X
 
 
+def ffn_fusable(D, Dff):
+    return D % 2 == 0 and D <= 208 and Dff % 32 == 0
+
+
+def ln_ffn(x, gamma, beta, eps, w1, b1, w2, b2, out=None):
+    """x + W2 gelu(W1 LayerNorm(x) + b1) + b2 in one kernel (dyg_ln_ffn_bf16x3); the hidden activation never reaches HBM."""
+    M, D = x.shape
+    Dff = w1.shape[0]
+    if out is None:
+        out = torch.empty_like(x)
+    w1s, w2s = split_weight(w1), split_weight(w2)
+    with _Timed('ln_ffn_bf16x3_kernel', 4.0 * M * D * Dff, 8.0 * M * D):
+        _native.check(_lib().dyg_ln_ffn_bf16x3(_p(x), int(x.stride(0)), _p(gamma), _p(beta), float(eps), _p(w1s.hi), _p(w1s.mid),
+                                               int(w1s.ld), _p(b1), _p(w2s.hi), _p(w2s.mid), int(w2s.ld), _p(b2), _p(out), int(out.stride(0)),
+                                               int(M), int(D), int(Dff), _stream()))
+    _count()
+    return out
+
+
 def layernorm_split(x, gamma, beta, eps=1e-5, out=None, y=None):
     """LayerNorm(x) as a Split (and optionally also as fp32 ``y``)."""
     M, D = x.shape

@@ -156,3 +156,21 @@ def test_patch_project_vs_float64(P, B, ns, nd):
         assert rel_err(got[..., ch * C:(ch + 1) * C], want[..., ch * C:(ch + 1) * C]) < 5e-5, ch
     # time channel: torch's fp32 addcmul may round the argument differently from a single FMA (arguments reach 3e5 rad)
     assert rel_err(got[..., 2 * C:3 * C], want[..., 2 * C:3 * C]) < 5e-3
+
+
+@pytest.mark.parametrize('M,D,Dff', [(256, 200, 800), (1, 200, 800), (300, 200, 800), (5000, 200, 800), (777, 64, 32), (1000, 208, 256),
+                                     (148 * 256 + 77, 200, 800)])
+def test_ln_ffn_fused(M, D, Dff):
+    g = torch.Generator(device='cuda').manual_seed(M + D + Dff)
+    x = torch.randn(M, D, device='cuda', generator=g) * 2 + 0.5
+    gm = 1 + 0.1 * torch.randn(D, device='cuda', generator=g)
+    bt = 0.1 * torch.randn(D, device='cuda', generator=g)
+    w1 = torch.randn(Dff, D, device='cuda', generator=g) / np.sqrt(D)
+    b1 = torch.randn(Dff, device='cuda', generator=g)
+    w2 = torch.randn(D, Dff, device='cuda', generator=g) / np.sqrt(Dff)
+    b2 = torch.randn(D, device='cuda', generator=g)
+    got = ops.ln_ffn(x, gm, bt, 1e-5, w1, b1, w2, b2)
+    xd = x.double()
+    y = torch.nn.functional.layer_norm(xd, (D,), gm.double(), bt.double(), 1e-5)
+    want = xd + torch.nn.functional.gelu(y @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
+    assert rel_err(got, want) < 5e-5, rel_err(got, want)
