@@ -73,8 +73,14 @@ class MemoryBank(nn.Module):
         """``__init_memory_bank__`` (``models/MemoryModel.py:325-332``)."""
         self.node_memories.data.zero_()
         self.node_last_updated_times.data.zero_()
-        self._state = None
-        self._ensure()
+        if self._state is None or self._state['mem_view'].device != self.node_memories.device:
+            self._state = None
+            self._ensure()
+        else:   # in place: a captured CUDA graph keeps pointing at these buffers
+            st = self._state
+            for k in ('mem_view', 'lu_view', 'pending', 'msg_store', 'msg_time', 'flag'):
+                st[k].zero_()
+            st['winner'].fill_(-1)
 
     def get_memories(self, node_ids):
         ids = _as_dev(node_ids, torch.int64, self.node_memories.device)
@@ -108,9 +114,11 @@ class MemoryBank(nn.Module):
 
     def reload_memory_bank(self, backup_memory_bank: tuple):
         """``reload_memory_bank`` (``models/MemoryModel.py:362-372``)."""
-        self.node_memories.data = backup_memory_bank[0].clone()
-        self.node_last_updated_times.data = backup_memory_bank[1].clone()
-        self._state = {k: v.clone() for k, v in backup_memory_bank[2].items()}
+        self.node_memories.data.copy_(backup_memory_bank[0])
+        self.node_last_updated_times.data.copy_(backup_memory_bank[1])
+        st = self._ensure()
+        for k, v in backup_memory_bank[2].items():   # in place (graph-safe)
+            st[k].copy_(v)
 
     def detach_memory_bank(self):
         """``detach_memory_bank`` (``models/MemoryModel.py:374-387``): nothing carries gradients here."""

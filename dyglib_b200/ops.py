@@ -116,7 +116,7 @@ def seg_time(dt, w, b, mask_ids=None, group=1, t_query=None, tq_div=1):
 # tensor-core dispatch: rows at or above this use dyg_linear_tc (tcgen05 BF16x3); 0 disables it
 TC_MIN_ROWS = 512
 # dense (un-gathered) contractions with at least this many rows go to dyg_gemm_bf16x3 (TMA + tcgen05 CTA pairs)
-GEMM_MIN_ROWS = 2048
+GEMM_MIN_ROWS = 256
 _tc_weights = {}
 
 

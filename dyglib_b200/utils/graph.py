@@ -1,0 +1,48 @@
+"""CUDA-graph replay of a fixed-shape step.
+
+The memory models advance one 200-event batch at a time through ~30 small kernels: at that size the
+step is launch-bound, not bandwidth-bound.  Every op of the package is a plain stream-ordered launch through the C ABI
+with no host synchronisation, so a whole step (sampling, embedding, memory update, link scores) can be captured once
+into a CUDA graph and replayed with new inputs copied into the captured buffers.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+class GraphedStep:
+    """``fn(*tensors) -> tensor`` captured for one input signature; ``__call__`` copies the inputs into the captured
+    buffers (device-to-device, or host-to-device from pinned memory) and replays the graph.
+
+    ``fn`` must be free of host synchronisation and of data-dependent shapes; state it mutates in place (the TGN memory
+    bank) is mutated by every replay exactly as by a direct call.  ``warmup`` direct calls are made before capture so
+    that lazily built caches exist; ``after_warmup`` (e.g. a memory reset) runs after them, before capture."""
+
+    def __init__(self, fn, example_inputs, warmup: int = 2, after_warmup=None):
+        self.fn = fn
+        self.static_in = [x.clone() for x in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if after_warmup is not None:
+            after_warmup()
+            torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+        self.launches = ops.launch_count - n0     # kernels of the package inside one replay
+        # capture records, it does not run: the state is still what after_warmup left
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        ops.launch_count += self.launches
+        return self.static_out
