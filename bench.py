@@ -402,6 +402,7 @@ def run_ours(args):
         return sum(a.elapsed_time(b) for a, b in evs), out
 
     step_fn = wl.step
+    graphed = None
     if wl.use_graph and not args.no_graph:
         from dyglib_b200.utils.graph import GraphedStep
         graphed = GraphedStep(wl.step, dev_steps[0], warmup=2, after_warmup=reset)
@@ -424,7 +425,7 @@ def run_ours(args):
         base = (W + K) if wl.sequential else 0
 
         def e2e_step(i):
-            sc = step_fn(*pinned[i]) if step_fn is not wl.step else wl.step(*[a.to(dev, non_blocking=True) for a in pinned[i]])
+            sc = graphed(*pinned[i]) if graphed is not None else wl.step(*[a.to(dev, non_blocking=True) for a in pinned[i]])
             out_host.copy_(sc, non_blocking=True)
             return sc
         for i in range(base, base + W):
@@ -487,7 +488,7 @@ def run_ours(args):
                    'sharding': ('replicas only (memory dependency chain)' if wl.sequential else
                                 'whole reference batches round-robin over ranks; CSR + feature tables replicated'),
                    'l2': 'flushed between timed steps (256 MiB write)', 'csr_build_s': round(wl.build_s, 4),
-                   'launch': 'CUDA graph replay of the captured step' if step_fn is not wl.step else 'direct launches'},
+                   'launch': 'CUDA graph replay of the captured step' if graphed is not None else 'direct launches'},
         'roofline': roofline,
         'e2e': {'value': events_total / (e2e_ms * 1e-3), 'unit': 'events/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': launches, 'clocks': clk,

@@ -39,19 +39,26 @@ static inline int dyg_num_sms() {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// cos of an fp32 argument of any magnitude, without the local-memory Payne-Hanek slow path of cosf():
-// two-term Cody-Waite reduction by 2*pi in float64 (exact to ~1e-15 rad for |x| < 2^40), then the
-// fast path of cosf on |r| <= pi.  The fp32 rounding of the *argument* is part of the reference's
-// semantics; only the evaluation of cos differs from libm, by < 3e-7 absolute.
+// cos of an fp32 argument of any magnitude (time deltas reach 1e8 rad), without the local-memory Payne-Hanek slow path
+// of cosf(): the quadrant count and a two-term Cody-Waite reduction by pi/2 run in float64 (exact to ~1e-16 rad for
+// |x| < 2^31), then one degree-3 minimax polynomial in r^2 (the cephes sinf / cosf kernels on |r| <= pi/4, coefficients
+// selected by the quadrant's parity).  7 FP64 + ~14 FP32 instructions, branch-free; |error| < 1.2e-7 against the
+// float64 cosine of the same fp32 argument.  The fp32 rounding of the *argument* is part of the reference's semantics
+// (SURVEY.md 7.3(3)); only the evaluation of cos differs from libm.
 __device__ __forceinline__ float dyg_cosf(float x) {
-    const double two_pi_hi = 6.283185307179586232e+00;
-    const double two_pi_lo = 2.449293598294706414e-16;
-    const double inv_two_pi = 1.591549430918953456e-01;
-    double xd = (double)x;
-    double q = rint(xd * inv_two_pi);
-    double r = fma(-q, two_pi_hi, xd);
-    r = fma(-q, two_pi_lo, r);
-    return cosf((float)r);
+    if (fabsf(x) > 2.0e9f) return cosf(x);                       // quadrant count would overflow int32 (never hit by time deltas)
+    const double xd = (double)x;
+    const double q = rint(xd * 0.63661977236758134308);          // 2 / pi
+    double r = fma(-q, 1.57079632679489655800e+00, xd);          // pi / 2, high part
+    r = fma(-q, 6.12323399573676603587e-17, r);                  // pi / 2, low part
+    const float rf = (float)r;                                   // |rf| <= pi / 4
+    const int n = (int)q;
+    const bool odd = n & 1;                                      // odd quadrants evaluate sin(r), even ones cos(r)
+    const float r2 = rf * rf;
+    float p = fmaf(odd ? -1.9515295891e-4f : 2.443315711809948e-5f, r2, odd ? 8.3321608736e-3f : -1.388731625493765e-3f);
+    p = fmaf(p, r2, odd ? -1.6666654611e-1f : 4.166664568298827e-2f);
+    const float res = (odd ? rf : 1.0f) + fmaf(odd ? rf * r2 : r2 * r2, p, odd ? 0.f : -0.5f * r2);
+    return ((n + 1) & 2) ? -res : res;                           // cos(r + n pi/2): +cos, -sin, -cos, +sin
 }
 
 // TimeEncoder element (models/modules.py:37): nn.Linear(1,T) on CPU is a single fp32 FMA, then cos.
