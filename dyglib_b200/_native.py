@@ -104,7 +104,7 @@ SIGNATURES = {
     'dyg_linear_tc_tile': [c_i],
     'dyg_linear_tc': [ctypes.POINTER(Seg), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
     'dyg_gemm_bf16x3': [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_p],
-    'dyg_ln_ffn_bf16x3': [c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_p],
+    'dyg_ln_ffn_bf16x3': [c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_p, c_l, c_p],
     'dyg_split_bf16': [c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p],
     'dyg_layernorm_split': [c_p, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_p],
     'dyg_patch_project_stages': [c_i, c_i, c_i, c_i, c_i, c_p],
@@ -145,6 +145,8 @@ def load():
         lib.dyg_last_error.argtypes = []
         lib.dyg_abi_version.restype = c_i
         lib.dyg_abi_version.argtypes = []
+        lib.dyg_ln_ffn_workspace_bytes.restype = c_l
+        lib.dyg_ln_ffn_workspace_bytes.argtypes = []
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = c_i

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 20);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -472,6 +472,7 @@ struct FfnArgs {
     int Dff;               // hidden width, multiple of 32
     int NT2;               // MMA N of GEMM2 (D rounded up to 16)
     float eps;
+    unsigned char* scratch;   // gridDim.x images of the A operand (F_KB1 * 16 KB each), L2 resident
 };
 
 __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __grid_constant__ CUtensorMap map_w1h,
@@ -500,18 +501,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
     uint64_t* a_free = bars + 23;          //     both:   last GEMM1 of the tile retired
     uint64_t* acc2_full = bars + 24;       //     both
     uint64_t* acc2_empty = bars + 25;      //     leader: final epilogue (EPI warps of both CTAs) drained acc2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    uint64_t* a_copy = bars + 26;          //     local:  bulk copy of the normalised tile into A landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int nmacro = (f.Dff + F_MC - 1) / F_MC;
     const int nkb1 = (f.D + G_BK - 1) / G_BK;
 
-    // zero the A region once: the K padding columns (D .. 32*nkb1) are never written again
-    for (int i = tid; i < F_KB1 * a_stage / 16; i += F_THREADS) reinterpret_cast<uint4*>(a_res)[i] = make_uint4(0, 0, 0, 0);
+    // zero this CTA's image of the A operand once: the K padding columns (D .. 32*nkb1) are never written again
+    unsigned char* a_img = f.scratch + (size_t)blockIdx.x * (F_KB1 * a_stage);
+    for (int i = tid; i < F_KB1 * a_stage / 16; i += F_THREADS) reinterpret_cast<uint4*>(a_img)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) {
             mbar_init(w1_full + s, 1); mbar_init(w1_empty + s, 1);
@@ -522,7 +525,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
             mbar_init(acc1_full + s, 1);
             mbar_init(acc1_empty + s, 2 * F_EPI_WARPS);
         }
-        mbar_init(a_full, 2 * F_LN_WARPS);
+        mbar_init(a_full, 2);                                   // one arrival per CTA, after its bulk copy landed
+        mbar_init(a_copy, 1);
         mbar_init(a_free, 1);
         mbar_init(acc2_full, 1);
         mbar_init(acc2_empty, 2 * F_EPI_WARPS);
@@ -706,95 +710,84 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
         }
     } else {
         // ------------------------------------------------------------------ LN warps: LayerNorm -> resident A operand
+        // The normalised rows of the NEXT tile are produced while the current tile computes: each warp normalises its 32
+        // rows (statistics and values from one read of x) and stores them as BF16x3 planes into this CTA's image of the
+        // A operand in global memory (L2 resident, already in the SWIZZLE_64B shared-memory layout).  When the MMA warp
+        // releases A, ONE bulk copy moves the 112 KB image into shared memory at engine speed; only that copy is exposed.
         const int quarter = warp & 3;
         const int r0 = quarter * 32;                                        // this warp's 32 rows of the CTA's 128
-        constexpr int RB = 8;                                               // statistics: rows per batch (32 float2 loads in flight per lane)
-        constexpr int WB = 4;                                               // write pass: rows per batch, two batches in flight
+        constexpr int RB = 8;                                               // rows per batch (16 float4 loads in flight per lane)
+        // lane l owns columns [8l, 8l+8) of a row: two 16-byte loads, and one 16-byte bf16 chunk per plane on the way out
+        const int c0 = 8 * lane;
+        const bool own = c0 < f.D;                                          // D % 8 == 0
+        const int kb = lane >> 2;
+        const uint32_t chunk = (uint32_t)(lane & 3);
+        float gm8[8], bt8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            gm8[j] = own ? __ldg(f.gamma + c0 + j) : 0.f;
+            bt8[j] = own ? __ldg(f.beta + c0 + j) : 0.f;
+        }
         int it = 0;
-        auto load_rows = [&](float2 (&v)[WB][4], int64_t mrow0) {
-#pragma unroll
-            for (int i = 0; i < WB; ++i) {
-                const int64_t m = mrow0 + i;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int c = 2 * lane + 64 * j;
-                    v[i][j] = (m < f.M && c < f.D) ? *reinterpret_cast<const float2*>(f.x + m * f.ldx + c) : make_float2(0.f, 0.f);
-                }
-            }
-        };
         for (int64_t ms = pair; ms < f.m_super; ms += npairs, ++it) {
             const int64_t m0 = ms * 2 * G_BM + (int64_t)rank * G_BM;
-            // pass 1: row statistics (lane i keeps mean / rstd of row r0 + i) while the previous tile computes; the rows
-            // also land in L2 for pass 2
-            float my_mean = 0.f, my_rstd = 0.f;
             for (int i0 = 0; i0 < 32; i0 += RB) {
-                float2 v[RB][4];
+                float4 v[RB][2];
 #pragma unroll
                 for (int i = 0; i < RB; ++i) {
                     const int64_t m = m0 + r0 + i0 + i;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = 2 * lane + 64 * j;
-                        v[i][j] = (m < f.M && c < f.D) ? *reinterpret_cast<const float2*>(f.x + m * f.ldx + c) : make_float2(0.f, 0.f);
+                    if (own && m < f.M) {
+                        const float4* xp = reinterpret_cast<const float4*>(f.x + m * f.ldx + c0);
+                        v[i][0] = xp[0];
+                        v[i][1] = xp[1];
+                    } else {
+                        v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i][1] = v[i][0];
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < RB; ++i) {
+                    const float xs[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
                     float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) sum += v[i][j].x + v[i][j].y;
+                    for (int j = 0; j < 8; ++j) sum += xs[j];
                     const float mean = warp_sum(sum) / (float)f.D;
                     float sq = 0.f;
+                    if (own) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (2 * lane + 64 * j < f.D) {
-                            const float dx = v[i][j].x - mean, dy = v[i][j].y - mean;
-                            sq += dx * dx + dy * dy;
+                        for (int j = 0; j < 8; ++j) {
+                            const float d = xs[j] - mean;
+                            sq += d * d;
                         }
                     }
                     const float rstd = rsqrtf(warp_sum(sq) / (float)f.D + f.eps);
-                    if (lane == i0 + i) { my_mean = mean; my_rstd = rstd; }
-                }
-            }
-            // pass 2: the first rows are re-read (L2) before A is released, later batches are loaded one batch ahead of the
-            // batch being normalised and written, so only one load latency is exposed after the release
-            float2 va[WB][4], vb[WB][4];
-            load_rows(va, m0 + r0);
-            mbar_wait(a_free, (uint32_t)((it & 1) ^ 1));                     // last GEMM1 of the previous tile retired
-            auto write_rows = [&](float2 (&v)[WB][4], int i0) {
+                    if (own) {
+                        uint32_t h[4], l[4];
 #pragma unroll
-                for (int i = 0; i < WB; ++i) {
-                    const int r = r0 + i0 + i;
-                    const float mean = __shfl_sync(0xffffffffu, my_mean, i0 + i), rstd = __shfl_sync(0xffffffffu, my_rstd, i0 + i);
-                    const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
-                    const uint32_t swz = (uint32_t)((r >> 1) & 3);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = 2 * lane + 64 * j;
-                        if (c < f.D) {
-                            const float2 gmm = __ldg(reinterpret_cast<const float2*>(f.gamma + c));
-                            const float2 bt = __ldg(reinterpret_cast<const float2*>(f.beta + c));
-                            const float y0 = (v[i][j].x - mean) * rstd * gmm.x + bt.x, y1 = (v[i][j].y - mean) * rstd * gmm.y + bt.y;
-                            uint32_t h, l;
-                            split_pack(y0, y1, h, l);
-                            const int kb = c >> 5, cc = c & 31;
-                            unsigned char* p = a_res + kb * a_stage + row_off + ((((uint32_t)cc >> 3) ^ swz) << 4) + (cc & 7) * 2;
-                            *reinterpret_cast<uint32_t*>(p) = h;
-                            *reinterpret_cast<uint32_t*>(p + G_A_PLANE) = l;
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            split_pack((xs[2 * j] - mean) * rstd * gm8[2 * j] + bt8[2 * j],
+                                       (xs[2 * j + 1] - mean) * rstd * gm8[2 * j + 1] + bt8[2 * j + 1], h[j], l[j]);
+                        const int r = r0 + i0 + i;
+                        unsigned char* p = a_img + kb * a_stage + (uint32_t)((r >> 3) * 512 + (r & 7) * 64) + ((chunk ^ (uint32_t)((r >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(p + G_A_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
                     }
                 }
-            };
-#pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += 2 * WB) {
-                load_rows(vb, m0 + r0 + i0 + WB);
-                write_rows(va, i0);
-                if (i0 + 2 * WB < 32) load_rows(va, m0 + r0 + i0 + 2 * WB);
-                write_rows(vb, i0 + WB);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(a_full);
+            asm volatile("fence.proxy.async;" ::: "memory");               // generic global writes -> visible to the bulk copy engine
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * F_LN_WARPS) : "memory");   // all four LN warps finished the image
+            if (warp == 2 + F_EPI_WARPS) {
+                mbar_wait(a_free, (uint32_t)((it & 1) ^ 1));                 // last GEMM1 of the previous tile retired
+                if (lane == 0) {
+                    mbar_expect_tx(a_copy, (uint32_t)(F_KB1 * a_stage));
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(a_res)),
+                                 "l"(a_img), "r"((uint32_t)(F_KB1 * a_stage)), "r"(smem_u32(a_copy))
+                                 : "memory");
+                }
+                mbar_wait(a_copy, (uint32_t)(it & 1));
+                if (lane == 0) mbar_arrive_leader(a_full);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * F_LN_WARPS) : "memory");   // the image may be overwritten for the next tile
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1060,16 +1053,21 @@ extern "C" int dyg_layernorm_split(const float* x, int ldx, const float* gamma, 
     return 0;
 }
 
+extern "C" int64_t dyg_ln_ffn_workspace_bytes(void) { return (int64_t)dyg_num_sms() * F_KB1 * 2 * G_A_PLANE; }
+
 extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W1_hi,
                                  const void* W1_mid, int ldw1, const float* b1, const void* W2_hi, const void* W2_mid, int ldw2,
-                                 const float* b2, float* out, int ldo, int64_t M, int D, int Dff, dyg_stream_t stream) {
+                                 const float* b2, float* out, int ldo, int64_t M, int D, int Dff, void* workspace,
+                                 int64_t workspace_bytes, dyg_stream_t stream) {
     DYG_CHECK_ARG(M >= 0 && D > 0 && Dff > 0, "dyg_ln_ffn_bf16x3: bad sizes");
-    DYG_CHECK_ARG(D <= 208 && (D % 2) == 0, "dyg_ln_ffn_bf16x3: model width %d unsupported (even, <= 208)", D);
+    DYG_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= dyg_ln_ffn_workspace_bytes(),
+                  "dyg_ln_ffn_bf16x3: workspace of %lld bytes (16-byte aligned) required", (long long)dyg_ln_ffn_workspace_bytes());
+    DYG_CHECK_ARG(D <= 208 && (D % 8) == 0, "dyg_ln_ffn_bf16x3: model width %d unsupported (multiple of 8, <= 208)", D);
     DYG_CHECK_ARG((Dff % F_SUB) == 0, "dyg_ln_ffn_bf16x3: hidden width %d must be a multiple of %d", Dff, F_SUB);
     DYG_CHECK_ARG(x && gamma && beta && W1_hi && W1_mid && b1 && W2_hi && W2_mid && b2 && out, "dyg_ln_ffn_bf16x3: NULL pointer");
-    DYG_CHECK_ARG((ldx % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7u) == 0 &&
+    DYG_CHECK_ARG((ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7u) == 0 &&
                       (reinterpret_cast<uintptr_t>(beta) & 7u) == 0 && (reinterpret_cast<uintptr_t>(b1) & 7u) == 0,
-                  "dyg_ln_ffn_bf16x3: fp32 inputs must be 8-byte aligned with even leading dimensions");
+                  "dyg_ln_ffn_bf16x3: x must be 16-byte aligned with ldx %% 4 == 0, the parameter vectors 8-byte aligned");
     DYG_CHECK_ARG((ldw1 % 8) == 0 && ldw1 >= D && (ldw2 % 8) == 0 && ldw2 >= Dff && aligned16(W1_hi) && aligned16(W1_mid) &&
                       aligned16(W2_hi) && aligned16(W2_mid),
                   "dyg_ln_ffn_bf16x3: weight planes must be 16-byte aligned with leading dimensions that are multiples of 8");
@@ -1080,6 +1078,7 @@ extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, co
     f.x = x; f.gamma = gamma; f.beta = beta; f.b1 = b1; f.b2 = b2; f.out = out;
     f.M = M; f.m_super = (M + 2 * G_BM - 1) / (2 * G_BM);
     f.ldx = ldx; f.ldo = ldo; f.D = D; f.Dff = Dff; f.NT2 = (D + 15) / 16 * 16; f.eps = eps;
+    f.scratch = reinterpret_cast<unsigned char*>(workspace);
     CUtensorMap m1h, m1m, m2h, m2m;
     if (!dyg_tensor_map_bf16(W1_hi, (uint64_t)Dff, (uint64_t)D, (uint64_t)ldw1, F_MC / 2, &m1h)) return 1;
     if (!dyg_tensor_map_bf16(W1_mid, (uint64_t)Dff, (uint64_t)D, (uint64_t)ldw1, F_MC / 2, &m1m)) return 1;

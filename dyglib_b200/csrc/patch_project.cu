@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
     StageInfo* stage_tab = reinterpret_cast<StageInfo*>(bars + 2 * PP_STAGES + 2);   // [nst]
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
     const int sd = (int64_t)blockIdx.x >= a.tiles0 ? 1 : 0;
     const dyg_proj_side_t& side = a.side[sd];
     const int64_t m0 = ((int64_t)blockIdx.x - (sd ? a.tiles0 : 0)) * PP_BM;

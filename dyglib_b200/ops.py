@@ -353,8 +353,19 @@ def patch_project(sides, node_planes, F_node, edge_planes, F_edge, lut_planes, F
     return X
 
 
+_ffn_ws = {}
+
+
+def _ffn_workspace(device):
+    """Per-device scratch of dyg_ln_ffn_bf16x3 (one A-operand image per CTA, stays in L2)."""
+    key = str(device)
+    if key not in _ffn_ws:
+        _ffn_ws[key] = torch.empty(int(_lib().dyg_ln_ffn_workspace_bytes()), dtype=torch.uint8, device=device)
+    return _ffn_ws[key]
+
+
 def ffn_fusable(D, Dff):
-    return D % 2 == 0 and D <= 208 and Dff % 32 == 0
+    return D % 8 == 0 and D <= 208 and Dff % 32 == 0
 
 
 def ln_ffn(x, gamma, beta, eps, w1, b1, w2, b2, out=None):
@@ -364,10 +375,11 @@ def ln_ffn(x, gamma, beta, eps, w1, b1, w2, b2, out=None):
     if out is None:
         out = torch.empty_like(x)
     w1s, w2s = split_weight(w1), split_weight(w2)
+    ws = _ffn_workspace(x.device)
     with _Timed('ln_ffn_bf16x3_kernel', 4.0 * M * D * Dff, 8.0 * M * D):
         _native.check(_lib().dyg_ln_ffn_bf16x3(_p(x), int(x.stride(0)), _p(gamma), _p(beta), float(eps), _p(w1s.hi), _p(w1s.mid),
                                                int(w1s.ld), _p(b1), _p(w2s.hi), _p(w2s.mid), int(w2s.ld), _p(b2), _p(out), int(out.stride(0)),
-                                               int(M), int(D), int(Dff), _stream()))
+                                               int(M), int(D), int(Dff), _p(ws), int(ws.numel()), _stream()))
     _count()
     return out
 

@@ -160,11 +160,14 @@ int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, const void* W_
 /* Feed-forward half of the transformer block fused into one kernel (models/DyGFormer.py:456-461):
  *   out = x + W2 gelu(W1 LayerNorm(x) + b1) + b2   (LayerNorm with gamma / beta / eps, exact-erf GELU).
  * x, out: (M, ld) fp32.  W1_hi | W1_mid: (Dff, ldw1) operand planes of linear_layers.0.weight (Dff x D);
- * W2_hi | W2_mid: (D, ldw2) operand planes of linear_layers.1.weight (D x Dff).  D even, <= 208; Dff a multiple of 32.
- * The normalised rows and the hidden activation stay in shared / tensor memory. */
+ * W2_hi | W2_mid: (D, ldw2) operand planes of linear_layers.1.weight (D x Dff).  D a multiple of 8, <= 208; Dff a multiple of 32.
+ * The hidden activation stays in shared / tensor memory; the normalised rows pass through `workspace`
+ * (dyg_ln_ffn_workspace_bytes() bytes, 16-byte aligned, L2 resident: one shared-memory image of the A operand per CTA). */
+int64_t dyg_ln_ffn_workspace_bytes(void);
 int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W1_hi,
                       const void* W1_mid, int ldw1, const float* b1, const void* W2_hi, const void* W2_mid, int ldw2,
-                      const float* b2, float* out, int ldo, int64_t M, int D, int Dff, dyg_stream_t stream);
+                      const float* b2, float* out, int ldo, int64_t M, int D, int Dff, void* workspace,
+                      int64_t workspace_bytes, dyg_stream_t stream);
 /* hi | mid planes (M,ld) of a fp32 matrix x (M,ldx), D columns. */
 int dyg_split_bf16(const float* x, int ldx, int64_t M, int D, void* hi, void* mid, int ld, dyg_stream_t stream);
 /* LayerNorm(x) * gamma + beta over D (even) columns written as hi | mid planes (and as fp32 y when y != NULL)

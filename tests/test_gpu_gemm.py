@@ -158,7 +158,7 @@ def test_patch_project_vs_float64(P, B, ns, nd):
     assert rel_err(got[..., 2 * C:3 * C], want[..., 2 * C:3 * C]) < 5e-3
 
 
-@pytest.mark.parametrize('M,D,Dff', [(256, 200, 800), (1, 200, 800), (300, 200, 800), (5000, 200, 800), (777, 64, 32), (1000, 208, 256),
+@pytest.mark.parametrize('M,D,Dff', [(256, 200, 800), (1, 200, 800), (300, 200, 800), (5000, 200, 800), (777, 64, 32), (1000, 208, 256), (333, 8, 96),
                                      (148 * 256 + 77, 200, 800)])
 def test_ln_ffn_fused(M, D, Dff):
     g = torch.Generator(device='cuda').manual_seed(M + D + Dff)
