@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
 //     GEMM1    acc1[mc&1] (TMEM, 128 cols) = LN(x) W1[mc]^T     (M=256, N=128, K=200: 13 k16 steps x 3 MMAs; W1 streamed
 //              per 32-wide k block through a 3-stage TMA ring)
 //     per 32-column sub chunk:
-//       EPI1   8 warps: tcgen05.ld -> + b1 -> GELU -> bf16 hi|mid -> h[.] in shared memory as the next A operand (3 buffers)
+//       EPI1   8 warps (the two warps of a TMEM lane quarter take sub chunks round-robin): tcgen05.ld -> + b1 -> GELU ->
+//              bf16 hi|mid -> h[.] in shared memory as the next A operand (3 buffers)
 //       GEMM2  acc2 (TMEM, 208 cols) += h[.] W2[:, sub]^T        (M=256, N=208, K=32: 2 x 3 MMAs; W2 through a 3-stage ring)
 //   GEMM1 of macro chunk mc+1 is issued before the GEMM2s of mc, so the tensor pipe works while the GELU of mc runs.
 // MMAs are sized so that each one is worth its issue cost (a first version with N=32 GEMM1s was bound by the issuing
@@ -454,7 +455,7 @@ constexpr int F_KB1 = 7;                  // k blocks of GEMM1 (K <= 224)
 constexpr int F_W1_PLANE = (F_MC / 2) * 64;
 constexpr int F_W1_STAGE = 2 * F_W1_PLANE;   // one k block of this CTA's half of a macro chunk, hi | mid
 constexpr int F_S1 = 3, F_S2 = 3, F_HB = 3;
-constexpr int F_EPI_WARPS = 8, F_LN_WARPS = 4;
+constexpr int F_EPI_WARPS = 8, F_LN_WARPS = 4;    // EPI warps per TMEM lane quarter: F_EPI_WARPS / 4, taking sub chunks round-robin
 constexpr int F_THREADS = 64 + 32 * (F_EPI_WARPS + F_LN_WARPS);
 constexpr int F_ACC1_COL = 256;           // acc2 at TMEM columns [0, 208), acc1 buffers at 256 and 384
 
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
         for (int s = 0; s < 3; ++s) {
             mbar_init(w1_full + s, 1); mbar_init(w1_empty + s, 1);
             mbar_init(w2_full + s, 1); mbar_init(w2_empty + s, 1);
-            mbar_init(h_full + s, 2 * F_EPI_WARPS); mbar_init(h_empty + s, 1);
+            mbar_init(h_full + s, 8); mbar_init(h_empty + s, 1);                 // one EPI warp per lane quarter and CTA writes a sub chunk
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(acc1_full + s, 1);
@@ -657,10 +658,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
         // ------------------------------------------------------------------ EPI1: bias + GELU + split of every hidden sub chunk
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                                  // TMEM lane == tile row
-        const int halfc = (warp - 2) >> 2;                                  // which 16 of the sub chunk's 32 columns
+        const int halfc = (warp - 2) >> 2;                                  // this warp's turn among the EPI warps of its lane quarter
         const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
         const uint32_t swz = (uint32_t)((r >> 1) & 3);
-        const uint32_t c16 = (uint32_t)halfc * 2u;
         int64_t gm = 0, gs = 0;
         int it = 0;
         GemmArgs eg;
@@ -673,13 +673,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                 mbar_wait(acc1_full + pb, (uint32_t)((gm >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int sub = 0; sub < nsub; ++sub, ++gs) {
+                    // the two warps of a TMEM lane quarter alternate over the sub chunks, each one converting all 32 columns
+                    // of its 32 rows: half as many barrier waits, proxy fences and arrivals per converted element
+                    if ((int)(gs % (F_EPI_WARPS / 4)) != halfc) continue;
                     const int hb = (int)(gs % F_HB);
-                    uint32_t rr[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(F_ACC1_COL + F_MC * pb + sub * F_SUB + 16 * halfc), rr);
-                    const float* bp = f.b1 + mc * F_MC + sub * F_SUB + 16 * halfc;
-                    uint32_t hi[8], mid[8];
+                    uint32_t rr[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(F_ACC1_COL + F_MC * pb + sub * F_SUB), rr);
+                    const float* bp = f.b1 + mc * F_MC + sub * F_SUB;
+                    uint32_t hi[16], mid[16];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 16; ++j) {
                         const float2 b2v = __ldg(reinterpret_cast<const float2*>(bp + 2 * j));
                         const float v0 = act_apply(__uint_as_float(rr[2 * j]) + b2v.x, DYG_ACT_GELU);
                         const float v1 = act_apply(__uint_as_float(rr[2 * j + 1]) + b2v.y, DYG_ACT_GELU);
@@ -687,10 +690,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                     }
                     mbar_wait(h_empty + hb, (uint32_t)(((gs / F_HB) & 1) ^ 1));       // GEMM2 of sub chunk gs-3 no longer reads h[hb]
                     unsigned char* rowp = h_buf + hb * a_stage + row_off;
-                    *reinterpret_cast<uint4*>(rowp + ((c16 ^ swz) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(rowp + (((c16 + 1) ^ swz) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    *reinterpret_cast<uint4*>(rowp + G_A_PLANE + ((c16 ^ swz) << 4)) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-                    *reinterpret_cast<uint4*>(rowp + G_A_PLANE + (((c16 + 1) ^ swz) << 4)) = make_uint4(mid[4], mid[5], mid[6], mid[7]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        *reinterpret_cast<uint4*>(rowp + (((uint32_t)c ^ swz) << 4)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(rowp + G_A_PLANE + (((uint32_t)c ^ swz) << 4)) =
+                            make_uint4(mid[4 * c], mid[4 * c + 1], mid[4 * c + 2], mid[4 * c + 3]);
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(h_full + hb);
@@ -703,7 +708,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
             // busy writing the next A operand
             mbar_wait(acc2_full, (uint32_t)(it & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile(eg, tmem_base + ((uint32_t)(quarter * 32) << 16), ms * 2 * G_BM + (int64_t)rank * G_BM + r, 0, f.D, halfc, 2);
+            epilogue_tile(eg, tmem_base + ((uint32_t)(quarter * 32) << 16), ms * 2 * G_BM + (int64_t)rank * G_BM + r, 0, f.D, halfc, F_EPI_WARPS / 4);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(acc2_empty);
