@@ -18,7 +18,6 @@
 //   warp 9     TMEM allocation + single-thread tcgen05.mma issue (M=128, N=64, K=16, BF16x3 = three MMAs per k step)
 // Two CTAs per SM (96 KB of shared memory, 256 TMEM columns each): one CTA's epilogue overlaps the other's gathers.
 #include <math.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -52,7 +51,6 @@ struct ProjArgs {
     float* X;
     int ldx;
     int64_t tiles0;                   // tiles of side 0 (side 1 tiles follow)
-    int dbg;
     int zero_rows;                    // bit u: row 0 of table u is all zero (padding id): skip its gather
 };
 
@@ -152,27 +150,36 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
         int64_t idx = 0;        // gathered row of the current unit
         float dt = 0.f;         // time stages: delta of the current unit
         bool masked = true;
+        int64_t nidx = 0;       // the same three, prefetched for the next unit
+        float ndt = 0.f;
+        bool nmasked = true;
+        auto load_unit = [&](const StageInfo& u) {
+            const int64_t q = m * a.P + u.p;
+            nidx = 0;
+            nmasked = true;
+            if (valid) {
+                if (u.ty == 0) nidx = __ldg(side.ids + q);
+                else if (u.ty == 1) nidx = __ldg(side.eids + q);
+                else if (u.ty == 2) {
+                    nmasked = __ldg(side.ids + q) == 0;
+                    ndt = (float)(tq - (double)__ldg(side.t_nbr + q));
+                } else if (u.ty == 3) nidx = __ldg(side.cnt_a + q);
+                else nidx = __ldg(side.cnt_b + q);
+            }
+        };
+        load_unit(stage_tab[0]);
         for (int s = 0; s < nst; ++s) {
             const int slot = s % PP_STAGES;
             const uint32_t ph = (uint32_t)((s / PP_STAGES) & 1);
             const StageInfo si = stage_tab[s];
             if (si.blk == 0) {
-                const int64_t q = m * a.P + si.p;
-                if (!valid) {
-                    idx = 0;
-                    masked = true;
-                } else if (si.ty == 0) {
-                    idx = __ldg(side.ids + q);
-                } else if (si.ty == 1) {
-                    idx = __ldg(side.eids + q);
-                } else if (si.ty == 2) {
-                    masked = __ldg(side.ids + q) == 0;
-                    dt = (float)(tq - (double)__ldg(side.t_nbr + q));
-                } else if (si.ty == 3) {
-                    idx = __ldg(side.cnt_a + q);
-                } else {
-                    idx = __ldg(side.cnt_b + q);
-                }
+                // the index (and time) of this unit were requested one unit ago; request the next unit's now, so the
+                // dependent load -> address -> cp.async chain never waits for memory
+                idx = nidx;
+                masked = nmasked;
+                dt = ndt;
+                const int s2 = s + a.nblk[si.ty];                   // first stage of the next unit
+                if (s2 < nst) load_unit(stage_tab[s2]);
             }
             mbar_wait(empty_bar + slot, ph ^ 1u);
             unsigned char* st = base + slot * PP_STAGE_BYTES;
@@ -189,15 +196,9 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        if (c < nchunk && !(a.dbg & 4)) cp_async16(dst + (((uint32_t)c ^ swz) << 4), src + c * 8);
+                        if (c < nchunk) cp_async16(dst + (((uint32_t)c ^ swz) << 4), src + c * 8);
                 }
-                if (a.dbg & 2) {
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_cta(full_bar + slot);
-                } else {
-                    cp_async_arrive_noinc(full_bar + slot);
-                }
+                cp_async_arrive_noinc(full_bar + slot);
             } else {
                 if (half < si.nk16) {
                     const int c0 = si.blk * 32 + half * 16;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
                     for (int j = 0; j < 8; ++j) {
                         const int c = c0 + 2 * j;
                         float v0 = 0.f, v1 = 0.f;
-                        if (!masked && !(a.dbg & 1)) {
+                        if (!masked) {
                             if (c < a.T) v0 = dyg_time_enc(dt, __ldg(a.tw + c), __ldg(a.tb + c));
                             if (c + 1 < a.T) v1 = dyg_time_enc(dt, __ldg(a.tw + c + 1), __ldg(a.tb + c + 1));
                         }
@@ -369,7 +370,6 @@ extern "C" int dyg_patch_project(const dyg_proj_side_t* sides_host, int nsides, 
     a.t_query = t_query; a.tw = tw; a.tb = tb; a.T = T; a.P = P; a.C = C; a.S = S;
     a.bias = bias; a.X = X; a.ldx = ldx;
     a.zero_rows = zero_rows & 3;
-    { const char* e = getenv("DYG_PP_DBG"); a.dbg = e ? atoi(e) : 0; }
     CUtensorMap mwh, mwm;
     if (!dyg_tensor_map_bf16(W_hi, PP_NT, (uint64_t)nst * 32, (uint64_t)ldw, PP_NT, &mwh)) return 1;
     if (!dyg_tensor_map_bf16(W_mid, PP_NT, (uint64_t)nst * 32, (uint64_t)ldw, PP_NT, &mwm)) return 1;
