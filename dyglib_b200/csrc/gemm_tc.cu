@@ -663,6 +663,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
         const uint32_t swz = (uint32_t)((r >> 1) & 3);
         int64_t gm = 0, gs = 0;
         int it = 0;
+        // 256-bit row accesses need 32-byte aligned rows (D % 8 == 0 holds): otherwise the generic tile epilogue is used
+        const bool fast_out = ((f.ldx & 7) == 0) && ((f.ldo & 7) == 0) && (((reinterpret_cast<uintptr_t>(f.x) | reinterpret_cast<uintptr_t>(f.out)) & 31u) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(f.b2) & 3u) == 0);
         GemmArgs eg;
         eg.bias = f.b2; eg.residual = f.x; eg.C = f.out; eg.Chi = nullptr; eg.Cmid = nullptr;
         eg.M = f.M; eg.ldr = f.ldx; eg.ldc = f.ldo; eg.ldcs = 0; eg.N = f.D; eg.K = 0; eg.act = DYG_ACT_NONE;
@@ -706,9 +709,63 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
             }
             // final epilogue of the tile: these warps are idle until the next tile's first GEMM1 retires, the LN warps are
             // busy writing the next A operand
-            mbar_wait(acc2_full, (uint32_t)(it & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile(eg, tmem_base + ((uint32_t)(quarter * 32) << 16), ms * 2 * G_BM + (int64_t)rank * G_BM + r, 0, f.D, halfc, F_EPI_WARPS / 4);
+            {
+                constexpr int STEP = F_EPI_WARPS / 4, PRE = 4;
+                const int64_t m = ms * 2 * G_BM + (int64_t)rank * G_BM + r;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+                if (!fast_out) {
+                    mbar_wait(acc2_full, (uint32_t)(it & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    epilogue_tile(eg, taddr, m, 0, f.D, halfc, STEP);
+                } else {
+                    // the residual rows do not depend on the MMAs: the first PRE chunks of this warp are requested before the
+                    // accumulator is awaited, so their L2 / HBM latency hides behind the last GEMM2s
+                    const bool rowok = m < f.M;
+                    const float* xr = f.x + m * f.ldx;
+                    float res[PRE][16];
+#pragma unroll
+                    for (int k = 0; k < PRE; ++k) {
+                        const int col = 16 * (halfc + k * STEP);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) res[k][j] = 0.f;
+                        if (rowok && col < f.D) {
+                            ld_v8(xr + col, res[k]);
+                            if (col + 8 < f.D) ld_v8(xr + col + 8, res[k] + 8);
+                        }
+                    }
+                    mbar_wait(acc2_full, (uint32_t)(it & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    auto emit = [&](int col, const float (&rv)[16]) {
+                        uint32_t rr[16];
+                        tmem_ld16(taddr + (uint32_t)col, rr);
+                        if (rowok) {
+                            uint32_t o[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                o[j] = __float_as_uint(__uint_as_float(rr[j]) + rv[j] + ((col + j < f.D) ? __ldg(f.b2 + col + j) : 0.f));
+                            float* dst = f.out + m * f.ldo + col;
+                            st_v8(dst, o);
+                            if (col + 8 < f.D) st_v8(dst + 8, o + 8);
+                        }
+                        __syncwarp();
+                    };
+#pragma unroll
+                    for (int k = 0; k < PRE; ++k) {
+                        const int col = 16 * (halfc + k * STEP);
+                        if (col < f.D) emit(col, res[k]);                          // warp-uniform
+                    }
+                    for (int col = 16 * (halfc + PRE * STEP); col < f.D; col += 16 * STEP) {
+                        float rv[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) rv[j] = 0.f;
+                        if (rowok) {
+                            ld_v8(xr + col, rv);
+                            if (col + 8 < f.D) ld_v8(xr + col + 8, rv + 8);
+                        }
+                        emit(col, rv);
+                    }
+                }
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(acc2_empty);
