@@ -692,6 +692,7 @@ extern "C" int dyg_seq_attention_tc(const float* qkv, int ld_qkv, int64_t B, int
                                     void* out_hi, void* out_mid, int ldos, dyg_stream_t stream) {
     DYG_CHECK_ARG(B >= 0 && S > 0 && H > 0 && hd > 0, "dyg_seq_attention_tc: bad sizes");
     DYG_CHECK_ARG(S <= 128 && hd <= 128 && (hd % 2) == 0, "dyg_seq_attention_tc: S=%d (max 128), head_dim=%d (even, max 128) unsupported", S, hd);
+    if (B == 0) return 0;
     DYG_CHECK_ARG((ld_qkv % 2) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 7u) == 0, "dyg_seq_attention_tc: qkv must be 8-byte aligned with an even leading dimension");
     DYG_CHECK_ARG(out || (out_hi && out_mid), "dyg_seq_attention_tc: no output given");
     DYG_CHECK_ARG((out_hi == nullptr) == (out_mid == nullptr), "dyg_seq_attention_tc: out_hi and out_mid go together");

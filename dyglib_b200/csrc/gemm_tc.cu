@@ -1016,6 +1016,7 @@ extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, con
     DYG_CHECK_ARG(M >= 0 && N > 0 && K > 0, "dyg_gemm_bf16x3: bad sizes");
     DYG_CHECK_ARG(M < ((int64_t)1 << 31) - G_BM, "dyg_gemm_bf16x3: M too large");
     DYG_CHECK_ARG(act >= DYG_ACT_NONE && act <= DYG_ACT_SIGMOID, "dyg_gemm_bf16x3: unknown activation %d", act);
+    if (M == 0) return 0;
     DYG_CHECK_ARG(A_hi && A_mid && W_hi && W_mid, "dyg_gemm_bf16x3: operand planes must not be NULL");
     DYG_CHECK_ARG(aligned16(A_hi) && aligned16(A_mid) && aligned16(W_hi) && aligned16(W_mid),
                   "dyg_gemm_bf16x3: operand planes must be 16-byte aligned");
@@ -1086,8 +1087,8 @@ extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, con
 
 extern "C" int dyg_split_bf16(const float* x, int ldx, int64_t M, int D, void* hi, void* mid, int ld, dyg_stream_t stream) {
     DYG_CHECK_ARG(M >= 0 && D > 0 && ld >= D && ldx >= D, "dyg_split_bf16: bad sizes");
-    DYG_CHECK_ARG(x && hi && mid, "dyg_split_bf16: NULL pointer");
     if (M == 0) return 0;
+    DYG_CHECK_ARG(x && hi && mid, "dyg_split_bf16: NULL pointer");
     const int64_t n = M * ((D + 1) / 2);
     split_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, M, D, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                              reinterpret_cast<__nv_bfloat16*>(mid), ld);
@@ -1099,6 +1100,7 @@ extern "C" int dyg_layernorm_split(const float* x, int ldx, const float* gamma, 
                                    void* hi, void* mid, int ld, int64_t M, int D, dyg_stream_t stream) {
     DYG_CHECK_ARG(M >= 0 && D > 0 && D <= 1024 && (D % 2) == 0, "dyg_layernorm_split: D=%d unsupported (even, max 1024)", D);
     DYG_CHECK_ARG((ldx % 2) == 0 && (ld % 2) == 0 && (!y || (ldy % 2) == 0), "dyg_layernorm_split: leading dims must be even");
+    if (M == 0) return 0;
     DYG_CHECK_ARG(x && hi && mid && gamma && beta, "dyg_layernorm_split: NULL pointer");
     DYG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 7u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7u) == 0 &&
                       (reinterpret_cast<uintptr_t>(beta) & 7u) == 0 && (!y || (reinterpret_cast<uintptr_t>(y) & 7u) == 0),
@@ -1126,6 +1128,7 @@ extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, co
                   "dyg_ln_ffn_bf16x3: workspace of %lld bytes (16-byte aligned) required", (long long)dyg_ln_ffn_workspace_bytes());
     DYG_CHECK_ARG(D <= 208 && (D % 8) == 0, "dyg_ln_ffn_bf16x3: model width %d unsupported (multiple of 8, <= 208)", D);
     DYG_CHECK_ARG((Dff % F_SUB) == 0, "dyg_ln_ffn_bf16x3: hidden width %d must be a multiple of %d", Dff, F_SUB);
+    if (M == 0) return 0;
     DYG_CHECK_ARG(x && gamma && beta && W1_hi && W1_mid && b1 && W2_hi && W2_mid && b2 && out, "dyg_ln_ffn_bf16x3: NULL pointer");
     DYG_CHECK_ARG((ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 7u) == 0 &&
                       (reinterpret_cast<uintptr_t>(beta) & 7u) == 0 && (reinterpret_cast<uintptr_t>(b1) & 7u) == 0,

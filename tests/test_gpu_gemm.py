@@ -174,3 +174,31 @@ def test_ln_ffn_fused(M, D, Dff):
     y = torch.nn.functional.layer_norm(xd, (D,), gm.double(), bt.double(), 1e-5)
     want = xd + torch.nn.functional.gelu(y @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
     assert rel_err(got, want) < 5e-5, rel_err(got, want)
+
+
+def test_empty_and_tiny_inputs():
+    """M = 0 is a no-op for every tensor-core entry point; single rows work (tiles are padded by TMA zero fill)."""
+    dev = 'cuda'
+    w = torch.randn(200, 200, device=dev)
+    out = ops.gemm(ops.split_bf16(torch.zeros(0, 200, device=dev)), w)
+    assert out.shape == (0, 200)
+    x0 = torch.zeros(0, 200, device=dev)
+    g1, b1 = torch.ones(200, device=dev), torch.zeros(200, device=dev)
+    assert ops.ln_ffn(x0, g1, b1, 1e-5, torch.randn(800, 200, device=dev), torch.zeros(800, device=dev), torch.randn(200, 800, device=dev),
+                      torch.zeros(200, device=dev)).shape == (0, 200)
+    assert ops.layernorm_split(x0, g1, b1).rows == 0
+    sp = ops.seq_attention_tc(torch.zeros(0, 600, device=dev), 0, 64, 2, 100, want='split')
+    assert sp.rows == 0
+    x1 = torch.randn(1, 200, device=dev)
+    got = ops.gemm(ops.split_bf16(x1), w)
+    assert rel_err(got, x1.double() @ w.double().t()) < 3e-5
+
+
+def test_gemm_rejects_bad_arguments():
+    a = ops.split_bf16(torch.randn(4, 200, device='cuda'))
+    with pytest.raises(ValueError):
+        ops.gemm(a, torch.randn(8, 100, device='cuda'))          # K mismatch
+    with pytest.raises(ValueError):
+        ops.ln_ffn(torch.randn(4, 50, device='cuda'), torch.ones(50, device='cuda'), torch.zeros(50, device='cuda'), 1e-5,
+                   torch.randn(64, 50, device='cuda'), torch.zeros(64, device='cuda'), torch.randn(50, 64, device='cuda'),
+                   torch.zeros(50, device='cuda'))                # D % 8 != 0
