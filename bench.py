@@ -56,6 +56,11 @@ class ClockSampler:
                                        '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi's start-up (NVML initialisation) contends with kernel launches for tens of milliseconds: wait for its
+        # first sample before returning, so that only the periodic 100 ms queries overlap the timed region
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 5.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
 
     def stop(self):
         if self.p is None:
@@ -410,10 +415,10 @@ def run_ours(args):
     with torch.no_grad():
         # ---------------- device-resident inputs
         reset()
+        clocks = ClockSampler(torch.cuda.current_device())   # started before the warm-up: see ClockSampler.__init__
         for i in range(W):
             step_fn(*dev_steps[i])
         barrier()
-        clocks = ClockSampler(torch.cuda.current_device())
         launches0 = ops.launch_count
         total_ms, scores = timed(lambda i: step_fn(*dev_steps[i]), W)
         scores = scores.clone()
@@ -594,12 +599,12 @@ def run_sampler_sweep(args):
     res = {}
     K, W = args.steps, max(args.warmup, 3)
     for strat, s in samplers.items():
+        clocks = ClockSampler(torch.cuda.current_device()) if strat == 'recent' else None
         for _ in range(W):
             s.get_historical_neighbors_device(nodes, times, k)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        clocks = ClockSampler(torch.cuda.current_device()) if strat == 'recent' else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(K):

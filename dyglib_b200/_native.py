@@ -90,14 +90,15 @@ SIGNATURES = {
     'dyg_csr_pack': [c_p, c_p, c_p, c_p, c_p, c_l, c_p, c_p],
     'dyg_csr_tia_tables': [c_p, c_p, c_l, c_d, c_p, c_p, c_p],
     'dyg_csr_tia_cum': [c_p, c_p, c_l, c_p, c_p],
-    'dyg_count_before': [c_p, c_p, c_l, c_p, c_p, c_l, c_p, c_p],
-    'dyg_sample_recent': [c_p, c_p, c_l, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p],
+    'dyg_csr_fence_build': [c_p, c_l, c_p, c_p],
+    'dyg_count_before': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_l, c_p, c_p],
+    'dyg_sample_recent': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p, c_p],
     'dyg_sample_indexed': [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p, c_p],
     'dyg_draw_uniform': [c_p, c_p, c_l, c_i, c_p, c_p],
     'dyg_draw_tia': [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p],
     'dyg_philox_uniform': [c_u64, c_u64, c_l, c_p, c_p],
-    'dyg_sample_random': [c_p, c_p, c_l, c_p, c_p, c_p, c_l, c_i, c_u64, c_u64, c_p, c_p, c_p, c_p],
-    'dyg_first_hop_pad': [c_p, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
+    'dyg_sample_random': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_i, c_u64, c_u64, c_p, c_p, c_p, c_p],
+    'dyg_first_hop_pad': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     'dyg_cooc_count': [c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     'dyg_time_encode': [c_p, c_l, c_p, c_p, c_i, c_p, c_p],
     'dyg_linear': [ctypes.POINTER(Seg), c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -146,6 +147,8 @@ def load():
         lib.dyg_abi_version.restype = c_i
         lib.dyg_abi_version.argtypes = []
         lib.dyg_ln_ffn_workspace_bytes.restype = c_l
+        lib.dyg_csr_fence_entries.restype = c_l
+        lib.dyg_csr_fence_entries.argtypes = [c_l]
         lib.dyg_ln_ffn_workspace_bytes.argtypes = []
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)

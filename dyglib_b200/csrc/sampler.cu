@@ -3,6 +3,7 @@
 // then a contiguous tail gather.  No tensor cores here by design.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -94,6 +95,111 @@ __device__ __forceinline__ int64_t lower_bound_time_coop(const dyg_halfedge_t* h
     return lo;
 }
 
+// Fence index over the half-edge array (dyg_csr_fence_build): level l >= 1 holds, for every complete block of 16^l
+// records (aligned globally, not per node), the time of the block's last record: lvl[l][i] = t[(i + 1) * 16^l - 1].
+// Inside one node's run the records are time-sorted, so the fence entries of the complete blocks inside the run are
+// sorted too and the lower bound descends level by level: one 128-byte line of 16 entries per level instead of one
+// 32-byte sector per binary-search probe, and the top levels (1/256 of the records and less) stay in L2.
+#define DYG_FENCE_MAX_LEVELS 8
+struct Fence {
+    const double* lvl[DYG_FENCE_MAX_LEVELS + 1];   // lvl[0] unused
+    int nlev;
+};
+// Index arithmetic runs in uint32 when the half-edge array has fewer than 2^31 records (half the integer instructions).
+// Entries < tq of fence level `f` in [lo, hi), counted by the LANES lanes of a query group (sorted -> a prefix): 16-byte
+// loads of entry pairs, all loads of the unrolled rounds issued before the first compare; the group sum is an xor-shuffle
+// butterfly, so EVERY lane of the warp must call it (groups with nothing to do pass lo == hi).  Pairs may start one entry
+// before lo / end one entry after hi: both stay inside the level's padded allocation and are masked out.
+template <int LANES, typename I>
+__device__ __forceinline__ int count_fence(const double* __restrict__ f, I lo, I hi, double tq, int lane) {
+    constexpr int UNROLL = (32 + 2 * LANES - 1) / (2 * LANES);
+    const I i0 = (lo & ~(I)1) + 2 * (I)lane;
+    double2 v[UNROLL];
+#pragma unroll
+    for (int r = 0; r < UNROLL; ++r) {
+        const I i = i0 + (I)(r * 2 * LANES);
+        v[r] = make_double2(0.0, 0.0);
+        if (i < hi) v[r] = __ldg(reinterpret_cast<const double2*>(f + i));
+    }
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < UNROLL; ++r) {
+        const I i = i0 + (I)(r * 2 * LANES);
+        c += (i >= lo && i < hi && v[r].x < tq) + (i + 1 < hi && v[r].y < tq);
+    }
+#pragma unroll 1
+    for (I i = i0 + (I)(UNROLL * 2 * LANES); i < hi; i += (I)(2 * LANES)) {
+        const double2 w = __ldg(reinterpret_cast<const double2*>(f + i));
+        c += (w.x < tq) + (i + 1 < hi && w.y < tq);
+    }
+#pragma unroll
+    for (int o = 1; o < LANES; o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
+}
+// same over the records' time fields (8-byte loads at a 16-byte stride)
+template <int LANES, typename I>
+__device__ __forceinline__ int count_records(const dyg_halfedge_t* __restrict__ he, I lo, I hi, double tq, int lane) {
+    constexpr int UNROLL = (16 + LANES - 1) / LANES;
+    const I i0 = lo + (I)lane;
+    double v[UNROLL];
+#pragma unroll
+    for (int r = 0; r < UNROLL; ++r) {
+        const I i = i0 + (I)(r * LANES);
+        v[r] = 0.0;
+        if (i < hi) v[r] = load_time(he, (int64_t)i);
+    }
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < UNROLL; ++r) c += (i0 + (I)(r * LANES) < hi) && (v[r] < tq);
+#pragma unroll 1
+    for (I i = i0 + (I)(UNROLL * LANES); i < hi; i += (I)LANES) c += load_time(he, (int64_t)i) < tq;
+#pragma unroll
+    for (int o = 1; o < LANES; o <<= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
+}
+
+// number of half-edges of [a, a+deg) with t < tq, through the fence index.  Warp-uniform control flow: every lane of
+// the warp calls it (lanes without a query pass deg = 0) and the level loop runs from the highest level any group of
+// the warp needs; groups that start lower idle through the upper iterations.  The start level is the first one with at
+// most ~32 entries in the run; every level below scans one 16-entry block (up to 31 entries at the run's two ends).
+template <int LANES, typename I>
+__device__ __forceinline__ I lower_bound_time_fenced(const dyg_halfedge_t* __restrict__ he, const Fence& fx, I a, I deg,
+                                                     double tq, int lane) {
+    const I b = a + deg;
+    int top = 0;
+    for (I d = deg; d > 32 && top < fx.nlev; d >>= 4) ++top;
+    I lo = (a + (((I)1 << (4 * top)) - 1)) >> (4 * top), hi = b >> (4 * top);
+    if (hi < lo) hi = lo;
+    for (int l = __reduce_max_sync(0xffffffffu, top); l > 0; --l) {   // l is warp-uniform
+        const bool on = l <= top;
+        const int c = count_fence<LANES, I>(fx.lvl[l], on ? lo : (I)0, on ? hi : (I)0, tq, lane);
+        if (on) {
+            const I pos = lo + (I)c;
+            const I s_l = (a + (((I)1 << (4 * l)) - 1)) >> (4 * l);
+            I e_l = b >> (4 * l);
+            if (e_l < s_l) e_l = s_l;
+            lo = pos == s_l ? (a + (((I)1 << (4 * (l - 1))) - 1)) >> (4 * (l - 1)) : pos << 4;
+            hi = pos == e_l ? b >> (4 * (l - 1)) : (pos << 4) + 16;
+        }
+    }
+    return lo + (I)count_records<LANES, I>(he, lo, hi, tq, lane) - a;
+}
+
+// MODE 0: no fence index (cooperative (LANES+1)-ary search over the records); 1: fence index, uint32 index arithmetic
+// (fewer than 2^31 half-edges); 2: fence index, int64 index arithmetic.  Every lane of the warp must call it.
+template <int LANES, int MODE>
+__device__ __forceinline__ int64_t search_before(const dyg_halfedge_t* __restrict__ he, const Fence& fx, int64_t a, int64_t deg,
+                                                 double tq, int lane) {
+    if (MODE == 1) return (int64_t)lower_bound_time_fenced<LANES, uint32_t>(he, fx, (uint32_t)a, (uint32_t)deg, tq, lane);
+    if (MODE == 2) return lower_bound_time_fenced<LANES, int64_t>(he, fx, a, deg, tq, lane);
+    return lower_bound_time_coop<LANES>(he, a, deg, tq, lane);
+}
+static inline int search_mode(const double* fence, int64_t n_half) {
+    if (!fence) return 0;
+    if (getenv("DYG_FENCE_INDEX64")) return 2;   // test hook: exercise the int64 variant on small graphs
+    return n_half < ((int64_t)1 << 31) - 64 ? 1 : 2;
+}
+
 // ---------------------------------------------------------------- CSR build
 __global__ void csr_degrees_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
                                    int64_t num_nodes, unsigned long long* __restrict__ deg) {
@@ -118,6 +224,12 @@ __global__ void csr_pack_kernel(const int64_t* __restrict__ order, const int64_t
         r.w = (int)eid[e];
         reinterpret_cast<int4*>(out)[i] = r;
     }
+}
+// one fence level: out[i] = (level 1) time of record 16 i + 15, (level > 1) previous level's entry 16 i + 15
+__global__ void csr_fence_kernel(const dyg_halfedge_t* __restrict__ he, const double* __restrict__ prev, int64_t n_out,
+                                 double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = prev ? prev[16 * i + 15] : load_time(he, 16 * i + 15);
 }
 __global__ void csr_tia_kernel(const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
                                double tsf, double* __restrict__ prob, double* __restrict__ cum,
@@ -147,21 +259,29 @@ __global__ void csr_tia_kernel(const dyg_halfedge_t* __restrict__ he, const int6
 }
 
 // ---------------------------------------------------------------- queries
-__global__ void count_before_kernel(const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr,
-                                    int64_t num_nodes, const int64_t* __restrict__ node_ids,
+// 8 lanes per query (search_before)
+template <int MODE>
+__global__ void __launch_bounds__(256) count_before_kernel(const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr,
+                                    int64_t num_nodes, const __grid_constant__ Fence fx, const int64_t* __restrict__ node_ids,
                                     const double* __restrict__ times, int64_t n, int32_t* __restrict__ cnt) {
-    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    int64_t a, deg;
-    node_range(indptr, num_nodes, node_ids[q], a, deg);
-    cnt[q] = (int32_t)lower_bound_time(he, a, deg, times[q]);
+    const int lane = threadIdx.x % 8;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 8;
+    const bool valid = q < n;
+    int64_t a = 0, deg = 0;
+    double tq = 0.0;
+    if (valid) {
+        node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
+        tq = __ldg(times + q);
+    }
+    const int64_t c = search_before<8, MODE>(he, fx, a, deg, tq, lane);
+    if (valid && lane == 0) cnt[q] = (int32_t)c;
 }
 
 // LANES threads cooperate on one query: (LANES+1)-ary search (lower_bound_time_coop),
 // per probe per group), then the lanes split the k-entry tail gather and the (n,k) row writes.
-template <int LANES>
+template <int LANES, int MODE>
 __global__ void __launch_bounds__(256) sample_recent_kernel(
-    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes, const __grid_constant__ Fence fx,
     const int64_t* __restrict__ node_ids, const double* __restrict__ times, int64_t n, int k,
     int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid, float* __restrict__ out_t,
     int32_t* __restrict__ cnt_out) {
@@ -174,7 +294,7 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(
         node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
         tq = __ldg(times + q);
     }
-    const int64_t cnt = lower_bound_time_coop<LANES>(he, a, deg, tq, lane);
+    const int64_t cnt = search_before<LANES, MODE>(he, fx, a, deg, tq, lane);
     if (!valid) return;
     if (cnt_out && lane == 0) cnt_out[q] = (int32_t)cnt;
     const int64_t base = q * (int64_t)k;
@@ -195,8 +315,9 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(
 }
 
 // One warp per query: [self, last min(cnt, L-1) neighbours, zeros...] (models/DyGFormer.py:214-242).
+template <int MODE>
 __global__ void __launch_bounds__(256) first_hop_pad_kernel(
-    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes, const __grid_constant__ Fence fx,
     const int64_t* __restrict__ node_ids, const double* __restrict__ times, int64_t n, int L, int row_stride,
     int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid, float* __restrict__ out_t,
     int32_t* __restrict__ out_len, int32_t* __restrict__ group_max, int group_size) {
@@ -207,7 +328,7 @@ __global__ void __launch_bounds__(256) first_hop_pad_kernel(
     const double tq = __ldg(times + q);
     int64_t a, deg;
     node_range(indptr, num_nodes, v, a, deg);
-    const int64_t cnt = lower_bound_time_coop<32>(he, a, deg, tq, lane);
+    const int64_t cnt = search_before<32, MODE>(he, fx, a, deg, tq, lane);
     const int m = (int)(cnt < (int64_t)(L - 1) ? cnt : (int64_t)(L - 1));
     if (lane == 0) {
         if (out_len) out_len[q] = m + 1;
@@ -372,9 +493,9 @@ __device__ __forceinline__ double philox_u01(uint64_t seed, uint64_t ctr) {
     return ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-template <int LANES, bool TIA>
+template <int LANES, bool TIA, int MODE>
 __global__ void __launch_bounds__(256) sample_random_kernel(
-    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes,
+    const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes, const __grid_constant__ Fence fx,
     const double* __restrict__ cum, const int64_t* __restrict__ node_ids, const double* __restrict__ times,
     int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid,
     float* __restrict__ out_t) {
@@ -395,7 +516,7 @@ __global__ void __launch_bounds__(256) sample_random_kernel(
             node_range(indptr, num_nodes, __ldg(node_ids + q), a, deg);
             tq = __ldg(times + q);
         }
-        cnt = lower_bound_time_coop<LANES>(he, a, deg, tq, lane);
+        cnt = search_before<LANES, MODE>(he, fx, a, deg, tq, lane);
     }
     const int64_t base = q * (int64_t)k;
     if (valid && cnt > 0) {
@@ -445,11 +566,63 @@ __global__ void __launch_bounds__(256) sample_random_kernel(
 }
 
 // ---------------------------------------------------------------- C ABI
+#define DISPATCH_MODE(mode, LAUNCH) \
+    do {                            \
+        if ((mode) == 1) LAUNCH(1); \
+        else if ((mode) == 2) LAUNCH(2); \
+        else LAUNCH(0);             \
+    } while (0)
 static inline unsigned blocks_for(int64_t work, int threads, int64_t cap = (1ll << 30)) {
     int64_t b = (work + threads - 1) / threads;
     if (b < 1) b = 1;
     if (b > cap) b = cap;
     return (unsigned)b;
+}
+
+// level sizes / offsets of the fence buffer (every level starts on a 128-byte line)
+static inline int fence_levels(int64_t n_half, int64_t* off, int64_t* cnt) {
+    int nlev = 0;
+    int64_t pos = 0, n = n_half >> 4;
+    while (n > 0 && nlev < DYG_FENCE_MAX_LEVELS) {
+        ++nlev;
+        off[nlev] = pos;
+        cnt[nlev] = n;
+        pos += (n + 15) & ~(int64_t)15;
+        n >>= 4;
+    }
+    off[0] = pos;   // total entries
+    return nlev;
+}
+static inline Fence make_fence(const double* fence, int64_t n_half) {
+    Fence fx;
+    memset(&fx, 0, sizeof(fx));
+    if (fence) {
+        int64_t off[DYG_FENCE_MAX_LEVELS + 1], cnt[DYG_FENCE_MAX_LEVELS + 1];
+        fx.nlev = fence_levels(n_half, off, cnt);
+        for (int l = 1; l <= fx.nlev; ++l) fx.lvl[l] = fence + off[l];
+    }
+    return fx;
+}
+
+extern "C" int64_t dyg_csr_fence_entries(int64_t num_half_edges) {
+    int64_t off[DYG_FENCE_MAX_LEVELS + 1], cnt[DYG_FENCE_MAX_LEVELS + 1];
+    if (num_half_edges < 0) return 0;
+    fence_levels(num_half_edges, off, cnt);
+    return off[0];
+}
+
+extern "C" int dyg_csr_fence_build(const dyg_halfedge_t* he, int64_t num_half_edges, double* fence, dyg_stream_t stream) {
+    DYG_CHECK_ARG(num_half_edges >= 0, "dyg_csr_fence_build: bad size");
+    int64_t off[DYG_FENCE_MAX_LEVELS + 1], cnt[DYG_FENCE_MAX_LEVELS + 1];
+    const int nlev = fence_levels(num_half_edges, off, cnt);
+    if (nlev == 0) return 0;
+    DYG_CHECK_ARG(he && fence && (reinterpret_cast<uintptr_t>(fence) & 127u) == 0, "dyg_csr_fence_build: fence must be 128-byte aligned");
+    for (int l = 1; l <= nlev; ++l) {
+        csr_fence_kernel<<<blocks_for(cnt[l], 256, 148 * 16), 256, 0, as_stream(stream)>>>(
+            he, l == 1 ? nullptr : fence + off[l - 1], cnt[l], fence + off[l]);
+        DYG_LAUNCH_CHECK("dyg_csr_fence_build");
+    }
+    return 0;
 }
 
 extern "C" int dyg_csr_degrees(const int64_t* src, const int64_t* dst, int64_t E, int64_t num_nodes, int64_t* deg,
@@ -488,31 +661,41 @@ extern "C" int dyg_csr_tia_cum(const double* prob, const int64_t* indptr, int64_
     return 0;
 }
 
-extern "C" int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
-                                const int64_t* node_ids, const double* times, int64_t n, int32_t* cnt,
+extern "C" int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                                int64_t num_half_edges, const int64_t* node_ids, const double* times, int64_t n, int32_t* cnt,
                                 dyg_stream_t stream) {
     DYG_CHECK_ARG(n >= 0, "dyg_count_before: bad size");
     if (n == 0) return 0;
-    count_before_kernel<<<blocks_for(n, 128), 128, 0, as_stream(stream)>>>(he, indptr, num_nodes, node_ids, times, n, cnt);
+    const Fence fx = make_fence(fence, num_half_edges);
+#define LAUNCH_COUNT(MODE) count_before_kernel<MODE><<<blocks_for(n * 8, 256), 256, 0, as_stream(stream)>>>(he, indptr, num_nodes, fx, node_ids, times, n, cnt)
+    DISPATCH_MODE(search_mode(fence, num_half_edges), LAUNCH_COUNT);
+#undef LAUNCH_COUNT
     DYG_LAUNCH_CHECK("dyg_count_before");
     return 0;
 }
 
-extern "C" int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
-                                 const int64_t* node_ids, const double* times, int64_t n, int k, int64_t* out_nbr,
-                                 int64_t* out_eid, float* out_t, int32_t* cnt, dyg_stream_t stream) {
+extern "C" int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                                 int64_t num_half_edges, const int64_t* node_ids, const double* times, int64_t n, int k,
+                                 int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* cnt, dyg_stream_t stream) {
     DYG_CHECK_ARG(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
     DYG_CHECK_ARG(n >= 0, "dyg_sample_recent: bad size");
     if (n == 0) return 0;
     cudaStream_t s = as_stream(stream);
-#define LAUNCH_RECENT(L) \
-    sample_recent_kernel<L><<<blocks_for(n * L, 256), 256, 0, s>>>(he, indptr, num_nodes, node_ids, times, n, k, out_nbr, out_eid, out_t, cnt)
+    const Fence fx = make_fence(fence, num_half_edges);
+    const int mode = search_mode(fence, num_half_edges);
+#define LAUNCH_RECENT_M(MODE) sample_recent_kernel<LR, MODE><<<blocks_for(n * LR, 256), 256, 0, s>>>(he, indptr, num_nodes, fx, node_ids, times, n, k, out_nbr, out_eid, out_t, cnt)
+#define LAUNCH_RECENT(L)                          \
+    do {                                          \
+        constexpr int LR = L;                     \
+        DISPATCH_MODE(mode, LAUNCH_RECENT_M);     \
+    } while (0)
     if (k <= 4) LAUNCH_RECENT(2);
     else if (k <= 12) LAUNCH_RECENT(4);
     else if (k <= 32) LAUNCH_RECENT(8);
     else if (k <= 96) LAUNCH_RECENT(16);
     else LAUNCH_RECENT(32);
 #undef LAUNCH_RECENT
+#undef LAUNCH_RECENT_M
     DYG_LAUNCH_CHECK("dyg_sample_recent");
     return 0;
 }
@@ -564,41 +747,57 @@ extern "C" int dyg_philox_uniform(uint64_t seed, uint64_t offset, int64_t count,
     return 0;
 }
 
-extern "C" int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
-                                 const int64_t* node_ids, const double* times, int64_t n, int L, int row_stride,
-                                 int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* out_len,
+extern "C" int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                                 int64_t num_half_edges, const int64_t* node_ids, const double* times, int64_t n, int L,
+                                 int row_stride, int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* out_len,
                                  int32_t* group_max, int group_size, dyg_stream_t stream) {
     DYG_CHECK_ARG(L - 1 > 0, "Maximal number of neighbors for each node should be greater than 1!");
     DYG_CHECK_ARG(row_stride >= L, "dyg_first_hop_pad: row_stride %d < max_input_sequence_length %d", row_stride, L);
     DYG_CHECK_ARG(!group_max || group_size > 0, "dyg_first_hop_pad: group_size must be positive");
     if (n == 0) return 0;
-    first_hop_pad_kernel<<<blocks_for(n * 32, 256), 256, 0, as_stream(stream)>>>(
-        he, indptr, num_nodes, node_ids, times, n, L, row_stride, out_nbr, out_eid, out_t, out_len, group_max,
-        group_size > 0 ? group_size : 1);
+    const Fence fx = make_fence(fence, num_half_edges);
+#define LAUNCH_PAD(MODE)                                                                                      \
+    first_hop_pad_kernel<MODE><<<blocks_for(n * 32, 256), 256, 0, as_stream(stream)>>>(                       \
+        he, indptr, num_nodes, fx, node_ids, times, n, L, row_stride, out_nbr, out_eid, out_t, out_len, group_max, \
+        group_size > 0 ? group_size : 1)
+    DISPATCH_MODE(search_mode(fence, num_half_edges), LAUNCH_PAD);
+#undef LAUNCH_PAD
     DYG_LAUNCH_CHECK("dyg_first_hop_pad");
     return 0;
 }
 
-extern "C" int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* cum,
-                                 const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed,
-                                 uint64_t offset, int64_t* out_nbr, int64_t* out_eid, float* out_t, dyg_stream_t stream) {
+extern "C" int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                                 int64_t num_half_edges, const double* cum, const int64_t* node_ids, const double* times,
+                                 int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* out_nbr, int64_t* out_eid,
+                                 float* out_t, dyg_stream_t stream) {
     DYG_CHECK_ARG(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
     DYG_CHECK_ARG((size_t)k * 12 <= 40 * 1024, "dyg_sample_random: num_neighbors %d too large (max 3413)", k);
     if (n == 0) return 0;
     cudaStream_t s = as_stream(stream);
+    const Fence fx = make_fence(fence, num_half_edges);
+    const int mode = search_mode(fence, num_half_edges);
+#define LAUNCH_RANDOM_T(MODE) sample_random_kernel<LR, true, MODE><<<grid_, block_, smem_, s>>>(he, indptr, num_nodes, fx, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t)
+#define LAUNCH_RANDOM_F(MODE) sample_random_kernel<LR, false, MODE><<<grid_, block_, smem_, s>>>(he, indptr, num_nodes, fx, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t)
+#define DISPATCH_RANDOM(L, GRID, BLOCK, SMEM)                        \
+    do {                                                             \
+        constexpr int LR = L;                                        \
+        const unsigned grid_ = GRID, block_ = BLOCK;                 \
+        const size_t smem_ = SMEM;                                   \
+        if (cum) DISPATCH_MODE(mode, LAUNCH_RANDOM_T);               \
+        else DISPATCH_MODE(mode, LAUNCH_RANDOM_F);                   \
+    } while (0)
     if (k <= 32) {
         const int threads = 256, groups = threads / 8;
-        const size_t smem = (size_t)groups * k * 12;
-        if (cum) sample_random_kernel<8, true><<<blocks_for(n, groups), threads, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
-        else sample_random_kernel<8, false><<<blocks_for(n, groups), threads, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
+        DISPATCH_RANDOM(8, blocks_for(n, groups), threads, (size_t)groups * k * 12);
     } else {
         int groups = (int)((40 * 1024) / ((size_t)k * 12));
         if (groups > 8) groups = 8;
         if (groups < 1) groups = 1;
-        const size_t smem = (size_t)groups * k * 12;
-        if (cum) sample_random_kernel<32, true><<<blocks_for(n, groups), groups * 32, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
-        else sample_random_kernel<32, false><<<blocks_for(n, groups), groups * 32, smem, s>>>(he, indptr, num_nodes, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t);
+        DISPATCH_RANDOM(32, blocks_for(n, groups), groups * 32, (size_t)groups * k * 12);
     }
+#undef DISPATCH_RANDOM
+#undef LAUNCH_RANDOM_T
+#undef LAUNCH_RANDOM_F
     DYG_LAUNCH_CHECK("dyg_sample_random");
     return 0;
 }

@@ -57,6 +57,7 @@ class NeighborSampler:
         self.seed = seed
         self.device = torch.device(device)
         self.rng = rng
+        self.use_fence = True
         if sample_neighbor_strategy == 'time_interval_aware':
             self.time_scaling_factor = time_scaling_factor
         if _edges is not None:
@@ -148,6 +149,12 @@ class NeighborSampler:
             ops._count()
             del order
         self.num_half_edges = int(n_half)
+        # fence index: last time of every complete 16^l-record block (dyg_csr_fence_build), 1/15 of a double per record
+        n_f = int(lib.dyg_csr_fence_entries(int(n_half)))
+        self.fence = torch.empty(n_f, dtype=torch.float64, device=dev) if n_f and self.use_fence else None
+        if self.fence is not None:
+            _native.check(lib.dyg_csr_fence_build(_p(self.halfedges), int(n_half), _p(self.fence), _stream()))
+            ops._count()
         self._prob_host = None
         self.tia_cum = None
         self._philox_offset = 0
@@ -220,7 +227,7 @@ class NeighborSampler:
 
     def count_before_device(self, ids, tq):
         cnt = torch.empty(ids.numel(), dtype=torch.int32, device=self.device)
-        _native.check(_native.load().dyg_count_before(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(ids), _p(tq),
+        _native.check(_native.load().dyg_count_before(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(self.fence), self.num_half_edges, _p(ids), _p(tq),
                                                       ids.numel(), _p(cnt), _stream()))
         ops._count()
         return cnt
@@ -240,14 +247,14 @@ class NeighborSampler:
         out_t = torch.empty((n, k), dtype=torch.float32, device=dev)
         lib = _native.load()
         if strat == 'recent':
-            _native.check(lib.dyg_sample_recent(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(ids), _p(tq), n, k,
+            _native.check(lib.dyg_sample_recent(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(self.fence), self.num_half_edges, _p(ids), _p(tq), n, k,
                                                 _p(out_n), _p(out_e), _p(out_t), None, _stream()))
             ops._count()
             return out_n, out_e, out_t
         if self.rng == 'philox':
             # throughput mode: one fused kernel, counter-based draws (not the reference's RandomState stream)
             off = self._philox_offset
-            _native.check(lib.dyg_sample_random(_p(self.halfedges), _p(self.indptr), self.num_nodes,
+            _native.check(lib.dyg_sample_random(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(self.fence), self.num_half_edges,
                                                 _p(self.tia_cum) if strat == 'time_interval_aware' else None,
                                                 _p(ids), _p(tq), n, k, int(self.seed or 0), int(off),
                                                 _p(out_n), _p(out_e), _p(out_t), _stream()))
@@ -318,7 +325,7 @@ class NeighborSampler:
         gmax = None
         if group_size > 0:
             gmax = torch.zeros((n + group_size - 1) // group_size, dtype=torch.int32, device=dev)
-        _native.check(_native.load().dyg_first_hop_pad(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(ids), _p(tq), n,
+        _native.check(_native.load().dyg_first_hop_pad(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(self.fence), self.num_half_edges, _p(ids), _p(tq), n,
                                                        L, W, _p(pn), _p(pe), _p(pt), _p(ln), _p(gmax), int(group_size), _stream()))
         ops._count()
         return pn, pe, pt, ln, gmax

@@ -55,14 +55,22 @@ int dyg_csr_tia_tables(const dyg_halfedge_t* he, const int64_t* indptr, int64_t 
 /* cum from a given prob table (used when prob was computed on the host for bit-exactness). */
 int dyg_csr_tia_cum(const double* prob, const int64_t* indptr, int64_t num_nodes, double* cum, dyg_stream_t stream);
 
+/* Fence index of the CSR (no counterpart in the reference; it replaces the O(log2 deg) probes of np.searchsorted,
+ * utils/utils.py:141, by O(log16 deg) 128-byte line reads).  Level l >= 1 holds, for every complete block of 16^l records of
+ * the half-edge array, the time of its last record; levels are concatenated, each starting on a multiple of 16 entries.
+ * dyg_csr_fence_entries: doubles to allocate (128-byte aligned); dyg_csr_fence_build fills them.  Every query entry point
+ * takes `fence` (NULL: search the records directly) and `num_half_edges` (defines the level offsets). */
+int64_t dyg_csr_fence_entries(int64_t num_half_edges);
+int dyg_csr_fence_build(const dyg_halfedge_t* he, int64_t num_half_edges, double* fence, dyg_stream_t stream);
+
 /* ---- a2: find_neighbors_before (utils/utils.py:130-147): cnt[q] = #{j : t_j < times[q]} ---- */
-int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
-                     const int64_t* node_ids, const double* times, int64_t n, int32_t* cnt, dyg_stream_t stream);
+int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                     int64_t num_half_edges, const int64_t* node_ids, const double* times, int64_t n, int32_t* cnt, dyg_stream_t stream);
 
 /* ---- a3: get_historical_neighbors, strategy 'recent' (utils/utils.py:149-175, 200-209) ----
  * last min(cnt,k) entries, left-padded with zeros. out_* are (n,k) row-major. cnt may be NULL. */
-int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
-                      const int64_t* node_ids, const double* times, int64_t n, int k,
+int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                      int64_t num_half_edges, const int64_t* node_ids, const double* times, int64_t n, int k,
                       int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* cnt, dyg_stream_t stream);
 
 /* ---- a4/a5: 'uniform' and 'time_interval_aware' (utils/utils.py:176-199) ----
@@ -81,16 +89,16 @@ int dyg_draw_tia(const double* cum, const int64_t* indptr, const int64_t* node_i
 int dyg_philox_uniform(uint64_t seed, uint64_t offset, int64_t count, double* u, dyg_stream_t stream);
 /* Fused throughput path (labelled non-parity): search + Philox draw (counter offset + q*k + j) + gather + time
  * re-sort in one kernel.  cum == NULL: uniform (floor(u*cnt)); cum != NULL: time_interval_aware prefix-CDF search. */
-int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* cum,
-                      const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed, uint64_t offset,
+int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                      int64_t num_half_edges, const double* cum, const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed, uint64_t offset,
                       int64_t* out_nbr, int64_t* out_eid, float* out_t, dyg_stream_t stream);
 
 /* ---- a7 + a12: get_all_first_hop_neighbors + DyGFormer.pad_sequences (utils/utils.py:254-273,
  * models/DyGFormer.py:196-245) ----  row q = [node_ids[q], last min(cnt,L-1) neighbours..., 0...] over
  * row_stride columns (row_stride >= L); out_t[q,0] = (float)times[q]; out_len[q] = min(cnt,L-1)+1.
  * group_max[q / group_size] = max over the group of out_len (atomicMax; caller zeroes it; may be NULL). */
-int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes,
-                      const int64_t* node_ids, const double* times, int64_t n, int max_input_sequence_length,
+int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
+                      int64_t num_half_edges, const int64_t* node_ids, const double* times, int64_t n, int max_input_sequence_length,
                       int row_stride, int64_t* out_nbr, int64_t* out_eid, float* out_t, int32_t* out_len,
                       int32_t* group_max, int group_size, dyg_stream_t stream);
 

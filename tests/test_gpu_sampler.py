@@ -228,3 +228,60 @@ def test_full_size_properties():
     assert np.array_equal(np.minimum(cnt, 20), valid.sum(1))
     deg = np.bincount(np.concatenate([g.src_node_ids, g.dst_node_ids]), minlength=g.num_nodes)
     assert (cnt <= deg[nodes]).all()
+
+
+@pytest.mark.parametrize('dups,index64', [(False, False), (True, False), (True, True)])
+def test_fence_index_matches_searchsorted(dups, index64, monkeypatch):
+    """The fenced lower bound (dyg_csr_fence_build + level descent) equals np.searchsorted(side='left') on every node's
+    run, for hubs spanning 1-5 fence levels, runs that start / end inside a 16-record block, duplicate timestamps, and
+    query times equal to / between / outside the stored times; the un-indexed search gives the same counts."""
+    from dyglib_b200.utils.utils import NeighborSampler
+    if index64:
+        monkeypatch.setenv('DYG_FENCE_INDEX64', '1')      # int64 index arithmetic (CSR of 2^31 half-edges and more)
+    rng = np.random.default_rng(11 + dups)
+    degs = [0, 1, 15, 16, 17, 31, 47, 48, 49, 63, 255, 256, 257, 700, 4095, 4097, 70001, 3, 1048590 // 4, 5]
+    owner = np.repeat(np.arange(1, len(degs) + 1), degs)
+    n_half = len(owner)
+    t = (rng.integers(0, 3000, n_half) if dups else rng.permutation(n_half * 2)[:n_half]).astype(np.float64)
+    dev = torch.device('cuda')
+    # half-edge h owned by owner[h] at time t[h] (adjacency-list constructor path: unsorted input, stable sort)
+    s = object.__new__(NeighborSampler)
+    s.device, s.use_fence, s.sample_neighbor_strategy, s.seed, s.rng = dev, True, 'recent', None, 'numpy_replay'
+    s._build(owner, rng.integers(1, 100, n_half), np.arange(1, n_half + 1), t, len(degs) + 1, False, 'auto')
+    assert s.fence is not None
+    indptr = s.indptr.cpu().numpy()
+    rec_t = s.halfedges[:n_half, 0].cpu().numpy()
+    nq = 20000
+    nodes = rng.integers(0, len(degs) + 1, nq)
+    times = np.empty(nq)
+    for i, v in enumerate(nodes):
+        a, b = indptr[v], indptr[v + 1]
+        mode = i % 4
+        if b == a or mode == 0:
+            times[i] = rng.integers(-5, 2 * n_half + 5)
+        elif mode == 1:
+            times[i] = rec_t[rng.integers(a, b)]            # equal to a stored time: strict <
+        elif mode == 2:
+            times[i] = rec_t[rng.integers(a, b)] + 0.5
+        else:
+            times[i] = rec_t[b - 1] + rng.integers(0, 2)     # at / past the end
+    want = np.array([np.searchsorted(rec_t[indptr[v]:indptr[v + 1]], tq, side='left') for v, tq in zip(nodes, times)], dtype=np.int32)
+    ids, tq = s._queries(nodes, times)
+    got = s.count_before_device(ids, tq).cpu().numpy()
+    assert np.array_equal(got, want)
+    fence, s.fence = s.fence, None
+    assert np.array_equal(s.count_before_device(ids, tq).cpu().numpy(), want)
+    s.fence = fence
+    for k in (3, 10, 20, 50, 100):                          # every lane width of sample_recent + the first-hop kernel
+        a = s.get_historical_neighbors_device(ids, tq, k)
+        s.fence = None
+        b = s.get_historical_neighbors_device(ids, tq, k)
+        s.fence = fence
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        last = a[2][:, -1].cpu().numpy()
+        idx = indptr[nodes] + want - 1
+        assert np.array_equal(last[want > 0], rec_t[idx[want > 0]].astype(np.float32))
+    a = s.get_all_first_hop_neighbors_device(ids, tq, 64, 2)
+    s.fence = None
+    b = s.get_all_first_hop_neighbors_device(ids, tq, 64, 2)
+    assert all(torch.equal(x, y) for x, y in zip(a[:4], b[:4]))
