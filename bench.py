@@ -45,24 +45,75 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML queried from a thread of this process every
+    DYG_CLOCK_PERIOD_MS (default 100) ms (nvidia_ml_py).  A looping ``nvidia-smi -lms`` child was measured to stall the GPU for tens of milliseconds per
+    sample (a 35 ms region of sampler launches read 65 ms whenever a sample fell inside it); it remains the fall-back when
+    NVML cannot be loaded, started early so that only its periodic queries overlap the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
+        self.sm, self.mx, self.reasons, self.p, self.thread = [], [], set(), None, None
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # torch's device index counts within CUDA_VISIBLE_DEVICES; map it to the NVML index through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = None
+            for i in range(nv.nvmlDeviceGetCount()):
+                hi = nv.nvmlDeviceGetHandleByIndex(i)
+                u = nv.nvmlDeviceGetUUID(hi)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hi
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            bits = {'hw_slowdown': nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, 'nvmlClocksEventReasonHwSlowdown') else 0x8,
+                    'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+            self._stop = threading.Event()
+            self.period = float(os.environ.get('DYG_CLOCK_PERIOD_MS', '100')) / 1e3
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        try:
+                            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.source = 'nvml'
+            return
+        except Exception:
+            self.thread = None
+        self.source = 'nvidia-smi'
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                        '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
-        # nvidia-smi's start-up (NVML initialisation) contends with kernel launches for tens of milliseconds: wait for its
-        # first sample before returning, so that only the periodic 100 ms queries overlap the timed region
         t0 = time.time()
         while self.p is not None and time.time() - t0 < 5.0 and os.path.getsize(self.f.name) == 0:
             time.sleep(0.02)
 
     def stop(self):
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join()
+            return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                    'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': f'nvml, {self.period * 1e3:.0f} ms period'}
         if self.p is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -83,7 +134,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi -lms 100'}
 
 
 def dist_env():
@@ -547,6 +598,17 @@ def device_power_law_graph(E, nu, ni, seed, dev):
     return src, dst, eid, t, nu + ni + 1
 
 
+def sweep_traffic(E, Q, k):
+    """DRAM bytes per sample_recent launch (GB) from the committed ncu --set full capture of the same sweep configuration."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_sampler_traffic.json')))
+        if (d['events'], d['queries'], d['k']) == (E, Q, k):
+            return d['sample_recent_kernel']['dram_read_gb'] + d['sample_recent_kernel']['dram_write_gb']
+    except Exception:
+        pass
+    return None
+
+
 def run_sampler_sweep(args):
     rank, world, local = dist_env()
     import torch.distributed as dist
@@ -601,17 +663,20 @@ def run_sampler_sweep(args):
     for strat, s in samplers.items():
         clocks = ClockSampler(torch.cuda.current_device()) if strat == 'recent' else None
         for _ in range(W):
-            s.get_historical_neighbors_device(nodes, times, k)
+            # keep the previous outputs alive while the next ones are allocated, exactly as the timed loop does: otherwise the
+            # second set of (n, k) output buffers (6.7 GB) is cudaMalloc'ed inside the first timed region
+            out = s.get_historical_neighbors_device(nodes, times, k)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(K):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        ev[0].record()
+        for i in range(K):
             out = s.get_historical_neighbors_device(nodes, times, k)
-        e1.record()
+            ev[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[K])
+        per_launch = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
         if clocks is not None:
             clk = clocks.stop()
         if world > 1:
@@ -619,7 +684,7 @@ def run_sampler_sweep(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         gbs = alg[strat] * K / (ms * 1e-3) / 1e9
-        res[strat] = {'queries_per_s': Q * world * K / (ms * 1e-3), 'ms_per_launch': ms / K, 'alg_bytes_per_query': alg[strat] / Q,
+        res[strat] = {'queries_per_s': Q * world * K / (ms * 1e-3), 'ms_per_launch': ms / K, 'ms_per_launch_median': per_launch[K // 2], 'alg_bytes_per_query': alg[strat] / Q,
                       'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / pk['hbm'],
                       'checksum': int(out[1].sum().item())}
     line = {'metric': 'sampler queries/s', 'value': res['recent']['queries_per_s'], 'unit': 'queries/s', 'n_gpus': world,
@@ -627,9 +692,12 @@ def run_sampler_sweep(args):
             'vs_baseline': None, 'dtype': 'f64 compare / int32 ids', 'data': 'synthetic',
             'config': {'workload': f'sampler_sweep: {E} events, {num_nodes} nodes power-law, {Q} queries per GPU in the last 30 %, k={k}',
                        'csr_build_s': round(build_s, 3), 'csr_bytes': int(base.halfedges.numel() * 8 + base.indptr.numel() * 8),
+                       'fence_bytes': int(base.fence.numel() * 8) if base.fence is not None else 0,
                        'l2': 'CSR (>= 3 GB at 1e8 events) and outputs far exceed L2', 'random_strategies': 'philox (throughput mode, non-parity)'},
             'roofline': {'kernel': 'sample_recent_kernel', 'bound': 'hbm', 'achieved': res['recent']['achieved_gbs'], 'peak': pk['hbm'],
-                         'unit': 'GB/s', 'frac': res['recent']['frac_of_hbm_peak'], 'traffic': None, 'peak_source': pk['source']},
+                         'unit': 'GB/s', 'frac': res['recent']['frac_of_hbm_peak'], 'traffic': sweep_traffic(E, Q, k), 'peak_source': pk['source'],
+                         'note': 'achieved = algorithmic bytes (SURVEY 8d formula, summed over the actual queries) / launch time; traffic = '
+                                 'dram read + write bytes per launch from the committed ncu capture (profiles/r01_sampler_ncu.md), GB'},
             'strategies': res, 'gpu_launches': K * 3, 'clocks': clk}
     if rank == 0 and world == 1 and args.cpu_queries > 0:
         # CPU baseline: the oracle's per-query loop (port of utils/utils.py:149-214) over arrays installed from the device CSR

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(
     const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes, const __grid_constant__ Fence fx,
     const int64_t* __restrict__ node_ids, const double* __restrict__ times, int64_t n, int k,
     int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid, float* __restrict__ out_t,
-    int32_t* __restrict__ cnt_out) {
+    int32_t* __restrict__ cnt_out, bool pairs) {
     const int lane = threadIdx.x % LANES;
     const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
     const bool valid = q < n;
@@ -298,19 +298,43 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(
     if (!valid) return;
     if (cnt_out && lane == 0) cnt_out[q] = (int32_t)cnt;
     const int64_t base = q * (int64_t)k;
-    for (int j = lane; j < k; j += LANES) {
-        const int64_t s = cnt - k + j;  // left padding: valid entries sit at the back (utils/utils.py:206-209)
-        int64_t nb = 0, ei = 0;
-        float tf = 0.f;
-        if (s >= 0) {
-            const Rec r = load_rec(he, a + s);
-            nb = r.nbr;
-            ei = r.eid;
-            tf = (float)r.t;
+    const int64_t first = a + cnt - k;   // record of output column 0; columns j < k - cnt are the left padding (utils/utils.py:206-209)
+    const int pad = cnt < k ? (int)(k - cnt) : 0;
+    if (pairs) {
+        // even k, aligned rows: a lane owns column pairs, two 16-byte record loads -> 16 + 16 + 8 byte row stores (rows are 16-byte aligned)
+        for (int j = 2 * lane; j < k; j += 2 * LANES) {
+            longlong2 nb = make_longlong2(0, 0), ei = make_longlong2(0, 0);
+            float2 tf = make_float2(0.f, 0.f);
+            if (j >= pad) {
+                const Rec r = load_rec(he, first + j);
+                nb.x = r.nbr;
+                ei.x = r.eid;
+                tf.x = (float)r.t;
+            }
+            if (j + 1 >= pad) {
+                const Rec r = load_rec(he, first + j + 1);
+                nb.y = r.nbr;
+                ei.y = r.eid;
+                tf.y = (float)r.t;
+            }
+            *reinterpret_cast<longlong2*>(out_nbr + base + j) = nb;
+            *reinterpret_cast<longlong2*>(out_eid + base + j) = ei;
+            *reinterpret_cast<float2*>(out_t + base + j) = tf;
         }
-        out_nbr[base + j] = nb;
-        out_eid[base + j] = ei;
-        out_t[base + j] = tf;
+    } else {
+        for (int j = lane; j < k; j += LANES) {
+            int64_t nb = 0, ei = 0;
+            float tf = 0.f;
+            if (j >= pad) {
+                const Rec r = load_rec(he, first + j);
+                nb = r.nbr;
+                ei = r.eid;
+                tf = (float)r.t;
+            }
+            out_nbr[base + j] = nb;
+            out_eid[base + j] = ei;
+            out_t[base + j] = tf;
+        }
     }
 }
 
@@ -683,16 +707,19 @@ extern "C" int dyg_sample_recent(const dyg_halfedge_t* he, const int64_t* indptr
     cudaStream_t s = as_stream(stream);
     const Fence fx = make_fence(fence, num_half_edges);
     const int mode = search_mode(fence, num_half_edges);
-#define LAUNCH_RECENT_M(MODE) sample_recent_kernel<LR, MODE><<<blocks_for(n * LR, 256), 256, 0, s>>>(he, indptr, num_nodes, fx, node_ids, times, n, k, out_nbr, out_eid, out_t, cnt)
+    const bool pairs = (k % 2) == 0 && aligned16(out_nbr) && aligned16(out_eid) && (reinterpret_cast<uintptr_t>(out_t) & 7u) == 0;
+#define LAUNCH_RECENT_M(MODE) sample_recent_kernel<LR, MODE><<<blocks_for(n * LR, 256), 256, 0, s>>>(he, indptr, num_nodes, fx, node_ids, times, n, k, out_nbr, out_eid, out_t, cnt, pairs)
 #define LAUNCH_RECENT(L)                          \
     do {                                          \
         constexpr int LR = L;                     \
         DISPATCH_MODE(mode, LAUNCH_RECENT_M);     \
     } while (0)
-    if (k <= 4) LAUNCH_RECENT(2);
-    else if (k <= 12) LAUNCH_RECENT(4);
-    else if (k <= 32) LAUNCH_RECENT(8);
-    else if (k <= 96) LAUNCH_RECENT(16);
+    // lanes per query: the search's control flow is per warp, so fewer lanes per query = more queries per warp instruction
+    // (k = 20 on the sweep graph: 4 lanes 3.33 ms, 8 lanes 4.00 ms, 16 lanes 5.8 ms per 2^24 queries)
+    if (k <= 8) LAUNCH_RECENT(2);
+    else if (k <= 40) LAUNCH_RECENT(4);
+    else if (k <= 96) LAUNCH_RECENT(8);
+    else if (k <= 256) LAUNCH_RECENT(16);
     else LAUNCH_RECENT(32);
 #undef LAUNCH_RECENT
 #undef LAUNCH_RECENT_M
@@ -787,8 +814,13 @@ extern "C" int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr
         else DISPATCH_MODE(mode, LAUNCH_RANDOM_F);                   \
     } while (0)
     if (k <= 32) {
-        const int threads = 256, groups = threads / 8;
-        DISPATCH_RANDOM(8, blocks_for(n, groups), threads, (size_t)groups * k * 12);
+        if (!cum) {   // uniform: 4 lanes per query (6.6 ms vs 7.3 ms with 8 on the sweep); the CDF search of tia prefers 8 (34 vs 38 ms)
+            const int threads = 256, groups = threads / 4;
+            DISPATCH_RANDOM(4, blocks_for(n, groups), threads, (size_t)groups * k * 12);
+        } else {
+            const int threads = 256, groups = threads / 8;
+            DISPATCH_RANDOM(8, blocks_for(n, groups), threads, (size_t)groups * k * 12);
+        }
     } else {
         int groups = (int)((40 * 1024) / ((size_t)k * 12));
         if (groups > 8) groups = 8;
