@@ -355,12 +355,395 @@ __global__ void __launch_bounds__(128, 4) temporal_attend_split_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ring variant of temporal_attend_split_kernel (same math, same lane mapping) for time encodings computed in the kernel:
+// neighbour rows are moved by the bulk-copy engine (cp.async.bulk, completion on an mbarrier) into a per-warp ring of
+// RING_DEPTH stages in shared memory instead of by register loads with one row of lookahead.  A warp owns a contiguous
+// range of roots and streams their (root, neighbour) items through the ring, so RING_DEPTH rows per warp (16 warps per
+// SM: ~180 KB) are in flight across root boundaries; the split kernel held <= 2 rows per warp and was latency-bound
+// (DRAM 41 %, issue 35 %: profiles/).  Indices, time deltas and flags of 32 items at a time are loaded coalesced and
+// parked in shared memory; the lane that loaded an item's indices issues its copies, nothing is shuffled.
+constexpr int RING_DEPTH = 8;
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ring_bar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)));
+}
+__device__ __forceinline__ void ring_bar_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void ring_bar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "RW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra RW_DONE;\n\t"
+        "bra RW_LOOP;\n\t"
+        "RW_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int RING_GROUP = 4;   // neighbours whose scores are reduced / soft-maxed together
+__host__ __device__ constexpr int ring_stage_bytes(int F4, int E4, bool node2) { return (((F4 + E4 + (node2 ? F4 : 0)) * 16) + 127) & ~127; }
+__host__ __device__ constexpr int ring_warp_bytes(int F4, int E4, bool node2) {
+    return (RING_DEPTH * ring_stage_bytes(F4, E4, node2) + 64 * 24 + RING_DEPTH * 8 + RING_GROUP * 128 * 4 + 127) & ~127;
+}
+
+// All dimensions are template parameters (F4 / E4: float4 chunks of a node / edge row, T: time features): every bound in
+// the lane loops folds at compile time.  The first version with run-time dimensions spent half of its 350 warp
+// instructions per neighbour on predicates, selects and index arithmetic (ncu source page, profiles/).
+template <int H, bool NODE2, int F4, int E4, int T>
+__global__ void __launch_bounds__(128, NODE2 ? 2 : 3) temporal_attend_ring_kernel(
+    const float* __restrict__ qk, int ldq, int64_t n, int k,
+    const float* __restrict__ node_tab, int ld_node, const float* __restrict__ node_tab2, int ld_node2,
+    const int64_t* __restrict__ node_idx, const float* __restrict__ edge_tab, int ld_edge, const int64_t* __restrict__ edge_idx,
+    const double* __restrict__ t_query, const float* __restrict__ t_nbr,
+    const float* __restrict__ w, const float* __restrict__ b,
+    const int64_t* __restrict__ mask_ids, float* __restrict__ out_s, int lds, float* __restrict__ out_scores, int zero_row0) {
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    constexpr int G = RING_GROUP, V = G * H;          // V partial scores per group: (neighbour g, head h) -> index g * H + h
+    constexpr int SH = (V == 8) ? 2 : 3;              // after the transposing reduction lane l owns score index l >> SH
+    constexpr int NE4 = F4 + E4, Dk = NE4 * 4 + T;
+    constexpr int XR = (NE4 + 31) / 32;               // float4 rounds of the node | edge part
+    constexpr int TF = T / 32, TR = T % 32;           // full time-feature rounds, remainder
+    constexpr bool GROUPED_REM = TR > 0 && TR * G <= 32;   // remainder of the whole group computed in one round
+    constexpr int ROUNDS = (TR > 0 && !GROUPED_REM) ? TF + 1 : TF;
+    constexpr int TQ = (T + 31) / 32;
+    constexpr int STAGE = ring_stage_bytes(F4, E4, NODE2), WARP_BYTES = ring_warp_bytes(F4, E4, NODE2);
+    constexpr uint32_t NODE_BYTES = F4 * 16u, EDGE_BYTES = E4 * 16u;
+    static_assert(XR <= 3 && TQ <= 4, "key row too wide for the lane mapping");
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned char* wbase = ring_smem + (size_t)(threadIdx.x >> 5) * WARP_BYTES;
+    int64_t* s_rn = reinterpret_cast<int64_t*>(wbase + RING_DEPTH * STAGE);   // 2 x 32 items (two index chunks)
+    int64_t* s_re = s_rn + 64;
+    float* s_dt = reinterpret_cast<float*>(s_re + 64);
+    int* s_fl = reinterpret_cast<int*>(s_dt + 64);    // bit 0: masked, bit 1: node row is the zero padding row, bit 2: edge row is
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_fl + 64);
+    float* s_xt = reinterpret_cast<float*>(bars + RING_DEPTH);   // time encodings of the group's neighbours: G x 128
+    if (lane < RING_DEPTH) ring_bar_init(bars + lane);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+
+    const int64_t r0 = (n * gw) / nw, r1 = (n * (gw + 1)) / nw;
+    const int items = (int)((r1 - r0) * k);
+    if (items <= 0) return;
+    const int64_t gi0 = r0 * k;
+
+    // indices / time delta / flags of item 32 c + lane, loaded coalesced
+    int64_t c_rn = 0, c_re = 0;
+    float c_dt = 0.f;
+    int c_fl = 0;
+    auto load_chunk = [&](int c) {
+        const int t = 32 * c + lane;
+        c_rn = 0; c_re = 0; c_dt = 0.f; c_fl = 0;
+        if (t < items) {
+            const int64_t gi = gi0 + t;
+            c_rn = node_idx ? __ldg(node_idx + gi) : gi;
+            c_re = edge_idx ? __ldg(edge_idx + gi) : gi;
+            c_dt = (float)(__ldg(t_query + gi / k) - (double)__ldg(t_nbr + gi));
+            c_fl = (mask_ids ? (__ldg(mask_ids + gi) == 0) : 0) | ((node_idx && c_rn == 0 && (zero_row0 & 1)) ? 2 : 0) |
+                   ((edge_idx && c_re == 0 && (zero_row0 & 2)) ? 4 : 0);
+        }
+    };
+    auto park_chunk = [&](int c) {
+        const int slot = (c & 1) * 32 + lane;
+        s_rn[slot] = c_rn; s_re[slot] = c_re; s_dt[slot] = c_dt; s_fl[slot] = c_fl;
+    };
+    // the lane that parked item t's indices issues its copies into stage t % RING_DEPTH
+    auto issue = [&](int t) {
+        if (lane == (t & 31) && t < items) {
+            const int slot = t & 63;
+            const int fl = s_fl[slot];
+            const int64_t rn = s_rn[slot], re = s_re[slot];
+            unsigned char* dst = wbase + (t % RING_DEPTH) * STAGE;
+            uint64_t* bar = bars + (t % RING_DEPTH);
+            const uint32_t nb = (fl & 2) ? 0u : NODE_BYTES, eb = (fl & 4) ? 0u : EDGE_BYTES;
+            ring_bar_expect(bar, nb * (NODE2 ? 2u : 1u) + eb);
+            if (nb) {
+                bulk_g2s(dst, node_tab + rn * ld_node, nb, bar);
+                if (NODE2) bulk_g2s(dst + NODE_BYTES + EDGE_BYTES, node_tab2 + rn * ld_node2, nb, bar);
+            }
+            if (eb) bulk_g2s(dst + NODE_BYTES, edge_tab + re * ld_edge, eb, bar);
+        }
+    };
+    // row of item t from its ring stage; fl (warp-uniform) says which parts were not copied because they are zero rows
+    auto load_x = [&](int t, int fl, float4 (&x)[XR]) {
+        const float4* row = reinterpret_cast<const float4*>(wbase + (t % RING_DEPTH) * STAGE);
+#pragma unroll
+        for (int r = 0; r < XR; ++r) {
+            const int c = r * 32 + lane;
+            if ((r + 1) * 32 <= NE4 || c < NE4) {
+                x[r] = row[c];
+                if (NODE2 && (r * 32 < F4) && ((r + 1) * 32 <= F4 || c < F4)) {
+                    const float4 u = row[NE4 + c];
+                    x[r].x += u.x; x[r].y += u.y; x[r].z += u.z; x[r].w += u.w;
+                }
+            } else {
+                x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (fl & 6) {   // rare, warp-uniform: the skipped parts hold stale bytes
+#pragma unroll
+            for (int r = 0; r < XR; ++r) {
+                const int c = r * 32 + lane;
+                if (fl & (c < F4 ? 2 : 4)) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+
+    load_chunk(0);
+    park_chunk(0);
+    __syncwarp();
+#pragma unroll 1
+    for (int t = 0; t < RING_DEPTH; ++t) issue(t);
+    load_chunk(1);
+    int parked = 0;                           // highest index chunk parked in shared memory; chunk parked + 1 sits in registers
+
+    float tw[TQ], tb[TQ];
+#pragma unroll
+    for (int r = 0; r < TQ; ++r) {
+        const int c = r * 32 + lane;
+        tw[r] = c < T ? __ldg(w + c) : 0.f;
+        tb[r] = c < T ? __ldg(b + c) : 0.f;
+    }
+    // remainder features of the time encoder (T % 32 <= 8): one round for the whole group, lane = neighbour * TR + feature
+    const int rem_g = GROUPED_REM ? lane / (TR > 0 ? TR : 1) : G, rem_f = GROUPED_REM ? TF * 32 + lane % (TR > 0 ? TR : 1) : 0;
+    const float rem_w = (GROUPED_REM && rem_g < G) ? __ldg(w + rem_f) : 0.f, rem_b = (GROUPED_REM && rem_g < G) ? __ldg(b + rem_f) : 0.f;
+
+    float4 q[H][XR], acc[H][XR];
+    float qt[H][TQ], acct[H][TQ];
+    const int own = lane >> SH, own_g = own / H, own_h = own % H;
+    float m_own = -INFINITY, den_own = 0.f;   // running softmax state of head own_h (identical in all lanes of that head)
+    int j = 0;
+    int64_t root = r0;
+#pragma unroll 1
+    for (int t = 0; t < items;) {
+        if (j == 0) {   // new root: its folded query, fresh accumulators; warm L2 with the next root's query row
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float* qrow = qk + root * ldq + h * Dk;
+#pragma unroll
+                for (int r = 0; r < XR; ++r) {
+                    const int c = r * 32 + lane;
+                    q[h][r] = (c < NE4) ? __ldg(reinterpret_cast<const float4*>(qrow) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[h][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < TQ; ++r) {
+                    const int c = r * 32 + lane;
+                    qt[h][r] = (c < T) ? __ldg(qrow + NE4 * 4 + c) : 0.f;
+                    acct[h][r] = 0.f;
+                }
+            }
+            m_own = -INFINITY;
+            den_own = 0.f;
+            if (root + 1 < r1 && lane * 32 < H * Dk)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(qk + (root + 1) * ldq + lane * 32));
+        }
+        // chunk bookkeeping: chunk c+1 waits in registers while chunk c is consumed; it is parked (over chunk c-1, fully
+        // consumed) once item 32 c + 8 is reached, before the first lookahead into it at item 32 (c+1) - RING_DEPTH
+        if (parked == (t >> 5) && (t & 31) >= 8) {
+            park_chunk(parked + 1);
+            ++parked;
+            __syncwarp();
+            load_chunk(parked + 1);
+        }
+        const int g = (k - j) < G ? (k - j) : G;
+
+        // ---- pass 1: time encodings (parked in s_xt) and the partial scores of the group's neighbours
+        float part[V];
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) part[gi * H + h] = 0.f;
+            if (gi < g) {
+                const int tt = t + gi;
+                const float dt = s_dt[tt & 63];
+                float xt[TQ];
+#pragma unroll
+                for (int r = 0; r < TQ; ++r) {
+                    xt[r] = 0.f;
+                    if (r < ROUNDS) {
+                        const int c = r * 32 + lane;
+                        if ((r + 1) * 32 <= T || c < T) {
+                            xt[r] = dyg_time_enc(dt, tw[r], tb[r]);
+                            s_xt[gi * 128 + c] = xt[r];
+                        }
+                    }
+                }
+                ring_bar_wait(bars + (tt % RING_DEPTH), (uint32_t)((tt / RING_DEPTH) & 1));
+                float4 x[XR];
+                load_x(tt, s_fl[tt & 63], x);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float p0 = 0.f, p1 = 0.f;   // two chains
+#pragma unroll
+                    for (int r = 0; r < XR; ++r) {
+                        p0 = fmaf(q[h][r].x, x[r].x, p0);
+                        p1 = fmaf(q[h][r].y, x[r].y, p1);
+                        p0 = fmaf(q[h][r].z, x[r].z, p0);
+                        p1 = fmaf(q[h][r].w, x[r].w, p1);
+                    }
+#pragma unroll
+                    for (int r = 0; r < ROUNDS; ++r) p0 = fmaf(qt[h][r], xt[r], p0);
+                    part[gi * H + h] = p0 + p1;
+                }
+            }
+        }
+        if (GROUPED_REM) {
+            if (rem_g < g) s_xt[rem_g * 128 + rem_f] = dyg_time_enc(s_dt[(t + rem_g) & 63], rem_w, rem_b);
+            __syncwarp();
+            if (lane < TR) {
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    if (gi < g) {
+                        const float xr = s_xt[gi * 128 + TF * 32 + lane];
+#pragma unroll
+                        for (int h = 0; h < H; ++h) part[gi * H + h] = fmaf(qt[h][TQ - 1], xr, part[gi * H + h]);
+                    }
+                }
+            }
+        } else {
+            __syncwarp();
+        }
+        // ---- transposing reduction: V values per lane -> lane l holds the warp total of value l >> SH
+        {
+            int nv = V;
+#pragma unroll
+            for (int width = 16; nv > 1; width >>= 1, nv >>= 1) {
+                const bool up = lane & width;
+#pragma unroll
+                for (int i = 0; i < nv / 2; ++i) {
+                    const float send = up ? part[i] : part[i + nv / 2];
+                    const float keep = up ? part[i + nv / 2] : part[i];
+                    part[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
+                }
+            }
+#pragma unroll
+            for (int width = (1 << SH) >> 1; width > 0; width >>= 1) part[0] += __shfl_xor_sync(0xffffffffu, part[0], width);
+        }
+        // ---- softmax update of the group (lane-parallel over (neighbour, head))
+        float sc = -INFINITY;
+        if (own_g < g) sc = (s_fl[(t + own_g) & 63] & 1) ? -1e10f : part[0];   // -1e10, not -inf (models/modules.py:184)
+        if (out_scores && own_g < g && (lane & ((1 << SH) - 1)) == 0) out_scores[(root * H + own_h) * (int64_t)k + j + own_g] = sc;
+        float gm = fmaxf(sc, __shfl_xor_sync(0xffffffffu, sc, 16));
+        gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 8));
+        const float new_m = fmaxf(m_own, gm);
+        const float corr = __expf(m_own - new_m);
+        const float p_own = __expf(sc - new_m);
+        float ps = p_own + __shfl_xor_sync(0xffffffffu, p_own, 16);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 8);
+        den_own = fmaf(den_own, corr, ps);
+        m_own = new_m;
+        float corr_h[H];
+        bool rescale = false;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            corr_h[h] = __shfl_sync(0xffffffffu, corr, h << SH);
+            rescale |= corr_h[h] != 1.f;
+        }
+        if (rescale) {   // warp-uniform: a maximum moved
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+#pragma unroll
+                for (int r = 0; r < XR; ++r) {
+                    acc[h][r].x *= corr_h[h]; acc[h][r].y *= corr_h[h]; acc[h][r].z *= corr_h[h]; acc[h][r].w *= corr_h[h];
+                }
+#pragma unroll
+                for (int r = 0; r < TQ; ++r) acct[h][r] *= corr_h[h];
+            }
+        }
+        // ---- pass 2: weighted sums (rows re-read from the ring, time encodings from s_xt)
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+            if (gi < g) {
+                float pg[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) pg[h] = __shfl_sync(0xffffffffu, p_own, (gi * H + h) << SH);
+                float4 x[XR];
+                load_x(t + gi, s_fl[(t + gi) & 63], x);
+                float xt[TQ];
+#pragma unroll
+                for (int r = 0; r < TQ; ++r) xt[r] = ((r + 1) * 32 <= T || r * 32 + lane < T) ? s_xt[gi * 128 + r * 32 + lane] : 0.f;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+#pragma unroll
+                    for (int r = 0; r < XR; ++r) {
+                        acc[h][r].x = fmaf(pg[h], x[r].x, acc[h][r].x);
+                        acc[h][r].y = fmaf(pg[h], x[r].y, acc[h][r].y);
+                        acc[h][r].z = fmaf(pg[h], x[r].z, acc[h][r].z);
+                        acc[h][r].w = fmaf(pg[h], x[r].w, acc[h][r].w);
+                    }
+#pragma unroll
+                    for (int r = 0; r < TQ; ++r) acct[h][r] = fmaf(pg[h], xt[r], acct[h][r]);
+                }
+            }
+        }
+        __syncwarp();                         // every lane is done with the group's stages and s_xt: refill
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi)
+            if (gi < g) issue(t + gi + RING_DEPTH);
+        t += g;
+        j += g;
+        if (j == k) {   // root finished: normalise and write
+            float inv_h[H], mx_h[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                inv_h[h] = 1.f / __shfl_sync(0xffffffffu, den_own, h << SH);
+                mx_h[h] = __shfl_sync(0xffffffffu, m_own, h << SH);
+            }
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float inv = inv_h[h];
+                float* orow = out_s + root * lds + h * Dk;
+#pragma unroll
+                for (int r = 0; r < XR; ++r) {
+                    const int c = r * 32 + lane;
+                    if (c < NE4) {
+                        float4 v = acc[h][r];
+                        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+                        *(reinterpret_cast<float4*>(orow) + c) = v;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < TQ; ++r) {
+                    const int c = r * 32 + lane;
+                    if (c < T) orow[NE4 * 4 + c] = acct[h][r] * inv;
+                }
+            }
+            if (out_scores) {
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    for (int jj = lane; jj < k; jj += 32) {
+                        float* p = out_scores + (root * H + h) * (int64_t)k + jj;
+                        *p = expf(*p - mx_h[h]) * inv_h[h];
+                    }
+                }
+            }
+            j = 0;
+            ++root;
+        }
+    }
+}
+
 extern "C" int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H, const float* node_tab, int ld_node,
                                    const float* node_tab2, int ld_node2, const int64_t* node_idx, int F,
                                    const float* edge_tab, int ld_edge, const int64_t* edge_idx, int E,
                                    const float* time_feat, const double* t_query, const float* t_nbr, const float* w,
                                    const float* b, int T, const int64_t* mask_ids, float* out_s, int lds,
-                                   float* out_scores, dyg_stream_t stream) {
+                                   float* out_scores, int zero_row0, dyg_stream_t stream) {
     DYG_CHECK_ARG(n >= 0 && k > 0, "dyg_temporal_attend: bad sizes");
     DYG_CHECK_ARG(H == 1 || H == 2, "dyg_temporal_attend: num_heads=%d unsupported (1 or 2)", H);
     DYG_CHECK_ARG((F % 4) == 0 && (E % 4) == 0 && (T % 4) == 0 && F > 0 && E >= 0 && T >= 0,
@@ -379,7 +762,32 @@ extern "C" int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, i
     cudaStream_t s = as_stream(stream);
 #define ATTEND_ARGS qk, ldq, n, k, node_tab, ld_node, node_tab2, ld_node2, node_idx, F / 4, edge_tab, ld_edge, edge_idx, \
                     E / 4, time_feat, t_query, t_nbr, w, b, T / 4, mask_ids, out_s, lds, out_scores
-    if (F + E <= 384 && T <= 128) {
+    if (F == 172 && E == 172 && T == 100 && !time_feat) {
+        // the reference's feature widths (172-d node / edge rows, 100 time features): ring kernel, rows by the bulk-copy
+        // engine into a per-warp shared-memory ring
+        const bool node2 = node_tab2 != nullptr;
+        const int smem = 4 * ring_warp_bytes(43, 43, node2);
+        int64_t warps = (int64_t)dyg_num_sms() * (node2 ? 8 : 12);
+        if (warps > n) warps = n;
+        const unsigned rblocks = (unsigned)((warps + 3) / 4);
+#define ATTEND_RING_ARGS qk, ldq, n, k, node_tab, ld_node, node_tab2, ld_node2, node_idx, edge_tab, ld_edge, edge_idx, \
+                         t_query, t_nbr, w, b, mask_ids, out_s, lds, out_scores, zero_row0
+#define LAUNCH_RING(HH, N2)                                                                                                          \
+    do {                                                                                                                             \
+        static bool smem_set = false;                                                                                                \
+        if (!smem_set) {                                                                                                             \
+            cudaFuncSetAttribute(temporal_attend_ring_kernel<HH, N2, 43, 43, 100>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            smem_set = true;                                                                                                         \
+        }                                                                                                                            \
+        temporal_attend_ring_kernel<HH, N2, 43, 43, 100><<<rblocks, 128, smem, s>>>(ATTEND_RING_ARGS);                               \
+    } while (0)
+        if (H == 2 && node2) LAUNCH_RING(2, true);
+        else if (H == 2) LAUNCH_RING(2, false);
+        else if (node2) LAUNCH_RING(1, true);
+        else LAUNCH_RING(1, false);
+#undef LAUNCH_RING
+#undef ATTEND_RING_ARGS
+    } else if (F + E <= 384 && T <= 128) {
 #define ATTEND_SPLIT_ARGS qk, ldq, n, k, node_tab, ld_node, node_tab2, ld_node2, node_idx, F / 4, edge_tab, ld_edge, edge_idx, \
                           E / 4, time_feat, t_query, t_nbr, w, b, T, mask_ids, out_s, lds, out_scores
         if (H == 2) temporal_attend_split_kernel<2><<<blocks, 128, 0, s>>>(ATTEND_SPLIT_ARGS);

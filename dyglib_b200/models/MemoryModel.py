@@ -171,6 +171,8 @@ class GraphAttentionEmbedding(nn.Module):
         super().__init__()
         self.node_raw_features = node_raw_features
         self.edge_raw_features = edge_raw_features
+        # the memory table changes every batch: only the (static) edge table's padding row is declared zero
+        self._zero_row0 = ops.zero_row0_flags(None, edge_raw_features) & 2
         self.neighbor_sampler = neighbor_sampler
         self.time_encoder = time_encoder
         self.node_feat_dim = node_feat_dim
@@ -205,7 +207,8 @@ class GraphAttentionEmbedding(nn.Module):
         if layer > 1:
             nbr_dense = self._embed(mem, nbr.reshape(-1), nt.reshape(-1).double(), layer - 1, k, t0)
         return temporal_conv(self.temporal_conv_layers[layer - 1], self.merge_layers[layer - 1], self.time_encoder, t0,
-                             conv, feat, self.node_raw_features, mem, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k)
+                             conv, feat, self.node_raw_features, mem, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k,
+                             zero_row0=self._zero_row0)
 
 
 class MemoryModel(torch.nn.Module):

@@ -19,6 +19,7 @@ class TGAT(nn.Module):
         super().__init__()
         self.node_raw_features = torch.from_numpy(node_raw_features.astype(np.float32)).to(device).contiguous()
         self.edge_raw_features = torch.from_numpy(edge_raw_features.astype(np.float32)).to(device).contiguous()
+        self._zero_row0 = ops.zero_row0_flags(self.node_raw_features, self.edge_raw_features)
         self.neighbor_sampler = neighbor_sampler
         self.node_feat_dim = self.node_raw_features.shape[1]
         self.edge_feat_dim = self.edge_raw_features.shape[1]
@@ -64,7 +65,8 @@ class TGAT(nn.Module):
             # hop >= 2 queries run at the float32-rounded neighbour times (models/TGAT.py:107-110)
             nbr_dense = self._embed(nbr.reshape(-1), nt.reshape(-1).double(), layer - 1, k, t0)
         return temporal_conv(self.temporal_conv_layers[layer - 1], self.merge_layers[layer - 1], self.time_encoder, t0,
-                             conv, raw, self.node_raw_features, None, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k)
+                             conv, raw, self.node_raw_features, None, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k,
+                             zero_row0=self._zero_row0)
 
     def set_neighbor_sampler(self, neighbor_sampler: NeighborSampler):
         """``set_neighbor_sampler`` (``models/TGAT.py:138-147``)."""

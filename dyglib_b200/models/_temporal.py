@@ -22,7 +22,7 @@ def zero_time_features(time_encoder, device):
 
 
 def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node_tab2, nbr_ids, nbr_dense,
-                  edge_tab, nbr_eids, tq, nbr_t, k):
+                  edge_tab, nbr_eids, tq, nbr_t, k, zero_row0=0):
     """conv, root_feat: (n, F) dense; neighbours either lazily gathered from node_tab (+node_tab2) by nbr_ids
     (layer 1) or dense (n*k, F) rows ``nbr_dense`` (deeper layers).  tq float64 (n,), nbr_t float32 (n,k)."""
     n = conv.shape[0]
@@ -36,10 +36,10 @@ def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node
     flat_ids = nbr_ids.reshape(-1)
     if nbr_dense is None:
         s, _ = ops.temporal_attend(qk, n, k, H, node_tab, flat_ids, F_, edge_tab, nbr_eids.reshape(-1), E_, T_, flat_ids,
-                                   node_tab2=node_tab2, t_query=tq, t_nbr=nbr_t.reshape(-1), w=w, b=b)
+                                   node_tab2=node_tab2, t_query=tq, t_nbr=nbr_t.reshape(-1), w=w, b=b, zero_row0=zero_row0)
     else:
         s, _ = ops.temporal_attend(qk, n, k, H, nbr_dense, None, F_, edge_tab, nbr_eids.reshape(-1), E_, T_, flat_ids,
-                                   t_query=tq, t_nbr=nbr_t.reshape(-1), w=w, b=b)
+                                   t_query=tq, t_nbr=nbr_t.reshape(-1), w=w, b=b, zero_row0=zero_row0 & 2)
     o = ops.linear([ops.seg_rows(s)], n, wvr, attn.residual_fc.bias.detach())
     y = ops.layernorm(o, attn.layer_norm.weight.detach(), attn.layer_norm.bias.detach(), r1=conv, F1=F_, rconst=t0,
                       eps=attn.layer_norm.eps)

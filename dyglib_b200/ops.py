@@ -430,8 +430,17 @@ def time_encode(dt, w, b, out=None):
     return out
 
 
+def zero_row0_flags(node_tab, edge_tab, node_tab2=None):
+    """Which padding rows (row 0: node 0 / edge 0, preprocess_data/preprocess_data.py:101-108) of static tables are all
+    zeros, so that dyg_temporal_attend may skip reading them.  One host sync: call it at model construction."""
+    def z(t):
+        return t is None or bool(torch.count_nonzero(t[0]).item() == 0)
+    return (1 if (z(node_tab) and z(node_tab2)) else 0) | (2 if z(edge_tab) else 0)
+
+
 def temporal_attend(qk, n, k, H, node_tab, node_idx, F, edge_tab, edge_idx, E, T, mask_ids, node_tab2=None,
-                    time_feat=None, t_query=None, t_nbr=None, w=None, b=None, want_scores=False):
+                    time_feat=None, t_query=None, t_nbr=None, w=None, b=None, want_scores=False, zero_row0=0):
+    """zero_row0: see zero_row0_flags (bit 0: row 0 of node_tab / node_tab2 is zero, bit 1: row 0 of edge_tab is zero)."""
     Dk = F + E + T
     out = torch.empty((n, H * Dk), device=qk.device, dtype=torch.float32)
     scores = torch.empty((n, H, k), device=qk.device, dtype=torch.float32) if want_scores else None
@@ -441,7 +450,7 @@ def temporal_attend(qk, n, k, H, node_tab, node_idx, F, edge_tab, edge_idx, E, T
             _p(qk), qk.stride(0), int(n), int(k), int(H), _p(node_tab), node_tab.stride(-2), _p(node_tab2),
             node_tab2.stride(-2) if node_tab2 is not None else 0, _p(node_idx), int(F), _p(edge_tab), edge_tab.stride(-2),
             _p(edge_idx), int(E), _p(time_feat), _p(t_query), _p(t_nbr), _p(w), _p(b), int(T), _p(mask_ids),
-            _p(out), out.stride(0), _p(scores), _stream()))
+            _p(out), out.stride(0), _p(scores), int(zero_row0), _stream()))
     _count()
     return out, scores
 

@@ -231,14 +231,17 @@ int dyg_gather_rows(const float* tab, int ld, const float* tab2, int ld2, const 
  *   node row  = node_tab[r]  (+ node_tab2[r]),  r = node_idx ? node_idx[i*k+j] : i*k+j
  *   edge row  = edge_tab[e],                    e = edge_idx ? edge_idx[i*k+j] : i*k+j
  *   time enc  = time_feat ? time_feat[i*k+j,:] : cos(fma((float)(t_query[i]-(double)t_nbr[i*k+j]), w, b))
- * qk already holds scaling * W_k,h^T W_q,h [x_i | cos(b)] (H*Dk floats per root, Dk = F+E+T). */
+ * qk already holds scaling * W_k,h^T W_q,h [x_i | cos(b)] (H*Dk floats per root, Dk = F+E+T).
+ * zero_row0: bit 0 = row 0 of node_tab (and node_tab2) is all zeros, bit 1 = row 0 of edge_tab is all zeros (the padding
+ * rows of the reference's tables, preprocess_data/preprocess_data.py:101-108): the kernel then skips those reads. */
 int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H,
                         const float* node_tab, int ld_node, const float* node_tab2, int ld_node2,
                         const int64_t* node_idx, int F,
                         const float* edge_tab, int ld_edge, const int64_t* edge_idx, int E,
                         const float* time_feat, const double* t_query, const float* t_nbr,
                         const float* w, const float* b, int T,
-                        const int64_t* mask_ids, float* out_s, int lds, float* out_scores, dyg_stream_t stream);
+                        const int64_t* mask_ids, float* out_s, int lds, float* out_scores, int zero_row0,
+                        dyg_stream_t stream);
 
 /* ---- a16: nn.MultiheadAttention core inside DyGFormer's TransformerEncoder (models/DyGFormer.py:454) ----
  * qkv (B,S,3*H*hd) packed [q|k|v]; out (B,S,H*hd) = softmax(q k^T / sqrt(hd)) v per head; no mask. */
