@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128, 4) temporal_attend_split_kernel(
 // SM: ~180 KB) are in flight across root boundaries; the split kernel held <= 2 rows per warp and was latency-bound
 // (DRAM 41 %, issue 35 %: profiles/).  Indices, time deltas and flags of 32 items at a time are loaded coalesced and
 // parked in shared memory; the lane that loaded an item's indices issues its copies, nothing is shuffled.
-constexpr int RING_DEPTH = 8;
+constexpr int RING_DEPTH = 6;
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      (uint32_t)__cvta_generic_to_shared(dst)),
@@ -401,7 +401,7 @@ __host__ __device__ constexpr int ring_warp_bytes(int F4, int E4, bool node2) {
 // the lane loops folds at compile time.  The first version with run-time dimensions spent half of its 350 warp
 // instructions per neighbour on predicates, selects and index arithmetic (ncu source page, profiles/).
 template <int H, bool NODE2, int F4, int E4, int T>
-__global__ void __launch_bounds__(128, NODE2 ? 2 : 3) temporal_attend_ring_kernel(
+__global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kernel(
     const float* __restrict__ qk, int ldq, int64_t n, int k,
     const float* __restrict__ node_tab, int ld_node, const float* __restrict__ node_tab2, int ld_node2,
     const int64_t* __restrict__ node_idx, const float* __restrict__ edge_tab, int ld_edge, const int64_t* __restrict__ edge_idx,
@@ -767,7 +767,7 @@ extern "C" int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, i
         // engine into a per-warp shared-memory ring
         const bool node2 = node_tab2 != nullptr;
         const int smem = 4 * ring_warp_bytes(43, 43, node2);
-        int64_t warps = (int64_t)dyg_num_sms() * (node2 ? 8 : 12);
+        int64_t warps = (int64_t)dyg_num_sms() * (node2 ? 12 : 16);
         if (warps > n) warps = n;
         const unsigned rblocks = (unsigned)((warps + 3) / 4);
 #define ATTEND_RING_ARGS qk, ldq, n, k, node_tab, ld_node, node_tab2, ld_node2, node_idx, edge_tab, ld_edge, edge_idx, \
