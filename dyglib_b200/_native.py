@@ -114,7 +114,9 @@ SIGNATURES = {
     'dyg_layernorm': [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_l, c_i, c_p],
     'dyg_gather_rows': [c_p, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_i, c_p],
     'dyg_temporal_attend': [c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i,
-                            c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_p],
+                            c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p],
+    'dyg_temporal_attend_bwd': [c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i,
+                                c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p],
     'dyg_seq_attention': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_seq_attention_tc': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
     'dyg_mean_tokens': [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p],

@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
     const int64_t* __restrict__ node_idx, const float* __restrict__ edge_tab, int ld_edge, const int64_t* __restrict__ edge_idx,
     const double* __restrict__ t_query, const float* __restrict__ t_nbr,
     const float* __restrict__ w, const float* __restrict__ b,
-    const int64_t* __restrict__ mask_ids, float* __restrict__ out_s, int lds, float* __restrict__ out_scores, int zero_row0) {
+    const int64_t* __restrict__ mask_ids, float* __restrict__ out_s, int lds, float* __restrict__ out_scores, int zero_row0,
+    const float* __restrict__ prob_scale) {
     extern __shared__ __align__(128) unsigned char ring_smem[];
     constexpr int G = RING_GROUP, V = G * H;          // V partial scores per group: (neighbour g, head h) -> index g * H + h
     constexpr int SH = (V == 8) ? 2 : 3;              // after the transposing reduction lane l owns score index l >> SH
@@ -646,6 +647,8 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
         ps += __shfl_xor_sync(0xffffffffu, ps, 8);
         den_own = fmaf(den_own, corr, ps);
         m_own = new_m;
+        // training: dropout multipliers of the attention probabilities (models/modules.py:187) weigh the sum, not the normaliser
+        const float pw_own = (prob_scale && own_g < g) ? p_own * __ldg(prob_scale + (root * H + own_h) * (int64_t)k + j + own_g) : p_own;
         float corr_h[H];
         bool rescale = false;
 #pragma unroll
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
             if (gi < g) {
                 float pg[H];
 #pragma unroll
-                for (int h = 0; h < H; ++h) pg[h] = __shfl_sync(0xffffffffu, p_own, (gi * H + h) << SH);
+                for (int h = 0; h < H; ++h) pg[h] = __shfl_sync(0xffffffffu, pw_own, (gi * H + h) << SH);
                 float4 x[XR];
                 load_x(t + gi, s_fl[(t + gi) & 63], x);
                 float xt[TQ];
@@ -738,13 +741,223 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of dyg_temporal_attend (training path; the reference differentiates models/modules.py:157-193 with autograd).
+// With probs a_hj = softmax_j(q_h . x_j) (before dropout), m_hj the dropout multipliers, s_h = sum_j a_hj m_hj x_j and
+// g_h = dL/ds_h:   u_hj = g_h . x_j,  c_h = g_h . s_h,  dscore_hj = a_hj (m_hj u_hj - c_h)   (0 for masked neighbours:
+// masked_fill cuts the gradient of the score, models/modules.py:184),
+//   dL/dq_h = sum_j dscore_hj x_j,     dL/dx_j = sum_h (a_hj m_hj g_h + dscore_hj q_h).
+// dL/dx_j's node part is written when the neighbour rows are a dense trainable tensor (deeper layers), its time part is
+// chained through cos: dL/dw += -sin(arg) dt gx, dL/db += -sin(arg) gx, summed in registers and added once per warp.
+// One warp per root, the lane mapping of temporal_attend_split_kernel; neighbours are read once.
+template <int H>
+__global__ void __launch_bounds__(128) temporal_attend_bwd_kernel(
+    const float* __restrict__ qk, int ldq, int64_t n, int k,
+    const float* __restrict__ node_tab, int ld_node, const float* __restrict__ node_tab2, int ld_node2,
+    const int64_t* __restrict__ node_idx, int F4,
+    const float* __restrict__ edge_tab, int ld_edge, const int64_t* __restrict__ edge_idx, int E4,
+    const double* __restrict__ t_query, const float* __restrict__ t_nbr,
+    const float* __restrict__ w, const float* __restrict__ b, int T, const int64_t* __restrict__ mask_ids,
+    const float* __restrict__ probs, const float* __restrict__ prob_scale, const float* __restrict__ s_out, int lds,
+    const float* __restrict__ gs, int ldg, float* __restrict__ gqk, int ldgq, float* __restrict__ g_nbr, int ld_gn,
+    float* __restrict__ gw, float* __restrict__ gb) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int NE4 = F4 + E4;
+    const int Dk = NE4 * 4 + T;
+    float tw[4], tb[4], gw_acc[4], gb_acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int c = r * 32 + lane;
+        tw[r] = c < T ? __ldg(w + c) : 0.f;
+        tb[r] = c < T ? __ldg(b + c) : 0.f;
+        gw_acc[r] = 0.f;
+        gb_acc[r] = 0.f;
+    }
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        float4 q[H][3], g[H][3], gq[H][3];
+        float qt[H][4], gt[H][4], gqt[H][4];
+        float ch[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float* qrow = qk + i * ldq + h * Dk;
+            const float* grow = gs + i * ldg + h * Dk;
+            const float* srow = s_out + i * lds + h * Dk;
+            float c = 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int cc = r * 32 + lane;
+                const bool on = cc < NE4;
+                q[h][r] = on ? __ldg(reinterpret_cast<const float4*>(qrow) + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                g[h][r] = on ? __ldg(reinterpret_cast<const float4*>(grow) + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 sv = on ? __ldg(reinterpret_cast<const float4*>(srow) + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                c += g[h][r].x * sv.x + g[h][r].y * sv.y + g[h][r].z * sv.z + g[h][r].w * sv.w;
+                gq[h][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int cc = r * 32 + lane;
+                const bool on = cc < T;
+                qt[h][r] = on ? __ldg(qrow + NE4 * 4 + cc) : 0.f;
+                gt[h][r] = on ? __ldg(grow + NE4 * 4 + cc) : 0.f;
+                c += gt[h][r] * (on ? __ldg(srow + NE4 * 4 + cc) : 0.f);
+                gqt[h][r] = 0.f;
+            }
+            ch[h] = warp_sum(c);
+        }
+        const double tq = __ldg(t_query + i);
+        const int64_t base = i * (int64_t)k;
+        for (int j = 0; j < k; ++j) {
+            const int64_t rn = node_idx ? __ldg(node_idx + base + j) : base + j;
+            const int64_t re = edge_idx ? __ldg(edge_idx + base + j) : base + j;
+            const float dt = (float)(tq - (double)__ldg(t_nbr + base + j));
+            const bool masked = mask_ids ? (__ldg(mask_ids + base + j) == 0) : false;
+            float4 x[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int c = r * 32 + lane;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < F4) {
+                    v = __ldg(reinterpret_cast<const float4*>(node_tab + rn * ld_node) + c);
+                    if (node_tab2) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(node_tab2 + rn * ld_node2) + c);
+                        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                    }
+                } else if (c < NE4) {
+                    v = __ldg(reinterpret_cast<const float4*>(edge_tab + re * ld_edge) + (c - F4));
+                }
+                x[r] = v;
+            }
+            float xt[4], sn[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                xt[r] = 0.f;
+                sn[r] = 0.f;
+                if (r * 32 + lane < T) dyg_sincosf(fmaf(dt, tw[r], tb[r]), &sn[r], &xt[r]);
+            }
+            float u[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float p = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) p += g[h][r].x * x[r].x + g[h][r].y * x[r].y + g[h][r].z * x[r].z + g[h][r].w * x[r].w;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) p = fmaf(gt[h][r], xt[r], p);
+                u[h] = warp_sum(p);
+            }
+            float am[H], ds[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float a = __ldg(probs + (i * H + h) * (int64_t)k + j);
+                const float m = prob_scale ? __ldg(prob_scale + (i * H + h) * (int64_t)k + j) : 1.f;
+                am[h] = a * m;
+                ds[h] = masked ? 0.f : a * (m * u[h] - ch[h]);
+            }
+            float4 gx[3];
+            float gxt[4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                gx[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    gq[h][r].x = fmaf(ds[h], x[r].x, gq[h][r].x);
+                    gq[h][r].y = fmaf(ds[h], x[r].y, gq[h][r].y);
+                    gq[h][r].z = fmaf(ds[h], x[r].z, gq[h][r].z);
+                    gq[h][r].w = fmaf(ds[h], x[r].w, gq[h][r].w);
+                    gx[r].x += am[h] * g[h][r].x + ds[h] * q[h][r].x;
+                    gx[r].y += am[h] * g[h][r].y + ds[h] * q[h][r].y;
+                    gx[r].z += am[h] * g[h][r].z + ds[h] * q[h][r].z;
+                    gx[r].w += am[h] * g[h][r].w + ds[h] * q[h][r].w;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                gxt[r] = 0.f;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    gqt[h][r] = fmaf(ds[h], xt[r], gqt[h][r]);
+                    gxt[r] += am[h] * gt[h][r] + ds[h] * qt[h][r];
+                }
+                gb_acc[r] = fmaf(-sn[r], gxt[r], gb_acc[r]);
+                gw_acc[r] = fmaf(-sn[r] * dt, gxt[r], gw_acc[r]);
+            }
+            if (g_nbr) {
+                float* grow = g_nbr + (base + j) * (int64_t)ld_gn;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int c = r * 32 + lane;
+                    if (c < F4) *(reinterpret_cast<float4*>(grow) + c) = gx[r];
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float* orow = gqk + i * ldgq + h * Dk;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int c = r * 32 + lane;
+                if (c < NE4) *(reinterpret_cast<float4*>(orow) + c) = gq[h][r];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = r * 32 + lane;
+                if (c < T) orow[NE4 * 4 + c] = gqt[h][r];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int c = r * 32 + lane;
+        if (c < T) {
+            if (gw) atomicAdd(gw + c, gw_acc[r]);
+            if (gb) atomicAdd(gb + c, gb_acc[r]);
+        }
+    }
+}
+
+extern "C" int dyg_temporal_attend_bwd(const float* qk, int ldq, int64_t n, int k, int H, const float* node_tab, int ld_node,
+                                       const float* node_tab2, int ld_node2, const int64_t* node_idx, int F,
+                                       const float* edge_tab, int ld_edge, const int64_t* edge_idx, int E,
+                                       const double* t_query, const float* t_nbr, const float* w, const float* b, int T,
+                                       const int64_t* mask_ids, const float* probs, const float* prob_scale, const float* s_out,
+                                       int lds, const float* grad_s, int ldg, float* grad_qk, int ldgq, float* grad_nbr,
+                                       int ld_gn, float* grad_w, float* grad_b, dyg_stream_t stream) {
+    DYG_CHECK_ARG(n >= 0 && k > 0, "dyg_temporal_attend_bwd: bad sizes");
+    DYG_CHECK_ARG(H == 1 || H == 2, "dyg_temporal_attend_bwd: num_heads=%d unsupported (1 or 2)", H);
+    DYG_CHECK_ARG((F % 4) == 0 && (E % 4) == 0 && F > 0 && E >= 0 && T >= 0 && F + E <= 384 && T <= 128,
+                  "dyg_temporal_attend_bwd: unsupported feature dims %d / %d / %d", F, E, T);
+    DYG_CHECK_ARG((ld_node % 4) == 0 && (ld_edge % 4) == 0 && (ldq % 4) == 0 && (lds % 4) == 0 && (ldg % 4) == 0 &&
+                      (ldgq % 4) == 0 && (!node_tab2 || (ld_node2 % 4) == 0) && (!grad_nbr || (ld_gn % 4) == 0),
+                  "dyg_temporal_attend_bwd: leading dims must be multiples of 4");
+    DYG_CHECK_ARG(aligned16(qk) && aligned16(node_tab) && aligned16(edge_tab) && aligned16(s_out) && aligned16(grad_s) &&
+                      aligned16(grad_qk) && (!node_tab2 || aligned16(node_tab2)) && (!grad_nbr || aligned16(grad_nbr)),
+                  "dyg_temporal_attend_bwd: pointers must be 16-byte aligned");
+    DYG_CHECK_ARG(t_query && t_nbr && w && b && probs, "dyg_temporal_attend_bwd: NULL pointer");
+    if (n == 0) return 0;
+    int64_t warps = (int64_t)dyg_num_sms() * 16;
+    if (warps > n) warps = n;
+    const unsigned blocks = (unsigned)((warps + 3) / 4);
+    cudaStream_t s = as_stream(stream);
+#define ATTEND_BWD_ARGS qk, ldq, n, k, node_tab, ld_node, node_tab2, ld_node2, node_idx, F / 4, edge_tab, ld_edge, edge_idx, E / 4, \
+                        t_query, t_nbr, w, b, T, mask_ids, probs, prob_scale, s_out, lds, grad_s, ldg, grad_qk, ldgq, grad_nbr,   \
+                        ld_gn, grad_w, grad_b
+    if (H == 2) temporal_attend_bwd_kernel<2><<<blocks, 128, 0, s>>>(ATTEND_BWD_ARGS);
+    else temporal_attend_bwd_kernel<1><<<blocks, 128, 0, s>>>(ATTEND_BWD_ARGS);
+#undef ATTEND_BWD_ARGS
+    DYG_LAUNCH_CHECK("dyg_temporal_attend_bwd");
+    return 0;
+}
+
 extern "C" int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H, const float* node_tab, int ld_node,
                                    const float* node_tab2, int ld_node2, const int64_t* node_idx, int F,
                                    const float* edge_tab, int ld_edge, const int64_t* edge_idx, int E,
                                    const float* time_feat, const double* t_query, const float* t_nbr, const float* w,
                                    const float* b, int T, const int64_t* mask_ids, float* out_s, int lds,
-                                   float* out_scores, int zero_row0, dyg_stream_t stream) {
+                                   float* out_scores, int zero_row0, const float* prob_scale, dyg_stream_t stream) {
     DYG_CHECK_ARG(n >= 0 && k > 0, "dyg_temporal_attend: bad sizes");
+    DYG_CHECK_ARG(!prob_scale || (F == 172 && E == 172 && T == 100 && !time_feat),
+                  "dyg_temporal_attend: prob_scale (training) needs the 172 / 172 / 100 feature widths and in-kernel time encoding");
     DYG_CHECK_ARG(H == 1 || H == 2, "dyg_temporal_attend: num_heads=%d unsupported (1 or 2)", H);
     DYG_CHECK_ARG((F % 4) == 0 && (E % 4) == 0 && (T % 4) == 0 && F > 0 && E >= 0 && T >= 0,
                   "dyg_temporal_attend: feature dims must be multiples of 4");
@@ -771,7 +984,7 @@ extern "C" int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, i
         if (warps > n) warps = n;
         const unsigned rblocks = (unsigned)((warps + 3) / 4);
 #define ATTEND_RING_ARGS qk, ldq, n, k, node_tab, ld_node, node_tab2, ld_node2, node_idx, edge_tab, ld_edge, edge_idx, \
-                         t_query, t_nbr, w, b, mask_ids, out_s, lds, out_scores, zero_row0
+                         t_query, t_nbr, w, b, mask_ids, out_s, lds, out_scores, zero_row0, prob_scale
 #define LAUNCH_RING(HH, N2)                                                                                                          \
     do {                                                                                                                             \
         static bool smem_set = false;                                                                                                \

@@ -61,6 +61,29 @@ __device__ __forceinline__ float dyg_cosf(float x) {
     return ((n + 1) & 2) ? -res : res;                           // cos(r + n pi/2): +cos, -sin, -cos, +sin
 }
 
+// sin and cos of the same fp32 argument with the reduction of dyg_cosf (used by the time encoder's backward:
+// d cos(x) / dx = -sin(x) at the fp32 argument the forward pass used).
+__device__ __forceinline__ void dyg_sincosf(float x, float* sn, float* cs) {
+    if (fabsf(x) > 2.0e9f) { sincosf(x, sn, cs); return; }
+    const double xd = (double)x;
+    const double q = rint(xd * 0.63661977236758134308);
+    double r = fma(-q, 1.57079632679489655800e+00, xd);
+    r = fma(-q, 6.12323399573676603587e-17, r);
+    const float rf = (float)r;
+    const int n = (int)q;
+    const float r2 = rf * rf;
+    float ps = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    const float sr = rf + rf * r2 * ps;                                   // sin(r)
+    float pc = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    const float cr = 1.0f + fmaf(r2 * r2, pc, -0.5f * r2);                // cos(r)
+    // x = r + n pi/2:  n mod 4 = 0: (s, c) = (sr, cr); 1: (cr, -sr); 2: (-sr, -cr); 3: (-cr, sr)
+    const float s0 = (n & 1) ? cr : sr, c0 = (n & 1) ? sr : cr;
+    *sn = (n & 2) ? -s0 : s0;
+    *cs = ((n + 1) & 2) ? -c0 : c0;
+}
+
 // TimeEncoder element (models/modules.py:37): nn.Linear(1,T) on CPU is a single fp32 FMA, then cos.
 __device__ __forceinline__ float dyg_time_enc(float dt, float w, float b) { return dyg_cosf(fmaf(dt, w, b)); }
 

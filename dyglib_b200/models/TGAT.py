@@ -8,7 +8,7 @@ import torch.nn as nn
 from .. import ops
 from ..utils.utils import NeighborSampler, _as_dev
 from .modules import TimeEncoder, MergeLayer, MultiHeadAttention, _eval_only
-from ._temporal import temporal_conv, zero_time_features
+from ._temporal import temporal_conv, temporal_conv_train, zero_time_features
 
 
 class TGAT(nn.Module):
@@ -47,12 +47,25 @@ class TGAT(nn.Module):
     def compute_node_temporal_embeddings(self, node_ids, node_interact_times, current_layer_num: int, num_neighbors: int = 20):
         """``compute_node_temporal_embeddings`` (``models/TGAT.py:66-136``); accepts numpy arrays or CUDA tensors."""
         assert current_layer_num >= 0
-        _eval_only(self)
         dev = self.node_raw_features.device
         ids = _as_dev(node_ids, torch.int64, dev)
         tq = _as_dev(node_interact_times, torch.float64, dev)
+        if self.training and torch.is_grad_enabled():
+            return self._embed_train(ids, tq, current_layer_num, num_neighbors)
         t0 = zero_time_features(self.time_encoder, dev)
         return self._embed(ids, tq, current_layer_num, num_neighbors, t0)
+
+    def _embed_train(self, ids, tq, layer, k):
+        """The recursion of ``_embed`` with autograd (training mode)."""
+        raw = ops.gather_rows(self.node_raw_features, ids)
+        if layer == 0:
+            return raw
+        conv = raw if layer == 1 else self._embed_train(ids, tq, layer - 1, k)
+        nbr, eid, nt = self.neighbor_sampler.get_historical_neighbors_device(ids, tq, k)
+        nbr_dense = self._embed_train(nbr.reshape(-1), nt.reshape(-1).double(), layer - 1, k) if layer > 1 else None
+        return temporal_conv_train(self.temporal_conv_layers[layer - 1], self.merge_layers[layer - 1], self.time_encoder, conv, raw,
+                                   self.node_raw_features, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k,
+                                   zero_row0=self._zero_row0)
 
     def _embed(self, ids, tq, layer, k, t0):
         raw = ops.gather_rows(self.node_raw_features, ids)

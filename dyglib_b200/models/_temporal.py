@@ -46,3 +46,32 @@ def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node
     h = ops.linear([ops.seg_rows(y), ops.seg_rows(root_feat)], n, merge.fc1.weight.detach(), merge.fc1.bias.detach(),
                    act=ops.ACT_RELU)
     return ops.linear([ops.seg_rows(h)], n, merge.fc2.weight.detach(), merge.fc2.bias.detach())
+
+
+def temporal_conv_train(attn, merge, time_encoder, conv, root_feat, node_tab, nbr_ids, nbr_dense, edge_tab, nbr_eids, tq,
+                        nbr_t, k, zero_row0=0):
+    """Training-mode ``temporal_conv``: the same folded formulation with autograd (``dyglib_b200/autograd.py``).  The folded
+    weights are rebuilt from the parameters every step (four (136 x 272/444) products per head), so their gradients reach
+    ``query_projection`` / ``key_projection`` / ``value_projection`` / ``residual_fc``; dropout sits where the reference has
+    it (attention probabilities and the ``residual_fc`` output, ``models/modules.py:187,196``)."""
+    from .. import autograd as ag
+    n = conv.shape[0]
+    F_, E_, T_ = attn.node_feat_dim, attn.edge_feat_dim, attn.time_feat_dim
+    H, hd = attn.num_heads, attn.head_dim
+    wq, wk, wv, r = attn.query_projection.weight, attn.key_projection.weight, attn.value_projection.weight, attn.residual_fc.weight
+    wqk = torch.cat([attn.scaling_factor * (wk[h * hd:(h + 1) * hd].t() @ wq[h * hd:(h + 1) * hd]) for h in range(H)], dim=0)
+    wvr = torch.cat([r[:, h * hd:(h + 1) * hd] @ wv[h * hd:(h + 1) * hd] for h in range(H)], dim=1)
+    t0 = torch.cos(time_encoder.w.bias)                           # time encoding of a zero interval (models/TGAT.py:82)
+    query_in = torch.cat([conv, t0.unsqueeze(0).expand(n, T_)], dim=1)
+    qk = ag.linear(query_in, wqk)
+    flat_ids = nbr_ids.reshape(-1)
+    p = attn.dropout.p if attn.training else 0.0
+    s = ag.temporal_attend(qk, nbr_dense, time_encoder.w.weight, time_encoder.w.bias, n=n, k=k, H=H, node_tab=node_tab,
+                           node_idx=flat_ids, F=F_, edge_tab=edge_tab, edge_idx=nbr_eids.reshape(-1), E=E_, T=T_, mask_ids=flat_ids,
+                           t_query=tq, t_nbr=nbr_t.reshape(-1).contiguous(), zero_row0=zero_row0, dropout=p)
+    o = ag.linear(s, wvr, attn.residual_fc.bias)
+    o = torch.nn.functional.dropout(o, p, attn.training)
+    y = torch.nn.functional.layer_norm(o + query_in, (attn.query_dim,), attn.layer_norm.weight, attn.layer_norm.bias,
+                                       attn.layer_norm.eps)
+    h = ag.linear([y, root_feat], merge.fc1.weight, merge.fc1.bias, act=ops.ACT_RELU)
+    return ag.linear(h, merge.fc2.weight, merge.fc2.bias)

@@ -58,6 +58,10 @@ class MergeLayer(nn.Module):
 
     def forward(self, input_1: torch.Tensor, input_2: torch.Tensor):
         """fc2(relu(fc1([input_1 | input_2]))) -- the concatenation is never materialised."""
+        if self.training and torch.is_grad_enabled():
+            from .. import autograd as ag
+            h = ag.linear([input_1, input_2], self.fc1.weight, self.fc1.bias, act=ops.ACT_RELU)
+            return ag.linear(h, self.fc2.weight, self.fc2.bias)
         a, b = _f32(input_1), _f32(input_2)
         h = ops.linear([ops.seg_rows(a), ops.seg_rows(b)], a.shape[0], self.fc1.weight.detach(), self.fc1.bias.detach(),
                        act=ops.ACT_RELU)

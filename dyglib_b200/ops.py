@@ -439,7 +439,8 @@ def zero_row0_flags(node_tab, edge_tab, node_tab2=None):
 
 
 def temporal_attend(qk, n, k, H, node_tab, node_idx, F, edge_tab, edge_idx, E, T, mask_ids, node_tab2=None,
-                    time_feat=None, t_query=None, t_nbr=None, w=None, b=None, want_scores=False, zero_row0=0):
+                    time_feat=None, t_query=None, t_nbr=None, w=None, b=None, want_scores=False, zero_row0=0,
+                    prob_scale=None):
     """zero_row0: see zero_row0_flags (bit 0: row 0 of node_tab / node_tab2 is zero, bit 1: row 0 of edge_tab is zero)."""
     Dk = F + E + T
     out = torch.empty((n, H * Dk), device=qk.device, dtype=torch.float32)
@@ -450,9 +451,28 @@ def temporal_attend(qk, n, k, H, node_tab, node_idx, F, edge_tab, edge_idx, E, T
             _p(qk), qk.stride(0), int(n), int(k), int(H), _p(node_tab), node_tab.stride(-2), _p(node_tab2),
             node_tab2.stride(-2) if node_tab2 is not None else 0, _p(node_idx), int(F), _p(edge_tab), edge_tab.stride(-2),
             _p(edge_idx), int(E), _p(time_feat), _p(t_query), _p(t_nbr), _p(w), _p(b), int(T), _p(mask_ids),
-            _p(out), out.stride(0), _p(scores), int(zero_row0), _stream()))
+            _p(out), out.stride(0), _p(scores), int(zero_row0), _p(prob_scale), _stream()))
     _count()
     return out, scores
+
+
+def temporal_attend_bwd(qk, n, k, H, node_tab, node_idx, F, edge_tab, edge_idx, E, T, mask_ids, t_query, t_nbr, w, b, probs,
+                        prob_scale, s_out, grad_s, want_nbr=False, node_tab2=None):
+    """Backward of ``temporal_attend`` (dyg_temporal_attend_bwd): returns (grad_qk, grad_nbr or None, grad_w, grad_b)."""
+    Dk = F + E + T
+    dev = qk.device
+    gqk = torch.empty((n, H * Dk), device=dev, dtype=torch.float32)
+    gnbr = torch.empty((n * k, F), device=dev, dtype=torch.float32) if want_nbr else None
+    gw = torch.zeros(T, device=dev, dtype=torch.float32)
+    gb = torch.zeros(T, device=dev, dtype=torch.float32)
+    _native.check(_lib().dyg_temporal_attend_bwd(
+        _p(qk), qk.stride(0), int(n), int(k), int(H), _p(node_tab), node_tab.stride(-2), _p(node_tab2),
+        node_tab2.stride(-2) if node_tab2 is not None else 0, _p(node_idx), int(F), _p(edge_tab), edge_tab.stride(-2),
+        _p(edge_idx), int(E), _p(t_query), _p(t_nbr), _p(w), _p(b), int(T), _p(mask_ids), _p(probs), _p(prob_scale),
+        _p(s_out), s_out.stride(0), _p(grad_s), grad_s.stride(0), _p(gqk), gqk.stride(0), _p(gnbr),
+        gnbr.stride(0) if gnbr is not None else 0, _p(gw), _p(gb), _stream()))
+    _count()
+    return gqk, gnbr, gw, gb
 
 
 def seq_attention(qkv, B, S, H, hd, out=None):

@@ -233,7 +233,9 @@ int dyg_gather_rows(const float* tab, int ld, const float* tab2, int ld2, const 
  *   time enc  = time_feat ? time_feat[i*k+j,:] : cos(fma((float)(t_query[i]-(double)t_nbr[i*k+j]), w, b))
  * qk already holds scaling * W_k,h^T W_q,h [x_i | cos(b)] (H*Dk floats per root, Dk = F+E+T).
  * zero_row0: bit 0 = row 0 of node_tab (and node_tab2) is all zeros, bit 1 = row 0 of edge_tab is all zeros (the padding
- * rows of the reference's tables, preprocess_data/preprocess_data.py:101-108): the kernel then skips those reads. */
+ * rows of the reference's tables, preprocess_data/preprocess_data.py:101-108): the kernel then skips those reads.
+ * prob_scale (n,H,k) or NULL: multipliers applied to the softmax probabilities before the weighted sum (training-mode
+ * dropout of the attention scores, models/modules.py:187); out_scores stay the undropped probabilities. */
 int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H,
                         const float* node_tab, int ld_node, const float* node_tab2, int ld_node2,
                         const int64_t* node_idx, int F,
@@ -241,7 +243,21 @@ int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, int H,
                         const float* time_feat, const double* t_query, const float* t_nbr,
                         const float* w, const float* b, int T,
                         const int64_t* mask_ids, float* out_s, int lds, float* out_scores, int zero_row0,
-                        dyg_stream_t stream);
+                        const float* prob_scale, dyg_stream_t stream);
+/* Backward of dyg_temporal_attend for the training path (the reference differentiates models/modules.py:157-193 with
+ * autograd).  probs (n,H,k): softmax probabilities of the forward pass (its out_scores); prob_scale (n,H,k) or NULL: the
+ * dropout multipliers the forward pass applied (models/modules.py:187); s_out / grad_s: forward output and its gradient.
+ * Writes grad_qk (n, H*Dk); grad_nbr (n*k, F) = gradient of the neighbour node rows (NULL when they are constants);
+ * ADDS the time encoder's gradients into grad_w / grad_b (T floats each, caller zeroes them; may be NULL). */
+int dyg_temporal_attend_bwd(const float* qk, int ldq, int64_t n, int k, int H,
+                            const float* node_tab, int ld_node, const float* node_tab2, int ld_node2,
+                            const int64_t* node_idx, int F,
+                            const float* edge_tab, int ld_edge, const int64_t* edge_idx, int E,
+                            const double* t_query, const float* t_nbr, const float* w, const float* b, int T,
+                            const int64_t* mask_ids, const float* probs, const float* prob_scale,
+                            const float* s_out, int lds, const float* grad_s, int ldg,
+                            float* grad_qk, int ldgq, float* grad_nbr, int ld_gn, float* grad_w, float* grad_b,
+                            dyg_stream_t stream);
 
 /* ---- a16: nn.MultiheadAttention core inside DyGFormer's TransformerEncoder (models/DyGFormer.py:454) ----
  * qkv (B,S,3*H*hd) packed [q|k|v]; out (B,S,H*hd) = softmax(q k^T / sqrt(hd)) v per head; no mask. */

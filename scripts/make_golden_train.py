@@ -1,0 +1,38 @@
+"""Generate tests/golden/tgat_train.npz: loss and every parameter gradient of one training step of the UNMODIFIED reference
+TGAT + MergeLayer link predictor (train mode, dropout 0 so that the step is deterministic), /root/reference, build container only:
+    python scripts/make_golden_train.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, '/root/reference')
+
+from helpers import small_graph, deterministic_state_dict, tgat_train_step  # noqa: E402
+from utils.utils import get_neighbor_sampler  # noqa: E402  (reference)
+from utils.DataLoader import Data  # noqa: E402
+from models.TGAT import TGAT  # noqa: E402
+from models.modules import MergeLayer  # noqa: E402
+
+
+def main():
+    g = small_graph(seed=11)
+    data = Data(g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, g.labels)
+    m = TGAT(g.node_raw_features, g.edge_raw_features, get_neighbor_sampler(data, 'recent'), 100, 2, 2, 0.0).train()
+    m.load_state_dict(deterministic_state_dict(m.state_dict(), 1))
+    pred = MergeLayer(172, 172, 172, 1).train()
+    pred.load_state_dict(deterministic_state_dict(pred.state_dict(), 5))
+    params = {'model.' + k: v for k, v in m.named_parameters()}
+    params.update({'pred.' + k: v for k, v in pred.named_parameters()})
+    out = tgat_train_step(lambda s, d, t, k: m.compute_src_dst_node_temporal_embeddings(s, d, t, k), lambda a, b: pred(a, b), params)
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'tgat_train.npz'), **out)
+    print('loss', out['loss'], {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith('grad.')})
+
+
+if __name__ == '__main__':
+    main()

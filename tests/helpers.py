@@ -186,3 +186,72 @@ def cuda_factories():
 def load_golden(name):
     import os
     return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', name)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Training step (train_link_prediction.py:165-257): BCE over positive and negative link probabilities, one backward pass.
+def tgat_train_step(embed_fn, predictor_fn, params: dict, seed=11, start=2000, B=40, k=20):
+    """embed_fn(src, dst, t, k) -> (src_emb, dst_emb) torch tensors with autograd; predictor_fn(a, b) -> (n, 1) logits;
+    params: name -> tensor whose .grad is collected.  Returns {'loss': ..., 'grad.<name>': ...} as numpy."""
+    g = small_graph(seed=seed)
+    src, dst, t, _, neg = next(batches(g, start, 1, B))
+    ps, pd = embed_fn(src, dst, t, k)
+    ns, nd = embed_fn(src, neg, t, k)
+    pos = predictor_fn(ps, pd).squeeze(dim=-1).sigmoid()
+    negp = predictor_fn(ns, nd).squeeze(dim=-1).sigmoid()
+    predicts = torch.cat([pos, negp], dim=0)
+    labels = torch.cat([torch.ones_like(pos), torch.zeros_like(negp)], dim=0)
+    loss = torch.nn.functional.binary_cross_entropy(predicts, labels)
+    for p in params.values():
+        p.grad = None
+    loss.backward()
+    out = {'loss': np.asarray(loss.item(), dtype=np.float64), 'pos': pos.detach().cpu().numpy(), 'neg': negp.detach().cpu().numpy()}
+    for name, p in params.items():
+        out['grad.' + name] = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu().numpy()
+    return out
+
+
+def predictor_template():
+    from dyglib_b200.models.modules import MergeLayer
+    return MergeLayer(172, 172, 172, 1)
+
+
+def assert_grads_close(got: dict, want: dict, rtol=2e-3):
+    """Every gradient tensor within rtol of its own largest magnitude (fp32 accumulation order differs)."""
+    assert set(got) == set(want), set(got) ^ set(want)
+    for key in sorted(want):
+        a, b = np.asarray(got[key], dtype=np.float64), np.asarray(want[key], dtype=np.float64)
+        assert a.shape == b.shape, key
+        scale = max(float(np.abs(b).max()), 1e-7)
+        err = float(np.abs(a - b).max()) / scale
+        assert err < rtol, (key, err)
+
+
+def oracle_tgat_train_step():
+    """One training step of the oracle TGAT + link predictor (autograd through the oracle's torch-CPU restatement)."""
+    from oracle.models import merge_layer
+    _, tgat, _, _ = oracle_factories()
+    g = small_graph(seed=11)
+    m = tgat(g, 1)
+    m.sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in m.sd.items()}
+    psd = {k: v.clone().requires_grad_(True) for k, v in deterministic_state_dict(predictor_template().state_dict(), 5).items()}
+    params = {'model.' + k: v for k, v in m.sd.items()}
+    params.update({'pred.' + k: v for k, v in psd.items()})
+    return tgat_train_step(lambda s, d, t, k: m.compute_src_dst_node_temporal_embeddings(s, d, t, k),
+                           lambda a, b: merge_layer(psd, '', a, b), params)
+
+
+def cuda_tgat_train_step(dropout=0.0):
+    """The same step on the CUDA package (training mode, autograd through dyglib_b200/autograd.py)."""
+    _, tgat, _, _ = cuda_factories()
+    g = small_graph(seed=11)
+    m = tgat(g, 1)
+    for layer in m.temporal_conv_layers:
+        layer.dropout.p = dropout
+    m.train()
+    pred = predictor_template().to('cuda')
+    pred.load_state_dict(deterministic_state_dict(pred.state_dict(), 5))
+    pred.train()
+    params = {'model.' + k: v for k, v in m.named_parameters()}
+    params.update({'pred.' + k: v for k, v in pred.named_parameters()})
+    return tgat_train_step(lambda s, d, t, k: m.compute_src_dst_node_temporal_embeddings(s, d, t, k), lambda a, b: pred(a, b), params)

@@ -26,3 +26,13 @@ def test_oracle_models_match_golden(which):
     assert len(got) > 0
     for k in got:
         np.testing.assert_allclose(got[k], gold[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+
+def test_oracle_tgat_training_step_matches_golden():
+    """Loss and every parameter gradient of one training step (train_link_prediction.py:165-257) against the reference's
+    (scripts/make_golden_train.py)."""
+    from helpers import oracle_tgat_train_step, assert_grads_close
+    got = oracle_tgat_train_step()
+    gold = load_golden('tgat_train.npz')
+    np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+    assert_grads_close(got, gold, rtol=1e-3)
