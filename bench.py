@@ -575,6 +575,197 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ training configuration
+def run_train(args):
+    """TGAT training step (train_link_prediction.py:230-257: pos + neg embeddings, BCE, backward, Adam) on one reference batch
+    of 200 events per rank per step; data parallel over ranks with ONE gradient all-reduce (NCCL) per step over the flat
+    gradient bucket (the only collective on the path).  Dropout 0.1 as in the reference's defaults."""
+    rank, world, local = dist_env()
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    from dyglib_b200 import ops
+    from dyglib_b200.utils.dist import GradBucket
+    pk = peaks()
+    wl = TGATWL()
+    wl.build(dev)
+    model, pred, stream = wl.model.train(), wl.pred.train(), wl.stream
+    params = list(model.parameters()) + list(pred.parameters())
+    if world > 1:                                   # same initial weights on every rank
+        for p_ in params:
+            dist.broadcast(p_.data, 0)
+    bucket = GradBucket(params)
+    opt = torch.optim.Adam(bucket.params, lr=1e-4, capturable=not args.no_graph)
+    K, W = args.steps, args.warmup
+    host_steps = [stream.rows(shard_batches(i, 1, world, rank, stream.nb)) for i in range(W + K)]
+    to_dev = lambda hs: tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in hs)   # noqa: E731
+    dev_steps = [to_dev(hs) for hs in host_steps]
+    pinned = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in hs) for hs in host_steps]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def train_step(src, dst, neg, t, eid):
+        bucket.zero()
+        # the four root sets of the reference's two calls (models/TGAT.py:48-64 for (src, dst) and for (src, neg); the src
+        # embedding of the negative pair is recomputed under its own dropout masks) go through ONE recursion of 4 B roots
+        B = src.numel()
+        emb = model.compute_node_temporal_embeddings(torch.cat([src, dst, src, neg]), torch.cat([t, t, t, t]), 2, 20)
+        pos = pred(emb[:B], emb[B:2 * B]).squeeze(dim=-1).sigmoid()
+        negp = pred(emb[2 * B:3 * B], emb[3 * B:]).squeeze(dim=-1).sigmoid()
+        predicts = torch.cat([pos, negp], dim=0)
+        labels = torch.cat([torch.ones_like(pos), torch.zeros_like(negp)], dim=0)
+        loss = torch.nn.functional.binary_cross_entropy(predicts, labels)
+        loss.backward()
+        bucket.allreduce()
+        opt.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step):
+        evs = []
+        for i in range(W, W + K):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = run_step(i)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs), out
+
+    step_fn = train_step
+    if not args.no_graph:
+        # the whole step (sampling, forward, backward, all-reduce, Adam) replayed as one CUDA graph: at B=200 the direct
+        # step is bound by the host issuing ~130 kernels of ours plus the autograd / optimizer ops
+        from dyglib_b200.utils.graph import GraphedStep
+        step_fn = GraphedStep(train_step, dev_steps[0], warmup=3, grad=True)
+    clocks = ClockSampler(torch.cuda.current_device())
+    for i in range(W):
+        step_fn(*dev_steps[i])
+    bucket.check_views()
+    barrier()
+    launches0 = ops.launch_count
+    total_ms, loss = timed(lambda i: step_fn(*dev_steps[i]))
+    launches = ops.launch_count - launches0
+    clk = clocks.stop()
+
+    def e2e_step(i):
+        ls = step_fn(*pinned[i]) if step_fn is not train_step else train_step(*[a.to(dev, non_blocking=True) for a in pinned[i]])
+        loss_host.copy_(ls.reshape(1), non_blocking=True)
+        return ls
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    e2e_ms, _ = timed(e2e_step)
+    h2d = sum(a.numel() * a.element_size() for a in pinned[0])
+    # per-kernel pass (our launches only; the dense backward GEMMs are library calls and are not in this list)
+    ops.PROFILE = []
+    for i in range(W, W + K):
+        flush.zero_()
+        train_step(*dev_steps[i])
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    # gradient all-reduce alone (device time of the collective on the flat bucket)
+    ar_ms = None
+    if world > 1:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(bucket.flat)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_ms = e0.elapsed_time(e1) / 10
+        tt = torch.tensor([total_ms, e2e_ms, ar_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, ar_ms = tt.tolist()
+        # the ranks must have stayed in lock step: identical weights after the same averaged gradients
+        flatw = torch.cat([p_.detach().reshape(-1) for p_ in bucket.params])
+        ref = flatw.clone()
+        dist.broadcast(ref, 0)
+        in_sync = bool((ref == flatw).all().item())
+    else:
+        in_sync = True
+    per_kernel = {}
+    for name, e0, e1, fl, by in prof:
+        d = per_kernel.setdefault(name, [0.0, 0.0, 0.0, 0])
+        d[0] += e0.elapsed_time(e1)
+        d[1] += fl
+        d[2] += by
+        d[3] += 1
+    name, (ms, fl, by, cnt) = max(per_kernel.items(), key=lambda kv: kv[1][0])
+    if by > 0 and name.startswith('temporal_attend'):
+        achieved = by / (ms * 1e-3) / 1e9
+        roofline = {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s', 'frac': achieved / pk['hbm'],
+                    'traffic': None, 'peak_source': pk['source']}
+    else:
+        achieved = fl / (ms * 1e-3) / 1e12
+        roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+                    'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' (bf16 sustained)'}
+    roofline.update({'launches': cnt, 'avg_launch_us': 1e3 * ms / cnt,
+                     'share_of_timed_kernels': ms / max(sum(v[0] for v in per_kernel.values()), 1e-9),
+                     'note': 'B=200 training step: launch / latency bound (about 100 launches of small kernels per step)'})
+    events_total = K * REF_BATCH * world
+    line = {
+        'metric': 'link-pred training events/sec', 'value': events_total / (total_ms * 1e-3), 'unit': 'events/s', 'n_gpus': world,
+        'steps': K, 'warmup': W, 'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'tgat_train (TGAT 2 layers, 20 recent neighbours, dropout 0.1, batch 200 per rank, pos+neg, BCE, Adam lr 1e-4)',
+                   'events_per_step_per_gpu': REF_BATCH, 'reference_batch': REF_BATCH,
+                   'sharding': 'data parallel: one reference batch per rank per step, one NCCL all-reduce of the flat fp32 gradient '
+                               'bucket per step; CSR + feature tables replicated',
+                   'grad_elements': int(bucket.flat.numel()), 'l2': 'flushed between timed steps (256 MiB write)',
+                   'csr_build_s': round(wl.build_s, 4),
+                   'launch': 'direct launches' if step_fn is train_step else 'CUDA graph replay of the captured training step'},
+        'roofline': roofline,
+        'e2e': {'value': events_total / (e2e_ms * 1e-3), 'unit': 'events/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+        'gpu_launches': launches, 'clocks': clk, 'allreduce_ms': ar_ms, 'ranks_in_sync': in_sync, 'final_loss': float(loss.item()),
+        'kernels': {k: {'ms': round(v[0], 3), 'launches': v[3]} for k, v in per_kernel.items()},
+    }
+    if rank == 0 and world == 1:
+        # CPU arm: the oracle port's training step (autograd through the torch-CPU restatement) on the same batches
+        torch.set_num_threads(os.cpu_count() or 1)
+        from oracle.sampler import OracleSampler
+        from oracle.models import OracleTGAT, merge_layer
+        g = wl.g
+        sd = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+        psd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in pred.state_dict().items()}
+        samp = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
+        om = OracleTGAT(sd, g.node_raw_features, g.edge_raw_features, samp, 2, 2)
+        nb = args.cpu_batches or 2
+        t0 = None
+        for b in range(nb + 1):
+            if b == 1:
+                t0 = time.perf_counter()
+            src, dst, neg, t, _ = stream.rows([b % stream.nb])
+            ps, pd = om.compute_src_dst_node_temporal_embeddings(src, dst, t, 20)
+            ns, nd = om.compute_src_dst_node_temporal_embeddings(src, neg, t, 20)
+            pr = torch.cat([merge_layer(psd, '', ps, pd).squeeze(-1).sigmoid(), merge_layer(psd, '', ns, nd).squeeze(-1).sigmoid()])
+            lb = torch.cat([torch.ones(len(src)), torch.zeros(len(src))])
+            torch.nn.functional.binary_cross_entropy(pr, lb).backward()
+        v = nb * REF_BATCH / (time.perf_counter() - t0)
+        line['cpu_baseline'] = {'value': v, 'unit': 'events/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': f'{nb} training batches of 200 events (forward + backward, no dropout), oracle/ torch-CPU port, '
+                                          'after 1 warm-up batch'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        # the captured graph holds NCCL kernels: tearing the communicator down under it hung at exit; leave together instead
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------ sampler sweep
 def device_power_law_graph(E, nu, ni, seed, dev):
     """Config 5 (SURVEY.md 8(d)): 1e8-event power-law bipartite stream, strictly increasing integer times;
@@ -752,7 +943,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='dygformer_wiki',
-                    choices=['dygformer_wiki', 'dygformer_lastfm', 'tgat_myket', 'tgn_reddit', 'sampler_sweep'])
+                    choices=['dygformer_wiki', 'dygformer_lastfm', 'tgat_myket', 'tgn_reddit', 'sampler_sweep', 'tgat_train'])
     ap.add_argument('--batches-per-step', type=int, default=0)
     ap.add_argument('--cpu-batches', type=int, default=0)
     ap.add_argument('--events', type=int, default=100_000_000)
@@ -761,11 +952,14 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel directly instead of replaying the captured step')
     args = ap.parse_args()
     if args.impl == 'reference':
-        if args.workload == 'sampler_sweep':
+        if args.workload in ('sampler_sweep', 'tgat_train'):
             args.workload = 'dygformer_wiki'
         run_reference(args)
     elif args.workload == 'sampler_sweep':
         run_sampler_sweep(args)
+    elif args.workload == 'tgat_train':
+        args.warmup = max(args.warmup, 3)
+        run_train(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_ours(args)

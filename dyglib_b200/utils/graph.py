@@ -20,12 +20,15 @@ class GraphedStep:
     bank) is mutated by every replay exactly as by a direct call.  ``warmup`` direct calls are made before capture so
     that lazily built caches exist; ``after_warmup`` (e.g. a memory reset) runs after them, before capture."""
 
-    def __init__(self, fn, example_inputs, warmup: int = 2, after_warmup=None):
+    def __init__(self, fn, example_inputs, warmup: int = 2, after_warmup=None, grad: bool = False):
+        """``grad=True`` captures a whole training step (forward, ``backward()``, gradient all-reduce, a ``capturable``
+        optimizer step): gradients must then accumulate into preallocated buffers (``utils.dist.GradBucket``)."""
         self.fn = fn
+        mode = torch.enable_grad if grad else torch.no_grad
         self.static_in = [x.clone() for x in example_inputs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side), torch.no_grad():
+        with torch.cuda.stream(side), mode():
             for _ in range(warmup):
                 fn(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
@@ -35,7 +38,7 @@ class GraphedStep:
             torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        with mode(), torch.cuda.graph(self.graph):
             self.static_out = fn(*self.static_in)
         self.launches = ops.launch_count - n0     # kernels of the package inside one replay
         # capture records, it does not run: the state is still what after_warmup left
