@@ -97,7 +97,8 @@ SIGNATURES = {
     'dyg_draw_uniform': [c_p, c_p, c_l, c_i, c_p, c_p],
     'dyg_draw_tia': [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_p, c_p],
     'dyg_philox_uniform': [c_u64, c_u64, c_l, c_p, c_p],
-    'dyg_sample_random': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_l, c_i, c_u64, c_u64, c_p, c_p, c_p, c_p],
+    'dyg_sample_random': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_p, c_p, c_l, c_i, c_u64, c_u64, c_p, c_p, c_p, c_p],
+    'dyg_cum_fence_build': [c_p, c_l, c_p, c_p],
     'dyg_first_hop_pad': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     'dyg_cooc_count': [c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     'dyg_time_encode': [c_p, c_l, c_p, c_p, c_i, c_p, c_p],

@@ -185,6 +185,115 @@ __device__ __forceinline__ I lower_bound_time_fenced(const dyg_halfedge_t* __res
     return lo + (I)count_records<LANES, I>(he, lo, hi, tq, lane) - a;
 }
 
+// Entries <= x of the sorted double array f in [lo, hi), by ONE lane: 16-byte loads of aligned entry pairs (a pair may start
+// one entry before lo / end one after hi: both stay inside the allocation and are masked out).
+template <typename I>
+__device__ __forceinline__ int count_le(const double* __restrict__ f, I lo, I hi, double x) {
+    if ((lo & 15) == 0 && hi == lo + 16) {   // the common case below the start level: one whole 128-byte line, no masks
+        const double2* p = reinterpret_cast<const double2*>(f + lo);
+        double2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(p + i);
+        int c16 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c16 += (v[i].x <= x) + (v[i].y <= x);
+        return c16;
+    }
+    int c = 0;
+#pragma unroll 4
+    for (I i = lo & ~(I)1; i < hi; i += 2) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(f + i));
+        c += (i >= lo && v.x <= x) + (i + 1 < hi && v.y <= x);
+    }
+    return c;
+}
+// searchsorted(cum[a : a + cnt], target, 'right') for the time_interval_aware prefix table (one lane per draw), descending the
+// fence index of `cum` (same block structure as the CSR fence: level l holds cum[16^l i + 16^l - 1]).  cum is non-decreasing
+// inside a node's run, so the complete blocks inside [a, a + cnt) have sorted fence entries.  A binary search costs
+// ~log2(cnt) dependent probes, each its own DRAM access (profiles/: 10.4 KB read per query of 20 draws); here a draw reads
+// one 128-byte line per level, and the levels above the first (1/256 of the table and less) stay in L2.
+template <typename I>
+__device__ __forceinline__ I upper_bound_cum_fenced(const double* __restrict__ cum, const Fence& fx, I a, I cnt, double target) {
+    const I b = a + cnt;
+    int top = 0;
+    for (I d = cnt; d > 32 && top < fx.nlev; d >>= 4) ++top;
+    I lo = (a + (((I)1 << (4 * top)) - 1)) >> (4 * top), hi = b >> (4 * top);
+    if (hi < lo) hi = lo;
+    for (int l = top; l > 0; --l) {
+        const I pos = lo + (I)count_le<I>(fx.lvl[l], lo, hi, target);
+        const I s_l = (a + (((I)1 << (4 * l)) - 1)) >> (4 * l);
+        I e_l = b >> (4 * l);
+        if (e_l < s_l) e_l = s_l;
+        lo = pos == s_l ? (a + (((I)1 << (4 * (l - 1))) - 1)) >> (4 * (l - 1)) : pos << 4;
+        hi = pos == e_l ? b >> (4 * (l - 1)) : (pos << 4) + 16;
+    }
+    return lo + (I)count_le<I>(cum, lo, hi, target) - a;
+}
+
+// Interpolation start for the same search.  The table's increments are exp(p) with p in [0, 1] (utils/utils.py:112-128 feeds
+// probabilities, not logits, to the softmax of :183), i.e. within [1, e]: cum is close to linear inside a prefix and
+// a linearly interpolated position g is within a few entries of the answer.  Read the 128-byte line around the guess, step to the neighbouring
+// line while the target lies outside, and only then fall back to the fence descent on the remaining side.  The result is the
+// exact searchsorted position in every case; in the common case a draw costs one line read instead of one per level.
+template <typename I>
+__device__ __forceinline__ I upper_bound_cum_interp(const double* __restrict__ cum, const Fence& fx, I a, I cnt, I g, double target) {
+    const I b = a + cnt;
+    if (g >= cnt) g = cnt - 1;
+    I bs = (a + g) & ~(I)15;
+    int dir = 0;   // direction of the previous step: a reversal means the answer is the boundary between the two lines
+#pragma unroll 1
+    for (int tries = 0; tries < 4; ++tries) {
+        const I lo = bs > a ? bs : a, hi = bs + 16 < b ? bs + 16 : b;
+        const I c = (I)count_le<I>(cum, lo, hi, target);
+        if (c == 0 && lo > a) {
+            if (dir > 0) return lo - a;
+            if (tries == 3) return upper_bound_cum_fenced<I>(cum, fx, a, lo - a, target);
+            bs -= 16;
+            dir = -1;
+        } else if (c == hi - lo && hi < b) {
+            if (dir < 0) return hi - a;
+            if (tries == 3) return (hi - a) + upper_bound_cum_fenced<I>(cum, fx, hi, b - hi, target);
+            bs += 16;
+            dir = 1;
+        } else {
+            return lo + c - a;
+        }
+    }
+    return 0;   // not reached
+}
+
+// Secant refinement in front of it.  A divergent 16-byte load costs the L1 one wavefront per lane, so the 8 loads of a
+// whole line per draw bound the kernel on L1 wavefronts (20 draws x 8 loads x 32 lanes; profiles/).  Here a candidate
+// position s is checked by reading just cum[s-1] and cum[s] (one aligned pair when s is odd, two otherwise); a miss moves s
+// by (target - value) / local increment.  With increments in [1, e] the second or third candidate is the answer; after four
+// misses the line / fence search above takes over, so the result is exact for any table.
+template <typename I>
+__device__ __forceinline__ I upper_bound_cum_secant(const double* __restrict__ cum, const Fence& fx, I a, I cnt, I g, double target) {
+    I s = g > cnt ? cnt : g;
+#pragma unroll 1
+    for (int tries = 0; tries < 4; ++tries) {
+        double left, right;   // cum[a + s - 1], cum[a + s]
+        const I i = a + s;
+        if (s > 0 && s < cnt && (i & 1)) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(cum + i - 1));
+            left = v.x;
+            right = v.y;
+        } else {
+            left = s > 0 ? __ldg(cum + i - 1) : -INFINITY;
+            right = s < cnt ? __ldg(cum + i) : INFINITY;
+        }
+        if (left <= target && target < right) return s;
+        double m = (s > 0 && s < cnt) ? right - left : 1.0;
+        if (!(m > 1e-300)) m = 1.0;
+        double step;
+        if (target >= right) step = 1.0 + floor((target - right) / m);
+        else step = -1.0 - floor((left - target) / m);
+        const double ns = (double)s + step;
+        s = ns <= 0.0 ? (I)0 : (ns >= (double)cnt ? cnt : (I)ns);
+    }
+    return upper_bound_cum_interp<I>(cum, fx, a, cnt, g, target);
+}
+
 // MODE 0: no fence index (cooperative (LANES+1)-ary search over the records); 1: fence index, uint32 index arithmetic
 // (fewer than 2^31 half-edges); 2: fence index, int64 index arithmetic.  Every lane of the warp must call it.
 template <int LANES, int MODE>
@@ -520,9 +629,9 @@ __device__ __forceinline__ double philox_u01(uint64_t seed, uint64_t ctr) {
 template <int LANES, bool TIA, int MODE>
 __global__ void __launch_bounds__(256) sample_random_kernel(
     const dyg_halfedge_t* __restrict__ he, const int64_t* __restrict__ indptr, int64_t num_nodes, const __grid_constant__ Fence fx,
-    const double* __restrict__ cum, const int64_t* __restrict__ node_ids, const double* __restrict__ times,
-    int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* __restrict__ out_nbr, int64_t* __restrict__ out_eid,
-    float* __restrict__ out_t) {
+    const double* __restrict__ cum, const __grid_constant__ Fence cfx, const int64_t* __restrict__ node_ids,
+    const double* __restrict__ times, int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* __restrict__ out_nbr,
+    int64_t* __restrict__ out_eid, float* __restrict__ out_t) {
     extern __shared__ unsigned char smem_raw[];
     const int groups = blockDim.x / LANES;
     const int g = threadIdx.x / LANES;
@@ -551,12 +660,19 @@ __global__ void __launch_bounds__(256) sample_random_kernel(
             int64_t s;
             if (TIA && tot > 0.0) {
                 const double target = u * tot;
-                int64_t lo = 0, hi = cnt;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (__ldg(cum + a + mid) <= target) lo = mid + 1; else hi = mid;
+                const int64_t g = (int64_t)(u * (double)cnt);   // first guess: the table is close to linear (see upper_bound_cum_interp)
+                if (cfx.nlev > 0 && MODE == 1) {
+                    s = (int64_t)upper_bound_cum_secant<uint32_t>(cum, cfx, (uint32_t)a, (uint32_t)cnt, (uint32_t)g, target);
+                } else if (cfx.nlev > 0) {
+                    s = upper_bound_cum_secant<int64_t>(cum, cfx, a, cnt, g, target);
+                } else {
+                    int64_t lo = 0, hi = cnt;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (__ldg(cum + a + mid) <= target) lo = mid + 1; else hi = mid;
+                    }
+                    s = lo;
                 }
-                s = lo;
             } else {
                 s = (int64_t)floor(u * (double)cnt);
             }
@@ -645,6 +761,21 @@ extern "C" int dyg_csr_fence_build(const dyg_halfedge_t* he, int64_t num_half_ed
         csr_fence_kernel<<<blocks_for(cnt[l], 256, 148 * 16), 256, 0, as_stream(stream)>>>(
             he, l == 1 ? nullptr : fence + off[l - 1], cnt[l], fence + off[l]);
         DYG_LAUNCH_CHECK("dyg_csr_fence_build");
+    }
+    return 0;
+}
+
+extern "C" int dyg_cum_fence_build(const double* cum, int64_t num_half_edges, double* fence, dyg_stream_t stream) {
+    DYG_CHECK_ARG(num_half_edges >= 0, "dyg_cum_fence_build: bad size");
+    int64_t off[DYG_FENCE_MAX_LEVELS + 1], cnt[DYG_FENCE_MAX_LEVELS + 1];
+    const int nlev = fence_levels(num_half_edges, off, cnt);
+    if (nlev == 0) return 0;
+    DYG_CHECK_ARG(cum && fence && (reinterpret_cast<uintptr_t>(fence) & 127u) == 0 && (reinterpret_cast<uintptr_t>(cum) & 15u) == 0,
+                  "dyg_cum_fence_build: fence must be 128-byte aligned, cum 16-byte aligned");
+    for (int l = 1; l <= nlev; ++l) {
+        csr_fence_kernel<<<blocks_for(cnt[l], 256, 148 * 16), 256, 0, as_stream(stream)>>>(
+            nullptr, l == 1 ? cum : fence + off[l - 1], cnt[l], fence + off[l]);
+        DYG_LAUNCH_CHECK("dyg_cum_fence_build");
     }
     return 0;
 }
@@ -794,17 +925,18 @@ extern "C" int dyg_first_hop_pad(const dyg_halfedge_t* he, const int64_t* indptr
 }
 
 extern "C" int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
-                                 int64_t num_half_edges, const double* cum, const int64_t* node_ids, const double* times,
-                                 int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* out_nbr, int64_t* out_eid,
-                                 float* out_t, dyg_stream_t stream) {
+                                 int64_t num_half_edges, const double* cum, const double* cum_fence, const int64_t* node_ids,
+                                 const double* times, int64_t n, int k, uint64_t seed, uint64_t offset, int64_t* out_nbr,
+                                 int64_t* out_eid, float* out_t, dyg_stream_t stream) {
     DYG_CHECK_ARG(k > 0, "Number of sampled neighbors for each node should be greater than 0!");
     DYG_CHECK_ARG((size_t)k * 12 <= 40 * 1024, "dyg_sample_random: num_neighbors %d too large (max 3413)", k);
     if (n == 0) return 0;
     cudaStream_t s = as_stream(stream);
     const Fence fx = make_fence(fence, num_half_edges);
+    const Fence cfx = make_fence(cum ? cum_fence : nullptr, num_half_edges);
     const int mode = search_mode(fence, num_half_edges);
-#define LAUNCH_RANDOM_T(MODE) sample_random_kernel<LR, true, MODE><<<grid_, block_, smem_, s>>>(he, indptr, num_nodes, fx, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t)
-#define LAUNCH_RANDOM_F(MODE) sample_random_kernel<LR, false, MODE><<<grid_, block_, smem_, s>>>(he, indptr, num_nodes, fx, cum, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t)
+#define LAUNCH_RANDOM_T(MODE) sample_random_kernel<LR, true, MODE><<<grid_, block_, smem_, s>>>(he, indptr, num_nodes, fx, cum, cfx, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t)
+#define LAUNCH_RANDOM_F(MODE) sample_random_kernel<LR, false, MODE><<<grid_, block_, smem_, s>>>(he, indptr, num_nodes, fx, cum, cfx, node_ids, times, n, k, seed, offset, out_nbr, out_eid, out_t)
 #define DISPATCH_RANDOM(L, GRID, BLOCK, SMEM)                        \
     do {                                                             \
         constexpr int LR = L;                                        \
@@ -814,12 +946,9 @@ extern "C" int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr
         else DISPATCH_MODE(mode, LAUNCH_RANDOM_F);                   \
     } while (0)
     if (k <= 32) {
-        if (!cum) {   // uniform: 4 lanes per query (6.6 ms vs 7.3 ms with 8 on the sweep); the CDF search of tia prefers 8 (34 vs 38 ms)
+        {   // 4 lanes per query: uniform 6.6 ms vs 7.3 ms with 8 on the sweep, time_interval_aware 12.3 vs 13.4 ms
             const int threads = 256, groups = threads / 4;
             DISPATCH_RANDOM(4, blocks_for(n, groups), threads, (size_t)groups * k * 12);
-        } else {
-            const int threads = 256, groups = threads / 8;
-            DISPATCH_RANDOM(8, blocks_for(n, groups), threads, (size_t)groups * k * 12);
         }
     } else {
         int groups = (int)((40 * 1024) / ((size_t)k * 12));

@@ -157,6 +157,7 @@ class NeighborSampler:
             ops._count()
         self._prob_host = None
         self.tia_cum = None
+        self.tia_cum_fence = None
         self._philox_offset = 0
         if self.sample_neighbor_strategy == 'time_interval_aware':
             self._build_tia(tia_table)
@@ -188,6 +189,12 @@ class NeighborSampler:
             _native.check(lib.dyg_csr_tia_tables(_p(self.halfedges), _p(self.indptr), self.num_nodes,
                                                  float(self.time_scaling_factor), _p(self.tia_prob), _p(self.tia_cum), _stream()))
         ops._count()
+        # fence index over the prefix table (16-ary levels, like the CSR fence) for the fused throughput kernel's CDF search
+        n_f = int(lib.dyg_csr_fence_entries(int(n_half)))
+        self.tia_cum_fence = torch.empty(n_f, dtype=torch.float64, device=dev) if n_f and self.use_fence else None
+        if self.tia_cum_fence is not None:
+            _native.check(lib.dyg_cum_fence_build(_p(self.tia_cum), int(n_half), _p(self.tia_cum_fence), _stream()))
+            ops._count()
 
     # ------------------------------------------------------------------ reference-compatible attribute views
     def _node_slice(self, node_id):
@@ -256,6 +263,7 @@ class NeighborSampler:
             off = self._philox_offset
             _native.check(lib.dyg_sample_random(_p(self.halfedges), _p(self.indptr), self.num_nodes, _p(self.fence), self.num_half_edges,
                                                 _p(self.tia_cum) if strat == 'time_interval_aware' else None,
+                                                _p(self.tia_cum_fence) if strat == 'time_interval_aware' else None,
                                                 _p(ids), _p(tq), n, k, int(self.seed or 0), int(off),
                                                 _p(out_n), _p(out_e), _p(out_t), _stream()))
             self._philox_offset = off + n * k

@@ -62,6 +62,10 @@ int dyg_csr_tia_cum(const double* prob, const int64_t* indptr, int64_t num_nodes
  * takes `fence` (NULL: search the records directly) and `num_half_edges` (defines the level offsets). */
 int64_t dyg_csr_fence_entries(int64_t num_half_edges);
 int dyg_csr_fence_build(const dyg_halfedge_t* he, int64_t num_half_edges, double* fence, dyg_stream_t stream);
+/* The same index over the time_interval_aware prefix table `cum` (non-decreasing inside a node's run): level l holds
+ * cum[16^l i + 16^l - 1].  Same size as the CSR fence (dyg_csr_fence_entries).  dyg_sample_random descends it instead of
+ * binary-searching cum (np.searchsorted(cdf, u, 'right') inside RandomState.choice, utils/utils.py:187). */
+int dyg_cum_fence_build(const double* cum, int64_t num_half_edges, double* fence, dyg_stream_t stream);
 
 /* ---- a2: find_neighbors_before (utils/utils.py:130-147): cnt[q] = #{j : t_j < times[q]} ---- */
 int dyg_count_before(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
@@ -88,9 +92,10 @@ int dyg_draw_tia(const double* cum, const int64_t* indptr, const int64_t* node_i
 /* Counter-based uniforms for the sharded throughput mode (labelled non-parity): u[i] from (seed, offset+i). */
 int dyg_philox_uniform(uint64_t seed, uint64_t offset, int64_t count, double* u, dyg_stream_t stream);
 /* Fused throughput path (labelled non-parity): search + Philox draw (counter offset + q*k + j) + gather + time
- * re-sort in one kernel.  cum == NULL: uniform (floor(u*cnt)); cum != NULL: time_interval_aware prefix-CDF search. */
+ * re-sort in one kernel.  cum == NULL: uniform (floor(u*cnt)); cum != NULL: time_interval_aware prefix-CDF search, through
+ * cum_fence (dyg_cum_fence_build) when it is not NULL. */
 int dyg_sample_random(const dyg_halfedge_t* he, const int64_t* indptr, int64_t num_nodes, const double* fence,
-                      int64_t num_half_edges, const double* cum, const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed, uint64_t offset,
+                      int64_t num_half_edges, const double* cum, const double* cum_fence, const int64_t* node_ids, const double* times, int64_t n, int k, uint64_t seed, uint64_t offset,
                       int64_t* out_nbr, int64_t* out_eid, float* out_t, dyg_stream_t stream);
 
 /* ---- a7 + a12: get_all_first_hop_neighbors + DyGFormer.pad_sequences (utils/utils.py:254-273,

@@ -285,3 +285,63 @@ def test_fence_index_matches_searchsorted(dups, index64, monkeypatch):
     s.fence = None
     b = s.get_all_first_hop_neighbors_device(ids, tq, 64, 2)
     assert all(torch.equal(x, y) for x, y in zip(a[:4], b[:4]))
+
+
+@pytest.mark.parametrize('index64', [False, True])
+def test_tia_cum_fence_matches_binary_search_and_numpy(index64, monkeypatch):
+    """Fused throughput kernel, time_interval_aware: the CDF search through the fence index over the prefix table returns the
+    same draws as the plain binary search (fence disabled), and both equal np.searchsorted(cum[:cnt], u * cum[cnt-1], 'right')
+    with the kernel's own Philox uniforms.  Degrees cross every block / level boundary of the 16-ary index."""
+    if index64:
+        monkeypatch.setenv('DYG_FENCE_INDEX64', '1')
+    from dyglib_b200 import _native
+    from dyglib_b200.ops import _p, _stream
+    from dyglib_b200.utils.utils import NeighborSampler
+    rng = np.random.default_rng(23)
+    degs = [0, 1, 15, 16, 17, 31, 33, 47, 48, 49, 63, 255, 256, 257, 511, 513, 700, 4095, 4097, 70001, 3, 300000, 5]
+    owner = np.repeat(np.arange(1, len(degs) + 1), degs)
+    n_half = len(owner)
+    t = rng.permutation(n_half * 2)[:n_half].astype(np.float64)
+    dev = torch.device('cuda')
+    s = object.__new__(NeighborSampler)
+    s.device, s.use_fence, s.sample_neighbor_strategy, s.seed, s.rng = dev, True, 'time_interval_aware', 9, 'philox'
+    s.time_scaling_factor = 3e-5
+    s._build(owner, rng.integers(1, 100, n_half), np.arange(1, n_half + 1), t, len(degs) + 1, False, 'device')
+    assert s.tia_cum_fence is not None
+    indptr = s.indptr.cpu().numpy()
+    rec_t = s.halfedges[:n_half, 0].cpu().numpy()
+    cum = s.tia_cum[:n_half].cpu().numpy()
+    nq, k = 6000, 20
+    nodes = rng.integers(0, len(degs) + 1, nq)
+    times = np.empty(nq)
+    for i, v in enumerate(nodes):
+        a, b = indptr[v], indptr[v + 1]
+        times[i] = rng.integers(-5, 2 * n_half + 5) if (b == a or i % 3 == 0) else rec_t[rng.integers(a, b)] + (i % 2)
+    ids, tq = s._queries(nodes, times)
+    s._philox_offset = 0
+    with_fence = s.get_historical_neighbors_device(ids, tq, k)
+    fence, s.tia_cum_fence = s.tia_cum_fence, None
+    s._philox_offset = 0
+    without = s.get_historical_neighbors_device(ids, tq, k)
+    s.tia_cum_fence = fence
+    assert all(torch.equal(x, y) for x, y in zip(with_fence, without))
+    # numpy restatement from the same uniforms
+    # draw (q, j) of the fused kernel = first double of Philox counter q * k + j = element 2 (q k + j) of dyg_philox_uniform
+    u = torch.empty(2 * nq * k, dtype=torch.float64, device=dev)
+    _native.check(_native.load().dyg_philox_uniform(9, 0, 2 * nq * k, _p(u), _stream()))
+    u = u.cpu().numpy()[::2].reshape(nq, k)
+    cnt = s.count_before_device(ids, tq).cpu().numpy()
+    rec = s.halfedges[:n_half].cpu().numpy()
+    eids = rec[:, 1].copy().view(np.int32).reshape(-1, 2)[:, 1]
+    got_e = with_fence[1].cpu().numpy()
+    for q in range(nq):
+        a, c = indptr[nodes[q]], cnt[q]
+        if c == 0:
+            assert (got_e[q] == 0).all()
+            continue
+        tot = cum[a + c - 1]
+        sel = np.searchsorted(cum[a:a + c], u[q] * tot, side='right') if tot > 0 else np.floor(u[q] * c).astype(np.int64)
+        sel = np.minimum(sel, c - 1)
+        want_t = rec_t[a + sel].astype(np.float32)
+        order = np.lexsort((np.arange(k), want_t))
+        assert np.array_equal(got_e[q], eids[a + sel][order].astype(np.int64)), q
