@@ -407,6 +407,16 @@ def run_reference(args):
         'gpu_launches': 0}))
 
 
+def kernel_traffic(workload, kernel, G):
+    """DRAM bytes per launch (GB) of the dominant kernel from the committed ncu --set full capture of the same workload at the
+    same launch sizes; None when there is no capture for this configuration."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_kernel_traffic.json')))[workload]
+        return d.get(kernel) if d.get('batches_per_step') == G else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     rank, world, local = dist_env()
@@ -536,6 +546,9 @@ def run_ours(args):
                     'frac': achieved / pk['hbm'], 'traffic': None, 'peak_source': pk['source'],
                     'note': 'algorithmic bytes = gathered rows + indices + query/result vectors per launch'}
     roofline.update({'launches': cnt, 'avg_launch_us': 1e3 * ms / cnt, 'share_of_timed_kernels': share})
+    roofline['traffic'] = kernel_traffic(wl.name, name, G)
+    if roofline['traffic'] is not None:
+        roofline['traffic_unit'] = 'GB per launch (dram read + write, committed ncu capture: profiles/r01_kernel_traffic.json)'
     line = {
         'metric': 'link-pred events/sec', 'value': value, 'unit': 'events/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',

@@ -140,31 +140,38 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
 
     if (warp < 8) {
         // ------------------------------------------------------------------ producers
-        const int r = tid >> 1;                 // tile row
-        const int half = tid & 1;               // gather stages: operand plane (0 hi, 1 mid); time stages: 16-column half
+        // Time stages: thread = (tile row r, 16-column half).  Gather stages: four consecutive lanes copy the four 16-byte
+        // chunks of one (row, plane) piece, so the 32 lanes of a cp.async instruction touch 8 contiguous 64-byte pieces
+        // (8 L1 wavefronts) instead of 32 different rows (32 wavefronts): with one piece per thread the kernel was bound
+        // by L1 wavefronts, 2.9 TB/s of L2-resident rows with DRAM at 6 % and L2 at 30 % (profiles/).  Instruction i of
+        // warp w covers rows 16 w + 4 i + (lane >> 3), plane (lane >> 2) & 1, chunk lane & 3.
+        const int r = tid >> 1;
+        const int half = tid & 1;
         const int64_t m = m0 + r;
         const bool valid = m < side.tokens;
-        const uint32_t row_off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64);
+        const uint32_t row_off = (uint32_t)(r * 64);
         const uint32_t swz = (uint32_t)((r >> 1) & 3);
         const double tq = valid ? __ldg(a.t_query + m / side.ntok) : 0.0;
-        int64_t idx = 0;        // gathered row of the current unit
-        float dt = 0.f;         // time stages: delta of the current unit
-        bool masked = true;
-        int64_t nidx = 0;       // the same three, prefetched for the next unit
-        float ndt = 0.f;
-        bool nmasked = true;
+        const int g_row0 = 16 * warp + (lane >> 3);      // + 4 i
+        const int g_plane = (lane >> 2) & 1, g_chunk = lane & 3;
+        int64_t idx4[4] = {0, 0, 0, 0}, nidx4[4] = {0, 0, 0, 0};   // gathered rows of the current / next unit (per instruction)
+        float dt = 0.f, ndt = 0.f;                                // time stages: delta of the current / next unit
+        bool masked = true, nmasked = true;
         auto load_unit = [&](const StageInfo& u) {
-            const int64_t q = m * a.P + u.p;
-            nidx = 0;
-            nmasked = true;
-            if (valid) {
-                if (u.ty == 0) nidx = __ldg(side.ids + q);
-                else if (u.ty == 1) nidx = __ldg(side.eids + q);
-                else if (u.ty == 2) {
+            if (u.ty == 2) {
+                nmasked = true;
+                if (valid) {
+                    const int64_t q = m * a.P + u.p;
                     nmasked = __ldg(side.ids + q) == 0;
                     ndt = (float)(tq - (double)__ldg(side.t_nbr + q));
-                } else if (u.ty == 3) nidx = __ldg(side.cnt_a + q);
-                else nidx = __ldg(side.cnt_b + q);
+                }
+            } else {
+                const int64_t* src = u.ty == 0 ? side.ids : (u.ty == 1 ? side.eids : (u.ty == 3 ? side.cnt_a : side.cnt_b));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t mm = m0 + g_row0 + 4 * i;
+                    nidx4[i] = mm < side.tokens ? __ldg(src + mm * a.P + u.p) : 0;
+                }
             }
         };
         load_unit(stage_tab[0]);
@@ -173,9 +180,10 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
             const uint32_t ph = (uint32_t)((s / PP_STAGES) & 1);
             const StageInfo si = stage_tab[s];
             if (si.blk == 0) {
-                // the index (and time) of this unit were requested one unit ago; request the next unit's now, so the
+                // the indices (and time) of this unit were requested one unit ago; request the next unit's now, so the
                 // dependent load -> address -> cp.async chain never waits for memory
-                idx = nidx;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) idx4[i] = nidx4[i];
                 masked = nmasked;
                 dt = ndt;
                 const int s2 = s + a.nblk[si.ty];                   // first stage of the next unit
@@ -184,20 +192,25 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
             mbar_wait(empty_bar + slot, ph ^ 1u);
             unsigned char* st = base + slot * PP_STAGE_BYTES;
             if (si.ty != 2) {
-                const __nv_bfloat16* src = (half ? a.tab_mid[si.ty] : a.tab_hi[si.ty]) + idx * a.ld[si.ty] + si.blk * 32;
-                const uint32_t dst = smem_u32(st + half * PP_A_PLANE) + row_off;
-                const int nchunk = si.nk16 * 2;
-                if (idx == 0 && ((a.zero_rows >> si.ty) & 1)) {
-                    // padded position of a table whose row 0 is zero: no memory traffic (and no L2 hot spot on that row)
+                const __nv_bfloat16* tab = (g_plane ? a.tab_mid[si.ty] : a.tab_hi[si.ty]) + si.blk * 32 + g_chunk * 8;
+                const uint32_t dst0 = smem_u32(st + g_plane * PP_A_PLANE);
+                const bool zr = (a.zero_rows >> si.ty) & 1;
+                const bool live = g_chunk < si.nk16 * 2;
+                bool stored = false;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c < nchunk) asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst + (((uint32_t)c ^ swz) << 4)), "r"(0u) : "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c < nchunk) cp_async16(dst + (((uint32_t)c ^ swz) << 4), src + c * 8);
+                for (int i = 0; i < 4; ++i) {
+                    const int row = g_row0 + 4 * i;
+                    const uint32_t dst = dst0 + (uint32_t)row * 64u + ((((uint32_t)g_chunk) ^ ((uint32_t)(row >> 1) & 3u)) << 4);
+                    if (!live) continue;
+                    if (idx4[i] == 0 && zr) {
+                        // padded position of a table whose row 0 is zero: no memory traffic (and no L2 hot spot on that row)
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+                        stored = true;
+                    } else {
+                        cp_async16(dst, tab + idx4[i] * a.ld[si.ty]);
+                    }
                 }
+                if (stored) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 cp_async_arrive_noinc(full_bar + slot);
             } else {
                 if (half < si.nk16) {
