@@ -400,7 +400,8 @@ __host__ __device__ constexpr int ring_warp_bytes(int F4, int E4, bool node2) {
 // All dimensions are template parameters (F4 / E4: float4 chunks of a node / edge row, T: time features): every bound in
 // the lane loops folds at compile time.  The first version with run-time dimensions spent half of its 350 warp
 // instructions per neighbour on predicates, selects and index arithmetic (ncu source page, profiles/).
-template <int H, bool NODE2, int F4, int E4, int T>
+// FULLG: k is a multiple of RING_GROUP, so every group is full and the per-neighbour "gi < g" tests fold away.
+template <int H, bool NODE2, int F4, int E4, int T, bool FULLG>
 __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kernel(
     const float* __restrict__ qk, int ldq, int64_t n, int k,
     const float* __restrict__ node_tab, int ld_node, const float* __restrict__ node_tab2, int ld_node2,
@@ -461,14 +462,20 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
         const int slot = (c & 1) * 32 + lane;
         s_rn[slot] = c_rn; s_re[slot] = c_re; s_dt[slot] = c_dt; s_fl[slot] = c_fl;
     };
-    // the lane that parked item t's indices issues its copies into stage t % RING_DEPTH
-    auto issue = [&](int t) {
-        if (lane == (t & 31) && t < items) {
-            const int slot = t & 63;
+    // Items t0 .. t0 + cnt - 1 (cnt <= RING_GROUP, consecutive ring stages starting at stage0) are issued in ONE pass: the lane
+    // that parked item u's indices (lane u & 31) issues its copies.  Stage and phase of an item are carried as counters (the
+    // ring depth is not a power of two: t % 6 and t / 6 cost a multiply-high sequence each, several times per neighbour).
+    auto issue_group = [&](int t0, int cnt, int stage0) {
+        const int off = (lane - t0) & 31;
+        const int u = t0 + off;
+        if (off < cnt && u < items) {
+            int stg = stage0 + off;
+            if (stg >= RING_DEPTH) stg -= RING_DEPTH;
+            const int slot = u & 63;
             const int fl = s_fl[slot];
             const int64_t rn = s_rn[slot], re = s_re[slot];
-            unsigned char* dst = wbase + (t % RING_DEPTH) * STAGE;
-            uint64_t* bar = bars + (t % RING_DEPTH);
+            unsigned char* dst = wbase + stg * STAGE;
+            uint64_t* bar = bars + stg;
             const uint32_t nb = (fl & 2) ? 0u : NODE_BYTES, eb = (fl & 4) ? 0u : EDGE_BYTES;
             ring_bar_expect(bar, nb * (NODE2 ? 2u : 1u) + eb);
             if (nb) {
@@ -479,8 +486,8 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
         }
     };
     // row of item t from its ring stage; fl (warp-uniform) says which parts were not copied because they are zero rows
-    auto load_x = [&](int t, int fl, float4 (&x)[XR]) {
-        const float4* row = reinterpret_cast<const float4*>(wbase + (t % RING_DEPTH) * STAGE);
+    auto load_x = [&](int stg, int fl, float4 (&x)[XR]) {
+        const float4* row = reinterpret_cast<const float4*>(wbase + stg * STAGE);
 #pragma unroll
         for (int r = 0; r < XR; ++r) {
             const int c = r * 32 + lane;
@@ -506,8 +513,7 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
     load_chunk(0);
     park_chunk(0);
     __syncwarp();
-#pragma unroll 1
-    for (int t = 0; t < RING_DEPTH; ++t) issue(t);
+    issue_group(0, RING_DEPTH, 0);   // RING_DEPTH <= 32: one pass
     load_chunk(1);
     int parked = 0;                           // highest index chunk parked in shared memory; chunk parked + 1 sits in registers
 
@@ -528,6 +534,8 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
     float m_own = -INFINITY, den_own = 0.f;   // running softmax state of head own_h (identical in all lanes of that head)
     int j = 0;
     int64_t root = r0;
+    int stage_t = 0;            // t % RING_DEPTH
+    uint32_t phase_t = 0;       // (t / RING_DEPTH) & 1
 #pragma unroll 1
     for (int t = 0; t < items;) {
         if (j == 0) {   // new root: its folded query, fresh accumulators; warm L2 with the next root's query row
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
             __syncwarp();
             load_chunk(parked + 1);
         }
-        const int g = (k - j) < G ? (k - j) : G;
+        const int g = FULLG ? G : ((k - j) < G ? (k - j) : G);
 
         // ---- pass 1: time encodings (parked in s_xt) and the partial scores of the group's neighbours
         float part[V];
@@ -568,8 +576,11 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
         for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
             for (int h = 0; h < H; ++h) part[gi * H + h] = 0.f;
-            if (gi < g) {
+            if (FULLG || gi < g) {
                 const int tt = t + gi;
+                int stg = stage_t + gi;
+                uint32_t ph = phase_t;
+                if (stg >= RING_DEPTH) { stg -= RING_DEPTH; ph ^= 1u; }
                 const float dt = s_dt[tt & 63];
                 float xt[TQ];
 #pragma unroll
@@ -583,9 +594,9 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
                         }
                     }
                 }
-                ring_bar_wait(bars + (tt % RING_DEPTH), (uint32_t)((tt / RING_DEPTH) & 1));
+                ring_bar_wait(bars + stg, ph);
                 float4 x[XR];
-                load_x(tt, s_fl[tt & 63], x);
+                load_x(stg, s_fl[tt & 63], x);
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                     float p0 = 0.f, p1 = 0.f;   // two chains
@@ -608,7 +619,7 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
             if (lane < TR) {
 #pragma unroll
                 for (int gi = 0; gi < G; ++gi) {
-                    if (gi < g) {
+                    if (FULLG || gi < g) {
                         const float xr = s_xt[gi * 128 + TF * 32 + lane];
 #pragma unroll
                         for (int h = 0; h < H; ++h) part[gi * H + h] = fmaf(qt[h][TQ - 1], xr, part[gi * H + h]);
@@ -618,22 +629,25 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
         } else {
             __syncwarp();
         }
-        // ---- transposing reduction: V values per lane -> lane l holds the warp total of value l >> SH
-        {
-            int nv = V;
-#pragma unroll
-            for (int width = 16; nv > 1; width >>= 1, nv >>= 1) {
-                const bool up = lane & width;
-#pragma unroll
-                for (int i = 0; i < nv / 2; ++i) {
-                    const float send = up ? part[i] : part[i + nv / 2];
-                    const float keep = up ? part[i + nv / 2] : part[i];
-                    part[i] = keep + __shfl_xor_sync(0xffffffffu, send, width);
-                }
-            }
-#pragma unroll
-            for (int width = (1 << SH) >> 1; width > 0; width >>= 1) part[0] += __shfl_xor_sync(0xffffffffu, part[0], width);
+        // ---- transposing reduction: V values per lane -> lane l holds the warp total of value l >> SH.  Written out per
+        // step with compile-time bounds: a loop over a shrinking count left `part` dynamically indexed (in local memory).
+#define DYG_XSTEP(NV, WIDTH)                                                        \
+    {                                                                               \
+        const bool up = lane & (WIDTH);                                             \
+        _Pragma("unroll") for (int i = 0; i < (NV) / 2; ++i) {                      \
+            const float send = up ? part[i] : part[i + (NV) / 2];                   \
+            const float keep = up ? part[i + (NV) / 2] : part[i];                   \
+            part[i] = keep + __shfl_xor_sync(0xffffffffu, send, (WIDTH));           \
+        }                                                                           \
+    }
+        if (V == 8) {
+            DYG_XSTEP(8, 16) DYG_XSTEP(4, 8) DYG_XSTEP(2, 4)
+        } else {
+            DYG_XSTEP(4, 16) DYG_XSTEP(2, 8)
         }
+#undef DYG_XSTEP
+#pragma unroll
+        for (int width = (1 << SH) >> 1; width > 0; width >>= 1) part[0] += __shfl_xor_sync(0xffffffffu, part[0], width);
         // ---- softmax update of the group (lane-parallel over (neighbour, head))
         float sc = -INFINITY;
         if (own_g < g) sc = (s_fl[(t + own_g) & 63] & 1) ? -1e10f : part[0];   // -1e10, not -inf (models/modules.py:184)
@@ -670,12 +684,14 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
         // ---- pass 2: weighted sums (rows re-read from the ring, time encodings from s_xt)
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) {
-            if (gi < g) {
+            if (FULLG || gi < g) {
                 float pg[H];
 #pragma unroll
                 for (int h = 0; h < H; ++h) pg[h] = __shfl_sync(0xffffffffu, pw_own, (gi * H + h) << SH);
+                int stg = stage_t + gi;
+                if (stg >= RING_DEPTH) stg -= RING_DEPTH;
                 float4 x[XR];
-                load_x(t + gi, s_fl[(t + gi) & 63], x);
+                load_x(stg, s_fl[(t + gi) & 63], x);
                 float xt[TQ];
 #pragma unroll
                 for (int r = 0; r < TQ; ++r) xt[r] = ((r + 1) * 32 <= T || r * 32 + lane < T) ? s_xt[gi * 128 + r * 32 + lane] : 0.f;
@@ -694,11 +710,11 @@ __global__ void __launch_bounds__(128, NODE2 ? 3 : 4) temporal_attend_ring_kerne
             }
         }
         __syncwarp();                         // every lane is done with the group's stages and s_xt: refill
-#pragma unroll
-        for (int gi = 0; gi < G; ++gi)
-            if (gi < g) issue(t + gi + RING_DEPTH);
+        issue_group(t + RING_DEPTH, g, stage_t);   // item u + RING_DEPTH reuses the stage of item u
         t += g;
         j += g;
+        stage_t += g;
+        if (stage_t >= RING_DEPTH) { stage_t -= RING_DEPTH; phase_t ^= 1u; }
         if (j == k) {   // root finished: normalise and write
             float inv_h[H], mx_h[H];
 #pragma unroll
@@ -989,10 +1005,12 @@ extern "C" int dyg_temporal_attend(const float* qk, int ldq, int64_t n, int k, i
     do {                                                                                                                             \
         static bool smem_set = false;                                                                                                \
         if (!smem_set) {                                                                                                             \
-            cudaFuncSetAttribute(temporal_attend_ring_kernel<HH, N2, 43, 43, 100>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            cudaFuncSetAttribute(temporal_attend_ring_kernel<HH, N2, 43, 43, 100, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+            cudaFuncSetAttribute(temporal_attend_ring_kernel<HH, N2, 43, 43, 100, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             smem_set = true;                                                                                                         \
         }                                                                                                                            \
-        temporal_attend_ring_kernel<HH, N2, 43, 43, 100><<<rblocks, 128, smem, s>>>(ATTEND_RING_ARGS);                               \
+        if (k % RING_GROUP == 0) temporal_attend_ring_kernel<HH, N2, 43, 43, 100, true><<<rblocks, 128, smem, s>>>(ATTEND_RING_ARGS); \
+        else temporal_attend_ring_kernel<HH, N2, 43, 43, 100, false><<<rblocks, 128, smem, s>>>(ATTEND_RING_ARGS);                    \
     } while (0)
         if (H == 2 && node2) LAUNCH_RING(2, true);
         else if (H == 2) LAUNCH_RING(2, false);
