@@ -5,7 +5,11 @@ reference become flat device tables (see csrc/memory.cu): persisted memory, an i
 look-ahead view (what ``get_updated_memories`` would return for every node), and the last raw message of
 every node.  Per positive batch only the batch's <= 2B new messages go through the GRU; results are
 identical to recomputing all pending nodes each call because a pending node's inputs cannot change before
-its message is consumed.  This holds for fixed weights (eval); training would need the recompute path.
+its message is consumed.  This holds for fixed weights (eval).  In training mode (``.train()`` with grad enabled) the
+weights move between batches, so every call recomputes ``get_updated_memories`` for all pending nodes from the stored
+last messages with autograd (``models/MemoryModel.py:170-191``), embeds on those rows through ``dyglib_b200/autograd.py``
+and persists the recomputed rows; the gradient reaches the memory updater, the time encoder and the embedding module
+exactly where the reference's does.
 """
 from __future__ import annotations
 
@@ -19,7 +23,7 @@ from .. import _native, ops
 from ..ops import _p, _stream
 from ..utils.utils import NeighborSampler, _as_dev
 from .modules import TimeEncoder, MergeLayer, MultiHeadAttention, _eval_only
-from ._temporal import temporal_conv, zero_time_features
+from ._temporal import temporal_conv, temporal_conv_train, zero_time_features
 
 
 class MessageAggregator(nn.Module):
@@ -197,6 +201,19 @@ class GraphAttentionEmbedding(nn.Module):
         t0 = zero_time_features(self.time_encoder, dev)
         return self._embed(node_memories, ids, tq, current_layer_num, num_neighbors, t0)
 
+    def embed_train(self, mem, ids, tq, layer, k):
+        """The recursion of ``_embed`` with autograd: ``mem`` is the differentiable (num_nodes, memory_dim) table of updated
+        memories; layer-0 rows ``mem[ids] + raw[ids]`` are gathered by index (their backward is a scatter-add)."""
+        feat = mem[ids] + self.node_raw_features[ids]
+        if layer == 0:
+            return feat
+        conv = feat if layer == 1 else self.embed_train(mem, ids, tq, layer - 1, k)
+        nbr, eid, nt = self.neighbor_sampler.get_historical_neighbors_device(ids, tq, k)
+        nbr_dense = self.embed_train(mem, nbr.reshape(-1), nt.reshape(-1).double(), layer - 1, k)
+        return temporal_conv_train(self.temporal_conv_layers[layer - 1], self.merge_layers[layer - 1], self.time_encoder, conv, feat,
+                                   self.node_raw_features, nbr, nbr_dense, self.edge_raw_features, eid, tq, nt, k,
+                                   zero_row0=self._zero_row0)
+
     def _embed(self, mem, ids, tq, layer, k, t0):
         feat = ops.gather_rows(self.node_raw_features, ids, table2=mem)
         if layer == 0:
@@ -257,7 +274,17 @@ class MemoryModel(torch.nn.Module):
     def compute_src_dst_node_temporal_embeddings(self, src_node_ids: np.ndarray, dst_node_ids: np.ndarray, node_interact_times: np.ndarray,
                                                  edge_ids: np.ndarray, edges_are_positive: bool = True, num_neighbors: int = 20):
         """``compute_src_dst_node_temporal_embeddings`` (``models/MemoryModel.py:87-168``)."""
-        _eval_only(self)
+        if self.training and torch.is_grad_enabled():
+            self._view_stale = True
+            return self._forward_train(src_node_ids, dst_node_ids, node_interact_times, edge_ids, edges_are_positive, num_neighbors)
+        if getattr(self, '_view_stale', False):
+            # the look-ahead view of the pending nodes was built by earlier weights: rebuild it with the current ones
+            with torch.no_grad():
+                mem_upd, lu_upd = self._updated_memories_train()
+                st0 = self.memory_bank._ensure()
+                st0['mem_view'].copy_(mem_upd)
+                st0['lu_view'].copy_(lu_upd)
+            self._view_stale = False
         lib = _native.load()
         dev = self.node_raw_features.device
         bank = self.memory_bank
@@ -290,31 +317,99 @@ class MemoryModel(torch.nn.Module):
             ret = (src_emb, dst_emb)
         if edges_are_positive:
             assert edge_ids is not None
-            eid = _as_dev(edge_ids, torch.int64, dev)
-            mem, lu = bank.node_memories.data, bank.node_last_updated_times.data
-            if self.check_time_order:
-                _native.check(lib.dyg_tgn_check_time(_p(node_ids), 2 * B, _p(lu), _p(lu_view), _p(st['pending']), _p(st['flag']), _stream()))
-                ops._count()
-            # update_memories + clear_node_raw_messages for the batch's nodes (:142-145)
-            _native.check(lib.dyg_tgn_persist(_p(node_ids), 2 * B, _p(mem), _p(mem_view), _p(lu), _p(lu_view), _p(st['pending']), D, _stream()))
-            ops._count(2)
-            # new raw messages, src role then dst role (:148-161); last message per node wins
-            _native.check(lib.dyg_tgn_select_last(_p(src), _p(dst), B, _p(st['winner']), _stream()))
-            other = torch.cat([dst_emb, src_emb]).contiguous() if self.model_name == 'DyRep' else None
-            w, b = self.time_encoder.wb()
-            msg = torch.empty((2 * B, self.message_dim), dtype=torch.float32, device=dev)
-            _native.check(lib.dyg_tgn_build_messages(_p(src), _p(dst), _p(tq), _p(eid), B, _p(mem), _p(lu), D, _p(other), D,
-                                                     _p(self.edge_raw_features), self.edge_raw_features.stride(0), E,
-                                                     _p(w), _p(b), T, _p(msg), self.message_dim, _stream()))
-            cell = self.memory_updater.memory_updater
-            G = self.memory_updater.gates
-            gi = ops.linear([ops.seg_rows(msg)], 2 * B, cell.weight_ih.detach(), cell.bias_ih.detach())
-            gh = ops.linear([ops.seg_rows(mem, D, node_ids)], 2 * B, cell.weight_hh.detach(), cell.bias_hh.detach())
-            _native.check(lib.dyg_tgn_cell_commit(_p(gi), _p(gh), G, _p(src), _p(dst), _p(tq), B, _p(st['winner']), _p(mem),
-                                                  _p(mem_view), _p(lu_view), _p(st['pending']), D, _p(msg), self.message_dim,
-                                                  self.message_dim, _p(st['msg_store']), _p(st['msg_time']), _stream()))
-            ops._count(3)
+            self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), dst_emb, src_emb, None)
         return ret
+
+    def _advance(self, src, dst, tq, eid, dst_emb, src_emb, recomputed):
+        """update_memories + clear + new raw messages of a positive batch (``models/MemoryModel.py:139-161``).
+        ``recomputed``: training mode only, the (num_nodes, D) table of memories recomputed with the current weights; its rows
+        replace what ``dyg_tgn_persist`` copies from the look-ahead view (which earlier weights produced)."""
+        lib = _native.load()
+        dev = self.node_raw_features.device
+        bank = self.memory_bank
+        st = bank._ensure()
+        D, T, E = self.memory_dim, self.time_feat_dim, self.edge_feat_dim
+        B = src.numel()
+        node_ids = torch.cat([src, dst])
+        lu_view = st['lu_view']
+        mem_view = st['mem_view']
+        mem, lu = bank.node_memories.data, bank.node_last_updated_times.data
+        if recomputed is not None:
+            was_pending = node_ids[st['pending'][node_ids].bool()]
+            mem_view[was_pending] = recomputed[was_pending]
+        if self.check_time_order:
+            _native.check(lib.dyg_tgn_check_time(_p(node_ids), 2 * B, _p(lu), _p(lu_view), _p(st['pending']), _p(st['flag']), _stream()))
+            ops._count()
+        # update_memories + clear_node_raw_messages for the batch's nodes (:142-145)
+        _native.check(lib.dyg_tgn_persist(_p(node_ids), 2 * B, _p(mem), _p(mem_view), _p(lu), _p(lu_view), _p(st['pending']), D, _stream()))
+        ops._count(2)
+        # new raw messages, src role then dst role (:148-161); last message per node wins
+        _native.check(lib.dyg_tgn_select_last(_p(src), _p(dst), B, _p(st['winner']), _stream()))
+        other = torch.cat([dst_emb, src_emb]).detach().contiguous() if self.model_name == 'DyRep' else None
+        w, b = self.time_encoder.wb()
+        msg = torch.empty((2 * B, self.message_dim), dtype=torch.float32, device=dev)
+        _native.check(lib.dyg_tgn_build_messages(_p(src), _p(dst), _p(tq), _p(eid), B, _p(mem), _p(lu), D, _p(other), D,
+                                                 _p(self.edge_raw_features), self.edge_raw_features.stride(0), E,
+                                                 _p(w), _p(b), T, _p(msg), self.message_dim, _stream()))
+        cell = self.memory_updater.memory_updater
+        G = self.memory_updater.gates
+        gi = ops.linear([ops.seg_rows(msg)], 2 * B, cell.weight_ih.detach(), cell.bias_ih.detach())
+        gh = ops.linear([ops.seg_rows(mem, D, node_ids)], 2 * B, cell.weight_hh.detach(), cell.bias_hh.detach())
+        _native.check(lib.dyg_tgn_cell_commit(_p(gi), _p(gh), G, _p(src), _p(dst), _p(tq), B, _p(st['winner']), _p(mem),
+                                              _p(mem_view), _p(lu_view), _p(st['pending']), D, _p(msg), self.message_dim,
+                                              self.message_dim, _p(st['msg_store']), _p(st['msg_time']), _stream()))
+        ops._count(3)
+
+    def _updated_memories_train(self):
+        """``get_updated_memories`` over all nodes (``models/MemoryModel.py:170-191, 461-487``) with autograd: the recurrent
+        cell over every pending node's last message (gate GEMMs on ``autograd.linear``, gate math elementwise)."""
+        from .. import autograd as ag
+        bank = self.memory_bank
+        st = bank._ensure()
+        mem, lu = bank.node_memories.data, bank.node_last_updated_times.data
+        pend = torch.nonzero(st['pending']).reshape(-1)
+        if pend.numel() == 0:
+            return mem, lu
+        cell = self.memory_updater.memory_updater
+        h = mem[pend]
+        gi = ag.linear(st['msg_store'][pend], cell.weight_ih, cell.bias_ih)
+        gh = ag.linear(h, cell.weight_hh, cell.bias_hh)
+        if self.memory_updater.gates == 3:      # nn.GRUCell: gates r | z | n
+            i_r, i_z, i_n = gi.chunk(3, dim=1)
+            h_r, h_z, h_n = gh.chunk(3, dim=1)
+            r = torch.sigmoid(i_r + h_r)
+            z = torch.sigmoid(i_z + h_z)
+            n = torch.tanh(i_n + r * h_n)
+            new = (1.0 - z) * n + z * h
+        else:                                   # nn.RNNCell (tanh)
+            new = torch.tanh(gi + gh)
+        return mem.index_copy(0, pend, new), lu.index_copy(0, pend, st['msg_time'][pend].float())
+
+    def _forward_train(self, src_node_ids, dst_node_ids, node_interact_times, edge_ids, edges_are_positive, num_neighbors):
+        """Training-mode ``compute_src_dst_node_temporal_embeddings``."""
+        dev = self.node_raw_features.device
+        src = _as_dev(src_node_ids, torch.int64, dev)
+        dst = _as_dev(dst_node_ids, torch.int64, dev)
+        tq = _as_dev(node_interact_times, torch.float64, dev)
+        B = src.numel()
+        node_ids = torch.cat([src, dst])
+        mem_upd, lu_upd = self._updated_memories_train()
+        if self.model_name == 'JODIE':
+            em = self.embedding_module
+            tt = tq.float()
+            s_iv = (tt - lu_upd[src] - self.src_node_mean_time_shift) / self.src_node_std_time_shift
+            d_iv = (tt - lu_upd[dst] - self.dst_node_mean_time_shift_dst) / self.dst_node_std_time_shift
+            iv = torch.cat([s_iv, d_iv]).unsqueeze(1)
+            emb = em.dropout(mem_upd[node_ids] * (1 + em.linear_layer(iv)))      # models/MemoryModel.py:543
+        else:
+            emb = self.embedding_module.embed_train(mem_upd, node_ids, torch.cat([tq, tq]), self.num_layers, num_neighbors)
+        src_emb, dst_emb = emb[:B], emb[B:]
+        if edges_are_positive:
+            assert edge_ids is not None
+            self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), dst_emb, src_emb, mem_upd.detach())
+        if self.model_name == 'DyRep':
+            return mem_upd[src], mem_upd[dst]
+        return src_emb, dst_emb
 
     def assert_time_order(self):
         """Raises if any update went backwards in time (the reference asserts per call, ``:448-449``; here the

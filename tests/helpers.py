@@ -255,3 +255,56 @@ def cuda_tgat_train_step(dropout=0.0):
     params = {'model.' + k: v for k, v in m.named_parameters()}
     params.update({'pred.' + k: v for k, v in pred.named_parameters()})
     return tgat_train_step(lambda s, d, t, k: m.compute_src_dst_node_temporal_embeddings(s, d, t, k), lambda a, b: pred(a, b), params)
+
+
+# ---------------------------------------------------------------------------------------------
+# Memory-model training step (train_link_prediction.py:236-257): `warm` batches advance the memory without gradients, then one
+# batch (negative call first, then the positive call that also advances the memory) with BCE and one backward pass.
+def memory_train_step(model, predictor_fn, params: dict, warm=8, B=30, k=10, seed=13):
+    g = small_graph(seed=seed)
+    bs = list(batches(g, 0, warm + 1, B))
+    with torch.no_grad():
+        for src, dst, t, eid, neg in bs[:warm]:
+            model.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, k)
+            model.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, k)
+    src, dst, t, eid, neg = bs[warm]
+    ns, nd = model.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, k)
+    ps, pd = model.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, k)
+    pos = predictor_fn(ps, pd).squeeze(dim=-1).sigmoid()
+    negp = predictor_fn(ns, nd).squeeze(dim=-1).sigmoid()
+    predicts = torch.cat([pos, negp], dim=0)
+    labels = torch.cat([torch.ones_like(pos), torch.zeros_like(negp)], dim=0)
+    loss = torch.nn.functional.binary_cross_entropy(predicts, labels)
+    for p in params.values():
+        p.grad = None
+    loss.backward()
+    out = {'loss': np.asarray(loss.item(), dtype=np.float64), 'pos': pos.detach().cpu().numpy(), 'neg': negp.detach().cpu().numpy()}
+    for name, p in params.items():
+        out['grad.' + name] = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu().numpy()
+    return out
+
+
+def oracle_memory_train_step(name):
+    from oracle.models import merge_layer
+    _, _, _, memory = oracle_factories()
+    m, _ = memory(small_graph(seed=13), name, 3)
+    m.sd = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and 'memory_bank' not in k) else v.clone()) for k, v in m.sd.items()}
+    psd = {k: v.clone().requires_grad_(True) for k, v in deterministic_state_dict(predictor_template().state_dict(), 5).items()}
+    params = {'model.' + k: v for k, v in m.sd.items() if v.requires_grad and not k.startswith('embedding_module.time_encoder')}
+    params.update({'pred.' + k: v for k, v in psd.items()})
+    return memory_train_step(m, lambda a, b: merge_layer(psd, '', a, b), params)
+
+
+def cuda_memory_train_step(name):
+    _, _, _, memory = cuda_factories()
+    m, _ = memory(small_graph(seed=13), name, 3)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m.train()
+    pred = predictor_template().to('cuda')
+    pred.load_state_dict(deterministic_state_dict(pred.state_dict(), 5))
+    pred.train()
+    params = {'model.' + k: v for k, v in m.named_parameters() if v.requires_grad}
+    params.update({'pred.' + k: v for k, v in pred.named_parameters()})
+    return memory_train_step(m, lambda a, b: pred(a, b), params)

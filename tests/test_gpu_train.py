@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import cuda_tgat_train_step, oracle_tgat_train_step, assert_grads_close, load_golden
+from helpers import (cuda_tgat_train_step, oracle_tgat_train_step, assert_grads_close, load_golden, cuda_memory_train_step,
+                     oracle_memory_train_step)
 
 pytestmark = pytest.mark.gpu
 
@@ -19,6 +20,57 @@ def test_tgat_training_step_matches_reference_golden():
 
 def test_tgat_training_step_matches_oracle():
     assert_grads_close(cuda_tgat_train_step(dropout=0.0), oracle_tgat_train_step(), rtol=2e-3)
+
+
+@pytest.mark.parametrize('name', ['TGN', 'DyRep', 'JODIE'])
+def test_memory_model_training_step_matches_reference_golden_and_oracle(name):
+    """8 batches advance the memory on the eval kernels (no gradients), then one training batch: the recomputed
+    get_updated_memories, the embedding module and the link predictor give the reference's loss and parameter gradients."""
+    got = cuda_memory_train_step(name)
+    gold = {k[len(name) + 1:]: v for k, v in load_golden('memory_train.npz').items() if k.startswith(name + '.')}
+    np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+    np.testing.assert_allclose(got['pos'], gold['pos'], rtol=1e-3, atol=2e-4)
+    assert_grads_close(got, gold, rtol=2e-3)
+    assert_grads_close(got, oracle_memory_train_step(name), rtol=2e-3)
+
+
+def test_memory_model_eval_after_training_uses_current_weights():
+    """A training call marks the look-ahead view stale; the next eval call rebuilds it, so eval after a weight change equals a
+    fresh model with the new weights that replays the same stream."""
+    from helpers import cuda_factories, small_graph, batches
+    _, _, _, memory = cuda_factories()
+    g = small_graph(seed=13)
+    bs = list(batches(g, 0, 6, 30))
+
+    def run(m, train_last):
+        with torch.no_grad():
+            for src, dst, t, eid, neg in bs[:4]:
+                m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+        src, dst, t, eid, neg = bs[4]
+        if train_last:
+            m.train()
+            m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+            m.eval()
+        else:
+            with torch.no_grad():
+                m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+        with torch.no_grad():
+            cell = m.memory_updater.memory_updater
+            cell.weight_ih.mul_(1.5)
+            if not train_last:      # the eval-only model must be told: its view was built by the old weights too
+                m._view_stale = True
+            src, dst, t, eid, neg = bs[5]
+            a, b = m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+        return a.cpu().numpy(), b.cpu().numpy()
+    m1, _ = memory(g, 'TGN', 3)
+    m2, _ = memory(g, 'TGN', 3)
+    for mod in list(m1.modules()) + list(m2.modules()):
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    a1, b1 = run(m1, True)
+    a2, b2 = run(m2, False)
+    np.testing.assert_allclose(a1, a2, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(b1, b2, rtol=1e-4, atol=1e-5)
 
 
 def test_tgat_training_step_with_dropout_runs_and_differs():

@@ -36,3 +36,14 @@ def test_oracle_tgat_training_step_matches_golden():
     gold = load_golden('tgat_train.npz')
     np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
     assert_grads_close(got, gold, rtol=1e-3)
+
+
+@pytest.mark.parametrize('name', ['TGN', 'DyRep', 'JODIE'])
+def test_oracle_memory_training_step_matches_golden(name):
+    """Memory models: 8 batches advance the memory without gradients, then one training batch (negative call, positive call,
+    BCE, backward); loss and every parameter gradient against the reference's (scripts/make_golden_train.py)."""
+    from helpers import oracle_memory_train_step, assert_grads_close
+    got = oracle_memory_train_step(name)
+    gold = {k[len(name) + 1:]: v for k, v in load_golden('memory_train.npz').items() if k.startswith(name + '.')}
+    np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+    assert_grads_close(got, gold, rtol=1e-3)
