@@ -302,7 +302,7 @@ class TGNWL(Workload):
     use_graph = True
 
     def describe(self):
-        return 'tgn_reddit (TGN 1 layer, 10 recent neighbours, last-message + GRU memory, batch 200 sequential, neg then pos call)'
+        return 'tgn_reddit (TGN 1 layer, 10 recent neighbours, last-message + GRU memory, batch 200 sequential, neg + pos roots in one pass)'
 
     def build(self, dev):
         from dyglib_b200.utils.utils import get_neighbor_sampler, set_random_seed
@@ -320,8 +320,8 @@ class TGNWL(Workload):
         self.stream = Stream(g, start=0, region=1.0)
 
     def step(self, src, dst, neg, t, eid):
-        a, b = self.model.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, 10)
-        c, d = self.model.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+        # the reference loop's negative call then positive call (train_link_prediction.py:236-247) in one embedding pass
+        a, b, c, d = self.model.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10)
         return _predict(self.pred, torch.cat([c, a]), torch.cat([d, b]))
 
     def oracle(self):

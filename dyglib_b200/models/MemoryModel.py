@@ -277,6 +277,42 @@ class MemoryModel(torch.nn.Module):
         if self.training and torch.is_grad_enabled():
             self._view_stale = True
             return self._forward_train(src_node_ids, dst_node_ids, node_interact_times, edge_ids, edges_are_positive, num_neighbors)
+        self._refresh_view_if_stale()
+        dev = self.node_raw_features.device
+        src = _as_dev(src_node_ids, torch.int64, dev)
+        dst = _as_dev(dst_node_ids, torch.int64, dev)
+        tq = _as_dev(node_interact_times, torch.float64, dev)
+        B = src.numel()
+        emb, ret = self._embed_eval([src, dst], tq, num_neighbors)
+        if edges_are_positive:
+            assert edge_ids is not None
+            self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), emb[B:], emb[:B], None)
+        return ret[:B], ret[B:]
+
+    def compute_pos_neg_temporal_embeddings(self, src_node_ids, dst_node_ids, neg_dst_node_ids, node_interact_times, edge_ids,
+                                            num_neighbors: int = 20):
+        """Addition to the reference API: the two calls its loops make per batch (``train_link_prediction.py:236-247``,
+        ``evaluate_models_utils.py:60-80``) -- ``compute(src, neg, t, None, False)`` then ``compute(src, dst, t, edge_ids, True)``
+        -- in one.  Both read the same memory state, so the 4 B roots go through ONE embedding pass (half the kernel launches
+        of a latency-bound step), then the positive batch advances the memory.
+        Returns (neg_src_emb, neg_dst_emb, pos_src_emb, pos_dst_emb), equal to the two calls' results."""
+        if self.training and torch.is_grad_enabled():
+            a, b = self.compute_src_dst_node_temporal_embeddings(src_node_ids, neg_dst_node_ids, node_interact_times, None, False, num_neighbors)
+            c, d = self.compute_src_dst_node_temporal_embeddings(src_node_ids, dst_node_ids, node_interact_times, edge_ids, True, num_neighbors)
+            return a, b, c, d
+        self._refresh_view_if_stale()
+        dev = self.node_raw_features.device
+        src = _as_dev(src_node_ids, torch.int64, dev)
+        dst = _as_dev(dst_node_ids, torch.int64, dev)
+        neg = _as_dev(neg_dst_node_ids, torch.int64, dev)
+        tq = _as_dev(node_interact_times, torch.float64, dev)
+        B = src.numel()
+        emb, ret = self._embed_eval([src, neg, src, dst], tq, num_neighbors)
+        assert edge_ids is not None
+        self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), emb[3 * B:], emb[2 * B:3 * B], None)
+        return ret[:B], ret[B:2 * B], ret[2 * B:3 * B], ret[3 * B:]
+
+    def _refresh_view_if_stale(self):
         if getattr(self, '_view_stale', False):
             # the look-ahead view of the pending nodes was built by earlier weights: rebuild it with the current ones
             with torch.no_grad():
@@ -285,40 +321,33 @@ class MemoryModel(torch.nn.Module):
                 st0['mem_view'].copy_(mem_upd)
                 st0['lu_view'].copy_(lu_upd)
             self._view_stale = False
+
+    def _embed_eval(self, roles, tq, num_neighbors):
+        """Embeddings of the concatenated root sets ``roles`` (alternating src / dst roles, each B ids at times ``tq``) on the
+        look-ahead view == ``get_updated_memories`` of all nodes (``models/MemoryModel.py:108-136``).  Returns (embeddings,
+        what the model returns for them: DyRep returns the look-ahead memories instead, ``:163-166``)."""
         lib = _native.load()
         dev = self.node_raw_features.device
-        bank = self.memory_bank
-        st = bank._ensure()
-        D, T, E = self.memory_dim, self.time_feat_dim, self.edge_feat_dim
-        src = _as_dev(src_node_ids, torch.int64, dev)
-        dst = _as_dev(dst_node_ids, torch.int64, dev)
-        tq = _as_dev(node_interact_times, torch.float64, dev)
-        B = src.numel()
-        node_ids = torch.cat([src, dst])
-        tq2 = torch.cat([tq, tq])
-        mem_view, lu_view = st['mem_view'], st['lu_view']   # == get_updated_memories(all nodes) (:108-109)
+        st = self.memory_bank._ensure()
+        D = self.memory_dim
+        B = tq.numel()
+        node_ids = torch.cat(roles)
+        mem_view, lu_view = st['mem_view'], st['lu_view']
         if self.model_name == 'JODIE':
             ll = self.embedding_module.linear_layer
-            emb = torch.empty((2 * B, D), dtype=torch.float32, device=dev)
+            emb = torch.empty((len(roles) * B, D), dtype=torch.float32, device=dev)
             wv, bv = ll.weight.detach().reshape(-1), ll.bias.detach()
-            for ids, off, mean, std in ((src, 0, self.src_node_mean_time_shift, self.src_node_std_time_shift),
-                                        (dst, B, self.dst_node_mean_time_shift_dst, self.dst_node_std_time_shift)):
+            for r, ids in enumerate(roles):
+                mean, std = ((self.src_node_mean_time_shift, self.src_node_std_time_shift) if r % 2 == 0 else
+                             (self.dst_node_mean_time_shift_dst, self.dst_node_std_time_shift))
                 _native.check(lib.dyg_jodie_project(_p(mem_view), D, _p(lu_view), _p(ids), _p(tq), B, D, float(mean), float(std),
-                                                    _p(wv), _p(bv), _p(emb[off:off + B]), D, _stream()))
+                                                    _p(wv), _p(bv), _p(emb[r * B:(r + 1) * B]), D, _stream()))
                 ops._count()
         else:
-            emb = self.embedding_module.compute_node_temporal_embeddings(mem_view, node_ids, tq2, self.num_layers, num_neighbors)
-        src_emb, dst_emb = emb[:B], emb[B:]
-        if self.model_name == 'DyRep':
-            # DyRep returns the look-ahead memories computed before this batch's update (:163-166)
-            out = ops.gather_rows(mem_view, node_ids)
-            ret = (out[:B], out[B:])
-        else:
-            ret = (src_emb, dst_emb)
-        if edges_are_positive:
-            assert edge_ids is not None
-            self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), dst_emb, src_emb, None)
-        return ret
+            emb = self.embedding_module.compute_node_temporal_embeddings(mem_view, node_ids, torch.cat([tq] * len(roles)),
+                                                                         self.num_layers, num_neighbors)
+        ret = ops.gather_rows(mem_view, node_ids) if self.model_name == 'DyRep' else emb
+        return emb, ret
 
     def _advance(self, src, dst, tq, eid, dst_emb, src_emb, recomputed):
         """update_memories + clear + new raw messages of a positive batch (``models/MemoryModel.py:139-161``).

@@ -155,6 +155,23 @@ def test_tgn_many_batches_vs_oracle():
     assert float(exported[v][0][1]) == float(pend[v][-1][1])
 
 
+@pytest.mark.parametrize('name', ['TGN', 'DyRep', 'JODIE'])
+def test_memory_model_fused_pos_neg_call_equals_two_calls(name):
+    """compute_pos_neg_temporal_embeddings (one embedding pass over the 4 B roots) == the reference loop's negative call followed
+    by its positive call, batch after batch, including the memory it leaves behind."""
+    _, _, _, memory = cuda_factories()
+    g = small_graph(seed=19, E=3000, nu=70, ni=25)
+    (m1, mem_fn), (m2, _) = memory(g, name, 4), memory(g, name, 4)
+    with torch.no_grad():
+        for bi, (src, dst, t, eid, neg) in enumerate(batches(g, 0, 30, 40)):
+            a, b = m1.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, 10)
+            c, d = m1.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+            fa, fb, fc, fd = m2.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10)
+            for x, y in zip((a, b, c, d), (fa, fb, fc, fd)):
+                assert torch.equal(x, y), (name, bi)
+    assert torch.equal(mem_fn(m1)[0], mem_fn(m2)[0]) and torch.equal(mem_fn(m1)[1], mem_fn(m2)[1])
+
+
 def test_tgn_same_node_src_and_dst_in_batch():
     """Non-bipartite batch: the kept message is the last *appended* (src-role appends, then dst-role), which
     need not be the chronologically last."""
