@@ -15,10 +15,26 @@ import torch
 from .. import ops
 
 
+_const_cache = {}
+
+
+def _cached(tag, params, build):
+    """Per-weight-version constants of the eval path (they cost one tiny launch each, in steps that are launch-bound)."""
+    key = (tag,) + tuple((p.data_ptr(), p._version) for p in params)
+    ent = _const_cache.get(key)
+    if ent is None:
+        if len(_const_cache) > 64:
+            _const_cache.clear()
+        ent = _const_cache[key] = (build(), params)     # params kept alive so that data_ptr stays unique
+    return ent[0]
+
+
 def zero_time_features(time_encoder, device):
-    """cos(b): the time encoding of a zero interval, a per-forward constant (``models/TGAT.py:82``)."""
-    w, b = time_encoder.wb()
-    return ops.time_encode(torch.zeros(1, dtype=torch.float32, device=device), w, b).reshape(-1)
+    """cos(b): the time encoding of a zero interval, a constant of the weights (``models/TGAT.py:82``)."""
+    def build():
+        w, b = time_encoder.wb()
+        return ops.time_encode(torch.zeros(1, dtype=torch.float32, device=device), w, b).reshape(-1)
+    return _cached('t0', (time_encoder.w.weight, time_encoder.w.bias), build)
 
 
 def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node_tab2, nbr_ids, nbr_dense,
@@ -31,7 +47,8 @@ def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node
     wqk, wvr = attn.folded()
     w, b = time_encoder.wb()
     # constant part of the query: W_qk[:, F:] @ cos(b)
-    cq = ops.linear([ops.seg_rows(t0.reshape(1, T_))], 1, wqk[:, F_:], ldw=wqk.stride(0)).reshape(-1)
+    cq = _cached('cq', (attn.query_projection.weight, attn.key_projection.weight, time_encoder.w.weight, time_encoder.w.bias),
+                 lambda: ops.linear([ops.seg_rows(t0.reshape(1, T_))], 1, wqk[:, F_:], ldw=wqk.stride(0)).reshape(-1))
     qk = ops.linear([ops.seg_rows(conv)], n, wqk[:, :F_], bias=cq, ldw=wqk.stride(0))
     flat_ids = nbr_ids.reshape(-1)
     if nbr_dense is None:
