@@ -102,6 +102,7 @@ SIGNATURES = {
     'dyg_first_hop_pad': [c_p, c_p, c_l, c_p, c_l, c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     'dyg_cooc_count': [c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     'dyg_time_encode': [c_p, c_l, c_p, c_p, c_i, c_p, c_p],
+    'dyg_time_encode_bwd': [c_p, c_l, c_p, c_p, c_i, c_p, c_l, c_p, c_p, c_p],
     'dyg_linear': [ctypes.POINTER(Seg), c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
     'dyg_linear_tc_tile': [c_i],
     'dyg_linear_tc': [ctypes.POINTER(Seg), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],

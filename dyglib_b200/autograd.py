@@ -97,3 +97,28 @@ class _TemporalAttend(torch.autograd.Function):
 def temporal_attend(qk, nbr_dense, w, b, **cfg):
     """``w``: the time encoder's (T, 1) weight parameter, ``b``: its (T,) bias."""
     return _TemporalAttend.apply(qk, nbr_dense, w, b, cfg)
+
+
+class _TimeEncode(torch.autograd.Function):
+    """``TimeEncoder.forward`` (``models/modules.py:27-39``) with gradients for ``w`` / ``b``: forward on ``dyg_time_encode`` (the fp32
+    FMA argument of the reference), backward on ``dyg_time_encode_bwd`` (sin of the same argument)."""
+
+    @staticmethod
+    def forward(ctx, dt, w, b):
+        d = dt.detach().float().reshape(-1).contiguous()
+        wv, bv = w.detach().reshape(-1).contiguous(), b.detach().contiguous()
+        ctx.save_for_backward(d, wv, bv)
+        ctx.shape = tuple(dt.shape)
+        return ops.time_encode(d, wv, bv).reshape(*dt.shape, wv.numel())
+
+    @staticmethod
+    def backward(ctx, g):
+        d, wv, bv = ctx.saved_tensors
+        g2 = g.reshape(-1, wv.numel()).contiguous()
+        gw, gb = ops.time_encode_bwd(d, wv, bv, g2)
+        return None, gw.reshape(-1, 1), gb
+
+
+def time_encode(dt, w, b):
+    """Differentiable time encoding of ``dt`` (any shape) -> (*dt.shape, T); ``w``: (T, 1) weight, ``b``: (T,) bias."""
+    return _TimeEncode.apply(dt, w, b)

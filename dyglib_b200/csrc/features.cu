@@ -75,6 +75,41 @@ extern "C" int dyg_time_encode(const float* dt, int64_t n, const float* w, const
     return 0;
 }
 
+// backward of the time encoder (training path; the reference differentiates models/modules.py:37 with autograd):
+// out[i, c] = cos(a), a = fma(dt[i], w[c], b[c])  =>  gw[c] += sum_i g[i, c] (-sin a) dt[i],  gb[c] += sum_i g[i, c] (-sin a),
+// with sin of the same fp32 argument the forward pass used.  A thread owns feature columns, a block a stripe of rows.
+__global__ void time_encode_bwd_kernel(const float* __restrict__ dt, int64_t n, const float* __restrict__ w,
+                                       const float* __restrict__ b, int T, const float* __restrict__ g, int64_t ldg,
+                                       float* __restrict__ gw, float* __restrict__ gb) {
+    const int64_t rows_per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t i0 = blockIdx.x * rows_per, i1 = i0 + rows_per < n ? i0 + rows_per : n;
+    for (int c = threadIdx.x; c < T; c += blockDim.x) {
+        const float wc = __ldg(w + c), bc = __ldg(b + c);
+        float aw = 0.f, ab = 0.f;
+        for (int64_t i = i0; i < i1; ++i) {
+            const float d = __ldg(dt + i);
+            float sn, cs;
+            dyg_sincosf(fmaf(d, wc, bc), &sn, &cs);
+            const float t = -__ldg(g + i * ldg + c) * sn;
+            aw = fmaf(t, d, aw);
+            ab += t;
+        }
+        atomicAdd(gw + c, aw);
+        atomicAdd(gb + c, ab);
+    }
+}
+extern "C" int dyg_time_encode_bwd(const float* dt, int64_t n, const float* w, const float* b, int T, const float* grad_out,
+                                   int64_t ldg, float* grad_w, float* grad_b, dyg_stream_t stream) {
+    DYG_CHECK_ARG(n >= 0 && T > 0 && ldg >= T, "dyg_time_encode_bwd: bad sizes");
+    if (n == 0) return 0;
+    int64_t blocks = (n + 63) / 64;
+    const int64_t cap = (int64_t)dyg_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    time_encode_bwd_kernel<<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(dt, n, w, b, T, grad_out, ldg, grad_w, grad_b);
+    DYG_LAUNCH_CHECK("dyg_time_encode_bwd");
+    return 0;
+}
+
 // ------------------------------------------------------------------ row gather (+ add)
 __global__ void gather_rows_kernel(const float* __restrict__ tab, int ld, const float* __restrict__ tab2, int ld2,
                                    const int64_t* __restrict__ idx, int64_t M, int D, float* __restrict__ out, int ldo) {

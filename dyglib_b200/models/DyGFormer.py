@@ -94,7 +94,8 @@ class TransformerEncoder(nn.Module):
 
     def forward(self, inputs: torch.Tensor):
         """``TransformerEncoder.forward`` (``models/DyGFormer.py:442-461``): pre-norm block, no padding mask."""
-        _eval_only(self)
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(inputs)
         B, S, D = inputs.shape
         x = inputs.detach().to(torch.float32).contiguous().reshape(B * S, D)
         mha = self.multi_head_attention
@@ -116,6 +117,33 @@ class TransformerEncoder(nn.Module):
             y = ops.layernorm_split(x1, n1.weight.detach(), n1.bias.detach(), eps=n1.eps)
             h = ops.gemm(y, l0.weight, l0.bias.detach(), act=ops.ACT_GELU, want='split')
             out = ops.gemm(h, l1.weight, l1.bias.detach(), residual=x1)
+        return out.reshape(B, S, D)
+
+
+    def _forward_train(self, inputs):
+        """Training mode: the same block with autograd.  Dense layers run forward on the tcgen05 GEMM through
+        ``autograd.linear`` (backward: fp32 library GEMMs); LayerNorm, GELU, dropout and the 64-token softmax(QK^T)V core (5 % of
+        the block's flops) are library ops here.  Dropout sits where the reference has it: attention probabilities
+        (``nn.MultiheadAttention(dropout=...)``), the attention output, the hidden activation and the FFN output."""
+        from .. import autograd as ag
+        import torch.nn.functional as F
+        B, S, D = inputs.shape
+        H = self.num_heads
+        hd = D // H
+        mha = self.multi_head_attention
+        n0, n1 = self.norm_layers
+        l0, l1 = self.linear_layers
+        p = self.dropout.p
+        x = inputs.reshape(B * S, D)
+        y = F.layer_norm(x, (D,), n0.weight, n0.bias, n0.eps)
+        qkv = ag.linear(y, mha.in_proj_weight, mha.in_proj_bias).reshape(B, S, 3, H, hd)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))                       # (B, H, S, hd)
+        att = torch.softmax((q @ k.transpose(-1, -2)) * (hd ** -0.5), dim=-1)
+        att = F.dropout(att, mha.dropout, True)
+        a = (att @ v).transpose(1, 2).reshape(B * S, D)
+        x1 = x + F.dropout(ag.linear(a, mha.out_proj.weight, mha.out_proj.bias), p, True)
+        h = F.dropout(F.gelu(ag.linear(F.layer_norm(x1, (D,), n1.weight, n1.bias, n1.eps), l0.weight, l0.bias)), p, True)
+        out = x1 + F.dropout(ag.linear(h, l1.weight, l1.bias), p, True)
         return out.reshape(B, S, D)
 
 
@@ -224,7 +252,6 @@ class DyGFormer(nn.Module):
         ``batch_size`` (extension): the rows are treated as consecutive reference batches of that many events, each
         keeping its own padded length (the reference's padding unit); batches that share padded
         lengths run through the kernels together, so results equal calling the model once per batch."""
-        _eval_only(self)
         dev = self.node_raw_features.device
         P, L = self.patch_size, self.max_input_sequence_length
         tq = _as_dev(node_interact_times, torch.float64, dev)
@@ -273,6 +300,8 @@ class DyGFormer(nn.Module):
         S = ns + nd
         _, _, cs, cd = ops.cooc_count(s_pn, d_pn, want_float=False, want_int=True)
         Wmax = (self.max_input_sequence_length + P - 1) // P * P
+        if self.training and torch.is_grad_enabled():
+            return self._forward_padded_train(tq, s_pn, s_pe, s_pt, cs, d_pn, d_pe, d_pt, cd)
         lut = self.neighbor_co_occurrence_encoder.lut(2 * Wmax)   # one table for every padded length
         w, b = self.time_encoder.wb()
         X = torch.empty((B * S, D), dtype=torch.float32, device=dev)
@@ -293,6 +322,42 @@ class DyGFormer(nn.Module):
         ops.mean_tokens(x, B, S, D, 0, ns, out=means[:B])
         ops.mean_tokens(x, B, S, D, ns, nd, out=means[B:])
         out = ops.gemm(ops.split_bf16(means), self.output_layer.weight, self.output_layer.bias.detach())
+        return out[:B], out[B:]
+
+    def _forward_padded_train(self, tq, s_pn, s_pe, s_pt, cs, d_pn, d_pe, d_pt, cd):
+        """Training mode of ``_forward_padded`` (``models/DyGFormer.py:102-194`` under autograd).  Sampling, padding and the
+        co-occurrence counts come from the same kernels (integers, no gradient); node / edge rows are constant gathers; the
+        time encoding is ``autograd.time_encode`` (gradients for the encoder's w / b from ``dyg_time_encode_bwd``); the
+        co-occurrence MLP is evaluated once per distinct count (a differentiable table) and indexed; the four channel
+        projections, the transformer's dense layers and the output layer run on ``autograd.linear``."""
+        from .. import autograd as ag
+        import torch.nn.functional as F
+        P, C = self.patch_size, self.channel_embedding_dim
+        B = tq.numel()
+        pl = self.projection_layer
+        enc = self.neighbor_co_occurrence_encoder.neighbor_co_occurrence_encode_layer
+        max_count = int(max(cs[0].max().item(), cs[1].max().item(), cd[0].max().item(), cd[1].max().item()))
+        counts = torch.arange(max_count + 1, dtype=torch.float32, device=tq.device).reshape(-1, 1)
+        lut = enc[2](torch.relu(enc[0](counts)))                                          # (max_count + 1, C), models/DyGFormer.py:409-411
+        toks = []
+        for pn, pe, pt, cnt in ((s_pn, s_pe, s_pt, cs), (d_pn, d_pe, d_pt, cd)):
+            Lp = pn.shape[1]
+            nodef = self.node_raw_features[pn]
+            edgef = self.edge_raw_features[pe]
+            dt = (tq.reshape(B, 1) - pt.double()).float()
+            te = ag.time_encode(dt, self.time_encoder.w.weight, self.time_encoder.w.bias) * (pn != 0).unsqueeze(-1)
+            co = lut[cnt[0]] + lut[cnt[1]]
+            chans = []
+            for name, x in (('node', nodef), ('edge', edgef), ('time', te), ('neighbor_co_occurrence', co)):
+                patches = x.reshape(B * (Lp // P), P * x.shape[2])
+                chans.append(ag.linear(patches, pl[name].weight, pl[name].bias).reshape(B, Lp // P, C))
+            toks.append(torch.stack(chans, dim=2).reshape(B, Lp // P, self.num_channels * C))
+        ns = toks[0].shape[1]
+        x = torch.cat(toks, dim=1)
+        for tr in self.transformers:
+            x = tr(x)
+        means = torch.cat([x[:, :ns].mean(dim=1), x[:, ns:].mean(dim=1)], dim=0)
+        out = ag.linear(means, self.output_layer.weight, self.output_layer.bias)
         return out[:B], out[B:]
 
     def _project_unfused(self, X, tq, s_pn, s_pe, s_pt, cs, d_pn, d_pe, d_pt, cd, lut, w, b):

@@ -430,6 +430,17 @@ def time_encode(dt, w, b, out=None):
     return out
 
 
+def time_encode_bwd(dt, w, b, grad_out):
+    """(grad_w (T,), grad_b (T,)) of dyg_time_encode for ``grad_out`` (n, T)."""
+    n, T = dt.numel(), w.numel()
+    gw = torch.zeros(T, device=dt.device, dtype=torch.float32)
+    gb = torch.zeros(T, device=dt.device, dtype=torch.float32)
+    _native.check(_lib().dyg_time_encode_bwd(_p(dt), int(n), _p(w), _p(b), int(T), _p(grad_out), int(grad_out.stride(0)), _p(gw), _p(gb),
+                                             _stream()))
+    _count()
+    return gw, gb
+
+
 def zero_row0_flags(node_tab, edge_tab, node_tab2=None):
     """Which padding rows (row 0: node 0 / edge 0, preprocess_data/preprocess_data.py:101-108) of static tables are all
     zeros, so that dyg_temporal_attend may skip reading them.  One host sync: call it at model construction."""

@@ -116,6 +116,11 @@ int dyg_cooc_count(const int64_t* src_ids, int ld_src, const int64_t* dst_ids, i
 
 /* ---- a8: TimeEncoder.forward (models/modules.py:27-39): out[i,c] = cos(fma(dt[i], w[c], b[c])) ---- */
 int dyg_time_encode(const float* dt, int64_t n, const float* w, const float* b, int T, float* out, dyg_stream_t stream);
+/* Backward of dyg_time_encode for the training path (the reference differentiates models/modules.py:37 with autograd):
+ * grad_w[c] += sum_i grad_out[i, c] * (-sin(fma(dt[i], w[c], b[c]))) * dt[i], grad_b[c] += the same without dt[i];
+ * grad_out is (n, ldg) row-major.  Accumulates (the caller zeroes grad_w / grad_b). */
+int dyg_time_encode_bwd(const float* dt, int64_t n, const float* w, const float* b, int T, const float* grad_out, int64_t ldg,
+                        float* grad_w, float* grad_b, dyg_stream_t stream);
 
 /* ---- dense contractions with fused gathers (nn.Linear call sites of models/modules.py:155-199,65-67;
  * models/DyGFormer.py:148-157,442-461; nn.GRUCell of models/MemoryModel.py:501) ----

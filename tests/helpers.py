@@ -308,3 +308,55 @@ def cuda_memory_train_step(name):
     params = {'model.' + k: v for k, v in m.named_parameters() if v.requires_grad}
     params.update({'pred.' + k: v for k, v in pred.named_parameters()})
     return memory_train_step(m, lambda a, b: pred(a, b), params)
+
+
+# ---------------------------------------------------------------------------------------------
+# DyGFormer training step: positive and negative pair batch, BCE, one backward pass (dropout 0 for determinism).
+def dygformer_train_step(model, predictor_fn, params: dict, seed=12, start=1000, B=50):
+    g = small_graph(seed=seed)
+    src, dst, t, _, neg = next(batches(g, start, 1, B))
+    ps, pd = model.compute_src_dst_node_temporal_embeddings(src, dst, t)
+    ns, nd = model.compute_src_dst_node_temporal_embeddings(src, neg, t)
+    pos = predictor_fn(ps, pd).squeeze(dim=-1).sigmoid()
+    negp = predictor_fn(ns, nd).squeeze(dim=-1).sigmoid()
+    predicts = torch.cat([pos, negp], dim=0)
+    labels = torch.cat([torch.ones_like(pos), torch.zeros_like(negp)], dim=0)
+    loss = torch.nn.functional.binary_cross_entropy(predicts, labels)
+    for p in params.values():
+        p.grad = None
+    loss.backward()
+    out = {'loss': np.asarray(loss.item(), dtype=np.float64), 'pos': pos.detach().cpu().numpy(), 'neg': negp.detach().cpu().numpy()}
+    for name, p in params.items():
+        out['grad.' + name] = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu().numpy()
+    return out
+
+
+DYG_TRAIN_CASES = ((4, 32),)
+
+
+def oracle_dygformer_train_step(P, L):
+    from oracle.models import merge_layer
+    _, _, dygformer, _ = oracle_factories()
+    m = dygformer(small_graph(seed=12), P, L, 2)
+    m.sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in m.sd.items()}
+    psd = {k: v.clone().requires_grad_(True) for k, v in deterministic_state_dict(predictor_template().state_dict(), 5).items()}
+    params = {'model.' + k: v for k, v in m.sd.items()}
+    params.update({'pred.' + k: v for k, v in psd.items()})
+    return dygformer_train_step(m, lambda a, b: merge_layer(psd, '', a, b), params)
+
+
+def cuda_dygformer_train_step(P, L):
+    _, _, dygformer, _ = cuda_factories()
+    m = dygformer(small_graph(seed=12), P, L, 2)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, torch.nn.MultiheadAttention):
+            mod.dropout = 0.0
+    m.train()
+    pred = predictor_template().to('cuda')
+    pred.load_state_dict(deterministic_state_dict(pred.state_dict(), 5))
+    pred.train()
+    params = {'model.' + k: v for k, v in m.named_parameters()}
+    params.update({'pred.' + k: v for k, v in pred.named_parameters()})
+    return dygformer_train_step(m, lambda a, b: pred(a, b), params)

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from helpers import (cuda_tgat_train_step, oracle_tgat_train_step, assert_grads_close, load_golden, cuda_memory_train_step,
-                     oracle_memory_train_step)
+                     oracle_memory_train_step, cuda_dygformer_train_step, oracle_dygformer_train_step, DYG_TRAIN_CASES)
 
 pytestmark = pytest.mark.gpu
 
@@ -32,6 +32,44 @@ def test_memory_model_training_step_matches_reference_golden_and_oracle(name):
     np.testing.assert_allclose(got['pos'], gold['pos'], rtol=1e-3, atol=2e-4)
     assert_grads_close(got, gold, rtol=2e-3)
     assert_grads_close(got, oracle_memory_train_step(name), rtol=2e-3)
+
+
+@pytest.mark.parametrize('P,L', DYG_TRAIN_CASES)
+def test_dygformer_training_step_matches_reference_golden_and_oracle(P, L):
+    got = cuda_dygformer_train_step(P, L)
+    gold = {k[len(f'P{P}_L{L}.'):]: v for k, v in load_golden('dygformer_train.npz').items() if k.startswith(f'P{P}_L{L}.')}
+    np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+    np.testing.assert_allclose(got['pos'], gold['pos'], rtol=1e-3, atol=2e-4)
+    assert_grads_close(got, gold, rtol=2e-3)
+    assert_grads_close(got, oracle_dygformer_train_step(P, L), rtol=2e-3)
+
+
+def test_time_encode_backward_against_float64():
+    """dyg_time_encode_bwd: gradients of w / b against autograd through cos of the same fp32-rounded argument in float64."""
+    from dyglib_b200 import autograd as ag
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(3)
+    n, T = 3001, 100
+    dt = torch.rand(n, device=dev, generator=g) * 2e6
+    w = (1.0 / 10 ** torch.linspace(0, 9, T, device=dev)).reshape(T, 1).requires_grad_(True)
+    b = (0.1 * torch.randn(T, device=dev, generator=g)).requires_grad_(True)
+    go = torch.randn(n, T, device=dev, generator=g)
+    out = ag.time_encode(dt, w, b)
+    out.backward(go)
+    w2, b2 = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    val = dt.double().unsqueeze(1) * w2.reshape(1, T) + b2
+    arg = val + (torch.addcmul(b.detach(), dt.unsqueeze(1), w.detach().reshape(1, T)).double() - val).detach()
+    want = torch.cos(arg)
+    # the comparison argument is rounded to fp32 like the kernel's FMA (torch's CUDA addcmul may or may not fuse: keep rows that agree)
+    ok = (out.detach().double() - want.detach()).abs().max(dim=1).values < 1e-5
+    assert float(ok.float().mean()) > 0.9
+    (want * go.double() * ok.unsqueeze(1)).sum().backward()
+    out2 = ag.time_encode(dt, w.detach().requires_grad_(True), b.detach().requires_grad_(True))
+    ws, bs = out2.grad_fn.next_functions[1][0].variable, out2.grad_fn.next_functions[2][0].variable
+    out2.backward(go * ok.unsqueeze(1))
+    for got_, want_ in ((ws.grad.reshape(-1), w2.grad.reshape(-1)), (bs.grad, b2.grad)):
+        scale = float(want_.abs().max())
+        assert float((got_.double() - want_).abs().max()) / scale < 1e-3
 
 
 def test_memory_model_eval_after_training_uses_current_weights():

@@ -47,3 +47,13 @@ def test_oracle_memory_training_step_matches_golden(name):
     gold = {k[len(name) + 1:]: v for k, v in load_golden('memory_train.npz').items() if k.startswith(name + '.')}
     np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
     assert_grads_close(got, gold, rtol=1e-3)
+
+
+def test_oracle_dygformer_training_step_matches_golden():
+    """DyGFormer (patch 4, length 32): loss and every parameter gradient of one training step against the reference's."""
+    from helpers import oracle_dygformer_train_step, assert_grads_close, DYG_TRAIN_CASES
+    for P, L in DYG_TRAIN_CASES:
+        got = oracle_dygformer_train_step(P, L)
+        gold = {k[len(f'P{P}_L{L}.'):]: v for k, v in load_golden('dygformer_train.npz').items() if k.startswith(f'P{P}_L{L}.')}
+        np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+        assert_grads_close(got, gold, rtol=1e-3)
