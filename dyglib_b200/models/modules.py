@@ -1,7 +1,8 @@
 """Drop-ins for the reference's shared modules (``models/modules.py``): ``TimeEncoder``, ``MergeLayer``,
 ``MultiHeadAttention``.  Same constructor arguments, parameter names and shapes (``state_dict``-compatible);
-``forward`` runs the sm_100a kernels of libdygb200.so.  Inference only: there is no autograd through the
-kernels yet, so calling a module in training mode raises instead of silently skipping dropout.
+``forward`` runs the sm_100a kernels of libdygb200.so.  ``MergeLayer`` differentiates through them in training mode
+(``dyglib_b200/autograd.py``); the models train through ``_temporal.temporal_conv_train``, so the stand-alone
+``MultiHeadAttention.forward`` is eval only and raises in training mode instead of silently skipping dropout.
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ from .. import ops
 
 def _eval_only(module):
     if module.training:
-        raise NotImplementedError(f'{type(module).__name__}: the CUDA path is forward/eval only in this round; call .eval()')
+        raise NotImplementedError(f'{type(module).__name__}: this module's stand-alone forward is eval only (the models train through temporal_conv_train); call .eval()')
 
 
 def _f32(x):
