@@ -387,3 +387,49 @@ def get_neighbor_sampler(data, sample_neighbor_strategy: str = 'uniform', time_s
     presorted = bool(E == 0 or np.all(t[1:] >= t[:-1]))
     return NeighborSampler(None, sample_neighbor_strategy, time_scaling_factor, seed, device, rng, tia_table,
                            _edges=(src, dst, eid, t, num_nodes, presorted))
+
+
+class NegativeEdgeSampler(object):
+    """``NegativeEdgeSampler`` (``utils/utils.py:303-390``), ``random`` strategy: the negative sources / destinations of a batch are
+    drawn uniformly from the unique sources / destinations with the reference's ``RandomState(seed).randint`` stream (global
+    ``np.random`` without a seed), so a seeded sampler returns the reference's ids.  ``sample_device`` returns them as CUDA
+    tensors for the fused models.  The ``historical`` / ``inductive`` strategies enumerate python sets of edge tuples whose
+    iteration order is an implementation detail of the reference; they are outside this path and raise."""
+
+    def __init__(self, src_node_ids: np.ndarray, dst_node_ids: np.ndarray, interact_times: np.ndarray = None,
+                 last_observed_time: float = None, negative_sample_strategy: str = 'random', seed: int = None):
+        self.seed = seed
+        self.negative_sample_strategy = negative_sample_strategy
+        self.src_node_ids = src_node_ids
+        self.dst_node_ids = dst_node_ids
+        self.interact_times = interact_times
+        self.unique_src_node_ids = np.unique(src_node_ids)
+        self.unique_dst_node_ids = np.unique(dst_node_ids)
+        self.last_observed_time = last_observed_time
+        if self.seed is not None:
+            self.random_state = np.random.RandomState(self.seed)
+
+    def sample(self, size: int, batch_src_node_ids: np.ndarray = None, batch_dst_node_ids: np.ndarray = None,
+               current_batch_start_time: float = 0.0, current_batch_end_time: float = 0.0):
+        """``sample`` (``utils/utils.py:349-376``)."""
+        if self.negative_sample_strategy == 'random':
+            return self.random_sample(size=size)
+        if self.negative_sample_strategy in ('historical', 'inductive'):
+            raise NotImplementedError(f'negative_sample_strategy {self.negative_sample_strategy}: use the reference sampler (host-side set logic)')
+        raise ValueError(f'Not implemented error for negative_sample_strategy {self.negative_sample_strategy}!')
+
+    def random_sample(self, size: int):
+        """``random_sample`` (``utils/utils.py:378-390``): source draw first, then destination draw."""
+        rs = np.random if self.seed is None else self.random_state
+        si = rs.randint(0, len(self.unique_src_node_ids), size)
+        di = rs.randint(0, len(self.unique_dst_node_ids), size)
+        return self.unique_src_node_ids[si], self.unique_dst_node_ids[di]
+
+    def sample_device(self, size: int, device='cuda'):
+        """``random_sample`` as int64 CUDA tensors (same stream, same ids)."""
+        s, d = self.random_sample(size)
+        return torch.from_numpy(np.ascontiguousarray(s)).to(device), torch.from_numpy(np.ascontiguousarray(d)).to(device)
+
+    def reset_random_state(self):
+        """``reset_random_state`` (``utils/utils.py:472-477``)."""
+        self.random_state = np.random.RandomState(self.seed)
