@@ -53,7 +53,7 @@ class NeighborCooccurrenceEncoder(nn.Module):
         """Rows c = 0..max_count of MLP(c) = W2 relu(W1 c + b1) + b2, padded to a multiple of 4 columns.
         Counts are small integers, so the per-position MLP of the reference (``:409-411``) is a table lookup."""
         l0, l2 = self.neighbor_co_occurrence_encode_layer[0], self.neighbor_co_occurrence_encode_layer[2]
-        key = (max_count,) + tuple((p.data_ptr(), p._version) for p in (l0.weight, l0.bias, l2.weight, l2.bias))
+        key = (max_count, ops.WEIGHTS_EPOCH) + tuple((p.data_ptr(), p._version) for p in (l0.weight, l0.bias, l2.weight, l2.bias))
         if key != self._lut_key:
             dev = l0.weight.device
             C = self.neighbor_co_occurrence_feat_dim
@@ -235,7 +235,7 @@ class DyGFormer(nn.Module):
     def _cooc_weight(self):
         """projection_layer['neighbor_co_occurrence'].weight with every patch slot padded to the LUT row width."""
         wt = self.projection_layer['neighbor_co_occurrence'].weight
-        key = (wt.data_ptr(), wt._version)
+        key = (wt.data_ptr(), wt._version, ops.WEIGHTS_EPOCH)
         if key != self._cooc_w_key:
             C, P = self.neighbor_co_occurrence_feat_dim, self.patch_size
             Cp = (C + 3) // 4 * 4
@@ -394,7 +394,7 @@ class DyGFormer(nn.Module):
         pl = self.projection_layer
         ps = [pl[k].weight for k in ('node', 'edge', 'time', 'neighbor_co_occurrence')] + \
              [pl[k].bias for k in ('node', 'edge', 'time', 'neighbor_co_occurrence')]
-        key = (lut.data_ptr(), tuple(lut.shape)) + tuple((q.data_ptr(), q._version) for q in ps)
+        key = (lut.data_ptr(), tuple(lut.shape), ops.WEIGHTS_EPOCH) + tuple((q.data_ptr(), q._version) for q in ps)
         if key != self._proj_key:
             C = self.neighbor_co_occurrence_feat_dim
             lut_pl = ops.table_planes(lut[:, :C])

@@ -20,7 +20,7 @@ _const_cache = {}
 
 def _cached(tag, params, build):
     """Per-weight-version constants of the eval path (they cost one tiny launch each, in steps that are launch-bound)."""
-    key = (tag,) + tuple((p.data_ptr(), p._version) for p in params)
+    key = (tag, ops.WEIGHTS_EPOCH) + tuple((p.data_ptr(), p._version) for p in params)
     ent = _const_cache.get(key)
     if ent is None:
         if len(_const_cache) > 64:

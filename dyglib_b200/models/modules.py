@@ -15,7 +15,8 @@ from .. import ops
 
 def _eval_only(module):
     if module.training:
-        raise NotImplementedError(f'{type(module).__name__}: this module's stand-alone forward is eval only (the models train through temporal_conv_train); call .eval()')
+        raise NotImplementedError(f'{type(module).__name__}: the stand-alone forward of this module is eval only (the models train '
+                                  f'through temporal_conv_train); call .eval()')
 
 
 def _f32(x):
@@ -97,7 +98,7 @@ class MultiHeadAttention(nn.Module):
         residual_fc(concat_h(W_v,h sum_j a_j x_j)) = sum_h (R[:, h] W_v,h) (sum_j a_hj x_j) + bias.
         Returns W_qk (H*Dk, Dq) and W_vr (Dq, H*Dk), folded in float64 once per weight version."""
         ps = (self.query_projection.weight, self.key_projection.weight, self.value_projection.weight, self.residual_fc.weight)
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (ops.WEIGHTS_EPOCH,) + tuple((p.data_ptr(), p._version) for p in ps)
         if key != self._fold_key:
             H, hd = self.num_heads, self.head_dim
             wq, wk, wv, r = (p.detach().double() for p in ps)

@@ -49,6 +49,17 @@ def _count(n=1):
     launch_count += n
 
 
+# Caches of weight-derived operands (BF16x3 planes, folded attention weights, LUTs) are keyed on (data_ptr, tensor version).
+# A CUDA-graph replay of a training step updates the parameters without touching their version counters, so every such key also
+# carries this epoch; utils.graph.GraphedStep bumps it after each replay of a step captured with grad=True.
+WEIGHTS_EPOCH = 0
+
+
+def bump_weights_epoch():
+    global WEIGHTS_EPOCH
+    WEIGHTS_EPOCH += 1
+
+
 # optional per-launch timing (bench.py roofline pass): PROFILE = [] enables it; each entry is
 # (kernel name, start event, end event, algorithmic flops, algorithmic bytes)
 PROFILE = None
@@ -122,7 +133,7 @@ _tc_weights = {}
 
 def _split_weight(weight, K, ldw):
     """bf16 hi / mid copies of weight[:, :K], zero padded to (n_pad, k_pad); cached per weight version."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), int(ldw), int(K))
+    key = (weight.data_ptr(), weight._version, WEIGHTS_EPOCH, tuple(weight.shape), int(ldw), int(K))
     ent = _tc_weights.get(key)
     if ent is None:
         N = weight.shape[0]
@@ -243,7 +254,7 @@ _split_weights = {}
 
 def split_weight(weight):
     """Cached BF16x3 planes of a (N, K) fp32 weight (re-split when the parameter changes)."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), tuple(weight.stride()))
+    key = (weight.data_ptr(), weight._version, WEIGHTS_EPOCH, tuple(weight.shape), tuple(weight.stride()))
     ent = _split_weights.get(key)
     if ent is None:
         if len(_split_weights) > 256:

@@ -24,6 +24,7 @@ class GraphedStep:
         """``grad=True`` captures a whole training step (forward, ``backward()``, gradient all-reduce, a ``capturable``
         optimizer step): gradients must then accumulate into preallocated buffers (``utils.dist.GradBucket``)."""
         self.fn = fn
+        self.grad = grad
         mode = torch.enable_grad if grad else torch.no_grad
         self.static_in = [x.clone() for x in example_inputs]
         side = torch.cuda.Stream()
@@ -47,5 +48,7 @@ class GraphedStep:
         for dst, src in zip(self.static_in, inputs):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        if self.grad:
+            ops.bump_weights_epoch()   # the replay moved the parameters without bumping their version counters
         ops.launch_count += self.launches
         return self.static_out

@@ -127,3 +127,14 @@ def test_link_metrics_match_sklearn(ties):
         assert abs(got['roc_auc'] - roc_auc_score(labels.numpy(), p.numpy())) < 1e-12
         ap, auc = link_prediction_metrics_tensors(p, labels)
         assert ap.dtype == torch.float64 and ap.dim() == 0 and auc.dim() == 0
+
+
+def test_every_source_file_compiles():
+    """A syntax error in a module that only the GPU tests import would otherwise surface on the GPU box."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [f for pat in ('dyglib_b200/**/*.py', 'oracle/*.py', 'tests/*.py', 'scripts/*.py', '*.py') for f in glob.glob(os.path.join(root, pat), recursive=True)]
+    assert len(files) > 20
+    for f in files:
+        py_compile.compile(f, doraise=True, cfile=os.devnull)
