@@ -1,5 +1,5 @@
 """Oracle restatement (torch CPU, fp32) of the float part of the path:
-TimeEncoder, temporal MultiHeadAttention, MergeLayer, TGAT, DyGFormer, MemoryModel(TGN).
+TimeEncoder, temporal MultiHeadAttention, MergeLayer, TGAT, DyGFormer, MemoryModel(TGN / DyRep / JODIE), GraphMixer.
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Eval-mode semantics
 (dropout = identity).  Weights come in as a ``state_dict`` with the reference's
@@ -288,3 +288,47 @@ class OracleMemoryModel:
         if self.model_name == 'DyRep':
             s_emb, d_emb = mem[_ids(src)], mem[_ids(dst)]
         return s_emb, d_emb
+
+
+class OracleGraphMixer:
+    """``GraphMixer`` (``models/GraphMixer.py:58-151``, ``:164-238``), eval-mode semantics."""
+
+    def __init__(self, sd, node_raw_features, edge_raw_features, sampler: OracleSampler, num_layers=2):
+        self.sd = sd
+        self.nf = torch.from_numpy(node_raw_features.astype(np.float32))
+        self.ef = torch.from_numpy(edge_raw_features.astype(np.float32))
+        self.sampler = sampler
+        self.num_layers = num_layers
+
+    def _ffn(self, prefix, x):
+        sd = self.sd
+        h = F.gelu(F.linear(x, sd[prefix + 'ffn.0.weight'], sd[prefix + 'ffn.0.bias']))
+        return F.linear(h, sd[prefix + 'ffn.3.weight'], sd[prefix + 'ffn.3.bias'])
+
+    def _mixer(self, i, x):
+        sd, p = self.sd, f'mlp_mixers.{i}.'
+        k, c = x.shape[1], x.shape[2]
+        h = F.layer_norm(x.permute(0, 2, 1), (k,), sd[p + 'token_norm.weight'], sd[p + 'token_norm.bias'])
+        out = self._ffn(p + 'token_feedforward.', h).permute(0, 2, 1) + x
+        h = F.layer_norm(out, (c,), sd[p + 'channel_norm.weight'], sd[p + 'channel_norm.bias'])
+        return self._ffn(p + 'channel_feedforward.', h) + out
+
+    def node_embeddings(self, node_ids, times, k=20, time_gap=2000):
+        sd = self.sd
+        nn_, ne_, nt_ = self.sampler.get_historical_neighbors(node_ids, times, k)
+        te = time_encode(sd, 'time_encoder.', torch.from_numpy(np.asarray(times)[:, None] - nt_).float())
+        te = te * (_ids(nn_) != 0).unsqueeze(-1)                                                     # (:103-104)
+        x = F.linear(torch.cat([self.ef[_ids(ne_)], te], dim=-1), sd['projection_layer.weight'], sd['projection_layer.bias'])
+        for i in range(self.num_layers):
+            x = self._mixer(i, x)
+        link = x.mean(dim=1)
+        gap, _, _ = self.sampler.get_historical_neighbors(node_ids, times, time_gap)
+        mask = torch.from_numpy((gap > 0).astype(np.float32))
+        mask[mask == 0] = -1e10
+        scores = torch.softmax(mask, dim=1)
+        agg = torch.mean(self.nf[_ids(gap)] * scores.unsqueeze(-1), dim=1)                          # (:139)
+        node = agg + self.nf[_ids(node_ids)]
+        return F.linear(torch.cat([link, node], dim=1), sd['output_layer.weight'], sd['output_layer.bias'])
+
+    def compute_src_dst_node_temporal_embeddings(self, src, dst, times, num_neighbors=20, time_gap=2000):
+        return (self.node_embeddings(src, times, num_neighbors, time_gap), self.node_embeddings(dst, times, num_neighbors, time_gap))

@@ -220,3 +220,23 @@ def test_dygformer_grouped_equals_per_batch():
             q = slice(b * bs, (b + 1) * bs)
             es, ed = m.compute_src_dst_node_temporal_embeddings(src[q], dst[q], t[q])
             assert torch.equal(gs[q], es) and torch.equal(gd[q], ed), b
+
+
+def test_graphmixer_matches_golden_and_oracle():
+    """GraphMixer on the device sampler (k = 20 recent neighbours + a 300-deep window for the node encoder), the fused gather-GEMM
+    projection and the tcgen05 GEMMs: eval embeddings against the reference's golden vectors and the oracle."""
+    from helpers import cuda_graphmixer, oracle_graphmixer, run_graphmixer_cases
+    gold = load_golden('graphmixer.npz')
+    got = run_graphmixer_cases(cuda_graphmixer())
+    want = run_graphmixer_cases(oracle_graphmixer())
+    for k in got:
+        np.testing.assert_allclose(got[k], gold[k], rtol=1e-3, atol=2e-4, err_msg=k)
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-3, atol=2e-4, err_msg=k)
+
+
+def test_graphmixer_training_step_matches_golden():
+    from helpers import cuda_graphmixer_train_step, assert_grads_close
+    gold = {k[len('train.'):]: v for k, v in load_golden('graphmixer.npz').items() if k.startswith('train.')}
+    got = cuda_graphmixer_train_step()
+    np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+    assert_grads_close(got, gold, rtol=2e-3)

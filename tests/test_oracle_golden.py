@@ -57,3 +57,17 @@ def test_oracle_dygformer_training_step_matches_golden():
         gold = {k[len(f'P{P}_L{L}.'):]: v for k, v in load_golden('dygformer_train.npz').items() if k.startswith(f'P{P}_L{L}.')}
         np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
         assert_grads_close(got, gold, rtol=1e-3)
+
+
+def test_oracle_graphmixer_matches_golden():
+    """GraphMixer (a caller of the path): eval embeddings of two batches and one training step against the reference's
+    (scripts/make_golden_graphmixer.py)."""
+    from helpers import oracle_graphmixer, oracle_graphmixer_train_step, run_graphmixer_cases, assert_grads_close
+    gold = load_golden('graphmixer.npz')
+    got = run_graphmixer_cases(oracle_graphmixer())
+    for k in got:
+        np.testing.assert_allclose(got[k], gold[k], rtol=1e-4, atol=1e-5, err_msg=k)
+    tr = oracle_graphmixer_train_step()
+    gtr = {k[len('train.'):]: v for k, v in gold.items() if k.startswith('train.')}
+    np.testing.assert_allclose(tr['loss'], gtr['loss'], rtol=1e-5)
+    assert_grads_close(tr, gtr, rtol=1e-3)
