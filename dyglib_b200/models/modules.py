@@ -136,3 +136,51 @@ class MultiHeadAttention(nn.Module):
         out = ops.layernorm(o, self.layer_norm.weight.detach(), self.layer_norm.bias.detach(), r1=res, F1=self.query_dim,
                             eps=self.layer_norm.eps)
         return out, scores
+
+
+class TransformerEncoder(nn.Module):
+
+    def __init__(self, attention_dim: int, num_heads: int, dropout: float = 0.1):
+        """``TransformerEncoder`` (``models/modules.py:209-266``, used by TCL): post-norm block with an ``nn.MultiheadAttention``
+        parameter container (``state_dict``-compatible), separate query / key inputs and a key padding mask."""
+        super().__init__()
+        self.multi_head_attention = nn.MultiheadAttention(embed_dim=attention_dim, num_heads=num_heads, dropout=dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.linear_layers = nn.ModuleList([nn.Linear(attention_dim, 4 * attention_dim), nn.Linear(4 * attention_dim, attention_dim)])
+        self.norm_layers = nn.ModuleList([nn.LayerNorm(attention_dim), nn.LayerNorm(attention_dim)])
+        self.num_heads = num_heads
+
+    def forward(self, inputs_query: torch.Tensor, inputs_key: torch.Tensor = None, inputs_value: torch.Tensor = None, neighbor_masks=None):
+        """``TransformerEncoder.forward`` (``models/modules.py:233-266``).  The five dense layers run forward on the sm_100a GEMMs
+        (``autograd.linear``, which also gives the training path); the (B, H, Lq, Lk) masked softmax over ~21 positions,
+        LayerNorm, ReLU and dropout are library elementwise ops.  ``inputs_value`` must be ``inputs_key`` (as in every caller)."""
+        from .. import autograd as ag
+        import torch.nn.functional as F
+        if inputs_key is None or inputs_value is None:
+            assert inputs_key is None and inputs_value is None
+            inputs_key = inputs_value = inputs_query
+        assert inputs_value is inputs_key
+        B, Lq, D = inputs_query.shape
+        Lk = inputs_key.shape[1]
+        H = self.num_heads
+        hd = D // H
+        mha = self.multi_head_attention
+        p = self.dropout.p
+        W, bias = mha.in_proj_weight, mha.in_proj_bias
+        q = ag.linear(inputs_query.reshape(B * Lq, D), W[:D], bias[:D]).reshape(B, Lq, H, hd).transpose(1, 2)
+        kv = ag.linear(inputs_key.reshape(B * Lk, D), W[D:], bias[D:]).reshape(B, Lk, 2, H, hd)
+        k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+        att = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+        if neighbor_masks is not None:
+            if isinstance(neighbor_masks, np.ndarray):
+                neighbor_masks = torch.from_numpy(neighbor_masks)
+            pad = (neighbor_masks.to(inputs_query.device) == 0).reshape(B, 1, 1, Lk)
+            att = att.masked_fill(pad, float('-inf'))
+        att = F.dropout(torch.softmax(att, dim=-1), mha.dropout, self.training)
+        a = (att @ v).transpose(1, 2).reshape(B * Lq, D)
+        hidden = ag.linear(a, mha.out_proj.weight, mha.out_proj.bias).reshape(B, Lq, D)
+        n0, n1 = self.norm_layers
+        out = F.layer_norm(inputs_query + F.dropout(hidden, p, self.training), (D,), n0.weight, n0.bias, n0.eps)
+        h = F.dropout(torch.relu(ag.linear(out.reshape(B * Lq, D), self.linear_layers[0].weight, self.linear_layers[0].bias)), p, self.training)
+        h = ag.linear(h, self.linear_layers[1].weight, self.linear_layers[1].bias).reshape(B, Lq, D)
+        return F.layer_norm(out + F.dropout(h, p, self.training), (D,), n1.weight, n1.bias, n1.eps)

@@ -1,5 +1,5 @@
 """Oracle restatement (torch CPU, fp32) of the float part of the path:
-TimeEncoder, temporal MultiHeadAttention, MergeLayer, TGAT, DyGFormer, MemoryModel(TGN / DyRep / JODIE), GraphMixer.
+TimeEncoder, temporal MultiHeadAttention, MergeLayer, TGAT, DyGFormer, MemoryModel(TGN / DyRep / JODIE), GraphMixer, TCL.
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Eval-mode semantics
 (dropout = identity).  Weights come in as a ``state_dict`` with the reference's
@@ -332,3 +332,53 @@ class OracleGraphMixer:
 
     def compute_src_dst_node_temporal_embeddings(self, src, dst, times, num_neighbors=20, time_gap=2000):
         return (self.node_embeddings(src, times, num_neighbors, time_gap), self.node_embeddings(dst, times, num_neighbors, time_gap))
+
+
+class OracleTCL:
+    """``TCL`` (``models/TCL.py:56-183``) with the post-norm ``TransformerEncoder`` of ``models/modules.py:209-266``; the attention
+    itself is delegated to ``F.multi_head_attention_forward`` (what ``nn.MultiheadAttention`` calls in the reference)."""
+
+    def __init__(self, sd, node_raw_features, edge_raw_features, sampler: OracleSampler, num_layers=2, num_heads=2):
+        self.sd = sd
+        self.nf = torch.from_numpy(node_raw_features.astype(np.float32))
+        self.ef = torch.from_numpy(edge_raw_features.astype(np.float32))
+        self.sampler = sampler
+        self.num_layers = num_layers
+        self.num_heads = num_heads
+
+    def _block(self, i, q_in, k_in, key_ids):
+        sd, p = self.sd, f'transformers.{i}.'
+        D = q_in.shape[2]
+        pad = _ids(key_ids) == 0
+        h, _ = F.multi_head_attention_forward(
+            q_in.transpose(0, 1), k_in.transpose(0, 1), k_in.transpose(0, 1), D, self.num_heads,
+            sd[p + 'multi_head_attention.in_proj_weight'], sd[p + 'multi_head_attention.in_proj_bias'], None, None, False, 0.0,
+            sd[p + 'multi_head_attention.out_proj.weight'], sd[p + 'multi_head_attention.out_proj.bias'], training=False,
+            key_padding_mask=pad, need_weights=False)
+        out = F.layer_norm(q_in + h.transpose(0, 1), (D,), sd[p + 'norm_layers.0.weight'], sd[p + 'norm_layers.0.bias'])
+        h = F.linear(F.relu(F.linear(out, sd[p + 'linear_layers.0.weight'], sd[p + 'linear_layers.0.bias'])),
+                     sd[p + 'linear_layers.1.weight'], sd[p + 'linear_layers.1.bias'])
+        return F.layer_norm(out + h, (D,), sd[p + 'norm_layers.1.weight'], sd[p + 'norm_layers.1.bias'])
+
+    def _sequence(self, node_ids, times, k):
+        sd = self.sd
+        nn_, ne_, nt_ = self.sampler.get_historical_neighbors(node_ids, times, k)
+        ids = np.concatenate((np.asarray(node_ids)[:, None], nn_), axis=1)
+        eids = np.concatenate((np.zeros((len(node_ids), 1), dtype=np.int64), ne_), axis=1)
+        ts = np.concatenate((np.asarray(times)[:, None], nt_), axis=1)
+        te = time_encode(sd, 'time_encoder.', torch.from_numpy(np.asarray(times)[:, None] - ts).float())
+        x = (F.linear(self.nf[_ids(ids)], sd['projection_layer.node.weight'], sd['projection_layer.node.bias']) +
+             F.linear(self.ef[_ids(eids)], sd['projection_layer.edge.weight'], sd['projection_layer.edge.bias']) +
+             F.linear(te, sd['projection_layer.time.weight'], sd['projection_layer.time.bias']) + sd['depth_embedding.weight'])
+        return ids, x
+
+    def compute_src_dst_node_temporal_embeddings(self, src, dst, times, num_neighbors=20):
+        sd = self.sd
+        s_ids, s = self._sequence(src, times, num_neighbors)
+        d_ids, d = self._sequence(dst, times, num_neighbors)
+        for i in range(self.num_layers):
+            s = self._block(i, s, s, s_ids)
+            d = self._block(i, d, d, d_ids)
+            s, d = self._block(i, s, d, d_ids), self._block(i, d, s, s_ids)
+        return (F.linear(s[:, 0], sd['output_layer.weight'], sd['output_layer.bias']),
+                F.linear(d[:, 0], sd['output_layer.weight'], sd['output_layer.bias']))

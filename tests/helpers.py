@@ -436,3 +436,79 @@ def cuda_graphmixer_train_step():
     params = {'model.' + k: v for k, v in m.named_parameters() if v.requires_grad}
     params.update({'pred.' + k: v for k, v in pred.named_parameters()})
     return graphmixer_train_step(m, lambda a, b: pred(a, b), params)
+
+
+# ---------------------------------------------------------------------------------------------
+# TCL (a caller of the path): eval embeddings of two batches and one training step (k = 20: 21 depths).
+def run_tcl_cases(model, k=20):
+    out = {}
+    g = small_graph(seed=15)
+    with torch.no_grad():
+        for bi, (src, dst, t, _, neg) in enumerate(batches(g, 1500, 2, 40)):
+            for tag, d in (('pos', dst), ('neg', neg)):
+                a, b = model.compute_src_dst_node_temporal_embeddings(src, d, t, k)
+                out[f'eval_{bi}_{tag}_src'], out[f'eval_{bi}_{tag}_dst'] = a.detach().cpu().numpy(), b.detach().cpu().numpy()
+    return out
+
+
+def tcl_train_step(model, predictor_fn, params: dict, k=20, B=40):
+    g = small_graph(seed=15)
+    src, dst, t, _, neg = next(batches(g, 2000, 1, B))
+    ps, pd = model.compute_src_dst_node_temporal_embeddings(src, dst, t, k)
+    ns, nd = model.compute_src_dst_node_temporal_embeddings(src, neg, t, k)
+    pos = predictor_fn(ps, pd).squeeze(dim=-1).sigmoid()
+    negp = predictor_fn(ns, nd).squeeze(dim=-1).sigmoid()
+    predicts = torch.cat([pos, negp], dim=0)
+    labels = torch.cat([torch.ones_like(pos), torch.zeros_like(negp)], dim=0)
+    loss = torch.nn.functional.binary_cross_entropy(predicts, labels)
+    for p in params.values():
+        p.grad = None
+    loss.backward()
+    out = {'loss': np.asarray(loss.item(), dtype=np.float64), 'pos': pos.detach().cpu().numpy(), 'neg': negp.detach().cpu().numpy()}
+    for name, p in params.items():
+        out['grad.' + name] = (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu().numpy()
+    return out
+
+
+def tcl_template():
+    from dyglib_b200.models.TCL import TCL
+    return TCL
+
+
+def oracle_tcl(train=False):
+    from oracle.sampler import OracleSampler
+    from oracle.models import OracleTCL
+    g = small_graph(seed=15)
+    sd = deterministic_state_dict(tcl_template()(g.node_raw_features, g.edge_raw_features, None, 100, 2, 2, 21, device='cpu').state_dict(), 7)
+    if train:
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    samp = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, 'recent')
+    return OracleTCL(sd, g.node_raw_features, g.edge_raw_features, samp, 2, 2)
+
+
+def oracle_tcl_train_step():
+    from oracle.models import merge_layer
+    m = oracle_tcl(train=True)
+    psd = {k: v.clone().requires_grad_(True) for k, v in deterministic_state_dict(predictor_template().state_dict(), 5).items()}
+    params = {'model.' + k: v for k, v in m.sd.items()}
+    params.update({'pred.' + k: v for k, v in psd.items()})
+    return tcl_train_step(m, lambda a, b: merge_layer(psd, '', a, b), params)
+
+
+def cuda_tcl(train=False):
+    from dyglib_b200.utils.utils import get_neighbor_sampler
+    g = small_graph(seed=15)
+    m = tcl_template()(g.node_raw_features, g.edge_raw_features, get_neighbor_sampler(g, 'recent'), 100, 2, 2, 21,
+                       dropout=0.0 if train else 0.1, device='cuda')
+    m.load_state_dict(deterministic_state_dict(m.state_dict(), 7))
+    return m.train() if train else m.eval()
+
+
+def cuda_tcl_train_step():
+    m = cuda_tcl(train=True)
+    pred = predictor_template().to('cuda')
+    pred.load_state_dict(deterministic_state_dict(pred.state_dict(), 5))
+    pred.train()
+    params = {'model.' + k: v for k, v in m.named_parameters()}
+    params.update({'pred.' + k: v for k, v in pred.named_parameters()})
+    return tcl_train_step(m, lambda a, b: pred(a, b), params)

@@ -240,3 +240,23 @@ def test_graphmixer_training_step_matches_golden():
     got = cuda_graphmixer_train_step()
     np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
     assert_grads_close(got, gold, rtol=2e-3)
+
+
+def test_tcl_matches_golden_and_oracle():
+    """TCL on the device sampler, the time-encode kernels and the tcgen05 GEMMs: eval embeddings against the reference's golden
+    vectors and the oracle."""
+    from helpers import cuda_tcl, oracle_tcl, run_tcl_cases
+    gold = load_golden('tcl.npz')
+    got = run_tcl_cases(cuda_tcl())
+    want = run_tcl_cases(oracle_tcl())
+    for k in got:
+        np.testing.assert_allclose(got[k], gold[k], rtol=1e-3, atol=2e-4, err_msg=k)
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-3, atol=2e-4, err_msg=k)
+
+
+def test_tcl_training_step_matches_golden():
+    from helpers import cuda_tcl_train_step, assert_grads_close
+    gold = {k[len('train.'):]: v for k, v in load_golden('tcl.npz').items() if k.startswith('train.')}
+    got = cuda_tcl_train_step()
+    np.testing.assert_allclose(got['loss'], gold['loss'], rtol=1e-5)
+    assert_grads_close(got, gold, rtol=2e-3)

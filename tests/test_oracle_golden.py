@@ -71,3 +71,17 @@ def test_oracle_graphmixer_matches_golden():
     gtr = {k[len('train.'):]: v for k, v in gold.items() if k.startswith('train.')}
     np.testing.assert_allclose(tr['loss'], gtr['loss'], rtol=1e-5)
     assert_grads_close(tr, gtr, rtol=1e-3)
+
+
+def test_oracle_tcl_matches_golden():
+    """TCL (a caller of the path): eval embeddings of two batches and one training step against the reference's
+    (scripts/make_golden_tcl.py)."""
+    from helpers import oracle_tcl, oracle_tcl_train_step, run_tcl_cases, assert_grads_close
+    gold = load_golden('tcl.npz')
+    got = run_tcl_cases(oracle_tcl())
+    for k in got:
+        np.testing.assert_allclose(got[k], gold[k], rtol=1e-4, atol=1e-5, err_msg=k)
+    tr = oracle_tcl_train_step()
+    gtr = {k[len('train.'):]: v for k, v in gold.items() if k.startswith('train.')}
+    np.testing.assert_allclose(tr['loss'], gtr['loss'], rtol=1e-5)
+    assert_grads_close(tr, gtr, rtol=1e-3)
