@@ -192,8 +192,8 @@ class Workload:
 
 def _predict(pred, a, b):
     from dyglib_b200 import ops
-    h = ops.linear([ops.seg_rows(a), ops.seg_rows(b)], a.shape[0], pred.fc1.weight.detach(), pred.fc1.bias.detach(), act=ops.ACT_RELU)
-    return ops.linear([ops.seg_rows(h)], h.shape[0], pred.fc2.weight.detach(), pred.fc2.bias.detach(), act=ops.ACT_SIGMOID)
+    return ops.mlp2([a, b], pred.fc1.weight.detach(), pred.fc1.bias.detach(), pred.fc2.weight.detach(), pred.fc2.bias.detach(),
+                    act2=ops.ACT_SIGMOID)
 
 
 class DyGFormerWL(Workload):
@@ -565,6 +565,17 @@ def run_ours(args):
                         'alg_gbs': round(v[2] / max(v[0], 1e-9) / 1e6, 1)} for k, v in per_kernel.items()},
         'score_checksum': checksum,
     }
+    if wl.sequential:
+        # the B = 200 memory-model step is launch / latency bound; state how far it is from the HBM time of its
+        # algorithmic bytes (per event: 4 roots x (k x 3 rows of 172 floats + 2 own rows + CSR) + 2 roles of message / memory traffic)
+        k_, F_ = 10, 172
+        bytes_per_event = 4 * (k_ * 3 * F_ * 4 + 2 * F_ * 4 + 288) + 2 * (2 * 616 * 4 + 4 * F_ * 4)
+        hbm_us = events_per_step * bytes_per_event / (pk['hbm'] * 1e9) * 1e6
+        line['step_roofline'] = {'bound': 'latency', 'alg_bytes_per_event': bytes_per_event, 'hbm_time_us': hbm_us,
+                                 'step_us': 1e3 * total_ms / K, 'frac': hbm_us / (1e3 * total_ms / K),
+                                 'launches_per_step': launches // K,
+                                 'note': 'dependency chain of small kernels replayed as a CUDA graph: the step time is launches x '
+                                         'per-launch latency, not bytes / bandwidth (SURVEY 7.3(6))'}
     if rank == 0 and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
         ostep = wl.oracle()

@@ -60,9 +60,7 @@ def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node
     o = ops.linear([ops.seg_rows(s)], n, wvr, attn.residual_fc.bias.detach())
     y = ops.layernorm(o, attn.layer_norm.weight.detach(), attn.layer_norm.bias.detach(), r1=conv, F1=F_, rconst=t0,
                       eps=attn.layer_norm.eps)
-    h = ops.linear([ops.seg_rows(y), ops.seg_rows(root_feat)], n, merge.fc1.weight.detach(), merge.fc1.bias.detach(),
-                   act=ops.ACT_RELU)
-    return ops.linear([ops.seg_rows(h)], n, merge.fc2.weight.detach(), merge.fc2.bias.detach())
+    return ops.mlp2([y, root_feat], merge.fc1.weight.detach(), merge.fc1.bias.detach(), merge.fc2.weight.detach(), merge.fc2.bias.detach())
 
 
 def temporal_conv_train(attn, merge, time_encoder, conv, root_feat, node_tab, nbr_ids, nbr_dense, edge_tab, nbr_eids, tq,

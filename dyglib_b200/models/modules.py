@@ -64,10 +64,8 @@ class MergeLayer(nn.Module):
             from .. import autograd as ag
             h = ag.linear([input_1, input_2], self.fc1.weight, self.fc1.bias, act=ops.ACT_RELU)
             return ag.linear(h, self.fc2.weight, self.fc2.bias)
-        a, b = _f32(input_1), _f32(input_2)
-        h = ops.linear([ops.seg_rows(a), ops.seg_rows(b)], a.shape[0], self.fc1.weight.detach(), self.fc1.bias.detach(),
-                       act=ops.ACT_RELU)
-        return ops.linear([ops.seg_rows(h)], h.shape[0], self.fc2.weight.detach(), self.fc2.bias.detach())
+        return ops.mlp2([_f32(input_1), _f32(input_2)], self.fc1.weight.detach(), self.fc1.bias.detach(), self.fc2.weight.detach(),
+                        self.fc2.bias.detach())
 
 
 class MultiHeadAttention(nn.Module):

@@ -249,6 +249,24 @@ def split_bf16(x, out=None, col=0):
     return out
 
 
+def mlp2(xs, w1, b1, w2, b2, act2=ACT_NONE):
+    """act2(W2 relu(W1 cat(xs) + b1) + b2) for dense fp32 row blocks ``xs`` (MergeLayer, models/modules.py:57-68).  With enough
+    rows for the tcgen05 GEMM the hidden activation leaves the first GEMM's epilogue as BF16x3 operand planes, so the second
+    GEMM needs no split launch (one launch less in steps that are launch-bound)."""
+    M = xs[0].shape[0]
+    K = sum(x.shape[1] for x in xs)
+    if GEMM_MIN_ROWS > 0 and M >= GEMM_MIN_ROWS and all(x.shape[1] % 2 == 0 for x in xs):
+        a = empty_split(M, K, xs[0].device)
+        col = 0
+        for x in xs:
+            split_bf16(x, out=a, col=col)
+            col += x.shape[1]
+        h = gemm(a, w1, b1, act=ACT_RELU, want='split')
+        return gemm(h, w2, b2, act=act2)
+    h = linear([seg_rows(x) for x in xs], M, w1, b1, act=ACT_RELU)
+    return linear([seg_rows(h)], M, w2, b2, act=act2)
+
+
 _split_weights = {}
 
 
