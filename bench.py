@@ -150,7 +150,8 @@ class Stream:
     """Chronological reference batches with seeded random negatives (the reference's `random` negative mode,
     utils/utils.py:378-390, drawn once on the host before timing)."""
 
-    def __init__(self, g, batch=REF_BATCH, region=0.15, seed=2, start=None):
+    def __init__(self, g, batch=None, region=0.15, seed=2, start=None):
+        batch = batch or REF_BATCH
         E = g.num_interactions
         self.start = int(E * (1 - region)) if start is None else start
         self.nb = (E - self.start) // batch
@@ -302,7 +303,7 @@ class TGNWL(Workload):
     use_graph = True
 
     def describe(self):
-        return 'tgn_reddit (TGN 1 layer, 10 recent neighbours, last-message + GRU memory, batch 200 sequential, neg + pos roots in one pass)'
+        return f'tgn_reddit (TGN 1 layer, 10 recent neighbours, last-message + GRU memory, batch {REF_BATCH} sequential, neg + pos roots in one pass)'
 
     def build(self, dev):
         from dyglib_b200.utils.utils import get_neighbor_sampler, set_random_seed
@@ -579,7 +580,7 @@ def run_ours(args):
     if rank == 0 and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
         ostep = wl.oracle()
-        nb = args.cpu_batches or wl.cpu_batches
+        nb = args.cpu_batches or max(1, wl.cpu_batches * 200 // REF_BATCH)
         first = 0 if wl.sequential else batches_of(W)[0]
         reset()
         # parity of the first batch, then the timed CPU sample (1 warm-up + nb batches)
@@ -974,7 +975,14 @@ def main():
     ap.add_argument('--queries', type=int, default=1 << 24)
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel directly instead of replaying the captured step')
+    ap.add_argument('--ref-batch', type=int, default=0,
+                    help='tgn_reddit only: events per sequential memory step instead of the reference default 200 (SURVEY 8d: B = 2,000 / '
+                         '20,000 are different-semantics throughput points: a larger batch sees staler memories)')
     args = ap.parse_args()
+    if args.ref_batch and args.ref_batch != REF_BATCH:
+        if args.workload != 'tgn_reddit' or args.impl != 'ours':
+            ap.error('--ref-batch applies to --workload tgn_reddit')
+        globals()['REF_BATCH'] = args.ref_batch
     if args.impl == 'reference':
         if args.workload in ('sampler_sweep', 'tgat_train'):
             args.workload = 'dygformer_wiki'
