@@ -287,11 +287,12 @@ def test_fence_index_matches_searchsorted(dups, index64, monkeypatch):
     assert all(torch.equal(x, y) for x, y in zip(a[:4], b[:4]))
 
 
-@pytest.mark.parametrize('index64', [False, True])
-def test_tia_cum_fence_matches_binary_search_and_numpy(index64, monkeypatch):
+@pytest.mark.parametrize('index64,tsf', [(False, 3e-5), (True, 3e-5), (False, 0.5)])
+def test_tia_cum_fence_matches_binary_search_and_numpy(index64, tsf, monkeypatch):
     """Fused throughput kernel, time_interval_aware: the CDF search through the fence index over the prefix table returns the
     same draws as the plain binary search (fence disabled), and both equal np.searchsorted(cum[:cnt], u * cum[cnt-1], 'right')
-    with the kernel's own Philox uniforms.  Degrees cross every block / level boundary of the 16-ary index."""
+    with the kernel's own Philox uniforms.  Degrees cross every block / level boundary of the 16-ary index; the large time
+    scaling factor produces runs of equal table entries (the secant step must not divide by a zero increment)."""
     if index64:
         monkeypatch.setenv('DYG_FENCE_INDEX64', '1')
     from dyglib_b200 import _native
@@ -305,7 +306,7 @@ def test_tia_cum_fence_matches_binary_search_and_numpy(index64, monkeypatch):
     dev = torch.device('cuda')
     s = object.__new__(NeighborSampler)
     s.device, s.use_fence, s.sample_neighbor_strategy, s.seed, s.rng = dev, True, 'time_interval_aware', 9, 'philox'
-    s.time_scaling_factor = 3e-5
+    s.time_scaling_factor = tsf     # 0.5: exp underflows for most of a run -> -1e10 rows, a flat (tied) start of the prefix table
     s._build(owner, rng.integers(1, 100, n_half), np.arange(1, n_half + 1), t, len(degs) + 1, False, 'device')
     assert s.tia_cum_fence is not None
     indptr = s.indptr.cpu().numpy()
