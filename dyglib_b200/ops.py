@@ -6,6 +6,7 @@ libdygb200.so on the current CUDA stream.  Nothing here falls back to the CPU.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -125,9 +126,9 @@ def seg_time(dt, w, b, mask_ids=None, group=1, t_query=None, tq_div=1):
 
 
 # tensor-core dispatch: rows at or above this use dyg_linear_tc (tcgen05 BF16x3); 0 disables it
-TC_MIN_ROWS = 512
+TC_MIN_ROWS = int(os.environ.get('DYG_TC_MIN_ROWS', 512))
 # dense (un-gathered) contractions with at least this many rows go to dyg_gemm_bf16x3 (TMA + tcgen05 CTA pairs)
-GEMM_MIN_ROWS = 256
+GEMM_MIN_ROWS = int(os.environ.get('DYG_GEMM_MIN_ROWS', 256))
 _tc_weights = {}
 
 
