@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 sys.path.insert(0, '/root/reference')
 
 from helpers import (small_graph, deterministic_state_dict, tgat_train_step, memory_train_step, dygformer_train_step,  # noqa: E402
-                     DYG_TRAIN_CASES)
+                     DYG_TRAIN_CASES, compact_grads)
 from utils.utils import get_neighbor_sampler  # noqa: E402  (reference)
 from utils.DataLoader import Data  # noqa: E402
 from models.TGAT import TGAT  # noqa: E402
@@ -34,7 +34,7 @@ def main():
     params = {'model.' + k: v for k, v in m.named_parameters()}
     params.update({'pred.' + k: v for k, v in pred.named_parameters()})
     out = tgat_train_step(lambda s, d, t, k: m.compute_src_dst_node_temporal_embeddings(s, d, t, k), lambda a, b: pred(a, b), params)
-    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'tgat_train.npz'), **out)
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'tgat_train.npz'), **compact_grads(out))
     print('loss', out['loss'], {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith('grad.')})
     g = small_graph(seed=13)
     data = Data(g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, g.labels)
@@ -52,7 +52,7 @@ def main():
         out = memory_train_step(m, lambda a, b: pred(a, b), params)
         print(name, 'loss', out['loss'], {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith('grad.')})
         allout.update({name + '.' + k: v for k, v in out.items()})
-    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'memory_train.npz'), **allout)
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'memory_train.npz'), **compact_grads(allout))
     g = small_graph(seed=12)
     data = Data(g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, g.labels)
     allout = {}
@@ -67,7 +67,7 @@ def main():
         out = dygformer_train_step(m, lambda a, b: pred(a, b), params)
         print('DyGFormer', P, L, 'loss', out['loss'], {k: float(np.abs(v).max()) for k, v in out.items() if k.startswith('grad.')})
         allout.update({f'P{P}_L{L}.' + k: v for k, v in out.items()})
-    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'dygformer_train.npz'), **allout)
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'dygformer_train.npz'), **compact_grads(allout))
 
 
 if __name__ == '__main__':

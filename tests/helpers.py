@@ -216,13 +216,44 @@ def predictor_template():
     return MergeLayer(172, 172, 172, 1)
 
 
+GRAD_SAMPLES = 1024
+
+
+def compact_grads(out: dict) -> dict:
+    """Fixture form of a training step's outputs: every gradient tensor (keys containing 'grad.') is replaced by a strided sample
+    of at most ~GRAD_SAMPLES elements ('gradc.') plus [size, sum, sum of magnitudes, largest magnitude] ('gradstat.'), so that the
+    committed golden files stay small; tensors of up to GRAD_SAMPLES elements are kept whole."""
+    res = {}
+    for k, v in out.items():
+        if 'grad.' in k and 'gradc.' not in k and 'gradstat.' not in k:
+            flat = np.asarray(v, dtype=np.float32).reshape(-1)
+            f64 = flat.astype(np.float64)
+            stride = max(1, flat.size // GRAD_SAMPLES)
+            res[k.replace('grad.', 'gradc.', 1)] = flat[::stride].copy()
+            res[k.replace('grad.', 'gradstat.', 1)] = np.array([flat.size, f64.sum(), np.abs(f64).sum(), np.abs(f64).max() if flat.size else 0.0])
+        else:
+            res[k] = v
+    return res
+
+
 def assert_grads_close(got: dict, want: dict, rtol=2e-3):
-    """Every gradient tensor within rtol of its own largest magnitude (fp32 accumulation order differs)."""
+    """Every gradient tensor within rtol of its own largest magnitude (fp32 accumulation order differs).  ``want`` may be in the
+    compact fixture form (``compact_grads``): then the sampled elements are compared the same way and the sum / sum of
+    magnitudes of the whole tensor within 10 rtol of the reference's sum of magnitudes."""
+    if any(k.startswith('gradc.') for k in want):
+        got = compact_grads(got)
     assert set(got) == set(want), set(got) ^ set(want)
     for key in sorted(want):
         a, b = np.asarray(got[key], dtype=np.float64), np.asarray(want[key], dtype=np.float64)
         assert a.shape == b.shape, key
+        if key.startswith('gradstat.'):
+            assert a[0] == b[0], key
+            tol = 10 * rtol * max(b[2], 1e-7)
+            assert abs(a[1] - b[1]) < tol and abs(a[2] - b[2]) < tol, (key, a, b)
+            continue
         scale = max(float(np.abs(b).max()), 1e-7)
+        if key.startswith('gradc.'):
+            scale = max(float(want['gradstat.' + key[6:]][3]), 1e-7)
         err = float(np.abs(a - b).max()) / scale
         assert err < rtol, (key, err)
 
