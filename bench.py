@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess
@@ -834,8 +833,7 @@ def run_sampler_sweep(args):
     else:
         torch.cuda.set_device(0)
     dev = torch.device('cuda', torch.cuda.current_device())
-    from dyglib_b200 import ops, _native
-    from dyglib_b200.ops import _p, _stream
+    from dyglib_b200 import ops
     from dyglib_b200.utils.utils import NeighborSampler
     pk = peaks()
     E, Q, k = args.events, args.queries, 20

@@ -16,7 +16,7 @@ from torch.nn import MultiheadAttention
 
 from .. import ops
 from ..utils.utils import NeighborSampler, _as_dev
-from .modules import TimeEncoder, _eval_only
+from .modules import TimeEncoder
 
 
 import os

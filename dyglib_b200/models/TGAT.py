@@ -7,7 +7,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..utils.utils import NeighborSampler, _as_dev
-from .modules import TimeEncoder, MergeLayer, MultiHeadAttention, _eval_only
+from .modules import TimeEncoder, MergeLayer, MultiHeadAttention
 from ._temporal import temporal_conv, temporal_conv_train, zero_time_features
 
 

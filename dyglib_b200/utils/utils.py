@@ -12,8 +12,6 @@ re-sort run on the device.  ``rng='philox'`` draws on the device (throughput mod
 """
 from __future__ import annotations
 
-import ctypes
-
 import numpy as np
 import torch
 
