@@ -33,6 +33,8 @@ def import_reference():
     mods['TGAT'] = importlib.import_module('models.TGAT')
     mods['DyGFormer'] = importlib.import_module('models.DyGFormer')
     mods['MemoryModel'] = importlib.import_module('models.MemoryModel')
+    mods['GraphMixer'] = importlib.import_module('models.GraphMixer')
+    mods['TCL'] = importlib.import_module('models.TCL')
     return mods
 
 

@@ -5,7 +5,7 @@ import torch
 
 from dyglib_b200.synthetic import make_graph
 from oracle.sampler import OracleSampler, pad_sequences, count_nodes_appearances
-from oracle.models import OracleTGAT, OracleDyGFormer, OracleMemoryModel
+from oracle.models import OracleTGAT, OracleDyGFormer, OracleMemoryModel, OracleGraphMixer, OracleTCL
 
 pytestmark = pytest.mark.reference
 
@@ -134,3 +134,35 @@ def test_memory_model_matches_reference(ref, name):
                 torch.testing.assert_close(x, y, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(m.memory_bank.node_memories.data, o.memory, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(m.memory_bank.node_last_updated_times.data, o.last_update)
+
+
+def test_graphmixer_matches_reference(ref):
+    """The reference's own default-initialised weights (not the fixture's), uniform sampling for the link encoder's neighbours:
+    the oracle must follow the reference's RandomState stream through both sampler calls of every root set."""
+    g = small_graph(seed=21)
+    torch.manual_seed(1)
+    m = ref['GraphMixer'].GraphMixer(g.node_raw_features, g.edge_raw_features, ref_sampler(ref, g, 'uniform', seed=4), 100, num_tokens=10,
+                                     num_layers=2, dropout=0.1).eval()
+    o = OracleGraphMixer(m.state_dict(), g.node_raw_features, g.edge_raw_features, oracle_sampler(g, 'uniform', seed=4), 2)
+    with torch.no_grad():
+        for src, dst, t, _, neg in _batches(g, 1500, 2, 30):
+            for d in (dst, neg):
+                ra = m.compute_src_dst_node_temporal_embeddings(src, d, t, 10, 50)
+                oa = o.compute_src_dst_node_temporal_embeddings(src, d, t, 10, 50)
+                for x, y in zip(ra, oa):
+                    torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-6)
+
+
+def test_tcl_matches_reference(ref):
+    g = small_graph(seed=22)
+    torch.manual_seed(2)
+    m = ref['TCL'].TCL(g.node_raw_features, g.edge_raw_features, ref_sampler(ref, g, 'recent'), 100, num_layers=2, num_heads=2,
+                       num_depths=11, dropout=0.1).eval()
+    o = OracleTCL(m.state_dict(), g.node_raw_features, g.edge_raw_features, oracle_sampler(g, 'recent'), 2, 2)
+    with torch.no_grad():
+        for src, dst, t, _, neg in _batches(g, 1500, 2, 30):
+            for d in (dst, neg):
+                ra = m.compute_src_dst_node_temporal_embeddings(src, d, t, 10)
+                oa = o.compute_src_dst_node_temporal_embeddings(src, d, t, 10)
+                for x, y in zip(ra, oa):
+                    torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-6)
