@@ -33,6 +33,73 @@ sys.path.insert(0, ROOT)
 from dyglib_b200.synthetic import make_config_graph  # noqa: E402
 
 REF_BATCH = 200
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def load_reference():
+    """The UNMODIFIED reference modules of the path (scripts/install_reference.py copies them byte for byte into the git-ignored
+    baseline/_ref/, which travels to the GPU box): {'utils': utils.utils, 'TGAT': models.TGAT, ...} or None when absent."""
+    if not os.path.isfile(os.path.join(REF_DIR, 'models', 'MemoryModel.py')):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import importlib
+    return {'utils': importlib.import_module('utils.utils'), 'modules': importlib.import_module('models.modules'),
+            'TGAT': importlib.import_module('models.TGAT'), 'DyGFormer': importlib.import_module('models.DyGFormer'),
+            'MemoryModel': importlib.import_module('models.MemoryModel')}
+
+
+class ReferenceRunner:
+    """One BASELINE config on the reference's own modules and sampler, driven the way evaluate_models_utils.py:67-138 drives
+    them (model.eval(), torch.no_grad(), full-graph sampler, positive / negative pair per batch; memory models: negative call
+    first).  ``device='cpu'`` is the CPU baseline, ``device='cuda:0'`` the "existing GPU path" (eager PyTorch on the same B200,
+    SURVEY 2.1).  Weights: the state_dict of the GPU arm's model (same keys by construction)."""
+
+    def __init__(self, ref, wl, sd, psd, device, sampler=None):
+        g = wl.g
+        t0 = time.perf_counter()
+        self.sampler = sampler or ref['utils'].get_neighbor_sampler(g, 'recent', seed=1)
+        self.sampler_build_s = time.perf_counter() - t0
+        self.kind = type(wl).__name__
+        if isinstance(wl, DyGFormerWL):
+            m = ref['DyGFormer'].DyGFormer(g.node_raw_features, g.edge_raw_features, self.sampler, 100, 50, wl.P, 2, 2, 0.1, wl.L, device)
+        elif isinstance(wl, TGATWL):
+            m = ref['TGAT'].TGAT(g.node_raw_features, g.edge_raw_features, self.sampler, 100, 2, 2, 0.1, device)
+        else:
+            m = ref['MemoryModel'].MemoryModel(g.node_raw_features, g.edge_raw_features, self.sampler, 100, 'TGN', 1, 2, 0.1, device=device)
+        sd = {k: (torch.zeros_like(v) if ('node_memories' in k or 'node_last_updated_times' in k) else v) for k, v in sd.items()}
+        m.load_state_dict(sd, strict=True)
+        pred = ref['modules'].MergeLayer(172, 172, 172, 1)
+        pred.load_state_dict(psd, strict=True)
+        self.model = torch.nn.Sequential(m, pred).to(device).eval()
+        self.device = device
+
+    def step(self, src, dst, neg, t, eid):
+        m, pred = self.model[0], self.model[1]
+        with torch.no_grad():
+            if self.kind == 'TGNWL':
+                a, b = m.compute_src_dst_node_temporal_embeddings(src_node_ids=src, dst_node_ids=neg, node_interact_times=t, edge_ids=None,
+                                                                  edges_are_positive=False, num_neighbors=10)
+                c, d = m.compute_src_dst_node_temporal_embeddings(src_node_ids=src, dst_node_ids=dst, node_interact_times=t, edge_ids=eid,
+                                                                  edges_are_positive=True, num_neighbors=10)
+            elif self.kind == 'TGATWL':
+                c, d = m.compute_src_dst_node_temporal_embeddings(src_node_ids=src, dst_node_ids=dst, node_interact_times=t, num_neighbors=20)
+                a, b = m.compute_src_dst_node_temporal_embeddings(src_node_ids=src, dst_node_ids=neg, node_interact_times=t, num_neighbors=20)
+            else:
+                c, d = m.compute_src_dst_node_temporal_embeddings(src_node_ids=src, dst_node_ids=dst, node_interact_times=t)
+                a, b = m.compute_src_dst_node_temporal_embeddings(src_node_ids=src, dst_node_ids=neg, node_interact_times=t)
+            pos = pred(input_1=c, input_2=d).squeeze(dim=-1).sigmoid()
+            negp = pred(input_1=a, input_2=b).squeeze(dim=-1).sigmoid()
+            return torch.cat([pos, negp]).reshape(-1, 1)
+
+    def copy_memory_state_to(self, other):
+        """TGN: hand the warmed-up memory bank (memories, last-update times, pending messages) to another runner."""
+        a, b = self.model[0].memory_bank, other.model[0].memory_bank
+        b.node_memories.data.copy_(a.node_memories.data)
+        b.node_last_updated_times.data.copy_(a.node_last_updated_times.data)
+        b.node_raw_messages = type(a.node_raw_messages)(list)
+        for v, lst in a.node_raw_messages.items():
+            b.node_raw_messages[v] = [(mm[0].to(other.device), mm[1]) for mm in lst]
 
 
 def peaks():
@@ -356,9 +423,78 @@ def make_workload(name):
     raise ValueError(name)
 
 
+# ------------------------------------------------------------------------------------------------ shared pieces
+class Ctx:
+    """Process-wide state of one bench run: rank / world, the device, torch.distributed (initialised once)."""
+
+    def __init__(self):
+        self.rank, self.world, self.local = dist_env()
+        import torch.distributed as dist
+        self.dist = dist
+        if self.world > 1:
+            torch.cuda.set_device(self.local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local))
+        else:
+            torch.cuda.set_device(0)
+        self.dev = torch.device('cuda', torch.cuda.current_device())
+        self.pk = peaks()
+        self.hold_graphs = []          # captured graphs with NCCL kernels are kept alive until the process exits
+        self.need_hard_exit = False
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def finish(self):
+        if self.world > 1:
+            if self.need_hard_exit:
+                # a captured graph holds NCCL kernels: tearing the communicator down under it hung at exit; leave together
+                self.dist.barrier()
+                torch.cuda.synchronize()
+                sys.stdout.flush()
+                sys.stderr.flush()
+                os._exit(0)
+            self.dist.destroy_process_group()
+
+
+def workload_config(wl, G):
+    """The `config` object of the JSON line: what is measured, identical for the GPU arm and for `--impl reference` (the CPU arm
+    times a bounded sample of the same workload, stated in its cpu_baseline.sample)."""
+    events_per_step = (1 if wl.sequential else G) * REF_BATCH
+    return {'workload': wl.describe(), 'events_per_step_per_gpu': events_per_step, 'reference_batch': REF_BATCH,
+            'sharding': ('replicas only (memory dependency chain)' if wl.sequential else
+                         'whole reference batches round-robin over ranks; CSR + feature tables replicated'),
+            'l2': 'GPU arm: flushed between timed steps (256 MiB write)'}
+
+
+def cpu_arm(wl, sd, psd):
+    """(step function, kind, what) of the CPU arm for workload ``wl``: the unmodified reference from baseline/_ref when it is
+    there (kind "reference"), else the oracle port (kind "port")."""
+    ref = load_reference()
+    if ref is not None:
+        r = ReferenceRunner(ref, wl, sd, psd, 'cpu')
+        return r.step, 'reference', r
+    return wl.oracle(), 'port', None
+
+
+def time_cpu(step, stream, first, warm, nb):
+    b = first
+    for _ in range(warm):
+        step(*stream.rows([b % stream.nb]))
+        b += 1
+    t0 = time.perf_counter()
+    for _ in range(nb):
+        step(*stream.rows([b % stream.nb]))
+        b += 1
+    return nb * REF_BATCH / (time.perf_counter() - t0)
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
-    """CPU arm: the oracle port of the reference path with all host threads, on the same config / metric."""
+    """`--impl reference`: the reference's own CPU implementation of the path (baseline/_ref, unmodified; the oracle port only when
+    that copy is absent) with all host threads, on the GPU arm's config / metric / unit; a step is a bounded sample of the
+    workload (a few reference batches) so that the run ends within minutes."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
@@ -382,8 +518,11 @@ def run_reference(args):
         wl.model = MemoryModel(g.node_raw_features, g.edge_raw_features, None, 100, 'TGN', 1, 2, 0.1, device='cpu')
         wl.stream = Stream(g, start=0, region=1.0)
     wl.pred = MergeLayer(172, 172, 172, 1)
-    step = wl.oracle()
-    per_step = 1 if isinstance(wl, TGATWL) else 2          # bounded sample per step
+    sd = {k: v.detach().cpu() for k, v in wl.model.state_dict().items()}
+    psd = {k: v.detach().cpu() for k, v in wl.pred.state_dict().items()}
+    step, kind, _ = cpu_arm(wl, sd, psd)
+    per_step = 1 if isinstance(wl, (TGATWL,)) or (isinstance(wl, DyGFormerWL) and wl.L > 64) else 2     # bounded sample per step
+    G = args.batches_per_step or wl.default_G
     b = 0
     for _ in range(args.warmup + (40 if isinstance(wl, TGNWL) else 0)):   # memory model: realistic pending set
         step(*wl.stream.rows([b % wl.stream.nb]))
@@ -396,13 +535,14 @@ def run_reference(args):
     total = time.perf_counter() - t0
     value = args.steps * per_step * REF_BATCH / total
     cores = torch.get_num_threads()
+    what = ('unmodified reference modules + NeighborSampler from baseline/_ref (python sampler loop single-core, torch ops '
+            f'{cores} threads)') if kind == 'reference' else f'oracle/ = torch-CPU port of the reference path (torch ops {cores} threads)'
     print(json.dumps({
         'impl': 'reference', 'metric': 'link-pred events/sec', 'value': value, 'unit': 'events/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': wl.describe()},
-        'cpu_baseline': {'value': value, 'unit': 'events/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{per_step} reference batch(es) of 200 events per step; oracle/ = torch-CPU port of the reference '
-                                   f'path (python sampler loop single-core, torch ops {cores} threads)'},
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(wl, G),
+        'cpu_baseline': {'value': value, 'unit': 'events/s', 'cores': cores, 'kind': kind,
+                         'sample': f'{per_step} reference batch(es) of {REF_BATCH} events (pos+neg) per step; {what}'},
         'e2e': {'value': value, 'unit': 'events/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -410,30 +550,26 @@ def run_reference(args):
 def kernel_traffic(workload, kernel, G):
     """DRAM bytes per launch (GB) of the dominant kernel from the committed ncu --set full capture of the same workload at the
     same launch sizes; None when there is no capture for this configuration."""
-    try:
-        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_kernel_traffic.json')))[workload]
-        return d.get(kernel) if d.get('batches_per_step') == G else None
-    except Exception:
-        return None
+    for name in ('r02_kernel_traffic.json', 'r01_kernel_traffic.json'):
+        try:
+            d = json.load(open(os.path.join(ROOT, 'profiles', name)))[workload]
+            if d.get('batches_per_step') == G and d.get(kernel) is not None:
+                return d.get(kernel), name
+        except Exception:
+            pass
+    return None, None
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
-    rank, world, local = dist_env()
-    import torch.distributed as dist
-    if world > 1:
-        torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    else:
-        torch.cuda.set_device(0)
-    dev = torch.device('cuda', torch.cuda.current_device())
+def measure_model(ctx, args, name, K, W, with_cpu=True):
+    """One BASELINE model config on this rank's GPU: device-resident `value`, end-to-end `e2e`, per-kernel roofline pass, and on
+    rank 0 of a 1-GPU run the parity check, the CPU baseline and the eager-PyTorch-on-B200 baseline.  Returns the JSON line."""
+    rank, world, dev, dist, pk = ctx.rank, ctx.world, ctx.dev, ctx.dist, ctx.pk
     from dyglib_b200 import ops
-    pk = peaks()
-    wl = make_workload(args.workload)
+    wl = make_workload(name)
     wl.build(dev)
     stream = wl.stream
     G = args.batches_per_step or wl.default_G
-    K, W = args.steps, args.warmup
     if wl.sequential:
         # dependency chain through the memory: every rank runs an independent replica of the same stream
         batches_of = lambda i: [i % stream.nb]   # noqa: E731
@@ -450,11 +586,6 @@ def run_ours(args):
     dev_steps = [to_dev(hs) for hs in host_steps]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(run_step, first):
         evs = []
         for i in range(first, first + K):
@@ -464,7 +595,7 @@ def run_ours(args):
             out = run_step(i)
             e1.record()
             evs.append((e0, e1))
-        barrier()
+        ctx.barrier()
         return sum(a.elapsed_time(b) for a, b in evs), out
 
     step_fn = wl.step
@@ -479,7 +610,7 @@ def run_ours(args):
         clocks = ClockSampler(torch.cuda.current_device())   # started before the warm-up: see ClockSampler.__init__
         for i in range(W):
             step_fn(*dev_steps[i])
-        barrier()
+        ctx.barrier()
         launches0 = ops.launch_count
         total_ms, scores = timed(lambda i: step_fn(*dev_steps[i]), W)
         scores = scores.clone()
@@ -496,7 +627,7 @@ def run_ours(args):
             return sc
         for i in range(base, base + W):
             e2e_step(i)
-        barrier()
+        ctx.barrier()
         e2e_ms, _ = timed(e2e_step, base + W)
         h2d = sum(a.numel() * a.element_size() for a in pinned[0])
         d2h = out_host.numel() * 4
@@ -521,8 +652,8 @@ def run_ours(args):
     else:
         checksum = float(scores.double().sum().item())
     per_kernel = {}
-    for name, e0, e1, fl, by in prof:
-        d = per_kernel.setdefault(name, [0.0, 0.0, 0.0, 0])
+    for kname, e0, e1, fl, by in prof:
+        d = per_kernel.setdefault(kname, [0.0, 0.0, 0.0, 0])
         d[0] += e0.elapsed_time(e1)
         d[1] += fl
         d[2] += by
@@ -530,34 +661,31 @@ def run_ours(args):
     events_per_step = (1 if wl.sequential else G) * REF_BATCH
     events_total = K * events_per_step * world
     value = events_total / (total_ms * 1e-3)
-    name, (ms, fl, by, cnt) = max(per_kernel.items(), key=lambda kv: kv[1][0])
+    kname, (ms, fl, by, cnt) = max(per_kernel.items(), key=lambda kv: kv[1][0])
     share = ms / max(sum(v[0] for v in per_kernel.values()), 1e-9)
-    if name in ('linear_kernel', 'linear_tc_kernel', 'gemm_bf16x3_kernel', 'ln_ffn_bf16x3_kernel'):
+    if kname in TENSOR_KERNELS:
         achieved = fl / (ms * 1e-3) / 1e12
-        roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
+        roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': achieved, 'peak': pk['tensor'], 'unit': 'TFLOP/s',
                     'frac': achieved / pk['tensor'], 'traffic': None, 'peak_source': pk['source'] + ' (bf16 sustained)',
-                    'note': 'algorithmic fp32 flops = sum of 2*M*N*K over the launches, against the measured bf16 peak; the '
-                            'contractions run as BF16x3 (3 bf16 MMAs per product for fp32 parity), so the fp32-equivalent '
-                            'ceiling is peak / 3 and the tensor pipe executes 3x the achieved figure',
-                    'mma_frac': 3.0 * achieved / pk['tensor'] if name != 'linear_kernel' else None}
+                    'note': 'algorithmic fp32 flops (sum of 2MNK) vs the measured bf16 peak; products run as BF16x3 (3 bf16 MMAs '
+                            'each, fp32 parity), so the fp32-equivalent ceiling is peak / 3',
+                    'mma_frac': 3.0 * achieved / pk['tensor'] if kname not in FFMA_KERNELS else None}
     else:
         achieved = by / (ms * 1e-3) / 1e9
-        roofline = {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
+        roofline = {'kernel': kname, 'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
                     'frac': achieved / pk['hbm'], 'traffic': None, 'peak_source': pk['source'],
                     'note': 'algorithmic bytes = gathered rows + indices + query/result vectors per launch'}
     roofline.update({'launches': cnt, 'avg_launch_us': 1e3 * ms / cnt, 'share_of_timed_kernels': share})
-    roofline['traffic'] = kernel_traffic(wl.name, name, G)
+    roofline['traffic'], src_file = kernel_traffic(wl.name, kname, G)
     if roofline['traffic'] is not None:
-        roofline['traffic_unit'] = 'GB per launch (dram read + write, committed ncu capture: profiles/r01_kernel_traffic.json)'
+        roofline['traffic_unit'] = f'GB per launch (dram read + write, committed ncu capture: profiles/{src_file})'
     line = {
         'metric': 'link-pred events/sec', 'value': value, 'unit': 'events/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic',
-        'config': {'workload': wl.describe(), 'events_per_step_per_gpu': events_per_step, 'reference_batch': REF_BATCH,
-                   'sharding': ('replicas only (memory dependency chain)' if wl.sequential else
-                                'whole reference batches round-robin over ranks; CSR + feature tables replicated'),
-                   'l2': 'flushed between timed steps (256 MiB write)', 'csr_build_s': round(wl.build_s, 4),
-                   'launch': 'CUDA graph replay of the captured step' if graphed is not None else 'direct launches'},
+        'data': 'synthetic', 'config': workload_config(wl, G),
+        'details': {'csr_build_s': round(wl.build_s, 4),
+                    'launch': 'CUDA graph replay of the captured step' if graphed is not None else 'direct launches',
+                    'e2e_inputs': 'pinned host numpy buffers (ids, times, precomputed seeded negatives) -> H2D inside the timed region'},
         'roofline': roofline,
         'e2e': {'value': events_total / (e2e_ms * 1e-3), 'unit': 'events/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': launches, 'clocks': clk,
@@ -565,62 +693,140 @@ def run_ours(args):
                         'alg_gbs': round(v[2] / max(v[0], 1e-9) / 1e6, 1)} for k, v in per_kernel.items()},
         'score_checksum': checksum,
     }
-    if wl.sequential:
-        # the B = 200 memory-model step is launch / latency bound; state how far it is from the HBM time of its
-        # algorithmic bytes (per event: 4 roots x (k x 3 rows of 172 floats + 2 own rows + CSR) + 2 roles of message / memory traffic)
-        k_, F_ = 10, 172
-        bytes_per_event = 4 * (k_ * 3 * F_ * 4 + 2 * F_ * 4 + 288) + 2 * (2 * 616 * 4 + 4 * F_ * 4)
-        hbm_us = events_per_step * bytes_per_event / (pk['hbm'] * 1e9) * 1e6
-        line['step_roofline'] = {'bound': 'latency', 'alg_bytes_per_event': bytes_per_event, 'hbm_time_us': hbm_us,
-                                 'step_us': 1e3 * total_ms / K, 'frac': hbm_us / (1e3 * total_ms / K),
-                                 'launches_per_step': launches // K,
-                                 'note': 'dependency chain of small kernels replayed as a CUDA graph: the step time is launches x '
-                                         'per-launch latency, not bytes / bandwidth (SURVEY 7.3(6))'}
-    if rank == 0 and world == 1:
+    line['step_roofline'] = step_roofline(wl, pk, events_per_step, total_ms / K, launches // max(K, 1))
+    if rank == 0 and world == 1 and with_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        ostep = wl.oracle()
+        sd = {k: v.detach().cpu() for k, v in wl.model.state_dict().items()}
+        psd = {k: v.detach().cpu() for k, v in wl.pred.state_dict().items()}
+        cstep, kind, runner = cpu_arm(wl, sd, psd)
         nb = args.cpu_batches or max(1, wl.cpu_batches * 200 // REF_BATCH)
         first = 0 if wl.sequential else batches_of(W)[0]
-        reset()
-        # parity of the first batch, then the timed CPU sample (1 warm-up + nb batches)
-        hs = stream.rows([first])
-        want = ostep(*hs)
-        got = wl.step(*to_dev(hs)).cpu()
-        line['parity_max_abs_err'] = float((want - got).abs().max())
         # memory models: the reference recomputes every pending node per call, so its cost depends on how many nodes hold a
-        # pending message; SURVEY 8d asks for >= 40 warm-up batches before timing so that the pending set is realistic
+        # pending message (>= 40 warm-up batches), and the memory path (last-message choice, GRU) is only exercised once
+        # there is state: parity is taken AFTER the warm-up batches, on three consecutive batches
         cpu_warm = max(0, 40 * 200 // REF_BATCH) if wl.sequential else 0
-        for b in range(1, 1 + cpu_warm):
-            ostep(*stream.rows([(first + b) % stream.nb]))
-        t0 = time.perf_counter()
-        for b in range(1 + cpu_warm, 1 + cpu_warm + nb):
-            ostep(*stream.rows([(first + b) % stream.nb]))
-        v = nb * REF_BATCH / (time.perf_counter() - t0)
-        line['cpu_baseline'] = {'value': v, 'unit': 'events/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                                'sample': f'{nb} reference batches of {REF_BATCH} events (pos+neg), oracle/ torch-CPU port, after '
-                                          f'{1 + cpu_warm} warm-up batch(es)'}
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        reset()
+        with torch.no_grad():
+            errs = []
+            for b in range(cpu_warm + 3):
+                hs = stream.rows([(first + b) % stream.nb])
+                want = cstep(*hs) if (wl.sequential or b >= cpu_warm) else None
+                got = wl.step(*to_dev(hs)).cpu() if (wl.sequential or b >= cpu_warm) else None
+                if b >= cpu_warm:
+                    errs.append(float((want.cpu() - got).abs().max()))
+        line['parity_max_abs_err'] = max(errs)
+        line['parity'] = {'against': 'unmodified reference (baseline/_ref) on CPU' if kind == 'reference' else 'oracle/ port on CPU',
+                          'batches': 3, 'after_batches_of_state': cpu_warm, 'max_abs_err_link_probability': max(errs)}
+        v = time_cpu(cstep, stream, first + cpu_warm + 3, 0 if wl.sequential else 1, nb)
+        line['cpu_baseline'] = {'value': v, 'unit': 'events/s', 'cores': torch.get_num_threads(), 'kind': kind,
+                                'sample': f'{nb} reference batches of {REF_BATCH} events (pos+neg) after {cpu_warm + 3 if wl.sequential else 1} '
+                                          f'warm-up batch(es); ' + ('unmodified reference modules + python NeighborSampler (baseline/_ref)'
+                                                                    if kind == 'reference' else 'oracle/ torch-CPU port')}
+        # the "existing GPU path": the same unmodified reference modules run eagerly by PyTorch on this B200
+        ref = load_reference()
+        if ref is not None and not args.no_eager:
+            try:
+                gr = ReferenceRunner(ref, wl, sd, psd, f'cuda:{torch.cuda.current_device()}', sampler=runner.sampler)
+                if wl.sequential:
+                    runner.copy_memory_state_to(gr)
+                ne = max(2, min(nb, 6))
+                f0 = first + cpu_warm + 3 + nb + 1
+                gr.step(*stream.rows([f0 % stream.nb]))
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for b in range(1, ne + 1):
+                    sc = gr.step(*stream.rows([(f0 + b) % stream.nb]))
+                    sc.cpu()
+                ev = ne * REF_BATCH / (time.perf_counter() - t0)
+                line['gpu_eager_baseline'] = {'value': ev, 'unit': 'events/s', 'kind': 'reference modules, device=cuda (eager PyTorch '
+                                              f'{torch.__version__}); its sampler / padding / co-occurrence loops run on the host as in the reference',
+                                              'sample': f'{ne} reference batches after 1 warm-up batch, wall clock incl. the score read-back'}
+                del gr
+            except Exception as e:   # noqa: BLE001
+                line['gpu_eager_baseline'] = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
+        else:
+            line['gpu_eager_baseline'] = {'unavailable': 'baseline/_ref absent' if ref is None else 'disabled (--no-eager)'}
+    return line
+
+
+TENSOR_KERNELS = ('linear_kernel', 'linear_tc_kernel', 'gemm_bf16x3_kernel', 'ln_ffn_bf16x3_kernel', 'qkv_ln_gemm_kernel',
+                  'seq_attention_tc5_kernel', 'tgn_step_kernel', 'gru_update_kernel')
+FFMA_KERNELS = ('linear_kernel', 'tgn_step_kernel', 'gru_update_kernel')
+
+
+def step_roofline(wl, pk, events_per_step, ms_per_step, launches_per_step):
+    """Step-level roofline (SURVEY 8d per-event figures): the time the whole step would take at the HBM / tensor roofline of its
+    algorithmic bytes / flops, over the measured step time."""
+    per_event = {   # (bytes, flops) per event, SURVEY.md section 8(d); TGAT counted with the 3 roots per event the step embeds
+        'tgat_myket': (3 * 616e3, 3 * 22 * 10.19e6), 'dygformer_wiki': (356e3, 274e6), 'dygformer_lastfm': (2.85e6, 380e6),
+        'tgn_reddit': (4 * (10 * 3 * 172 * 4 + 2 * 172 * 4 + 288) + 2 * (2 * 616 * 4 + 4 * 172 * 4), 23e6)}[wl.name]
+    hbm_us = events_per_step * per_event[0] / (pk['hbm'] * 1e9) * 1e6
+    tensor_us = events_per_step * per_event[1] / (pk['tensor'] * 1e12) * 1e6
+    bound = 'tensor' if tensor_us > hbm_us else 'hbm'
+    out = {'bound': bound if not wl.sequential else 'latency', 'alg_bytes_per_event': per_event[0], 'alg_flops_per_event': per_event[1],
+           'hbm_time_us': hbm_us, 'tensor_time_us': tensor_us, 'step_us': 1e3 * ms_per_step,
+           'frac': max(hbm_us, tensor_us) / (1e3 * ms_per_step), 'launches_per_step': launches_per_step}
+    if wl.sequential:
+        out['frac'] = hbm_us / (1e3 * ms_per_step)
+        out['note'] = 'B=200 dependency chain: the step time is launches x per-phase latency, not bytes / bandwidth (SURVEY 7.3(6))'
+    return out
+
+
+def compact(line):
+    """The per-workload record kept inside the default line's `workloads` object."""
+    keep = ('metric', 'value', 'unit', 'ms_per_step', 'steps', 'e2e', 'gpu_launches', 'parity_max_abs_err', 'cpu_baseline',
+            'gpu_eager_baseline', 'step_roofline', 'strategies', 'allreduce_ms', 'ranks_in_sync', 'parity_recent_bit_exact', 'error')
+    out = {k: line[k] for k in keep if k in line}
+    if 'roofline' in line:
+        out['roofline'] = {k: v for k, v in line['roofline'].items() if k not in ('note', 'traffic_unit', 'peak_source')}
+    if 'config' in line:
+        out['workload'] = line['config'].get('workload')
+    for k in ('cpu_baseline', 'gpu_eager_baseline'):
+        if k in out and isinstance(out[k], dict):
+            out[k] = {kk: vv for kk, vv in out[k].items() if kk not in ('sample',) or len(str(vv)) < 90}
+    if 'step_roofline' in out:
+        out['step_roofline'] = {k: v for k, v in out['step_roofline'].items() if k != 'note'}
+    return out
+
+
+def run_ours(ctx, args):
+    import gc
+    K, W = args.steps, args.warmup
+    line = measure_model(ctx, args, args.workload, K, W)
+    if args.workload == 'dygformer_wiki' and not args.only_headline and not args.batches_per_step:
+        # the default command carries every BASELINE config (headline stays configs[1]); each with its own value / e2e /
+        # roofline / parity / cpu_baseline, on fewer steps so that the whole run stays within minutes
+        line['workloads'] = {}
+        Kx = max(3, min(K, 10))
+        for name in ('tgat_myket', 'tgn_reddit', 'dygformer_lastfm', 'sampler_sweep') + (('tgat_train',) if ctx.world > 1 else ()):
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                if name == 'sampler_sweep':
+                    sub = measure_sampler_sweep(ctx, args, 5, 3)
+                elif name == 'tgat_train':
+                    sub = measure_train(ctx, args, max(K, 10), W)
+                else:
+                    sub = measure_model(ctx, args, name, Kx, W)
+            except Exception as e:   # noqa: BLE001   (an extra workload must not take the headline down)
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                sub = {'error': f'{type(e).__name__}: {e}'[:300]}
+            line['workloads'][name] = compact(sub)
+            if args.save_dir and ctx.rank == 0:
+                os.makedirs(args.save_dir, exist_ok=True)
+                json.dump(sub, open(os.path.join(args.save_dir, f'{name}_{ctx.world}gpu.json'), 'w'))
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ training configuration
-def run_train(args):
+def measure_train(ctx, args, K, W):
     """TGAT training step (train_link_prediction.py:230-257: pos + neg embeddings, BCE, backward, Adam) on one reference batch
     of 200 events per rank per step; data parallel over ranks with ONE gradient all-reduce (NCCL) per step over the flat
     gradient bucket (the only collective on the path).  Dropout 0.1 as in the reference's defaults."""
-    rank, world, local = dist_env()
-    import torch.distributed as dist
-    if world > 1:
-        torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    else:
-        torch.cuda.set_device(0)
-    dev = torch.device('cuda', torch.cuda.current_device())
+    rank, world, dev, dist, pk = ctx.rank, ctx.world, ctx.dev, ctx.dist, ctx.pk
     from dyglib_b200 import ops
     from dyglib_b200.utils.dist import GradBucket
-    pk = peaks()
     wl = TGATWL()
     wl.build(dev)
     model, pred, stream = wl.model.train(), wl.pred.train(), wl.stream
@@ -630,7 +836,6 @@ def run_train(args):
             dist.broadcast(p_.data, 0)
     bucket = GradBucket(params)
     opt = torch.optim.Adam(bucket.params, lr=1e-4, capturable=not args.no_graph)
-    K, W = args.steps, args.warmup
     host_steps = [stream.rows(shard_batches(i, 1, world, rank, stream.nb)) for i in range(W + K)]
     to_dev = lambda hs: tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in hs)   # noqa: E731
     dev_steps = [to_dev(hs) for hs in host_steps]
@@ -654,10 +859,7 @@ def run_train(args):
         opt.step()
         return loss.detach()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = ctx.barrier
 
     def timed(run_step):
         evs = []
@@ -677,6 +879,8 @@ def run_train(args):
         # step is bound by the host issuing ~130 kernels of ours plus the autograd / optimizer ops
         from dyglib_b200.utils.graph import GraphedStep
         step_fn = GraphedStep(train_step, dev_steps[0], warmup=3, grad=True)
+        ctx.hold_graphs.append(step_fn)
+        ctx.need_hard_exit = ctx.need_hard_exit or world > 1
     clocks = ClockSampler(torch.cuda.current_device())
     for i in range(W):
         step_fn(*dev_steps[i])
@@ -760,7 +964,7 @@ def run_train(args):
         'gpu_launches': launches, 'clocks': clk, 'allreduce_ms': ar_ms, 'ranks_in_sync': in_sync, 'final_loss': float(loss.item()),
         'kernels': {k: {'ms': round(v[0], 3), 'launches': v[3]} for k, v in per_kernel.items()},
     }
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.workload == 'tgat_train':
         # CPU arm: the oracle port's training step (autograd through the torch-CPU restatement) on the same batches
         torch.set_num_threads(os.cpu_count() or 1)
         from oracle.sampler import OracleSampler
@@ -785,15 +989,7 @@ def run_train(args):
         line['cpu_baseline'] = {'value': v, 'unit': 'events/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                                 'sample': f'{nb} training batches of 200 events (forward + backward, no dropout), oracle/ torch-CPU port, '
                                           'after 1 warm-up batch'}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        # the captured graph holds NCCL kernels: tearing the communicator down under it hung at exit; leave together instead
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ sampler sweep
@@ -830,18 +1026,10 @@ def sweep_traffic(E, Q, k):
     return None
 
 
-def run_sampler_sweep(args):
-    rank, world, local = dist_env()
-    import torch.distributed as dist
-    if world > 1:
-        torch.cuda.set_device(local)
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    else:
-        torch.cuda.set_device(0)
-    dev = torch.device('cuda', torch.cuda.current_device())
+def measure_sampler_sweep(ctx, args, K, W):
+    rank, world, dev, dist, pk = ctx.rank, ctx.world, ctx.dev, ctx.dist, ctx.pk
     from dyglib_b200 import ops
     from dyglib_b200.utils.utils import NeighborSampler
-    pk = peaks()
     E, Q, k = args.events, args.queries, 20
     nu, ni = max(8, int(E * 0.08)), max(4, int(E * 0.02))
     src, dst, eid, t, num_nodes = device_power_law_graph(E, nu, ni, 5, dev)
@@ -879,7 +1067,7 @@ def run_sampler_sweep(args):
            'uniform': float((32 + 8 * log_deg + 16 * torch.clamp(cnt, max=1) * k + 20 * k).sum()),
            'time_interval_aware': float((32 + 8 * log_deg + 16 * torch.clamp(cnt, max=1) * k + 8 * k * log_cnt + 20 * k).sum())}
     res = {}
-    K, W = args.steps, max(args.warmup, 3)
+    W = max(W, 3)
     for strat, s in samplers.items():
         clocks = ClockSampler(torch.cuda.current_device()) if strat == 'recent' else None
         for _ in range(W):
@@ -919,16 +1107,50 @@ def run_sampler_sweep(args):
                          'note': 'achieved = algorithmic bytes (SURVEY 8d formula, summed over the actual queries) / launch time; traffic = '
                                  'dram read + write bytes per launch from the committed ncu capture (profiles/r01_sampler_ncu.md), GB'},
             'strategies': res, 'gpu_launches': K * 3, 'clocks': clk}
+    # ---- bit-exact replay mode of the random strategies (counts D2H -> the reference's RandomState stream on the host -> gather on
+    # the device): a single sequential stream by construction, timed by wall clock on a bounded number of queries
+    replay_samplers = {}
+    for strat, nq_r in (('uniform', min(Q, 1 << 20)), ('time_interval_aware', min(Q, 256))):
+        r = object.__new__(NeighborSampler)
+        r.__dict__.update(samplers[strat].__dict__)
+        r.rng, r.seed = 'numpy_replay', 0
+        r._prob_host = None
+        r.reset_random_state()
+        replay_samplers[strat] = r
+        if strat == 'time_interval_aware':
+            # its host softmax needs the probability table of the queried rows only: fetch the needed slices lazily
+            r._prob_host = _LazyDeviceVector(samplers[strat].tia_prob)
+        try:
+            r.get_historical_neighbors_device(nodes[:min(nq_r, 64)], times[:min(nq_r, 64)], k)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            r.get_historical_neighbors_device(nodes[:nq_r], times[:nq_r], k)
+            torch.cuda.synchronize()
+            res[strat]['replay'] = {'queries': nq_r, 'queries_per_s': nq_r / (time.perf_counter() - t1),
+                                    'note': 'bit-exact mode: host MT19937 stream (one sequential stream), wall clock'}
+        except ValueError as e:
+            res[strat]['replay'] = {'queries': nq_r, 'raises': str(e)[:80],
+                                    'note': 'RandomState.choice(p=float32 softmax) rejects hub rows, exactly as utils/utils.py:183-187 does'}
     if rank == 0 and world == 1 and args.cpu_queries > 0:
-        # CPU baseline: the oracle's per-query loop (port of utils/utils.py:149-214) over arrays installed from the device CSR
-        from oracle.sampler import OracleSampler
-        o = object.__new__(OracleSampler)
+        # CPU baseline: the UNMODIFIED query code of the reference's NeighborSampler (utils/utils.py:130-214) over per-node slice views
+        # of the CSR arrays (its constructor cannot build 1e8 events: BASELINE.md 3.5); the oracle port when baseline/_ref is absent
         rec = base.halfedges[:base.num_half_edges].cpu().numpy()
-        o.t = np.ascontiguousarray(rec[:, 0])
+        t_all = np.ascontiguousarray(rec[:, 0])
         ints = np.ascontiguousarray(rec[:, 1]).view(np.int32).reshape(-1, 2)
-        o.nbr, o.eid = ints[:, 0].astype(np.int64), ints[:, 1].astype(np.int64)
-        o.indptr = base.indptr.cpu().numpy()
-        o.num_nodes, o.seed = num_nodes, 0
+        nbr_all, eid_all = ints[:, 0].astype(np.int64), ints[:, 1].astype(np.int64)
+        indptr_h = base.indptr.cpu().numpy()
+        ref = load_reference()
+        if ref is not None:
+            o = object.__new__(ref['utils'].NeighborSampler)
+            o.nodes_neighbor_ids, o.nodes_edge_ids = _NodeSlices(nbr_all, indptr_h), _NodeSlices(eid_all, indptr_h)
+            o.nodes_neighbor_times = _NodeSlices(t_all, indptr_h)
+            kind = 'reference'
+        else:
+            from oracle.sampler import OracleSampler
+            o = object.__new__(OracleSampler)
+            o.t, o.nbr, o.eid, o.indptr, o.num_nodes = t_all, nbr_all, eid_all, indptr_h, num_nodes
+            kind = 'port'
+        o.seed = 0
         nq = args.cpu_queries
         hn, ht = nodes[:nq].cpu().numpy(), times[:nq].cpu().numpy()
         cpu = {}
@@ -936,12 +1158,16 @@ def run_sampler_sweep(args):
             o.sample_neighbor_strategy = strat
             o.random_state = np.random.RandomState(0)
             if strat == 'time_interval_aware':
-                o.prob = samplers[strat].tia_prob[:base.num_half_edges].cpu().numpy()
+                prob_h = samplers[strat].tia_prob[:base.num_half_edges].cpu().numpy()
+                if kind == 'reference':
+                    o.nodes_neighbor_sampled_probabilities = _NodeSlices(prob_h, indptr_h)
+                else:
+                    o.prob = prob_h
             n_ = nq if strat != 'time_interval_aware' else max(100, nq // 20)
             t1 = time.perf_counter()
             if strat == 'time_interval_aware':
                 # RandomState.choice(p=float32 softmax) raises "probabilities do not sum to 1" on hubs with millions of
-                # neighbours (utils/utils.py:183-187 has the same limit): such queries are counted, not timed
+                # neighbours (utils/utils.py:183-187): such queries are counted, not timed
                 done = raised = 0
                 for q in range(n_):
                     try:
@@ -957,12 +1183,41 @@ def run_sampler_sweep(args):
             if strat == 'recent':
                 dv = samplers['recent'].get_historical_neighbors_device(nodes[:n_], times[:n_], k)
                 line['parity_recent_bit_exact'] = bool(all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(got, dv)))
-        line['cpu_baseline'] = {'value': cpu['recent'], 'unit': 'queries/s', 'cores': 1, 'kind': 'port',
-                                'sample': f'{nq} queries (tia: {max(100, nq // 20)}), oracle per-query python loop', 'strategies': cpu}
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+            if strat == 'uniform':
+                # the replay mode consumes the same RandomState(0) stream from its start: same draws, same rows
+                rr = replay_samplers['uniform']
+                rr.reset_random_state()
+                dv = rr.get_historical_neighbors_device(nodes[:n_], times[:n_], k)
+                line['parity_uniform_replay_bit_exact'] = bool(all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(got, dv)))
+        line['cpu_baseline'] = {'value': cpu['recent'], 'unit': 'queries/s', 'cores': 1, 'kind': kind,
+                                'sample': f'{nq} queries (tia: {max(100, nq // 20)}), ' +
+                                          ('unmodified reference query loop (utils/utils.py:130-214) over per-node slice views' if kind == 'reference'
+                                           else 'oracle per-query python loop'), 'strategies': cpu}
+    return line
+
+
+class _NodeSlices:
+    """``nodes_neighbor_ids``-style per-node arrays of the reference sampler as lazy slice views of one flat CSR array."""
+
+    def __init__(self, flat, indptr):
+        self.flat, self.indptr = flat, indptr
+
+    def __getitem__(self, node):
+        return self.flat[self.indptr[node]:self.indptr[node + 1]]
+
+    def __len__(self):
+        return len(self.indptr) - 1
+
+
+class _LazyDeviceVector:
+    """Host view of a device vector that copies only the slices asked for (the replay mode's per-query float32 softmax reads
+    tia_prob[a:a+c] for the queried rows; the whole 1e8-event table would be a 1.6 GB copy)."""
+
+    def __init__(self, vec):
+        self.vec = vec
+
+    def __getitem__(self, sl):
+        return self.vec[sl].cpu().numpy()
 
 
 def main():
@@ -979,6 +1234,10 @@ def main():
     ap.add_argument('--queries', type=int, default=1 << 24)
     ap.add_argument('--cpu-queries', type=int, default=20000)
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel directly instead of replaying the captured step')
+    ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch-on-GPU run of the reference modules')
+    ap.add_argument('--only-headline', action='store_true',
+                    help='default workload only: do not append the `workloads` records of the other BASELINE configs')
+    ap.add_argument('--save-dir', default='', help='also write the full JSON line of every extra workload into this directory')
     ap.add_argument('--ref-batch', type=int, default=0,
                     help='tgn_reddit only: events per sequential memory step instead of the reference default 200 (SURVEY 8d: B = 2,000 / '
                          '20,000 are different-semantics throughput points: a larger batch sees staler memories)')
@@ -991,14 +1250,18 @@ def main():
         if args.workload in ('sampler_sweep', 'tgat_train'):
             args.workload = 'dygformer_wiki'
         run_reference(args)
-    elif args.workload == 'sampler_sweep':
-        run_sampler_sweep(args)
+        return
+    args.warmup = max(args.warmup, 3)
+    ctx = Ctx()
+    if args.workload == 'sampler_sweep':
+        line = measure_sampler_sweep(ctx, args, args.steps, args.warmup)
     elif args.workload == 'tgat_train':
-        args.warmup = max(args.warmup, 3)
-        run_train(args)
+        line = measure_train(ctx, args, args.steps, args.warmup)
     else:
-        args.warmup = max(args.warmup, 3)
-        run_ours(args)
+        line = run_ours(ctx, args)
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.finish()
 
 
 if __name__ == '__main__':

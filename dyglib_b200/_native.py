@@ -18,6 +18,9 @@ LIB_PATH = os.path.join(_HERE, 'libdygb200.so')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
 
+# DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
+ABI_VERSION = 2
+
 _lock = threading.Lock()
 _lib = None
 
@@ -128,6 +131,8 @@ SIGNATURES = {
                                c_p, c_i, c_p],
     'dyg_tgn_cell_commit': [c_p, c_p, c_i, c_p, c_p, c_p, c_l, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_i,
                             c_p, c_p, c_p],
+    'dyg_gru_update_fwd': [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_l, c_p],
+    'dyg_gru_update_bwd': [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_p],
     'dyg_tgn_check_time': [c_p, c_l, c_p, c_p, c_p, c_p, c_p],
     'dyg_jodie_project': [c_p, c_i, c_p, c_p, c_p, c_l, c_i, c_f, c_f, c_p, c_p, c_p, c_i, c_p],
 }
@@ -140,11 +145,13 @@ def load():
         if _lib is not None:
             return _lib
         if _stale():
+            # no silent fallback, and no stale binary either: SIGNATURES below describe the CURRENT header, so binding them
+            # to an older build would pass mis-typed arguments to the kernels
             try:
                 build()
-            except Exception as e:  # no silent fallback: the product path needs the CUDA library
-                if not os.path.exists(LIB_PATH):
-                    raise RuntimeError(f'libdygb200.so is missing and could not be built: {e}') from e
+            except Exception as e:
+                what = 'is out of date' if os.path.exists(LIB_PATH) else 'is missing'
+                raise RuntimeError(f'libdygb200.so {what} and could not be rebuilt: {e}') from e
         lib = ctypes.CDLL(LIB_PATH)
         lib.dyg_last_error.restype = ctypes.c_char_p
         lib.dyg_last_error.argtypes = []
@@ -158,8 +165,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = c_i
             fn.argtypes = args
-        if lib.dyg_abi_version() != 1:
-            raise RuntimeError('libdygb200.so ABI version mismatch')
+        if lib.dyg_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'libdygb200.so ABI version {lib.dyg_abi_version()} != {ABI_VERSION} (include/dygb200.h)')
         _lib = lib
         return lib
 

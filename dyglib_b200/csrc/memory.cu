@@ -104,7 +104,7 @@ __global__ void tgn_cell_commit_kernel(const float* __restrict__ gi, const float
     if (winner[v] != (int32_t)c) return;  // warp-uniform
     const float* a = gi + c * (int64_t)(G * D);
     const float* hgt = gh + c * (int64_t)(G * D);
-    for (int j = lane; j < D; j += 32) {
+    for (int j = lane; gi && j < D; j += 32) {   // gi == NULL: dyg_gru_update_fwd already wrote mem_view[v]
         float hn;
         if (G == 3) {  // nn.GRUCell gate order r, z, n
             const float r = sigmoidf_(a[j] + hgt[j]);
@@ -132,6 +132,7 @@ extern "C" int dyg_tgn_cell_commit(const float* gi, const float* gh, int G, cons
                                    float* lu_view, uint8_t* pending, int D, const float* msg, int ldm, int msg_dim,
                                    float* msg_store, double* msg_time, dyg_stream_t stream) {
     DYG_CHECK_ARG(G == 1 || G == 3, "dyg_tgn_cell_commit: G must be 3 (GRU) or 1 (RNN)");
+    DYG_CHECK_ARG((gi == nullptr) == (gh == nullptr), "dyg_tgn_cell_commit: gi and gh must both be given or both be NULL");
     DYG_CHECK_ARG(B >= 0 && D > 0, "dyg_tgn_cell_commit: bad sizes");
     if (B == 0) return 0;
     tgn_cell_commit_kernel<<<(unsigned)((2 * B * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(

@@ -14,6 +14,7 @@ exactly where the reference's does.
 from __future__ import annotations
 
 from collections import defaultdict
+from collections.abc import MutableMapping
 
 import numpy as np
 import torch
@@ -26,6 +27,24 @@ from .modules import TimeEncoder, MergeLayer, MultiHeadAttention
 from ._temporal import temporal_conv, temporal_conv_train, zero_time_features
 
 
+def gru_update(cell, gates, msg, msg_idx, hid, hid_idx, out, out_idx, winner=None, save_gates=None):
+    """One launch of dyg_gru_update_fwd: rows of ``out`` = cell(msg rows, hid rows) (``nn.GRUCell`` / ``nn.RNNCell``)."""
+    P = int(hid_idx.numel() if hid_idx is not None else (msg_idx.numel() if msg_idx is not None else msg.shape[0]))
+    if P == 0:
+        return out
+    if out.data_ptr() == hid.data_ptr():
+        raise ValueError('gru_update: out must not alias hid')
+    D = hid.shape[1]
+    w_ih, w_hh = cell.weight_ih.detach(), cell.weight_hh.detach()
+    with ops._Timed('gru_update_kernel', 2.0 * P * gates * D * (msg.shape[1] + D), 4.0 * P * (msg.shape[1] + 2 * D)):
+        _native.check(_native.load().dyg_gru_update_fwd(
+            _p(msg), int(msg.stride(0)), _p(msg_idx), int(msg.shape[1]), _p(hid), int(hid.stride(0)), _p(hid_idx), int(D),
+            _p(w_ih), _p(cell.bias_ih.detach()), _p(w_hh), _p(cell.bias_hh.detach()), int(gates), _p(winner), _p(out), int(out.stride(0)),
+            _p(out_idx), _p(save_gates), P, _stream()))
+    ops._count()
+    return out
+
+
 class MessageAggregator(nn.Module):
     """``MessageAggregator`` (``models/MemoryModel.py:267-300``): keep the last message of every node."""
 
@@ -33,9 +52,17 @@ class MessageAggregator(nn.Module):
         super().__init__()
 
     def aggregate_messages(self, node_ids: np.ndarray, node_raw_messages: dict):
-        """Compat API over the reference's dict-of-lists format (host bookkeeping only; the fused model path
-        selects last messages on the device with dyg_tgn_select_last)."""
-        unique_node_ids = np.unique(node_ids)
+        """Compat API over the reference's dict-of-lists format; with the bank's own device-backed mapping the selection is one
+        gather (the fused model path never calls this: it selects last messages on the device with dyg_tgn_select_last)."""
+        unique_node_ids = np.unique(np.asarray(node_ids))
+        if isinstance(node_raw_messages, RawMessageStore):
+            st = node_raw_messages._bank._ensure()
+            dev = st['pending'].device
+            cand = torch.from_numpy(unique_node_ids.astype(np.int64)).to(dev)
+            ids = cand[st['pending'][cand].bool()]
+            if ids.numel() == 0:
+                return np.array([]), torch.Tensor([]), np.array([])
+            return ids.cpu().numpy(), ops.gather_rows(st['msg_store'], ids), st['msg_time'][ids].cpu().numpy()
         msgs, ts, ids = [], [], []
         for v in unique_node_ids:
             lst = node_raw_messages.get(v, []) if isinstance(node_raw_messages, dict) else node_raw_messages[v]
@@ -46,11 +73,106 @@ class MessageAggregator(nn.Module):
         return (np.array(ids), torch.stack(msgs, dim=0) if msgs else torch.Tensor([]), np.array(ts))
 
 
+class _MessageList(list):
+    """``node_raw_messages[node]``: the (message, time) tuples of one node; mutations write through to the device store."""
+
+    def __init__(self, store, node, items):
+        super().__init__(items)
+        self._store, self._node = store, node
+
+    def append(self, item):
+        super().append(item)
+        self._store[self._node] = list(self)
+
+    def extend(self, items):
+        super().extend(items)
+        self._store[self._node] = list(self)
+
+    def clear(self):
+        super().clear()
+        self._store[self._node] = []
+
+
+class RawMessageStore(MutableMapping):
+    """``MemoryBank.node_raw_messages`` (``models/MemoryModel.py:321-322``: ``{node_id: [(message, time), ...]}``) as a
+    mutable mapping over the device tables.  Only a node's LAST message ever reaches the memory updater
+    (``MessageAggregator.aggregate_messages``, ``:287-291``) and ``clear_node_raw_messages`` drops the whole list, so the
+    store keeps exactly that one row per node: reading gives a one-element list, assigning a list keeps its last entry.
+    It pickles as the reference's plain ``defaultdict(list)`` (``torch.save`` in ``utils/EarlyStopping.py:73-75``)."""
+
+    def __init__(self, bank):
+        self._bank = bank
+
+    def _node(self, key):
+        v = int(key)
+        if not 0 <= v < self._bank.num_nodes:
+            raise KeyError(key)
+        return v
+
+    def __getitem__(self, key):
+        v = self._node(key)
+        st = self._bank._ensure()
+        if not bool(st['pending'][v].item()):
+            return _MessageList(self, v, [])          # defaultdict(list) semantics
+        return _MessageList(self, v, [(st['msg_store'][v].clone(), np.float64(st['msg_time'][v].item()))])
+
+    def __setitem__(self, key, messages):
+        self._bank._load_messages({self._node(key): messages})
+
+    def __delitem__(self, key):
+        self._bank._load_messages({self._node(key): []})
+
+    def _pending(self):
+        return torch.nonzero(self._bank._ensure()['pending']).reshape(-1)
+
+    def __iter__(self):
+        return iter(self._pending().tolist())
+
+    def __len__(self):
+        return int(self._pending().numel())
+
+    def __contains__(self, key):
+        try:
+            v = self._node(key)
+        except (KeyError, TypeError, ValueError):
+            return False
+        return bool(self._bank._ensure()['pending'][v].item())
+
+    def items(self):
+        """One gather for all pending nodes (the loops of ``evaluate_link_prediction.py:152-156`` / ``backup_memory_bank``)."""
+        st = self._bank._ensure()
+        ids = self._pending()
+        rows = ops.gather_rows(st['msg_store'], ids) if ids.numel() else None
+        times = st['msg_time'][ids].cpu().numpy()
+        return [(v, _MessageList(self, v, [(rows[i], np.float64(times[i]))])) for i, v in enumerate(ids.tolist())]
+
+    def values(self):
+        return [m for _, m in self.items()]
+
+    def to_dict(self):
+        out = defaultdict(list)
+        for v, m in self.items():
+            out[v] = list(m)
+        return out
+
+    def __reduce__(self):
+        return (defaultdict, (list,), None, None, iter([(v, list(m)) for v, m in self.items()]))
+
+    def __repr__(self):
+        return f'RawMessageStore({len(self)} pending nodes)'
+
+
+_ANY_WEIGHTS = 'any'    # view key of a bank without pending messages: the look-ahead view equals the persisted state
+
+
 class MemoryBank(nn.Module):
 
     def __init__(self, num_nodes: int, memory_dim: int, message_dim: int = 0):
         """``MemoryBank`` (``models/MemoryModel.py:304-422``); ``node_memories`` and ``node_last_updated_times`` are
-        non-grad Parameters so they land in the state_dict like the reference's."""
+        non-grad Parameters so they land in the state_dict like the reference's.  Device state next to them
+        (``_state``): the look-ahead view ``mem_view`` / ``lu_view`` (== ``get_updated_memories`` of every node), the
+        ``pending`` flags and the last raw message of every node (``msg_store`` / ``msg_time``).  ``_view_key`` names the
+        recurrent-cell weights the view was computed with (None: unknown, rebuild before use)."""
         super().__init__()
         self.num_nodes = num_nodes
         self.memory_dim = memory_dim
@@ -58,11 +180,13 @@ class MemoryBank(nn.Module):
         self.node_memories = nn.Parameter(torch.zeros((num_nodes, memory_dim)), requires_grad=False)
         self.node_last_updated_times = nn.Parameter(torch.zeros(num_nodes), requires_grad=False)
         self._state = None
+        self._view_key = _ANY_WEIGHTS
 
     def _ensure(self):
         dev = self.node_memories.device
         if self._state is None or self._state['mem_view'].device != dev:
             N, D = self.num_nodes, self.memory_dim
+            old = self._state
             self._state = dict(
                 mem_view=self.node_memories.data.clone(),
                 lu_view=self.node_last_updated_times.data.clone(),
@@ -71,7 +195,19 @@ class MemoryBank(nn.Module):
                 msg_store=torch.zeros((N, max(self.message_dim, 1)), dtype=torch.float32, device=dev),
                 msg_time=torch.zeros(N, dtype=torch.float64, device=dev),
                 flag=torch.zeros(1, dtype=torch.int32, device=dev))
+            if old is not None:      # the module moved to another device: the pending messages move with it
+                for k in ('pending', 'msg_store', 'msg_time'):
+                    self._state[k].copy_(old[k])
+                self._view_key = None
         return self._state
+
+    def mark_view_stale(self):
+        self._view_key = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        # loaded memories replace the persisted state: the look-ahead view has to be rebuilt from them
+        super()._load_from_state_dict(*args, **kwargs)
+        self._view_key = None
 
     def __init_memory_bank__(self):
         """``__init_memory_bank__`` (``models/MemoryModel.py:325-332``)."""
@@ -85,6 +221,7 @@ class MemoryBank(nn.Module):
             for k in ('mem_view', 'lu_view', 'pending', 'msg_store', 'msg_time', 'flag'):
                 st[k].zero_()
             st['winner'].fill_(-1)
+        self._view_key = _ANY_WEIGHTS
 
     def get_memories(self, node_ids):
         ids = _as_dev(node_ids, torch.int64, self.node_memories.device)
@@ -92,37 +229,93 @@ class MemoryBank(nn.Module):
 
     def set_memories(self, node_ids, updated_node_memories: torch.Tensor):
         ids = _as_dev(node_ids, torch.int64, self.node_memories.device)
-        self.node_memories.data[ids] = updated_node_memories
-        st = self._ensure()
-        st['mem_view'][ids] = updated_node_memories
+        self.node_memories.data[ids] = updated_node_memories.detach()
+        self._view_key = None
 
     def get_node_last_updated_times(self, unique_node_ids):
         ids = _as_dev(unique_node_ids, torch.int64, self.node_memories.device)
         return self.node_last_updated_times.data[ids]
 
+    # ---- raw messages: the reference's dict-of-lists attribute, backed by the device tables
     @property
     def node_raw_messages(self):
-        """The pending messages in the reference's format {node_id: [(message, time)]} (export for checkpoints,
-        ``utils/EarlyStopping.py:73-86``)."""
+        """``{node_id: [(message, time)]}`` view of the pending messages (``models/MemoryModel.py:321-322``); assignable
+        (``utils/EarlyStopping.py:86``) and item-assignable (``evaluate_link_prediction.py:152-156``)."""
+        return RawMessageStore(self)
+
+    @node_raw_messages.setter
+    def node_raw_messages(self, messages):
         st = self._ensure()
-        out = defaultdict(list)
-        for v in torch.nonzero(st['pending']).reshape(-1).tolist():
-            out[v].append((st['msg_store'][v].clone(), np.float64(st['msg_time'][v].item())))
-        return out
+        if isinstance(messages, RawMessageStore) and messages._bank is self:
+            return
+        st['pending'].zero_()
+        self._view_key = None
+        self._load_messages(messages.to_dict() if isinstance(messages, RawMessageStore) else messages)
+
+    def _load_messages(self, messages):
+        """Install ``{node: [(message, time), ...]}``: the last entry of every non-empty list becomes the node's pending message,
+        an empty list clears it."""
+        st = self._ensure()
+        dev = st['pending'].device
+        keep_ids, rows, times, drop = [], [], [], []
+        for v, lst in messages.items():
+            v = int(v)
+            if not 0 <= v < self.num_nodes:
+                raise KeyError(v)
+            if len(lst) == 0:
+                drop.append(v)
+            else:
+                keep_ids.append(v)
+                rows.append(torch.as_tensor(lst[-1][0]).detach().to(device=dev, dtype=torch.float32).reshape(-1))
+                times.append(float(lst[-1][1]))
+        if drop:
+            st['pending'][torch.tensor(drop, dtype=torch.int64, device=dev)] = 0
+        if keep_ids:
+            ids = torch.tensor(keep_ids, dtype=torch.int64, device=dev)
+            block = torch.stack(rows)
+            if block.shape[1] != st['msg_store'].shape[1]:
+                raise ValueError(f'raw messages have {block.shape[1]} columns, the bank stores {st["msg_store"].shape[1]}')
+            st['msg_store'][ids] = block
+            st['msg_time'][ids] = torch.tensor(times, dtype=torch.float64, device=dev)
+            st['pending'][ids] = 1
+        if drop or keep_ids:
+            self._view_key = None
+
+    def store_node_raw_messages(self, node_ids, new_node_raw_messages: dict):
+        """``store_node_raw_messages`` (``models/MemoryModel.py:389-398``): append the new messages of ``node_ids``."""
+        self._load_messages({int(v): new_node_raw_messages[v] for v in np.asarray(node_ids).reshape(-1).tolist()
+                             if len(new_node_raw_messages[v]) > 0})
+
+    def clear_node_raw_messages(self, node_ids):
+        """``clear_node_raw_messages`` (``models/MemoryModel.py:400-407``)."""
+        st = self._ensure()
+        ids = _as_dev(node_ids, torch.int64, self.node_memories.device)
+        if ids.numel():
+            st['pending'][ids] = 0
+            self._view_key = None
 
     def backup_memory_bank(self):
-        """``backup_memory_bank`` (``models/MemoryModel.py:351-360``): flat device copies."""
+        """``backup_memory_bank`` (``models/MemoryModel.py:351-360``): flat device copies (the third element carries the
+        pending messages, the look-ahead view and the weights key that view belongs to)."""
         st = self._ensure()
-        return (self.node_memories.data.clone(), self.node_last_updated_times.data.clone(),
-                {k: v.clone() for k, v in st.items()})
+        third = {k: v.clone() for k, v in st.items()}
+        third['_view_key'] = self._view_key
+        return (self.node_memories.data.clone(), self.node_last_updated_times.data.clone(), third)
 
     def reload_memory_bank(self, backup_memory_bank: tuple):
-        """``reload_memory_bank`` (``models/MemoryModel.py:362-372``)."""
+        """``reload_memory_bank`` (``models/MemoryModel.py:362-372``).  The restored look-ahead view is only trusted if it was
+        built by the weights the model has now (``MemoryModel._refresh_view_if_stale`` compares the key)."""
         self.node_memories.data.copy_(backup_memory_bank[0])
         self.node_last_updated_times.data.copy_(backup_memory_bank[1])
         st = self._ensure()
-        for k, v in backup_memory_bank[2].items():   # in place (graph-safe)
-            st[k].copy_(v)
+        third = backup_memory_bank[2]
+        if '_view_key' in third or 'mem_view' in third:
+            for k, v in third.items():   # in place (graph-safe)
+                if k != '_view_key':
+                    st[k].copy_(v)
+            self._view_key = third.get('_view_key')
+        else:                            # a backup in the reference's format: {node: [(message, time)]}
+            self.node_raw_messages = third
 
     def detach_memory_bank(self):
         """``detach_memory_bank`` (``models/MemoryModel.py:374-387``): nothing carries gradients here."""
@@ -138,6 +331,40 @@ class MemoryUpdater(nn.Module):
     def __init__(self, memory_bank: MemoryBank):
         super().__init__()
         self.memory_bank = memory_bank
+
+    def _operands(self, unique_node_ids, unique_node_messages, unique_node_timestamps):
+        bank = self.memory_bank
+        dev = bank.node_memories.device
+        ids = _as_dev(unique_node_ids, torch.int64, dev)
+        msg = unique_node_messages.detach().to(device=dev, dtype=torch.float32).contiguous()
+        ts = _as_dev(unique_node_timestamps, torch.float64, dev).float()
+        assert bool((bank.node_last_updated_times.data[ids] <= ts).all().item()), 'Trying to update memory to time in the past!'
+        return ids, msg, ts
+
+    def update_memories(self, unique_node_ids, unique_node_messages: torch.Tensor, unique_node_timestamps):
+        """``update_memories`` (``models/MemoryModel.py:435-459``): persist cell(message, memory) and the message time for
+        ``unique_node_ids`` (one fused launch, dyg_gru_update_fwd)."""
+        if len(unique_node_ids) <= 0:
+            return
+        bank = self.memory_bank
+        ids, msg, ts = self._operands(unique_node_ids, unique_node_messages, unique_node_timestamps)
+        new = torch.empty((ids.numel(), bank.memory_dim), dtype=torch.float32, device=ids.device)
+        gru_update(self.memory_updater, self.gates, msg, None, bank.node_memories.data, ids, new, None)
+        bank.node_memories.data[ids] = new
+        bank.node_last_updated_times.data[ids] = ts
+        bank.mark_view_stale()
+
+    def get_updated_memories(self, unique_node_ids, unique_node_messages: torch.Tensor, unique_node_timestamps):
+        """``get_updated_memories`` (``models/MemoryModel.py:461-487``): copies of the whole memory / last-update tables with
+        the rows of ``unique_node_ids`` advanced by their messages; nothing is persisted."""
+        bank = self.memory_bank
+        mem, lu = bank.node_memories.data.clone(), bank.node_last_updated_times.data.clone()
+        if len(unique_node_ids) <= 0:
+            return mem, lu
+        ids, msg, ts = self._operands(unique_node_ids, unique_node_messages, unique_node_timestamps)
+        gru_update(self.memory_updater, self.gates, msg, None, bank.node_memories.data, ids, mem, ids)
+        lu[ids] = ts
+        return mem, lu
 
 
 class GRUMemoryUpdater(MemoryUpdater):
@@ -164,6 +391,24 @@ class TimeProjectionEmbedding(nn.Module):
         self.memory_dim = memory_dim
         self.dropout = nn.Dropout(dropout)
         self.linear_layer = nn.Linear(1, self.memory_dim)
+
+    def compute_node_temporal_embeddings(self, node_memories: torch.Tensor, node_ids, node_time_intervals: torch.Tensor):
+        """``compute_node_temporal_embeddings`` (``models/MemoryModel.py:534-545``):
+        dropout(memories[ids] * (1 + linear(intervals))); eval mode runs dyg_jodie_project."""
+        dev = node_memories.device
+        ids = _as_dev(node_ids, torch.int64, dev)
+        if self.training and torch.is_grad_enabled():
+            return self.dropout(node_memories[ids] * (1 + self.linear_layer(node_time_intervals.unsqueeze(dim=1))))
+        mem = node_memories.detach().float().contiguous()
+        iv = node_time_intervals.detach().to(device=dev, dtype=torch.float64).contiguous()
+        M, D = ids.numel(), self.memory_dim
+        out = torch.empty((M, D), dtype=torch.float32, device=dev)
+        zeros = torch.zeros(mem.shape[0], dtype=torch.float32, device=dev)   # "last update" 0: the interval is given directly
+        _native.check(_native.load().dyg_jodie_project(_p(mem), int(mem.stride(0)), _p(zeros), _p(ids), _p(iv), M, D, 0.0, 1.0,
+                                                       _p(self.linear_layer.weight.detach().reshape(-1)), _p(self.linear_layer.bias.detach()),
+                                                       _p(out), D, _stream()))
+        ops._count()
+        return out
 
 
 class GraphAttentionEmbedding(nn.Module):
@@ -275,7 +520,7 @@ class MemoryModel(torch.nn.Module):
                                                  edge_ids: np.ndarray, edges_are_positive: bool = True, num_neighbors: int = 20):
         """``compute_src_dst_node_temporal_embeddings`` (``models/MemoryModel.py:87-168``)."""
         if self.training and torch.is_grad_enabled():
-            self._view_stale = True
+            self.memory_bank.mark_view_stale()      # the weights move between training calls
             return self._forward_train(src_node_ids, dst_node_ids, node_interact_times, edge_ids, edges_are_positive, num_neighbors)
         self._refresh_view_if_stale()
         dev = self.node_raw_features.device
@@ -312,15 +557,88 @@ class MemoryModel(torch.nn.Module):
         self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), emb[3 * B:], emb[2 * B:3 * B], None)
         return ret[:B], ret[B:2 * B], ret[2 * B:3 * B], ret[3 * B:]
 
+    def _cell_key(self):
+        """Identity of the recurrent cell's weights (the look-ahead view of the pending nodes is a function of them)."""
+        return (ops.WEIGHTS_EPOCH,) + tuple((q.data_ptr(), q._version) for q in self.memory_updater.memory_updater.parameters())
+
     def _refresh_view_if_stale(self):
-        if getattr(self, '_view_stale', False):
-            # the look-ahead view of the pending nodes was built by earlier weights: rebuild it with the current ones
-            with torch.no_grad():
-                mem_upd, lu_upd = self._updated_memories_train()
-                st0 = self.memory_bank._ensure()
-                st0['mem_view'].copy_(mem_upd)
-                st0['lu_view'].copy_(lu_upd)
-            self._view_stale = False
+        """Make ``mem_view`` / ``lu_view`` equal ``get_updated_memories`` of all nodes under the CURRENT weights
+        (``models/MemoryModel.py:108-109``).  The view is maintained incrementally by ``_advance``; it is rebuilt from the
+        persisted memories and the stored last messages when the bank says it is unknown (after ``load_state_dict``, a
+        raw-message assignment, a compat mutator or a training step) or was built by other weights (``reload_memory_bank``
+        of a backup taken before the weights moved)."""
+        bank = self.memory_bank
+        key = self._cell_key()
+        if bank._view_key == _ANY_WEIGHTS:
+            bank._view_key = key
+        elif bank._view_key != key:
+            self._rebuild_view()
+            bank._view_key = key
+
+    def _rebuild_view(self):
+        bank = self.memory_bank
+        st = bank._ensure()
+        with torch.no_grad():
+            st['mem_view'].copy_(bank.node_memories.data)
+            st['lu_view'].copy_(bank.node_last_updated_times.data)
+            pend = torch.nonzero(st['pending']).reshape(-1)
+            if pend.numel():
+                gru_update(self.memory_updater.memory_updater, self.memory_updater.gates, st['msg_store'], pend,
+                           bank.node_memories.data, pend, st['mem_view'], pend)
+                st['lu_view'][pend] = st['msg_time'][pend].float()
+
+    # ------------------------------------------------------------------ the reference's sub-API (compat surface)
+    def get_updated_memories(self, node_ids, node_raw_messages):
+        """``get_updated_memories`` (``models/MemoryModel.py:170-191``): (memories, last-update times) of ALL nodes with the
+        rows of ``node_ids`` advanced by their last pending message; nothing is persisted.  With the bank's own message store
+        this is a masked copy of the look-ahead view; with any other ``{node: [(message, time)]}`` dict the messages are
+        aggregated on the host and run through the fused cell."""
+        bank = self.memory_bank
+        if isinstance(node_raw_messages, RawMessageStore) and node_raw_messages._bank is bank:
+            self._refresh_view_if_stale()
+            st = bank._ensure()
+            dev = bank.node_memories.device
+            sel = torch.zeros(self.num_nodes, dtype=torch.bool, device=dev)
+            sel[_as_dev(node_ids, torch.int64, dev)] = True
+            sel &= st['pending'].bool()
+            return (torch.where(sel.unsqueeze(1), st['mem_view'], bank.node_memories.data),
+                    torch.where(sel, st['lu_view'], bank.node_last_updated_times.data))
+        ids, msgs, ts = self.message_aggregator.aggregate_messages(node_ids=node_ids, node_raw_messages=node_raw_messages)
+        return self.memory_updater.get_updated_memories(unique_node_ids=ids, unique_node_messages=msgs, unique_node_timestamps=ts)
+
+    def update_memories(self, node_ids, node_raw_messages):
+        """``update_memories`` (``models/MemoryModel.py:193-210``): persist the update of ``node_ids`` from their last messages."""
+        ids, msgs, ts = self.message_aggregator.aggregate_messages(node_ids=node_ids, node_raw_messages=node_raw_messages)
+        self.memory_updater.update_memories(unique_node_ids=ids, unique_node_messages=msgs, unique_node_timestamps=ts)
+
+    def compute_new_node_raw_messages(self, src_node_ids, dst_node_ids, dst_node_embeddings, node_interact_times, edge_ids):
+        """``compute_new_node_raw_messages`` (``models/MemoryModel.py:212-251``): one message per event for the nodes in
+        ``src_node_ids``: [memory[src] | memory[dst] (DyRep: dst embedding) | time_enc(t - last_update[src]) | edge feature]
+        (dyg_tgn_build_messages), returned as (unique node ids, {node: [(message row, time), ...]})."""
+        dev = self.node_raw_features.device
+        bank = self.memory_bank
+        src = _as_dev(src_node_ids, torch.int64, dev)
+        dst = _as_dev(dst_node_ids, torch.int64, dev)
+        tq = _as_dev(node_interact_times, torch.float64, dev)
+        eid = _as_dev(edge_ids, torch.int64, dev)
+        B = src.numel()
+        D, T, E = self.memory_dim, self.time_feat_dim, self.edge_feat_dim
+        other = None
+        if self.model_name == 'DyRep':       # the kernel builds both roles; only the src-role half is asked for here
+            other = torch.zeros((2 * B, D), dtype=torch.float32, device=dev)
+            other[:B] = dst_node_embeddings.detach()
+        w, b = self.time_encoder.wb()
+        msg = torch.empty((2 * B, self.message_dim), dtype=torch.float32, device=dev)
+        _native.check(_native.load().dyg_tgn_build_messages(
+            _p(src), _p(dst), _p(tq), _p(eid), B, _p(bank.node_memories.data), _p(bank.node_last_updated_times.data), D, _p(other), D,
+            _p(self.edge_raw_features), self.edge_raw_features.stride(0), E, _p(w), _p(b), T, _p(msg), self.message_dim, _stream()))
+        ops._count()
+        src_h = np.asarray(src_node_ids) if not isinstance(src_node_ids, torch.Tensor) else src_node_ids.cpu().numpy()
+        t_h = np.asarray(node_interact_times) if not isinstance(node_interact_times, torch.Tensor) else node_interact_times.cpu().numpy()
+        new_node_raw_messages = defaultdict(list)
+        for i in range(B):
+            new_node_raw_messages[src_h[i]].append((msg[i], t_h[i]))
+        return np.unique(src_h), new_node_raw_messages
 
     def _embed_eval(self, roles, tq, num_neighbors):
         """Embeddings of the concatenated root sets ``roles`` (alternating src / dst roles, each B ids at times ``tq``) on the
@@ -380,14 +698,14 @@ class MemoryModel(torch.nn.Module):
         _native.check(lib.dyg_tgn_build_messages(_p(src), _p(dst), _p(tq), _p(eid), B, _p(mem), _p(lu), D, _p(other), D,
                                                  _p(self.edge_raw_features), self.edge_raw_features.stride(0), E,
                                                  _p(w), _p(b), T, _p(msg), self.message_dim, _stream()))
-        cell = self.memory_updater.memory_updater
+        # the recurrent cell of the winning candidates in one launch (gate GEMMs + gates + scatter into the look-ahead view),
+        # then the bookkeeping of the same candidates (message store, times, pending flags)
         G = self.memory_updater.gates
-        gi = ops.linear([ops.seg_rows(msg)], 2 * B, cell.weight_ih.detach(), cell.bias_ih.detach())
-        gh = ops.linear([ops.seg_rows(mem, D, node_ids)], 2 * B, cell.weight_hh.detach(), cell.bias_hh.detach())
-        _native.check(lib.dyg_tgn_cell_commit(_p(gi), _p(gh), G, _p(src), _p(dst), _p(tq), B, _p(st['winner']), _p(mem),
+        gru_update(self.memory_updater.memory_updater, G, msg, None, mem, node_ids, mem_view, node_ids, winner=st['winner'])
+        _native.check(lib.dyg_tgn_cell_commit(None, None, G, _p(src), _p(dst), _p(tq), B, _p(st['winner']), _p(mem),
                                               _p(mem_view), _p(lu_view), _p(st['pending']), D, _p(msg), self.message_dim,
                                               self.message_dim, _p(st['msg_store']), _p(st['msg_time']), _stream()))
-        ops._count(3)
+        ops._count(2)
 
     def _updated_memories_train(self):
         """``get_updated_memories`` over all nodes (``models/MemoryModel.py:170-191, 461-487``) with autograd: the recurrent

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 1
+#define DYG_ABI_VERSION 2
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -294,12 +294,29 @@ int dyg_tgn_build_messages(const int64_t* src, const int64_t* dst, const double*
                            const float* edge_tab, int ld_edge, int E, const float* w, const float* b, int T,
                            float* msg, int ldm, dyg_stream_t stream);
 /* GRU / RNN cell epilogue + commit for winning candidates: gi=(2B,G*D) input gates incl. bias_ih, gh=(2B,G*D)
- * hidden gates incl. bias_hh (G=3 GRU: r,z,n order of nn.GRUCell; G=1 tanh RNNCell).
+ * hidden gates incl. bias_hh (G=3 GRU: r,z,n order of nn.GRUCell; G=1 tanh RNNCell); gi = gh = NULL when
+ * dyg_gru_update_fwd has already written mem_view (then only the bookkeeping below is done).
  * mem_view[v]=h', lu_view[v]=(float)t, pending[v]=1, msg_store[v]=msg[c], msg_time[v]=t, winner[v] reset to -1. */
 int dyg_tgn_cell_commit(const float* gi, const float* gh, int G, const int64_t* src, const int64_t* dst,
                         const double* t, int64_t B, int32_t* winner, const float* memory, float* mem_view,
                         float* lu_view, uint8_t* pending, int D, const float* msg, int ldm, int msg_dim,
                         float* msg_store, double* msg_time, dyg_stream_t stream);
+/* Fused recurrent cell (nn.GRUCell / nn.RNNCell of models/MemoryModel.py:490-515, called at :452-453 and :481-482): in ONE
+ * launch, row m = cell(msg[msg_idx ? msg_idx[m] : m, :msg_dim], h = hid[hid_idx ? hid_idx[m] : m, :D]) with the gate GEMMs
+ * (w_ih (G*D, msg_dim), w_hh (G*D, D), contiguous fp32), the gate non-linearities (G=3: r, z, n order; G=1: tanh) and the
+ * scatter out[out_idx ? out_idx[m] : m, :D] = h'.  winner != NULL: only rows with winner[hid_idx[m]] == m are written (the
+ * last-message choice of dyg_tgn_select_last).  gates != NULL: (P, 4D) for G=3 holding r | z | n | (W_hn h + b_hn), (P, D)
+ * for G=1 holding h' -- what dyg_gru_update_bwd needs.  `out` must not alias `hid`.  Widths / leading dimensions % 4 == 0. */
+int dyg_gru_update_fwd(const float* msg, int ldm, const int64_t* msg_idx, int msg_dim, const float* hid, int ldh,
+                       const int64_t* hid_idx, int D, const float* w_ih, const float* b_ih, const float* w_hh,
+                       const float* b_hh, int G, const int32_t* winner, float* out, int ldo, const int64_t* out_idx,
+                       float* gates, int64_t P, dyg_stream_t stream);
+/* Element-wise half of the cell's backward (the reference differentiates models/MemoryModel.py:481-482 with autograd):
+ * from the saved gates and grad_out (P, ldg) it writes the gradients of the gate pre-activations d_gi (P, G*D) (input side)
+ * and d_gh (P, G*D) (hidden side) and d_h (P, D) = the direct term grad_out * z.  The caller finishes with four dense
+ * products: d_msg = d_gi W_ih, d_hid = d_h + d_gh W_hh, dW_ih = d_gi^T msg, dW_hh = d_gh^T h (bias gradients: column sums). */
+int dyg_gru_update_bwd(const float* gates, const float* hid, int ldh, const int64_t* hid_idx, const float* grad_out, int ldg,
+                       int G, float* d_gi, float* d_gh, float* d_h, int64_t P, int D, dyg_stream_t stream);
 /* reference's "Trying to update memory to time in the past" assert (models/MemoryModel.py:448-449):
  * flag[0] set to 1 if any last_update[v] > (float)msg_time for pending v in node_ids. */
 int dyg_tgn_check_time(const int64_t* node_ids, int64_t n, const float* last_update, const float* lu_view,

@@ -95,8 +95,7 @@ def test_memory_model_eval_after_training_uses_current_weights():
         with torch.no_grad():
             cell = m.memory_updater.memory_updater
             cell.weight_ih.mul_(1.5)
-            if not train_last:      # the eval-only model must be told: its view was built by the old weights too
-                m._view_stale = True
+            # no manual invalidation: the bank's view key names the cell weights (their version counters moved)
             src, dst, t, eid, neg = bs[5]
             a, b = m.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
         return a.cpu().numpy(), b.cpu().numpy()

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     for s in syms:
         assert hasattr(lib, s), f'{s} declared in include/dygb200.h but not exported'
-    assert lib.dyg_abi_version() == 1
+    assert lib.dyg_abi_version() == _native.ABI_VERSION
 
 
 def test_python_signatures_cover_header():
