@@ -262,3 +262,62 @@ def test_tcl_training_step_matches_golden():
     # 5e-3 of each gradient's largest magnitude: TCL's blocks gate with ReLU, and a pre-activation within the forward pass's
     # ~1e-5 rounding difference of zero flips its gate (observed 2.5e-3 on transformers.1.linear_layers.0.bias, < 2e-3 elsewhere)
     assert_grads_close(got, gold, rtol=5e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs at their full size (the graphs, batch size and hyper-parameters bench.py runs), CUDA vs the oracle.
+def test_tgat_myket_full_size_batches_vs_oracle():
+    """Config 1: TGAT, 2 layers, 20 recent neighbours, batch 200 on the 694 k-event myket-shaped graph; two batches from the last
+    15 % of the stream, positive and negative pairs."""
+    _, tgat, _, _ = cuda_factories()
+    _, otgat, _, _ = oracle_factories()
+    g = make_config_graph('tgat_myket')
+    m, o = tgat(g, 1), otgat(g, 1)
+    start = int(g.num_interactions * 0.85)
+    with torch.no_grad():
+        for src, dst, t, _, neg in batches(g, start, 2, 200):
+            for d in (dst, neg):
+                a = m.compute_src_dst_node_temporal_embeddings(src, d, t, 20)
+                b = o.compute_src_dst_node_temporal_embeddings(src, d, t, 20)
+                for x, y in zip(a, b):
+                    close(x, y)
+
+
+def test_tgn_reddit_full_size_60_batches_vs_oracle():
+    """Config 3: TGN (1 layer, 10 recent neighbours, last-message aggregation + GRU) over 60 consecutive 200-event batches of the
+    672 k-event reddit-shaped graph from zeroed memory, through the call bench.py times (negative + positive roots in one pass):
+    embeddings of every 10th batch, then the final memory, last-update times and the set of nodes holding a pending message."""
+    _, _, _, memory = cuda_factories()
+    _, _, _, omemory = oracle_factories()
+    g = make_config_graph('tgn_reddit')
+    (m, mem_fn), (o, omem_fn) = memory(g, 'TGN', 3), omemory(g, 'TGN', 3)
+    with torch.no_grad():
+        for bi, (src, dst, t, eid, neg) in enumerate(batches(g, 0, 60, 200)):
+            got = m.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10)
+            wa = o.compute_src_dst_node_temporal_embeddings(src, neg, t, None, False, 10)
+            wb = o.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
+            if bi % 10 == 9 or bi >= 57:
+                for x, y in zip(got, (wa[0], wa[1], wb[0], wb[1])):
+                    close(x, y, f'batch {bi}')
+    m.assert_time_order()
+    close(mem_fn(m)[0], omem_fn(o)[0], 'memory')
+    assert np.array_equal(mem_fn(m)[1].cpu().numpy(), omem_fn(o)[1].numpy())
+    pend = sorted(int(v) for v, lst in o.raw_messages.items() if len(lst) > 0)
+    assert len(pend) > 1000                                   # a realistic pending set (SURVEY 8d)
+    assert sorted(m.memory_bank.node_raw_messages) == pend
+
+
+def test_dygformer_lastfm_full_size_batch_vs_oracle():
+    """Config 4: DyGFormer patch 16, sequence length 512 on the 1.29 M-event lastfm-shaped graph (times up to 1.37e8 > 2^24, so the
+    float32 rounding of the neighbour times matters); one 200-event batch from the last 15 %, positive and negative pairs."""
+    _, _, dygformer, _ = cuda_factories()
+    _, _, odyg, _ = oracle_factories()
+    g = make_config_graph('dygformer_lastfm')
+    m, o = dygformer(g, 16, 512, 2), odyg(g, 16, 512, 2)
+    src, dst, t, _, neg = next(batches(g, int(g.num_interactions * 0.9), 1, 200))
+    with torch.no_grad():
+        for d in (dst, neg):
+            a = m.compute_src_dst_node_temporal_embeddings(src, d, t)
+            b = o.compute_src_dst_node_temporal_embeddings(src, d, t)
+            for x, y in zip(a, b):
+                close(x, y)

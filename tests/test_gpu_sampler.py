@@ -346,3 +346,48 @@ def test_tia_cum_fence_matches_binary_search_and_numpy(index64, tsf, monkeypatch
         want_t = rec_t[a + sel].astype(np.float32)
         order = np.lexsort((np.arange(k), want_t))
         assert np.array_equal(got_e[q], eids[a + sel][order].astype(np.int64)), q
+
+
+@pytest.mark.parametrize('strategy', ['uniform', 'time_interval_aware'])
+def test_philox_mode_follows_the_reference_sampling_law(strategy):
+    """The Philox throughput modes do not replay the reference's MT19937 stream, but they must draw from the same distribution
+    (utils/utils.py:176-199): index i of the prefix with probability 1 / cnt ('uniform') or softmax_f32(prob[:cnt])_i
+    ('time_interval_aware', prob from compute_sampled_probabilities, :112-128).  Chi-square test of the index histogram of 80,000
+    draws per hub query against those probabilities."""
+    from scipy import stats
+    from dyglib_b200.utils.utils import get_neighbor_sampler
+    tsf = 2e-5
+    g = small_graph(seed=53, E=6000, nu=40, ni=15)
+    c = get_neighbor_sampler(g, strategy, tsf, seed=11, rng='philox')
+    o = OracleSampler(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, g.num_nodes, strategy, tsf, 11)
+    deg = np.bincount(np.concatenate([g.src_node_ids, g.dst_node_ids]), minlength=g.num_nodes)
+    hubs = np.argsort(-deg)[[0, 3, 12]]
+    reps, k = 4000, 20
+    for v in hubs:
+        tq = float(np.quantile(g.node_interact_times, 0.8)) + 0.5
+        a, cnt = o.count_before(int(v), tq)
+        eid = o.eid[a:a + cnt]
+        assert cnt >= 30
+        if strategy == 'uniform':
+            p = np.full(cnt, 1.0 / cnt)
+        else:
+            p = torch.softmax(torch.from_numpy(o.prob[a:a + cnt]).float(), dim=0).double().numpy()
+            p /= p.sum()
+        _, ei, _ = c.get_historical_neighbors(np.full(reps, v), np.full(reps, tq), k)
+        pos = {int(e): i for i, e in enumerate(eid)}            # edge ids are unique per interaction
+        idx = np.array([pos[int(e)] for e in ei.reshape(-1)])
+        obs = np.bincount(idx, minlength=cnt).astype(np.float64)
+        exp = p * obs.sum()
+        # merge the bins whose expectation is too small for the chi-square approximation
+        small = exp < 5
+        if small.any():
+            obs = np.concatenate([obs[~small], [obs[small].sum()]])
+            exp = np.concatenate([exp[~small], [exp[small].sum()]])
+        stat, pval = stats.chisquare(obs, exp)
+        assert pval > 1e-4, (strategy, int(v), cnt, stat, pval)
+        # and the test has power: a law shifted towards recent entries is rejected
+        wrong = p * np.linspace(0.7, 1.3, cnt)
+        wrong /= wrong.sum()
+        we = wrong * obs.sum() if not small.any() else None
+        if we is not None:
+            assert stats.chisquare(obs, we)[1] < 1e-6
