@@ -388,8 +388,9 @@ class TGNWL(Workload):
 
     def step(self, src, dst, neg, t, eid):
         # the reference loop's negative call then positive call (train_link_prediction.py:236-247) in one embedding pass
-        a, b, c, d = self.model.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10)
-        return _predict(self.pred, torch.cat([c, a]), torch.cat([d, b]))
+        # ... and the link predictor of train_link_prediction.py:243-244 inside the same launch (dyg_tgn_step)
+        out = self.model.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10, link_predictor=self.pred)
+        return torch.cat([out[4], out[5]]).reshape(-1, 1)
 
     def oracle(self):
         from oracle.sampler import OracleSampler

@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lock = threading.Lock()
 _lib = None
@@ -87,6 +87,23 @@ class ProjSide(ctypes.Structure):
                 ('tokens', ctypes.c_int64), ('ntok', ctypes.c_int32), ('tok_off', ctypes.c_int32)]
 
 
+class TgnStep(ctypes.Structure):
+    """dyg_tgn_step_t (include/dygb200.h), field for field."""
+    _fields_ = ([('he', c_p), ('indptr', c_p), ('num_nodes', ctypes.c_int64), ('src', c_p), ('dst', c_p), ('t', c_p), ('eid', c_p),
+                 ('cand', c_p), ('roots', c_p)] +
+                [(n, ctypes.c_int32) for n in ('B', 'R', 'k', 'H', 'G', 'check_time')] +
+                [('node_raw', c_p), ('ld_node', ctypes.c_int32), ('edge_raw', c_p), ('ld_edge', ctypes.c_int32),
+                 ('F', ctypes.c_int32), ('E', ctypes.c_int32), ('T', ctypes.c_int32)] +
+                [(n, c_p) for n in ('memory', 'last_update', 'mem_view', 'lu_view', 'pending', 'winner', 'msg_store', 'msg_time', 'flag',
+                                    'time_w', 'time_b', 't0', 'wqk')] +
+                [('ld_wqk', ctypes.c_int32), ('cq', c_p), ('wvr', c_p), ('rbias', c_p), ('ln_g', c_p), ('ln_b', c_p), ('ln_eps', ctypes.c_float)] +
+                [(n, c_p) for n in ('m1_w', 'm1_b', 'm2_w', 'm2_b', 'w_ih', 'b_ih', 'w_hh', 'b_hh', 'p1_w', 'p1_b', 'p2_w', 'p2_b',
+                                    'pair_a', 'pair_b')] +
+                [('P', ctypes.c_int32)] +
+                [(n, c_p) for n in ('nbr_ids', 'nbr_eids', 'nbr_t', 'feat', 'qk', 's', 'o', 'y', 'h1', 'msg', 'hnew', 'ph', 'emb', 'prob',
+                                    'barrier', 'phase_ns')])
+
+
 # name -> argtypes, exactly the prototypes of include/dygb200.h (tests check the symbol list against the header)
 SIGNATURES = {
     'dyg_csr_degrees': [c_p, c_p, c_l, c_l, c_p, c_p],
@@ -133,6 +150,7 @@ SIGNATURES = {
                             c_p, c_p, c_p],
     'dyg_gru_update_fwd': [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_l, c_p],
     'dyg_gru_update_bwd': [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_l, c_i, c_p],
+    'dyg_tgn_step': [ctypes.POINTER(TgnStep), c_p],
     'dyg_tgn_check_time': [c_p, c_l, c_p, c_p, c_p, c_p, c_p],
     'dyg_jodie_project': [c_p, c_i, c_p, c_p, c_p, c_l, c_i, c_f, c_f, c_p, c_p, c_p, c_i, c_p],
 }
@@ -161,10 +179,14 @@ def load():
         lib.dyg_csr_fence_entries.restype = c_l
         lib.dyg_csr_fence_entries.argtypes = [c_l]
         lib.dyg_ln_ffn_workspace_bytes.argtypes = []
+        lib.dyg_tgn_step_sizeof.restype = c_l
+        lib.dyg_tgn_step_sizeof.argtypes = []
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = c_i
             fn.argtypes = args
+        if lib.dyg_tgn_step_sizeof() != ctypes.sizeof(TgnStep):
+            raise RuntimeError('dyg_tgn_step_t layout differs between include/dygb200.h and dyglib_b200/_native.py')
         if lib.dyg_abi_version() != ABI_VERSION:
             raise RuntimeError(f'libdygb200.so ABI version {lib.dyg_abi_version()} != {ABI_VERSION} (include/dygb200.h)')
         _lib = lib

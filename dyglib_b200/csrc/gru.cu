@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(tg::THREADS) gru_update_kernel(
     const float* __restrict__ w_ih, const float* __restrict__ b_ih, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
     const int32_t* __restrict__ winner, float* __restrict__ out, int64_t ldo, const int64_t* __restrict__ out_idx,
     float* __restrict__ gates, int64_t P) {
-    __shared__ __align__(16) float smem[tg::Tile<TM, G>::SMEM_FLOATS];
+    extern __shared__ __align__(16) float smem[];   // tg::Tile<TM, G>::SMEM_FLOATS
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
     const int64_t m0 = (int64_t)blockIdx.x * (16 * TM);
     const int u0 = blockIdx.y * 16;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(tg::THREADS) gru_update_kernel(
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[i][g] = 0.f;
     const tg::WGates wmap{u0, D, 16, G};
-    tg::gemm_accum<TM, G>(acc, tg::ASeg{msg, msg_idx, ldm, msg_dim}, m0, P, w_ih, msg_dim, wmap, smem);
+    tg::gemm_accum<TM, G>(acc, tg::ASeg{msg, msg_idx, ldm, msg_dim}, m0, P, w_ih, msg_dim, wmap, smem, t, 1);
     float in_n[TM];   // GRU: the candidate gate keeps its input and hidden halves apart (n = tanh(i_n + r * h_n))
     if (G == 3) {
 #pragma unroll
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(tg::THREADS) gru_update_kernel(
             acc[i][G - 1] = 0.f;
         }
     }
-    tg::gemm_accum<TM, G>(acc, tg::ASeg{hid, hid_idx, ldh, D}, m0, P, w_hh, D, wmap, smem);
+    tg::gemm_accum<TM, G>(acc, tg::ASeg{hid, hid_idx, ldh, D}, m0, P, w_hh, D, wmap, smem, t, 1);
     const int u = u0 + tx;
     if (u >= D) return;
 #pragma unroll
@@ -116,12 +116,17 @@ extern "C" int dyg_gru_update_fwd(const float* msg, int ldm, const int64_t* msg_
     if (P == 0) return 0;
     constexpr int TM = 2;
     dim3 grid((unsigned)((P + 16 * TM - 1) / (16 * TM)), (unsigned)((D + 15) / 16));
+    constexpr int smem3 = tg::Tile<TM, 3>::SMEM_FLOATS * 4, smem1 = tg::Tile<TM, 1>::SMEM_FLOATS * 4;
+    {   // per device and cheap: set on every call (one process may drive several devices)
+        cudaFuncSetAttribute(gru_update_kernel<TM, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+        cudaFuncSetAttribute(gru_update_kernel<TM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    }
     if (G == 3)
-        gru_update_kernel<TM, 3><<<grid, tg::THREADS, 0, as_stream(stream)>>>(msg, ldm, msg_idx, msg_dim, hid, ldh, hid_idx, D, w_ih, b_ih,
-                                                                               w_hh, b_hh, winner, out, ldo, out_idx, gates, P);
+        gru_update_kernel<TM, 3><<<grid, tg::THREADS, smem3, as_stream(stream)>>>(msg, ldm, msg_idx, msg_dim, hid, ldh, hid_idx, D, w_ih, b_ih,
+                                                                                   w_hh, b_hh, winner, out, ldo, out_idx, gates, P);
     else
-        gru_update_kernel<TM, 1><<<grid, tg::THREADS, 0, as_stream(stream)>>>(msg, ldm, msg_idx, msg_dim, hid, ldh, hid_idx, D, w_ih, b_ih,
-                                                                               w_hh, b_hh, winner, out, ldo, out_idx, gates, P);
+        gru_update_kernel<TM, 1><<<grid, tg::THREADS, smem1, as_stream(stream)>>>(msg, ldm, msg_idx, msg_dim, hid, ldh, hid_idx, D, w_ih, b_ih,
+                                                                                   w_hh, b_hh, winner, out, ldo, out_idx, gates, P);
     DYG_LAUNCH_CHECK("dyg_gru_update_fwd");
     return 0;
 }

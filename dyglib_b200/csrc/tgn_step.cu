@@ -26,6 +26,14 @@ namespace {
 
 typedef dyg_tgn_step_t P;
 
+__device__ __forceinline__ void stamp(const P& p, int slot) {
+    if (p.phase_ns && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.phase_ns[slot] = t;
+    }
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -33,8 +41,8 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
         __threadfence();
         atomicAdd(bar, 1u);
         unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        do {   // relaxed polling (an acquire load per poll invalidates the L1 every time: CCTL.IVALL); one fence after the exit
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
         __threadfence();
     }
@@ -344,12 +352,12 @@ template <int TM>
 __device__ __forceinline__ int gemm_tiles(const Gemm& g) { return (int)((g.M + 16 * TM - 1) / (16 * TM)) * ((g.N + 63) / 64); }
 
 template <int TM>
-__device__ __forceinline__ void gemm_tile(const Gemm& g, int tile, float* smem) {
+__device__ __forceinline__ void gemm_tile(const Gemm& g, int tile, float* smem, int t, int bar) {
     constexpr int TN = 4;
     const int ntn = (g.N + 63) / 64;
     const int64_t m0 = (int64_t)(tile / ntn) * (16 * TM);
     const int n0 = (tile % ntn) * 64;
-    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int tx = t & 15, ty = t >> 4;
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -358,7 +366,7 @@ __device__ __forceinline__ void gemm_tile(const Gemm& g, int tile, float* smem) 
     const tg::WRows wmap{n0, g.N};
     int koff = 0;
     for (int sidx = 0; sidx < g.nseg; ++sidx) {
-        tg::gemm_accum<TM, TN>(acc, g.seg[sidx], m0, g.M, g.W + koff, g.ldw, wmap, smem);
+        tg::gemm_accum<TM, TN>(acc, g.seg[sidx], m0, g.M, g.W + koff, g.ldw, wmap, smem, t, bar);
         koff += g.seg[sidx].width;
     }
 #pragma unroll
@@ -379,12 +387,12 @@ __device__ __forceinline__ void gemm_tile(const Gemm& g, int tile, float* smem) 
 
 // recurrent cell of the candidates (nn.GRUCell / nn.RNNCell, models/MemoryModel.py:490-515): 32 candidates x 16 hidden units per tile
 template <int G>
-__device__ __forceinline__ void cell_tile(const P& p, int tile, float* smem) {
+__device__ __forceinline__ void cell_tile(const P& p, int tile, float* smem, int t, int bar) {
     constexpr int TM = 2;
     const int D = p.F, MD = 2 * D + p.T + p.E, nu = (D + 15) / 16;
     const int64_t m0 = (int64_t)(tile / nu) * (16 * TM);
     const int u0 = (tile % nu) * 16;
-    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int tx = t & 15, ty = t >> 4;
     const int64_t Pn = 2 * (int64_t)p.B;
     float acc[TM][G];
 #pragma unroll
@@ -392,7 +400,7 @@ __device__ __forceinline__ void cell_tile(const P& p, int tile, float* smem) {
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[i][g] = 0.f;
     const tg::WGates wmap{u0, D, 16, G};
-    tg::gemm_accum<TM, G>(acc, tg::ASeg{p.msg, nullptr, MD, MD}, m0, Pn, p.w_ih, MD, wmap, smem);
+    tg::gemm_accum<TM, G>(acc, tg::ASeg{p.msg, nullptr, MD, MD}, m0, Pn, p.w_ih, MD, wmap, smem, t, bar);
     float in_n[TM];
     if (G == 3) {
 #pragma unroll
@@ -401,7 +409,7 @@ __device__ __forceinline__ void cell_tile(const P& p, int tile, float* smem) {
             acc[i][G - 1] = 0.f;
         }
     }
-    tg::gemm_accum<TM, G>(acc, tg::ASeg{p.memory, p.cand, D, D}, m0, Pn, p.w_hh, D, wmap, smem);
+    tg::gemm_accum<TM, G>(acc, tg::ASeg{p.memory, p.cand, D, D}, m0, Pn, p.w_hh, D, wmap, smem, t, bar);
     const int u = u0 + tx;
     if (u >= D) return;
 #pragma unroll
@@ -428,10 +436,21 @@ struct Plan {   // tile heights (TM) chosen on the host for the actual R / B so 
     int tm_qk, tm_o, tm_m1, tm_m2, tm_p1;
 };
 
+constexpr int TEAMS = 2;                       // tile teams (256 threads each) per CTA: four warps per scheduler instead of two
+constexpr int CTA_THREADS = TEAMS * tg::THREADS;
+constexpr int TEAM_SMEM_FLOATS = tg::Tile<4, 4>::SMEM_FLOATS;
+
+struct Team {
+    int id, n;        // global team index, number of teams in the grid
+    int t, bar;       // thread index inside the team, its named barrier
+    float* smem;
+};
+
+// warp tasks [0, ntasks) are handed out in groups of 8 (one per warp of a team); `task` counts groups from `first_task`
 template <class F>
-__device__ __forceinline__ void warp_tasks(int first_task, int ntasks, int task, F f) {
-    const int w = (task - first_task) * (tg::THREADS / 32) + (threadIdx.x >> 5);
-    if (w < ntasks) f(w, threadIdx.x & 31);
+__device__ __forceinline__ void warp_tasks(const Team& tm, int first_task, int ntasks, int task, F f) {
+    const int w = (task - first_task) * (tg::THREADS / 32) + (tm.t >> 5);
+    if (w < ntasks) f(w, tm.t & 31);
 }
 
 #define DYG_TM_SWITCH(tm, CALL) \
@@ -445,86 +464,104 @@ __device__ __forceinline__ int tiles_of(const Gemm& g, int tm) {
     const int h = tm == 1 ? 16 : tm == 2 ? 32 : 64;
     return (int)((g.M + h - 1) / h) * ((g.N + 63) / 64);
 }
-__device__ __forceinline__ void run_tile(const Gemm& g, int tm, int tile, float* smem) { DYG_TM_SWITCH(tm, gemm_tile<TM_>(g, tile, smem)); }
+__device__ __forceinline__ void run_tile(const Gemm& g, int tm, int tile, const Team& team) {
+    DYG_TM_SWITCH(tm, gemm_tile<TM_>(g, tile, team.smem, team.t, team.bar));
+}
 
 template <int H, int G>
-__global__ void __launch_bounds__(tg::THREADS, 1) tgn_step_kernel(const __grid_constant__ P p, const Plan plan) {
-    __shared__ __align__(16) float smem[tg::Tile<4, 4>::SMEM_FLOATS];
+__global__ void __launch_bounds__(CTA_THREADS, 1) tgn_step_kernel(const __grid_constant__ P p, const Plan plan) {
+    extern __shared__ __align__(16) float smem_all[];
     unsigned target = 0;
-    const int nb = gridDim.x, bid = blockIdx.x;
-    constexpr int WPB = tg::THREADS / 32;
+    Team team;
+    const int local = threadIdx.x / tg::THREADS;
+    team.id = blockIdx.x * TEAMS + local;
+    team.n = gridDim.x * TEAMS;
+    team.t = threadIdx.x % tg::THREADS;
+    team.bar = 1 + local;
+    team.smem = smem_all + local * TEAM_SMEM_FLOATS;
+    constexpr int WPT = tg::THREADS / 32;
     const int R = p.R, C2 = 2 * p.B;
     const int Dk = p.F + p.E + p.T, Dq = p.F + p.T;
-    auto groups = [](int n) { return (n + WPB - 1) / WPB; };
+    auto groups = [](int n) { return (n + WPT - 1) / WPT; };
 
+    stamp(p, 0);
     // ---- P0
     {
         const int g0 = groups(R), g1 = groups(C2);
-        for (int task = bid; task < g0 + g1; task += nb) {
-            if (task < g0) warp_tasks(0, R, task, [&](int w, int lane) { root_task(p, w, lane); });
-            else warp_tasks(g0, C2, task, [&](int w, int lane) { persist_task(p, w, lane); });
+        for (int task = team.id; task < g0 + g1; task += team.n) {
+            if (task < g0) warp_tasks(team, 0, R, task, [&](int w, int lane) { root_task(p, w, lane); });
+            else warp_tasks(team, g0, C2, task, [&](int w, int lane) { persist_task(p, w, lane); });
         }
     }
     grid_barrier(p.barrier, target);
+    stamp(p, 1);
     // ---- P1
     {
         const Gemm g{{tg::ASeg{p.feat, nullptr, p.F, p.F}, {}}, 1, p.wqk, p.ld_wqk, p.cq, 0, p.qk, H * Dk, R, H * Dk};
         const int nt = tiles_of(g, plan.tm_qk), g1 = groups(C2);
-        for (int task = bid; task < nt + g1; task += nb) {
-            if (task < nt) run_tile(g, plan.tm_qk, task, smem);
-            else warp_tasks(nt, C2, task, [&](int w, int lane) { message_task(p, w, lane); });
+        for (int task = team.id; task < nt + g1; task += team.n) {
+            if (task < nt) run_tile(g, plan.tm_qk, task, team);
+            else warp_tasks(team, nt, C2, task, [&](int w, int lane) { message_task(p, w, lane); });
         }
     }
     grid_barrier(p.barrier, target);
+    stamp(p, 2);
     // ---- P2
     {
         const int nt = ((C2 + 31) / 32) * ((p.F + 15) / 16), g1 = groups(R);
-        for (int task = bid; task < nt + g1; task += nb) {
-            if (task < nt) cell_tile<G>(p, task, smem);
-            else warp_tasks(nt, R, task, [&](int w, int lane) { attend_task<H>(p, w, lane); });
+        for (int task = team.id; task < nt + g1; task += team.n) {
+            if (task < nt) cell_tile<G>(p, task, team.smem, team.t, team.bar);
+            else warp_tasks(team, nt, R, task, [&](int w, int lane) { attend_task<H>(p, w, lane); });
         }
     }
     grid_barrier(p.barrier, target);
+    stamp(p, 3);
     // ---- P3
     {
         const Gemm g{{tg::ASeg{p.s, nullptr, H * Dk, H * Dk}, {}}, 1, p.wvr, H * Dk, p.rbias, 0, p.o, Dq, R, Dq};
         const int nt = tiles_of(g, plan.tm_o), g1 = groups(C2);
-        for (int task = bid; task < nt + g1; task += nb) {
-            if (task < nt) run_tile(g, plan.tm_o, task, smem);
-            else warp_tasks(nt, C2, task, [&](int w, int lane) { commit_task(p, w, lane); });
+        for (int task = team.id; task < nt + g1; task += team.n) {
+            if (task < nt) run_tile(g, plan.tm_o, task, team);
+            else warp_tasks(team, nt, C2, task, [&](int w, int lane) { commit_task(p, w, lane); });
         }
     }
     grid_barrier(p.barrier, target);
+    stamp(p, 4);
     // ---- P4
-    for (int task = bid; task < groups(R); task += nb) warp_tasks(0, R, task, [&](int w, int lane) { layernorm_task(p, w, lane); });
+    for (int task = team.id; task < groups(R); task += team.n) warp_tasks(team, 0, R, task, [&](int w, int lane) { layernorm_task(p, w, lane); });
     grid_barrier(p.barrier, target);
+    stamp(p, 5);
     // ---- P5
     {
         const Gemm g{{tg::ASeg{p.y, nullptr, Dq, Dq}, tg::ASeg{p.feat, nullptr, p.F, p.F}}, 2, p.m1_w, Dq + p.F, p.m1_b, 1, p.h1, p.F, R, p.F};
-        for (int task = bid; task < tiles_of(g, plan.tm_m1); task += nb) run_tile(g, plan.tm_m1, task, smem);
+        for (int task = team.id; task < tiles_of(g, plan.tm_m1); task += team.n) run_tile(g, plan.tm_m1, task, team);
     }
     grid_barrier(p.barrier, target);
+    stamp(p, 6);
     // ---- P6
     {
         const Gemm g{{tg::ASeg{p.h1, nullptr, p.F, p.F}, {}}, 1, p.m2_w, p.F, p.m2_b, 0, p.emb, p.F, R, p.F};
-        for (int task = bid; task < tiles_of(g, plan.tm_m2); task += nb) run_tile(g, plan.tm_m2, task, smem);
+        for (int task = team.id; task < tiles_of(g, plan.tm_m2); task += team.n) run_tile(g, plan.tm_m2, task, team);
     }
     if (p.p1_w) {
         grid_barrier(p.barrier, target);
+        stamp(p, 7);
         // ---- P7
         {
             const Gemm g{{tg::ASeg{p.emb, p.pair_a, p.F, p.F}, tg::ASeg{p.emb, p.pair_b, p.F, p.F}}, 2, p.p1_w, 2 * p.F, p.p1_b, 1, p.ph, p.F, p.P, p.F};
-            for (int task = bid; task < tiles_of(g, plan.tm_p1); task += nb) run_tile(g, plan.tm_p1, task, smem);
+            for (int task = team.id; task < tiles_of(g, plan.tm_p1); task += team.n) run_tile(g, plan.tm_p1, task, team);
         }
         grid_barrier(p.barrier, target);
+        stamp(p, 8);
         // ---- P8
-        for (int task = bid; task < groups(p.P); task += nb) warp_tasks(0, p.P, task, [&](int w, int lane) { score_task(p, w, lane); });
+        for (int task = team.id; task < groups(p.P); task += team.n) warp_tasks(team, 0, p.P, task, [&](int w, int lane) { score_task(p, w, lane); });
     }
+    stamp(p, 15);
     // the last CTA out re-arms the barrier for the next launch (every CTA has passed every barrier before it counts itself out)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(p.barrier + 1, 1u) == (unsigned)nb - 1) {
+        if (atomicAdd(p.barrier + 1, 1u) == (unsigned)gridDim.x - 1) {
             p.barrier[0] = 0;
             p.barrier[1] = 0;
         }
@@ -547,6 +584,8 @@ int pick_tm(int64_t M, int N, int ctas) {
 
 }  // namespace
 
+extern "C" int64_t dyg_tgn_step_sizeof(void) { return (int64_t)sizeof(dyg_tgn_step_t); }
+
 extern "C" int dyg_tgn_step(const dyg_tgn_step_t* ph, dyg_stream_t stream) {
     DYG_CHECK_ARG(ph != nullptr, "dyg_tgn_step: null parameter block");
     const P& p = *ph;
@@ -562,18 +601,24 @@ extern "C" int dyg_tgn_step(const dyg_tgn_step_t* ph, dyg_stream_t stream) {
                   "dyg_tgn_step: null scratch pointer");
     DYG_CHECK_ARG(!p.p1_w || (p.p1_b && p.p2_w && p.p2_b && p.pair_a && p.pair_b && p.ph && p.prob && p.P > 0), "dyg_tgn_step: incomplete link predictor");
     const int ctas = dyg_num_sms();
+    const int teams = ctas * TEAMS;
     const int Dk = p.F + p.E + p.T, Dq = p.F + p.T;
     Plan plan;
-    plan.tm_qk = pick_tm(p.R, p.H * Dk, ctas);
-    plan.tm_o = pick_tm(p.R, Dq, ctas);
-    plan.tm_m1 = pick_tm(p.R, p.F, ctas);
-    plan.tm_m2 = pick_tm(p.R, p.F, ctas);
-    plan.tm_p1 = pick_tm(p.P > 0 ? p.P : 1, p.F, ctas);
+    plan.tm_qk = pick_tm(p.R, p.H * Dk, teams);
+    plan.tm_o = pick_tm(p.R, Dq, teams);
+    plan.tm_m1 = pick_tm(p.R, p.F, teams);
+    plan.tm_m2 = pick_tm(p.R, p.F, teams);
+    plan.tm_p1 = pick_tm(p.P > 0 ? p.P : 1, p.F, teams);
+    constexpr int smem_bytes = TEAMS * TEAM_SMEM_FLOATS * 4;
+    {   // per device and cheap: set on every call (one process may drive several devices)
+        cudaFuncSetAttribute(tgn_step_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaFuncSetAttribute(tgn_step_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    }
     void* args[] = {(void*)&p, (void*)&plan};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3(tg::THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.blockDim = dim3(CTA_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = as_stream(stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;   // co-residency of the whole grid: the phase barrier spins

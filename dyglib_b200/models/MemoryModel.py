@@ -13,6 +13,8 @@ exactly where the reference's does.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from collections import defaultdict
 from collections.abc import MutableMapping
 
@@ -24,7 +26,7 @@ from .. import _native, ops
 from ..ops import _p, _stream
 from ..utils.utils import NeighborSampler, _as_dev
 from .modules import TimeEncoder, MergeLayer, MultiHeadAttention
-from ._temporal import temporal_conv, temporal_conv_train, zero_time_features
+from ._temporal import temporal_conv, temporal_conv_train, zero_time_features, query_constant
 
 
 def gru_update(cell, gates, msg, msg_idx, hid, hid_idx, out, out_idx, winner=None, save_gates=None):
@@ -514,6 +516,10 @@ class MemoryModel(torch.nn.Module):
                                                             self.time_encoder, self.node_feat_dim, self.edge_feat_dim,
                                                             self.time_feat_dim, self.num_layers, self.num_heads, self.dropout)
         self.check_time_order = True
+        # eval-mode batches of TGN with one attention layer run as ONE cooperative launch (dyg_tgn_step); False selects the
+        # kernel-per-step path (the same results up to fp32 summation order; tests compare the two)
+        self.fused_step = os.environ.get('DYG_TGN_FUSED_STEP', '1') != '0'
+        self._step_scratch = {}
         self.to(device)
 
     def compute_src_dst_node_temporal_embeddings(self, src_node_ids: np.ndarray, dst_node_ids: np.ndarray, node_interact_times: np.ndarray,
@@ -528,6 +534,10 @@ class MemoryModel(torch.nn.Module):
         dst = _as_dev(dst_node_ids, torch.int64, dev)
         tq = _as_dev(node_interact_times, torch.float64, dev)
         B = src.numel()
+        if edges_are_positive and self._fused_step_ok(B):
+            assert edge_ids is not None
+            emb, _ = self._fused_step(torch.cat([src, dst]), src, dst, tq, _as_dev(edge_ids, torch.int64, dev), num_neighbors)
+            return emb[:B], emb[B:]
         emb, ret = self._embed_eval([src, dst], tq, num_neighbors)
         if edges_are_positive:
             assert edge_ids is not None
@@ -535,16 +545,27 @@ class MemoryModel(torch.nn.Module):
         return ret[:B], ret[B:]
 
     def compute_pos_neg_temporal_embeddings(self, src_node_ids, dst_node_ids, neg_dst_node_ids, node_interact_times, edge_ids,
-                                            num_neighbors: int = 20):
+                                            num_neighbors: int = 20, link_predictor=None):
         """Addition to the reference API: the two calls its loops make per batch (``train_link_prediction.py:236-247``,
         ``evaluate_models_utils.py:60-80``) -- ``compute(src, neg, t, None, False)`` then ``compute(src, dst, t, edge_ids, True)``
         -- in one.  Both read the same memory state, so the 4 B roots go through ONE embedding pass (half the kernel launches
         of a latency-bound step), then the positive batch advances the memory.
-        Returns (neg_src_emb, neg_dst_emb, pos_src_emb, pos_dst_emb), equal to the two calls' results."""
+        Returns (neg_src_emb, neg_dst_emb, pos_src_emb, pos_dst_emb), equal to the two calls' results.
+        ``link_predictor`` (a ``MergeLayer``, ``model[1]`` of the reference's ``nn.Sequential``): additionally returns
+        ``(pos_prob, neg_prob)`` = ``link_predictor(src_emb, dst_emb).squeeze(-1).sigmoid()`` of the two pairs
+        (``train_link_prediction.py:243-244``); on the fused TGN path they come out of the same launch."""
+        def with_probs(a, b, c, d):
+            if link_predictor is None:
+                return a, b, c, d
+            lp = link_predictor
+            pr = ops.mlp2([torch.cat([c, a]), torch.cat([d, b])], lp.fc1.weight.detach(), lp.fc1.bias.detach(), lp.fc2.weight.detach(),
+                          lp.fc2.bias.detach(), act2=ops.ACT_SIGMOID).reshape(-1)
+            n = c.shape[0]
+            return a, b, c, d, pr[:n], pr[n:]
         if self.training and torch.is_grad_enabled():
             a, b = self.compute_src_dst_node_temporal_embeddings(src_node_ids, neg_dst_node_ids, node_interact_times, None, False, num_neighbors)
             c, d = self.compute_src_dst_node_temporal_embeddings(src_node_ids, dst_node_ids, node_interact_times, edge_ids, True, num_neighbors)
-            return a, b, c, d
+            return with_probs(a, b, c, d)
         self._refresh_view_if_stale()
         dev = self.node_raw_features.device
         src = _as_dev(src_node_ids, torch.int64, dev)
@@ -552,10 +573,101 @@ class MemoryModel(torch.nn.Module):
         neg = _as_dev(neg_dst_node_ids, torch.int64, dev)
         tq = _as_dev(node_interact_times, torch.float64, dev)
         B = src.numel()
-        emb, ret = self._embed_eval([src, neg, src, dst], tq, num_neighbors)
         assert edge_ids is not None
+        if self._fused_step_ok(B):
+            # the src embedding of the negative pair equals that of the positive pair (same memory state, same times): 3 B roots
+            emb, prob = self._fused_step(torch.cat([src, neg, dst]), src, dst, tq, _as_dev(edge_ids, torch.int64, dev), num_neighbors,
+                                         link_predictor=link_predictor, pairs='pos_neg')
+            out = (emb[:B], emb[B:2 * B], emb[:B], emb[2 * B:])
+            return out if link_predictor is None else out + (prob[:B], prob[B:])
+        emb, ret = self._embed_eval([src, neg, src, dst], tq, num_neighbors)
         self._advance(src, dst, tq, _as_dev(edge_ids, torch.int64, dev), emb[3 * B:], emb[2 * B:3 * B], None)
-        return ret[:B], ret[B:2 * B], ret[2 * B:3 * B], ret[3 * B:]
+        return with_probs(ret[:B], ret[B:2 * B], ret[2 * B:3 * B], ret[3 * B:])
+
+    # ------------------------------------------------------------------ one launch per batch (dyg_tgn_step)
+    def _fused_step_ok(self, B):
+        em = self.embedding_module
+        return (self.fused_step and self.model_name == 'TGN' and self.num_layers == 1 and self.num_heads == 2 and B > 0 and
+                em.neighbor_sampler.sample_neighbor_strategy == 'recent' and self.node_feat_dim % 4 == 0 and self.edge_feat_dim % 4 == 0 and
+                self.time_feat_dim % 4 == 0 and self.node_feat_dim + self.edge_feat_dim <= 384 and self.time_feat_dim <= 128 and
+                self.node_raw_features.stride(0) % 4 == 0 and self.edge_raw_features.stride(0) % 4 == 0)
+
+    def _fused_step(self, roots, src, dst, tq, eid, k, link_predictor=None, pairs=None):
+        """Embeddings of ``roots`` (root r at time tq[r % B]) on the look-ahead view, then the memory update of the positive batch
+        (src, dst, tq, eid), then optionally the link probabilities -- one cooperative launch (csrc/tgn_step.cu)."""
+        lib = _native.load()
+        dev = self.node_raw_features.device
+        bank, em, sampler = self.memory_bank, self.embedding_module, self.embedding_module.neighbor_sampler
+        st = bank._ensure()
+        attn, merge = em.temporal_conv_layers[0], em.merge_layers[0]
+        cell = self.memory_updater.memory_updater
+        F_, E_, T_ = self.node_feat_dim, self.edge_feat_dim, self.time_feat_dim
+        H = self.num_heads
+        Dk, Dq, MD = F_ + E_ + T_, F_ + T_, self.message_dim
+        B, R = src.numel(), roots.numel()
+        P_ = 2 * B if link_predictor is not None else 0
+        key = (R, B, P_, int(k), str(dev))
+        sc = self._step_scratch.get(key)
+        if sc is None:
+            f32 = dict(dtype=torch.float32, device=dev)
+            sc = dict(nbr_ids=torch.empty((R, k), dtype=torch.int64, device=dev), nbr_eids=torch.empty((R, k), dtype=torch.int64, device=dev),
+                      nbr_t=torch.empty((R, k), **f32), feat=torch.empty((R, F_), **f32), qk=torch.empty((R, H * Dk), **f32),
+                      s=torch.empty((R, H * Dk), **f32), o=torch.empty((R, Dq), **f32), y=torch.empty((R, Dq), **f32),
+                      h1=torch.empty((R, F_), **f32), msg=torch.empty((2 * B, MD), **f32), hnew=torch.empty((2 * B, F_), **f32),
+                      ph=torch.empty((max(P_, 1), F_), **f32), barrier=torch.zeros(2, dtype=torch.int32, device=dev))
+            if P_:
+                ar = torch.arange(B, dtype=torch.int64, device=dev)
+                sc['pair_a'] = torch.cat([ar, ar])                       # pos pairs (src, dst) then neg pairs (src, neg)
+                sc['pair_b'] = torch.cat([ar + 2 * B, ar + B])
+            if len(self._step_scratch) > 8:
+                self._step_scratch.clear()
+            self._step_scratch[key] = sc
+        emb = torch.empty((R, F_), dtype=torch.float32, device=dev)
+        prob = torch.empty(max(P_, 1), dtype=torch.float32, device=dev)
+        cand = torch.cat([src, dst])
+        t0 = zero_time_features(self.time_encoder, dev)
+        wqk, wvr = attn.folded()
+        cq = query_constant(attn, self.time_encoder, t0)
+        w, b = self.time_encoder.wb()
+        p = _native.TgnStep()
+        keep = []
+
+        def ptr(x):
+            keep.append(x)
+            return _p(x).value if x is not None else None
+        p.he, p.indptr, p.num_nodes = ptr(sampler.halfedges), ptr(sampler.indptr), sampler.num_nodes
+        p.src, p.dst, p.t, p.eid, p.cand, p.roots = ptr(src), ptr(dst), ptr(tq), ptr(eid), ptr(cand), ptr(roots)
+        p.B, p.R, p.k, p.H, p.G, p.check_time = B, R, int(k), H, self.memory_updater.gates, int(self.check_time_order)
+        p.node_raw, p.ld_node = ptr(self.node_raw_features), self.node_raw_features.stride(0)
+        p.edge_raw, p.ld_edge = ptr(self.edge_raw_features), self.edge_raw_features.stride(0)
+        p.F, p.E, p.T = F_, E_, T_
+        p.memory, p.last_update = ptr(bank.node_memories.data), ptr(bank.node_last_updated_times.data)
+        p.mem_view, p.lu_view, p.pending, p.winner = ptr(st['mem_view']), ptr(st['lu_view']), ptr(st['pending']), ptr(st['winner'])
+        p.msg_store, p.msg_time, p.flag = ptr(st['msg_store']), ptr(st['msg_time']), ptr(st['flag'])
+        p.time_w, p.time_b, p.t0 = ptr(w), ptr(b), ptr(t0)
+        p.wqk, p.ld_wqk, p.cq = ptr(wqk), wqk.stride(0), ptr(cq)
+        p.wvr, p.rbias = ptr(wvr), ptr(attn.residual_fc.bias.detach())
+        p.ln_g, p.ln_b, p.ln_eps = ptr(attn.layer_norm.weight.detach()), ptr(attn.layer_norm.bias.detach()), float(attn.layer_norm.eps)
+        p.m1_w, p.m1_b = ptr(merge.fc1.weight.detach()), ptr(merge.fc1.bias.detach())
+        p.m2_w, p.m2_b = ptr(merge.fc2.weight.detach()), ptr(merge.fc2.bias.detach())
+        p.w_ih, p.b_ih = ptr(cell.weight_ih.detach()), ptr(cell.bias_ih.detach())
+        p.w_hh, p.b_hh = ptr(cell.weight_hh.detach()), ptr(cell.bias_hh.detach())
+        if P_:
+            lp = link_predictor
+            p.p1_w, p.p1_b = ptr(lp.fc1.weight.detach()), ptr(lp.fc1.bias.detach())
+            p.p2_w, p.p2_b = ptr(lp.fc2.weight.detach().reshape(-1)), ptr(lp.fc2.bias.detach())
+            p.pair_a, p.pair_b, p.P = ptr(sc['pair_a']), ptr(sc['pair_b']), P_
+        for name in ('nbr_ids', 'nbr_eids', 'nbr_t', 'feat', 'qk', 's', 'o', 'y', 'h1', 'msg', 'hnew', 'ph', 'barrier'):
+            setattr(p, name, ptr(sc[name]))
+        p.emb, p.prob = ptr(emb), ptr(prob)
+        if getattr(self, 'phase_ns', None) is not None:      # profiling hook: per-phase globaltimer stamps (scripts/tgn_phases.py)
+            p.phase_ns = ptr(self.phase_ns)
+        flops = 2.0 * (R * (F_ * H * Dk + H * Dk * Dq + (Dq + F_) * F_ + F_ * F_) + 2 * B * self.memory_updater.gates * F_ * (MD + F_) +
+                       P_ * 2 * F_ * F_)
+        with ops._Timed('tgn_step_kernel', flops, 4.0 * (R * k * (2 * F_ + E_) + 2 * B * (2 * MD + 4 * F_))):
+            _native.check(lib.dyg_tgn_step(ctypes.byref(p), _stream()))
+        ops._count()
+        return emb, prob
 
     def _cell_key(self):
         """Identity of the recurrent cell's weights (the look-ahead view of the pending nodes is a function of them)."""

@@ -37,6 +37,14 @@ def zero_time_features(time_encoder, device):
     return _cached('t0', (time_encoder.w.weight, time_encoder.w.bias), build)
 
 
+def query_constant(attn, time_encoder, t0):
+    """W_qk[:, F:] @ cos(b): the part of the folded query that comes from the root's (zero-interval) time encoding."""
+    wqk, _ = attn.folded()
+    F_, T_ = attn.node_feat_dim, attn.time_feat_dim
+    return _cached('cq', (attn.query_projection.weight, attn.key_projection.weight, time_encoder.w.weight, time_encoder.w.bias),
+                   lambda: ops.linear([ops.seg_rows(t0.reshape(1, T_))], 1, wqk[:, F_:], ldw=wqk.stride(0)).reshape(-1))
+
+
 def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node_tab2, nbr_ids, nbr_dense,
                   edge_tab, nbr_eids, tq, nbr_t, k, zero_row0=0):
     """conv, root_feat: (n, F) dense; neighbours either lazily gathered from node_tab (+node_tab2) by nbr_ids
@@ -46,9 +54,7 @@ def temporal_conv(attn, merge, time_encoder, t0, conv, root_feat, node_tab, node
     H = attn.num_heads
     wqk, wvr = attn.folded()
     w, b = time_encoder.wb()
-    # constant part of the query: W_qk[:, F:] @ cos(b)
-    cq = _cached('cq', (attn.query_projection.weight, attn.key_projection.weight, time_encoder.w.weight, time_encoder.w.bias),
-                 lambda: ops.linear([ops.seg_rows(t0.reshape(1, T_))], 1, wqk[:, F_:], ldw=wqk.stride(0)).reshape(-1))
+    cq = query_constant(attn, time_encoder, t0)
     qk = ops.linear([ops.seg_rows(conv)], n, wqk[:, :F_], bias=cq, ldw=wqk.stride(0))
     flat_ids = nbr_ids.reshape(-1)
     if nbr_dense is None:

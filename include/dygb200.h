@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 2
+#define DYG_ABI_VERSION 3
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -321,6 +321,44 @@ int dyg_gru_update_bwd(const float* gates, const float* hid, int ldh, const int6
  * flag[0] set to 1 if any last_update[v] > (float)msg_time for pending v in node_ids. */
 int dyg_tgn_check_time(const int64_t* node_ids, int64_t n, const float* last_update, const float* lu_view,
                        const uint8_t* pending, int32_t* flag, dyg_stream_t stream);
+
+/* ---- a17-a20 in one launch: a whole batch of the TGN / DyRep-style memory model with a 1-layer graph-attention embedding
+ * (MemoryModel.compute_src_dst_node_temporal_embeddings, models/MemoryModel.py:87-168, called for the negative and the positive
+ * pair of a batch as train_link_prediction.py:236-247 does, plus the MergeLayer link predictor of :243-244) ----
+ * One cooperative, persistent kernel walks the dependency chain as phases separated by a grid barrier (csrc/tgn_step.cu):
+ * recent-neighbour search + gather for the R roots, folded attention on the look-ahead memories, LayerNorm, MergeLayer,
+ * optional link probabilities; and for the 2B candidate messages of the positive batch: time-order check, persist, last-message
+ * election, raw-message build, recurrent cell, commit into the look-ahead view / message store.  Semantics are those of the
+ * separate entry points above (dyg_sample_recent, dyg_gather_rows, dyg_linear, dyg_temporal_attend, dyg_layernorm,
+ * dyg_tgn_check_time / persist / select_last / build_messages, dyg_gru_update_fwd, dyg_tgn_cell_commit) run in that order.
+ * Root r is embedded at time t[r % B]; cand[c] = c < B ? src[c] : dst[c - B].  All widths / leading dimensions % 4 == 0,
+ * F + E <= 384, T <= 128, H = 2.  `barrier`: 2 uint32, zeroed once by the caller and left zero by every launch. */
+typedef struct {
+    const dyg_halfedge_t* he; const int64_t* indptr; int64_t num_nodes;              /* device CSR */
+    const int64_t* src; const int64_t* dst; const double* t; const int64_t* eid;      /* the positive batch (B events) */
+    const int64_t* cand;                                                              /* (2B) = [src | dst] */
+    const int64_t* roots;                                                             /* (R) node ids to embed */
+    int32_t B, R, k, H, G, check_time;
+    const float* node_raw; int32_t ld_node; const float* edge_raw; int32_t ld_edge; int32_t F, E, T;
+    float* memory; float* last_update; float* mem_view; float* lu_view; uint8_t* pending; int32_t* winner;
+    float* msg_store; double* msg_time; int32_t* flag;
+    const float* time_w; const float* time_b; const float* t0;                        /* TimeEncoder w, b and cos(b) */
+    const float* wqk; int32_t ld_wqk; const float* cq;                                /* folded query weights (H*Dk, >= F) and constant part (H*Dk) */
+    const float* wvr; const float* rbias;                                             /* folded value / residual_fc weights (Dq, H*Dk), bias (Dq) */
+    const float* ln_g; const float* ln_b; float ln_eps;
+    const float* m1_w; const float* m1_b; const float* m2_w; const float* m2_b;       /* MergeLayer (F, Dq + F), (F, F) */
+    const float* w_ih; const float* b_ih; const float* w_hh; const float* b_hh;       /* recurrent cell (G*F, 2F+T+E), (G*F, F) */
+    const float* p1_w; const float* p1_b; const float* p2_w; const float* p2_b;       /* link predictor MergeLayer or NULL */
+    const int64_t* pair_a; const int64_t* pair_b; int32_t P;                          /* prob[i] = predictor(emb[pair_a[i]], emb[pair_b[i]]) */
+    int64_t* nbr_ids; int64_t* nbr_eids; float* nbr_t;                                /* scratch (R, k) */
+    float* feat; float* qk; float* s; float* o; float* y; float* h1;                  /* scratch (R, F), (R, H*Dk) x2, (R, Dq) x2, (R, F) */
+    float* msg; float* hnew; float* ph;                                               /* scratch (2B, 2F+T+E), (2B, F), (P, F) */
+    float* emb; float* prob;                                                          /* outputs (R, F), (P) */
+    uint32_t* barrier;
+    unsigned long long* phase_ns;   /* NULL, or 16 slots: globaltimer at the start, after every phase and at the end (profiling) */
+} dyg_tgn_step_t;
+int dyg_tgn_step(const dyg_tgn_step_t* params_host, dyg_stream_t stream);
+int64_t dyg_tgn_step_sizeof(void); /* sizeof(dyg_tgn_step_t), for bindings to check their mirror of the struct */
 
 /* JODIE TimeProjectionEmbedding (models/MemoryModel.py:534-545) fused with the time-shift normalisation
  * (models/MemoryModel.py:114-118): out[m,:] = mem[ids[m],:] * (1 + ((t[m]-lu[ids[m]]-mean)/std) * w + b). */
