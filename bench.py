@@ -752,7 +752,7 @@ def measure_model(ctx, args, name, K, W, with_cpu=True):
 
 TENSOR_KERNELS = ('linear_kernel', 'linear_tc_kernel', 'gemm_bf16x3_kernel', 'ln_ffn_bf16x3_kernel', 'qkv_ln_gemm_kernel',
                   'seq_attention_tc5_kernel', 'tgn_step_kernel', 'gru_update_kernel')
-FFMA_KERNELS = ('linear_kernel', 'tgn_step_kernel', 'gru_update_kernel')
+FFMA_KERNELS = ('linear_kernel', 'gru_update_kernel')
 
 
 def step_roofline(wl, pk, events_per_step, ms_per_step, launches_per_step):

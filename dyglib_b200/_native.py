@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lock = threading.Lock()
 _lib = None
@@ -87,6 +87,11 @@ class ProjSide(ctypes.Structure):
                 ('tokens', ctypes.c_int64), ('ntok', ctypes.c_int32), ('tok_off', ctypes.c_int32)]
 
 
+class Planes(ctypes.Structure):
+    """dyg_planes_t (include/dygb200.h)."""
+    _fields_ = [('hi', c_p), ('mid', c_p), ('ld', ctypes.c_int64)]
+
+
 class TgnStep(ctypes.Structure):
     """dyg_tgn_step_t (include/dygb200.h), field for field."""
     _fields_ = ([('he', c_p), ('indptr', c_p), ('num_nodes', ctypes.c_int64), ('src', c_p), ('dst', c_p), ('t', c_p), ('eid', c_p),
@@ -95,13 +100,14 @@ class TgnStep(ctypes.Structure):
                 [('node_raw', c_p), ('ld_node', ctypes.c_int32), ('edge_raw', c_p), ('ld_edge', ctypes.c_int32),
                  ('F', ctypes.c_int32), ('E', ctypes.c_int32), ('T', ctypes.c_int32)] +
                 [(n, c_p) for n in ('memory', 'last_update', 'mem_view', 'lu_view', 'pending', 'winner', 'msg_store', 'msg_time', 'flag',
-                                    'time_w', 'time_b', 't0', 'wqk')] +
-                [('ld_wqk', ctypes.c_int32), ('cq', c_p), ('wvr', c_p), ('rbias', c_p), ('ln_g', c_p), ('ln_b', c_p), ('ln_eps', ctypes.c_float)] +
-                [(n, c_p) for n in ('m1_w', 'm1_b', 'm2_w', 'm2_b', 'w_ih', 'b_ih', 'w_hh', 'b_hh', 'p1_w', 'p1_b', 'p2_w', 'p2_b',
-                                    'pair_a', 'pair_b')] +
+                                    'time_w', 'time_b', 't0')] +
+                [(n, Planes) for n in ('wqk', 'wvr', 'm1', 'm2', 'w_ih', 'w_hh', 'p1')] +
+                [('cq', c_p), ('rbias', c_p), ('ln_g', c_p), ('ln_b', c_p), ('ln_eps', ctypes.c_float)] +
+                [(n, c_p) for n in ('m1_b', 'm2_b', 'b_ih', 'b_hh', 'p1_b', 'p2_w', 'p2_b', 'pair_a', 'pair_b')] +
                 [('P', ctypes.c_int32)] +
-                [(n, c_p) for n in ('nbr_ids', 'nbr_eids', 'nbr_t', 'feat', 'qk', 's', 'o', 'y', 'h1', 'msg', 'hnew', 'ph', 'emb', 'prob',
-                                    'barrier', 'phase_ns')])
+                [(n, c_p) for n in ('nbr_ids', 'nbr_eids', 'nbr_t', 'feat', 'qk', 'o', 'msg', 'hnew', 'ph')] +
+                [(n, Planes) for n in ('feat_pl', 'msg_pl', 's_pl', 'y_pl', 'h1_pl')] +
+                [(n, c_p) for n in ('emb', 'prob', 'barrier', 'phase_ns')])
 
 
 # name -> argtypes, exactly the prototypes of include/dygb200.h (tests check the symbol list against the header)

@@ -5,8 +5,9 @@
 // predictor of train_link_prediction.py:243-244) moves ~1 GFLOP and ~20 MB through a chain of dependent steps.  As separate
 // kernels that chain was 25-29 launches at ~10 us each (round 1: 269 us per step, 1 % of its HBM time).  Here a persistent grid
 // (one CTA per SM, cooperative launch) walks the chain as PHASES separated by a grid barrier; inside a phase every CTA takes
-// tile tasks (fp32 FFMA tiles of tile_gemm.cuh, 256 threads) and warp tasks (one warp per root / candidate message) from a
-// static list.  The embedding chain and the memory-update chain of the same batch are independent until the commit, so they
+// tile tasks (BF16x3 mma.sync tiles of mma_tile.cuh, teams of 256 threads, two teams per CTA) and warp tasks (one warp per root /
+// candidate message) from a static list.  Every operand of a dense phase is written as BF16x3 planes by the phase that produces it,
+// so a tile stage is plain 16-byte cp.async copies.  The embedding chain and the memory-update chain of the same batch are independent until the commit, so they
 // share phases:
 //   P0  roots: lower bound on the CSR + recent-neighbour gather + layer-0 features (memory view + raw)
 //       candidates: time-order check, persist the look-ahead memories of the batch's nodes, last-message election
@@ -14,13 +15,16 @@
 //   P2  roots: folded temporal attention (gather + time encoding + softmax + sum)   | GRU / RNN cell tiles of the candidates
 //   P3  o = s Wvr^T + b                                    | winners: commit new look-ahead memories + message store
 //   P4  y = LayerNorm(o + [feat | cos(b)])
-//   P5  h = relu([y | feat] W1^T + b1)       P6  emb = h W2^T + b2
-//   P7  ph = relu([emb[a] | emb[b]] Wp1^T + bp1)           P8  prob = sigmoid(ph . wp2 + bp2)         (optional link predictor)
+//   P5  h = relu([y | feat] W1^T + b1)
+//   P6  emb = h W2^T + b2                                  | ph = relu([h[a] | h[b]] (Wp1 W2)^T + const)   (link predictor folded onto h)
+//   P8  prob = sigmoid(ph . wp2 + bp2)
 // Reads of the look-ahead view (P0, P2) precede its update (P3); every scratch buffer is written in one phase and read in a
 // later one through L2 (cp.async.cg / ld.global.cg), so no SM can hold a stale L1 line of it.
+// History (profiles/r02_tgn_step.md): fp32 FFMA tiles, one CTA per SM: 164 us per step (shared-memory bound: every LDS.128 is four
+// wavefronts; "compute only" 85 % of a phase); this version: see the phase table there.
 #include <cooperative_groups.h>
 #include <math.h>
-#include "tile_gemm.cuh"
+#include "mma_tile.cuh"
 
 namespace {
 
@@ -50,6 +54,26 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
 }
 
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ mt::Planes planes(const dyg_planes_t& d) {
+    return mt::Planes{reinterpret_cast<const mt::bf16*>(d.hi), reinterpret_cast<const mt::bf16*>(d.mid), d.ld};
+}
+__device__ __forceinline__ mt::bf16* hi_of(const dyg_planes_t& d) { return reinterpret_cast<mt::bf16*>(const_cast<void*>(d.hi)); }
+__device__ __forceinline__ mt::bf16* mid_of(const dyg_planes_t& d) { return reinterpret_cast<mt::bf16*>(const_cast<void*>(d.mid)); }
+// four consecutive values at columns c .. c + 3 (c % 4 == 0) of row `row`
+__device__ __forceinline__ void store_planes4(const dyg_planes_t& d, int64_t row, int c, float4 v) {
+    uint32_t h0, m0, h1, m1;
+    mt::split2(v.x, v.y, h0, m0);
+    mt::split2(v.z, v.w, h1, m1);
+    *reinterpret_cast<uint2*>(hi_of(d) + row * d.ld + c) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(mid_of(d) + row * d.ld + c) = make_uint2(m0, m1);
+}
+// one value per lane at column c0 + lane (c0 even; `valid`: this lane's column exists): even lanes store the pair (own, next lane's)
+__device__ __forceinline__ void store_planes_lane(const dyg_planes_t& d, int64_t row, int c0, int lane, float v, bool valid) {
+    const float nxt = __shfl_down_sync(0xffffffffu, v, 1);
+    const bool nvalid = __shfl_down_sync(0xffffffffu, (int)valid, 1) != 0;
+    if (valid && !(lane & 1)) mt::store_split2(hi_of(d), mid_of(d), d.ld, row, c0 + lane, v, (lane < 31 && nvalid) ? nxt : 0.f);
+}
 
 // rows with t < tq among the deg records from a: the 32 lanes probe 32 evenly spaced records per round (33-ary search)
 __device__ __forceinline__ int64_t warp_lower_bound(const dyg_halfedge_t* __restrict__ he, int64_t a, int64_t deg, double tq, int lane) {
@@ -101,7 +125,9 @@ __device__ __forceinline__ void root_task(const P& p, int r, int lane) {
     for (int c = lane * 4; c < p.F; c += 128) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(raw + c));
         const float4 m = *reinterpret_cast<const float4*>(mem + c);
-        *reinterpret_cast<float4*>(out + c) = make_float4(x.x + m.x, x.y + m.y, x.z + m.z, x.w + m.w);
+        const float4 f = make_float4(x.x + m.x, x.y + m.y, x.z + m.z, x.w + m.w);
+        *reinterpret_cast<float4*>(out + c) = f;
+        store_planes4(p.feat_pl, r, c, f);
     }
 }
 
@@ -127,13 +153,25 @@ __device__ __forceinline__ void message_task(const P& p, int c, int lane) {
     const int D = p.F;
     float* o = p.msg + (int64_t)c * (2 * D + p.T + p.E);
     for (int j = lane * 4; j < D; j += 128) {
-        *reinterpret_cast<float4*>(o + j) = ldcg4(p.memory + owner * D + j);
-        *reinterpret_cast<float4*>(o + D + j) = ldcg4(p.memory + other * D + j);
+        const float4 a = ldcg4(p.memory + owner * D + j), b = ldcg4(p.memory + other * D + j);
+        *reinterpret_cast<float4*>(o + j) = a;
+        *reinterpret_cast<float4*>(o + D + j) = b;
+        store_planes4(p.msg_pl, c, j, a);
+        store_planes4(p.msg_pl, c, D + j, b);
     }
     const float dt = (float)p.t[ev] - __ldcg(p.last_update + owner);
-    for (int j = lane; j < p.T; j += 32) o[2 * D + j] = dyg_time_enc(dt, __ldg(p.time_w + j), __ldg(p.time_b + j));
+    for (int j0 = 0; j0 < p.T; j0 += 32) {
+        const int j = j0 + lane;
+        const float v = j < p.T ? dyg_time_enc(dt, __ldg(p.time_w + j), __ldg(p.time_b + j)) : 0.f;
+        if (j < p.T) o[2 * D + j] = v;
+        store_planes_lane(p.msg_pl, c, 2 * D + j0, lane, v, j < p.T);
+    }
     const float* ep = p.edge_raw + p.eid[ev] * p.ld_edge;
-    for (int j = lane * 4; j < p.E; j += 128) *reinterpret_cast<float4*>(o + 2 * D + p.T + j) = __ldg(reinterpret_cast<const float4*>(ep + j));
+    for (int j = lane * 4; j < p.E; j += 128) {
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(ep + j));
+        *reinterpret_cast<float4*>(o + 2 * D + p.T + j) = e4;
+        store_planes4(p.msg_pl, c, 2 * D + p.T + j, e4);
+    }
     if (lane == 0) p.pending[owner] = 0;   // clear_node_raw_messages (:145); winners are set again by the commit
 }
 
@@ -278,211 +316,222 @@ __device__ __forceinline__ void attend_task(const P& p, int r, int lane) {
             }
         }
     }
+    // s[r, h, :] as operand planes of the next contraction (o = s Wvr^T)
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         const float inv = 1.f / den[h];
-        float* orow = p.s + (int64_t)r * (H * Dk) + h * Dk;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int c = i * 32 + lane;
             if (c < NE4) {
                 float4 v = acc[h][i];
                 v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-                *(reinterpret_cast<float4*>(orow) + c) = v;
+                store_planes4(p.s_pl, r, h * Dk + 4 * c, v);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = i * 32 + lane;
-            if (c < T) orow[NE4 * 4 + c] = acct[h][i] * inv;
-        }
+        for (int i = 0; i < 4; ++i) store_planes_lane(p.s_pl, r, h * Dk + NE4 * 4 + i * 32, lane, acct[h][i] * inv, i * 32 + lane < T);
     }
 }
 
-// y = LayerNorm(o + [feat | cos(b)]) (models/modules.py:199 with the residual of :155,:197); Dq = F + T <= 512
+// y = LayerNorm(o + [feat | cos(b)]) (models/modules.py:199 with the residual of :155,:197); Dq = F + T <= 512.  Every load of the row
+// (o, residual, gamma, beta) is issued before the first use: a first version that fetched gamma / beta inside the store loop spent
+// ~6 us per row on nine exposed L2 round trips.
 __device__ __forceinline__ void layernorm_task(const P& p, int r, int lane) {
     const int Dq = p.F + p.T;
-    float v[16];
-    float sum = 0.f;
+    float v[16], gm[16], bt[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int c = i * 32 + lane;
-        float x = 0.f;
-        if (c < Dq) x = __ldcg(p.o + (int64_t)r * Dq + c) + (c < p.F ? __ldcg(p.feat + (int64_t)r * p.F + c) : __ldg(p.t0 + c - p.F));
-        v[i] = x;
-        sum += x;
+        const int c = i * 32 + lane, cc = c < Dq ? c : Dq - 1;
+        v[i] = gm[i] = bt[i] = 0.f;
+        if (i * 32 < Dq) {   // warp-uniform
+            const float* rp = cc < p.F ? p.feat + (int64_t)r * p.F + cc : p.t0 + (cc - p.F);
+            const float a = __ldcg(p.o + (int64_t)r * Dq + cc), b = __ldcg(rp);
+            gm[i] = __ldg(p.ln_g + cc);
+            bt[i] = __ldg(p.ln_b + cc);
+            v[i] = c < Dq ? a + b : 0.f;
+        }
     }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sum += v[i];
     const float mean = warp_sum(sum) / Dq;
     float var = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int c = i * 32 + lane;
-        const float d = c < Dq ? v[i] - mean : 0.f;
+        const float d = (i * 32 + lane < Dq) ? v[i] - mean : 0.f;
         var = fmaf(d, d, var);
     }
     const float rstd = rsqrtf(warp_sum(var) / Dq + p.ln_eps);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int c = i * 32 + lane;
-        if (c < Dq) p.y[(int64_t)r * Dq + c] = (v[i] - mean) * rstd * __ldg(p.ln_g + c) + __ldg(p.ln_b + c);
-    }
+    for (int i = 0; i < 16; ++i)
+        if (i * 32 < Dq) store_planes_lane(p.y_pl, r, i * 32, lane, (v[i] - mean) * rstd * gm[i] + bt[i], i * 32 + lane < Dq);
 }
 
 __device__ __forceinline__ void score_task(const P& p, int i, int lane) {
     float d = 0.f;
     for (int c = lane; c < p.F; c += 32) d = fmaf(__ldcg(p.ph + (int64_t)i * p.F + c), __ldg(p.p2_w + c), d);
     d = warp_sum(d);
-    if (lane == 0) p.prob[i] = tg::sigmoidf_(d + __ldg(p.p2_b));
+    if (lane == 0) p.prob[i] = mt::sigmoidf_(d + __ldg(p.p2_b));
 }
 
 // ------------------------------------------------------------------------------------------------ tile tasks
 struct Gemm {
-    tg::ASeg seg[2];
+    mt::ASeg seg[2];
+    int wcol[2];          // first column of each segment inside the (segment-padded) weight planes
     int nseg;
-    const float* W;
-    int64_t ldw;
+    mt::Planes W;
     const float* bias;
     int relu;
-    float* C;
+    float* C;             // fp32 output (may be NULL)
     int64_t ldc;
+    dyg_planes_t Cp;      // plane output (hi NULL: none)
     int64_t M;
     int N;
 };
-template <int TM>
-__device__ __forceinline__ int gemm_tiles(const Gemm& g) { return (int)((g.M + 16 * TM - 1) / (16 * TM)) * ((g.N + 63) / 64); }
 
-template <int TM>
-__device__ __forceinline__ void gemm_tile(const Gemm& g, int tile, float* smem, int t, int bar) {
-    constexpr int TN = 4;
-    const int ntn = (g.N + 63) / 64;
-    const int64_t m0 = (int64_t)(tile / ntn) * (16 * TM);
-    const int n0 = (tile % ntn) * 64;
-    const int tx = t & 15, ty = t >> 4;
-    float acc[TM][TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    const tg::WRows wmap{n0, g.N};
-    int koff = 0;
-    for (int sidx = 0; sidx < g.nseg; ++sidx) {
-        tg::gemm_accum<TM, TN>(acc, g.seg[sidx], m0, g.M, g.W + koff, g.ldw, wmap, smem, t, bar);
-        koff += g.seg[sidx].width;
-    }
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-        const int n = n0 + tx + 16 * j;
-        if (n >= g.N) continue;
-        const float b = g.bias ? __ldg(g.bias + n) : 0.f;
-#pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            const int64_t m = m0 + ty + 16 * i;
-            if (m >= g.M) continue;
-            float v = acc[i][j] + b;
-            if (g.relu) v = fmaxf(v, 0.f);
-            g.C[m * g.ldc + n] = v;
+// 8 warps as 2 x 4; MI = 1: 32 x 64 tiles, MI = 2: 64 x 64 tiles
+template <int MI>
+__device__ __forceinline__ void gemm_tile(const Gemm& g, int tile, mt::bf16* smem, int t, int bar, unsigned long long* dbg = nullptr) {
+    constexpr int WM = 2, WN = 4, NI = 2, BM = WM * MI * 16, BN = WN * NI * 8;
+    auto tick = [&](int slot) {
+        if (dbg && t == 0) {
+            unsigned long long x;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(x));
+            dbg[slot] = x;
         }
+    };
+    tick(9);
+    const int ntn = (g.N + BN - 1) / BN;
+    const int64_t m0 = (int64_t)(tile / ntn) * BM;
+    const int n0 = (tile % ntn) * BN;
+    float acc[MI][NI][4];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+    const mt::WRows wmap{n0, g.N};
+    for (int sidx = 0; sidx < g.nseg; ++sidx) mt::gemm_accum<WM, WN, MI, NI>(acc, g.seg[sidx], m0, g.M, g.W, g.wcol[sidx], wmap, smem, t, bar);
+    tick(10);
+    const int warp = t >> 5, lane = t & 31, wm = warp / WN, wn = warp % WN, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+        const int n = n0 + wn * NI * 8 + j * 8 + 2 * tq;
+        if (n >= g.N) continue;      // N is even: n + 1 < N too
+        const float b0 = g.bias ? __ldg(g.bias + n) : 0.f, b1 = g.bias ? __ldg(g.bias + n + 1) : 0.f;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int64_t m = m0 + wm * MI * 16 + i * 16 + gq + 8 * half;
+                if (m >= g.M) continue;
+                float v0 = acc[i][j][2 * half] + b0, v1 = acc[i][j][2 * half + 1] + b1;
+                if (g.relu) {
+                    v0 = fmaxf(v0, 0.f);
+                    v1 = fmaxf(v1, 0.f);
+                }
+                if (g.C) *reinterpret_cast<float2*>(g.C + m * g.ldc + n) = make_float2(v0, v1);
+                if (g.Cp.hi) mt::store_split2(hi_of(g.Cp), mid_of(g.Cp), g.Cp.ld, m, n, v0, v1);
+            }
     }
+    tick(11);
 }
 
-// recurrent cell of the candidates (nn.GRUCell / nn.RNNCell, models/MemoryModel.py:490-515): 32 candidates x 16 hidden units per tile
+// recurrent cell of the candidates (nn.GRUCell / nn.RNNCell, models/MemoryModel.py:490-515): 64 candidates x 16 hidden units per tile,
+// 8 warps as 4 x 2; the NI = G column blocks of a warp are the G gates of the same 8 units (mt::WGates)
 template <int G>
-__device__ __forceinline__ void cell_tile(const P& p, int tile, float* smem, int t, int bar) {
-    constexpr int TM = 2;
-    const int D = p.F, MD = 2 * D + p.T + p.E, nu = (D + 15) / 16;
-    const int64_t m0 = (int64_t)(tile / nu) * (16 * TM);
+__device__ __forceinline__ void cell_tile(const P& p, int tile, mt::bf16* smem, int t, int bar) {
+    constexpr int WM = 4, WN = 2, MI = 1, NI = G;
+    const int D = p.F, MD = 2 * D + p.T + p.E, Fp = (D + 7) & ~7, nu = (D + 15) / 16;
+    const int64_t m0 = (int64_t)(tile / nu) * (WM * 16);
     const int u0 = (tile % nu) * 16;
-    const int tx = t & 15, ty = t >> 4;
     const int64_t Pn = 2 * (int64_t)p.B;
-    float acc[TM][G];
+    float acc[MI][NI][4];
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[i][g] = 0.f;
-    const tg::WGates wmap{u0, D, 16, G};
-    tg::gemm_accum<TM, G>(acc, tg::ASeg{p.msg, nullptr, MD, MD}, m0, Pn, p.w_ih, MD, wmap, smem, t, bar);
-    float in_n[TM];
+    for (int j = 0; j < NI; ++j) acc[0][j][0] = acc[0][j][1] = acc[0][j][2] = acc[0][j][3] = 0.f;
+    const mt::WGates wmap{u0, D, G};
+    const mt::Planes msg = planes(p.msg_pl);
+    mt::gemm_accum<WM, WN, MI, NI>(acc, mt::ASeg{msg, nullptr, 0, MD}, m0, Pn, planes(p.w_ih), 0, wmap, smem, t, bar);
+    float in_n[4];   // GRU: the candidate gate keeps its input and hidden halves apart (n = tanh(i_n + r * h_n))
     if (G == 3) {
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            in_n[i] = acc[i][G - 1];
-            acc[i][G - 1] = 0.f;
+        for (int e = 0; e < 4; ++e) {
+            in_n[e] = acc[0][G - 1][e];
+            acc[0][G - 1][e] = 0.f;
         }
     }
-    tg::gemm_accum<TM, G>(acc, tg::ASeg{p.memory, p.cand, D, D}, m0, Pn, p.w_hh, D, wmap, smem, t, bar);
-    const int u = u0 + tx;
-    if (u >= D) return;
+    // the hidden state of candidate c is memory[owner(c)] = the first F columns of its message (columns F .. Fp - 1 meet zero weights)
+    mt::gemm_accum<WM, WN, MI, NI>(acc, mt::ASeg{msg, nullptr, 0, Fp}, m0, Pn, planes(p.w_hh), 0, wmap, smem, t, bar);
+    const int warp = t >> 5, lane = t & 31, wm = warp / WN, wn = warp % WN, gq = lane >> 2, tq = lane & 3;
 #pragma unroll
-    for (int i = 0; i < TM; ++i) {
-        const int64_t m = m0 + ty + 16 * i;
+    for (int half = 0; half < 2; ++half) {
+        const int64_t m = m0 + wm * 16 + gq + 8 * half;
         if (m >= Pn) continue;
         const int64_t v = p.cand[m];
         if (__ldcg(p.winner + v) != (int32_t)m) continue;
-        float hn;
-        if (G == 3) {
-            const float r = tg::sigmoidf_(acc[i][0] + p.b_ih[u] + p.b_hh[u]);
-            const float z = tg::sigmoidf_(acc[i][1] + p.b_ih[D + u] + p.b_hh[D + u]);
-            const float ng = tanhf(in_n[i] + p.b_ih[2 * D + u] + r * (acc[i][G - 1] + p.b_hh[2 * D + u]));
-            const float h = __ldcg(p.memory + v * D + u);
-            hn = ng + z * (h - ng);
-        } else {
-            hn = tanhf(acc[i][0] + p.b_ih[u] + p.b_hh[u]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int u = u0 + wn * 8 + 2 * tq + e;
+            if (u >= D) continue;
+            const int ci = 2 * half + e;
+            float hn;
+            if (G == 3) {
+                const float r = mt::sigmoidf_(acc[0][0][ci] + p.b_ih[u] + p.b_hh[u]);
+                const float z = mt::sigmoidf_(acc[0][1][ci] + p.b_ih[D + u] + p.b_hh[D + u]);
+                const float ng = tanhf(in_n[ci] + p.b_ih[2 * D + u] + r * (acc[0][G - 1][ci] + p.b_hh[2 * D + u]));
+                const float h = __ldcg(p.memory + v * D + u);
+                hn = ng + z * (h - ng);
+            } else {
+                hn = tanhf(acc[0][0][ci] + p.b_ih[u] + p.b_hh[u]);
+            }
+            p.hnew[m * D + u] = hn;
         }
-        p.hnew[m * D + u] = hn;
     }
 }
 
-struct Plan {   // tile heights (TM) chosen on the host for the actual R / B so that every GEMM phase is ~one wave
-    int tm_qk, tm_o, tm_m1, tm_m2, tm_p1;
+struct Plan {   // tile heights chosen on the host for the actual R / B (MI = 1: 32-row tiles, 2: 64-row tiles)
+    int mi_qk, mi_o, mi_m1, mi_m2, mi_p1;
 };
 
-constexpr int TEAMS = 2;                       // tile teams (256 threads each) per CTA: four warps per scheduler instead of two
-constexpr int CTA_THREADS = TEAMS * tg::THREADS;
-constexpr int TEAM_SMEM_FLOATS = tg::Tile<4, 4>::SMEM_FLOATS;
+constexpr int TEAMS = 2;                       // tile teams (256 threads each) per CTA
+constexpr int CTA_THREADS = TEAMS * mt::THREADS;
+constexpr int TEAM_SMEM_BYTES = mt::Tile<64, 64>::SMEM_BYTES;
 
 struct Team {
     int id, n;        // global team index, number of teams in the grid
     int t, bar;       // thread index inside the team, its named barrier
-    float* smem;
+    mt::bf16* smem;
 };
 
 // warp tasks [0, ntasks) are handed out in groups of 8 (one per warp of a team); `task` counts groups from `first_task`
 template <class F>
 __device__ __forceinline__ void warp_tasks(const Team& tm, int first_task, int ntasks, int task, F f) {
-    const int w = (task - first_task) * (tg::THREADS / 32) + (tm.t >> 5);
+    const int w = (task - first_task) * (mt::THREADS / 32) + (tm.t >> 5);
     if (w < ntasks) f(w, tm.t & 31);
 }
 
-#define DYG_TM_SWITCH(tm, CALL) \
-    switch (tm) {               \
-        case 1: { constexpr int TM_ = 1; CALL; } break; \
-        case 2: { constexpr int TM_ = 2; CALL; } break; \
-        default: { constexpr int TM_ = 4; CALL; } break; \
-    }
-
-__device__ __forceinline__ int tiles_of(const Gemm& g, int tm) {
-    const int h = tm == 1 ? 16 : tm == 2 ? 32 : 64;
-    return (int)((g.M + h - 1) / h) * ((g.N + 63) / 64);
-}
-__device__ __forceinline__ void run_tile(const Gemm& g, int tm, int tile, const Team& team) {
-    DYG_TM_SWITCH(tm, gemm_tile<TM_>(g, tile, team.smem, team.t, team.bar));
+__device__ __forceinline__ int tiles_of(const Gemm& g, int mi) { return (int)((g.M + 32 * mi - 1) / (32 * mi)) * ((g.N + 63) / 64); }
+__device__ __forceinline__ void run_tile(const Gemm& g, int mi, int tile, const Team& team, unsigned long long* dbg = nullptr) {
+    if (mi == 1) gemm_tile<1>(g, tile, team.smem, team.t, team.bar, dbg);
+    else gemm_tile<2>(g, tile, team.smem, team.t, team.bar, dbg);
 }
 
 template <int H, int G>
 __global__ void __launch_bounds__(CTA_THREADS, 1) tgn_step_kernel(const __grid_constant__ P p, const Plan plan) {
-    extern __shared__ __align__(16) float smem_all[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
     unsigned target = 0;
     Team team;
-    const int local = threadIdx.x / tg::THREADS;
-    team.id = blockIdx.x * TEAMS + local;
-    team.n = gridDim.x * TEAMS;
-    team.t = threadIdx.x % tg::THREADS;
+    const int local = threadIdx.x / mt::THREADS;
+    team.id = local * gridDim.x + blockIdx.x;     // consecutive tasks land on different SMs (a phase with <= 148 tasks uses one team per SM:
+    team.n = gridDim.x * TEAMS;                   // the L2 -> SM fill rate of an SM, not the tensor pipe, bounds a tile)
+    team.t = threadIdx.x % mt::THREADS;
     team.bar = 1 + local;
-    team.smem = smem_all + local * TEAM_SMEM_FLOATS;
-    constexpr int WPT = tg::THREADS / 32;
+    team.smem = reinterpret_cast<mt::bf16*>(smem_all + local * TEAM_SMEM_BYTES);
+    constexpr int WPT = mt::THREADS / 32;
     const int R = p.R, C2 = 2 * p.B;
-    const int Dk = p.F + p.E + p.T, Dq = p.F + p.T;
+    const int Dk = p.F + p.E + p.T, Dq = p.F + p.T, Fp = (p.F + 7) & ~7;
     auto groups = [](int n) { return (n + WPT - 1) / WPT; };
+    const dyg_planes_t none{nullptr, nullptr, 0};
 
     stamp(p, 0);
     // ---- P0
@@ -497,31 +546,31 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) tgn_step_kernel(const __grid_c
     stamp(p, 1);
     // ---- P1
     {
-        const Gemm g{{tg::ASeg{p.feat, nullptr, p.F, p.F}, {}}, 1, p.wqk, p.ld_wqk, p.cq, 0, p.qk, H * Dk, R, H * Dk};
-        const int nt = tiles_of(g, plan.tm_qk), g1 = groups(C2);
+        const Gemm g{{mt::ASeg{planes(p.feat_pl), nullptr, 0, Fp}, {}}, {0, 0}, 1, planes(p.wqk), p.cq, 0, p.qk, H * Dk, none, R, H * Dk};
+        const int nt = tiles_of(g, plan.mi_qk), g1 = groups(C2);
         for (int task = team.id; task < nt + g1; task += team.n) {
-            if (task < nt) run_tile(g, plan.tm_qk, task, team);
+            if (task < nt) run_tile(g, plan.mi_qk, task, team);
             else warp_tasks(team, nt, C2, task, [&](int w, int lane) { message_task(p, w, lane); });
         }
     }
     grid_barrier(p.barrier, target);
     stamp(p, 2);
-    // ---- P2
+    // ---- P2: attention groups first (longer tasks), then the cell tiles
     {
-        const int nt = ((C2 + 31) / 32) * ((p.F + 15) / 16), g1 = groups(R);
-        for (int task = team.id; task < nt + g1; task += team.n) {
-            if (task < nt) cell_tile<G>(p, task, team.smem, team.t, team.bar);
-            else warp_tasks(team, nt, R, task, [&](int w, int lane) { attend_task<H>(p, w, lane); });
+        const int g1 = groups(R), nt = ((C2 + 63) / 64) * ((p.F + 15) / 16);
+        for (int task = team.id; task < g1 + nt; task += team.n) {
+            if (task < g1) warp_tasks(team, 0, R, task, [&](int w, int lane) { attend_task<H>(p, w, lane); });
+            else cell_tile<G>(p, task - g1, team.smem, team.t, team.bar);
         }
     }
     grid_barrier(p.barrier, target);
     stamp(p, 3);
     // ---- P3
     {
-        const Gemm g{{tg::ASeg{p.s, nullptr, H * Dk, H * Dk}, {}}, 1, p.wvr, H * Dk, p.rbias, 0, p.o, Dq, R, Dq};
-        const int nt = tiles_of(g, plan.tm_o), g1 = groups(C2);
+        const Gemm g{{mt::ASeg{planes(p.s_pl), nullptr, 0, H * Dk}, {}}, {0, 0}, 1, planes(p.wvr), p.rbias, 0, p.o, Dq, none, R, Dq};
+        const int nt = tiles_of(g, plan.mi_o), g1 = groups(C2);
         for (int task = team.id; task < nt + g1; task += team.n) {
-            if (task < nt) run_tile(g, plan.tm_o, task, team);
+            if (task < nt) run_tile(g, plan.mi_o, task, team, (p.phase_ns && team.id == 0) ? p.phase_ns : nullptr);
             else warp_tasks(team, nt, C2, task, [&](int w, int lane) { commit_task(p, w, lane); });
         }
     }
@@ -533,25 +582,27 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) tgn_step_kernel(const __grid_c
     stamp(p, 5);
     // ---- P5
     {
-        const Gemm g{{tg::ASeg{p.y, nullptr, Dq, Dq}, tg::ASeg{p.feat, nullptr, p.F, p.F}}, 2, p.m1_w, Dq + p.F, p.m1_b, 1, p.h1, p.F, R, p.F};
-        for (int task = team.id; task < tiles_of(g, plan.tm_m1); task += team.n) run_tile(g, plan.tm_m1, task, team);
+        const Gemm g{{mt::ASeg{planes(p.y_pl), nullptr, 0, Dq}, mt::ASeg{planes(p.feat_pl), nullptr, 0, Fp}}, {0, Dq}, 2, planes(p.m1), p.m1_b, 1,
+                     nullptr, 0, p.h1_pl, R, p.F};
+        for (int task = team.id; task < tiles_of(g, plan.mi_m1); task += team.n) run_tile(g, plan.mi_m1, task, team);
     }
     grid_barrier(p.barrier, target);
     stamp(p, 6);
-    // ---- P6
+    // ---- P6: emb = h W2^T + b2, and the link predictor's first layer on the SAME input: fc1([emb_a | emb_b]) with emb = W2 h + b2 is
+    //      (Wp1a W2) h_a + (Wp1b W2) h_b + const, folded on the host like the attention weights (exact algebra, different rounding)
     {
-        const Gemm g{{tg::ASeg{p.h1, nullptr, p.F, p.F}, {}}, 1, p.m2_w, p.F, p.m2_b, 0, p.emb, p.F, R, p.F};
-        for (int task = team.id; task < tiles_of(g, plan.tm_m2); task += team.n) run_tile(g, plan.tm_m2, task, team);
+        const Gemm g{{mt::ASeg{planes(p.h1_pl), nullptr, 0, Fp}, {}}, {0, 0}, 1, planes(p.m2), p.m2_b, 0, p.emb, p.F, none, R, p.F};
+        const mt::Planes h1 = planes(p.h1_pl);
+        const Gemm gp{{mt::ASeg{h1, p.pair_a, 0, Fp}, mt::ASeg{h1, p.pair_b, 0, Fp}}, {0, Fp}, 2, planes(p.p1), p.p1_b, 1, p.ph, p.F, none, p.P, p.F};
+        const int nt = tiles_of(g, plan.mi_m2), ntp = p.p1.hi ? tiles_of(gp, plan.mi_p1) : 0;
+        for (int task = team.id; task < nt + ntp; task += team.n) {
+            if (task < nt) run_tile(g, plan.mi_m2, task, team);
+            else run_tile(gp, plan.mi_p1, task - nt, team);
+        }
     }
-    if (p.p1_w) {
+    if (p.p1.hi) {
         grid_barrier(p.barrier, target);
         stamp(p, 7);
-        // ---- P7
-        {
-            const Gemm g{{tg::ASeg{p.emb, p.pair_a, p.F, p.F}, tg::ASeg{p.emb, p.pair_b, p.F, p.F}}, 2, p.p1_w, 2 * p.F, p.p1_b, 1, p.ph, p.F, p.P, p.F};
-            for (int task = team.id; task < tiles_of(g, plan.tm_p1); task += team.n) run_tile(g, plan.tm_p1, task, team);
-        }
-        grid_barrier(p.barrier, target);
         stamp(p, 8);
         // ---- P8
         for (int task = team.id; task < groups(p.P); task += team.n) warp_tasks(team, 0, p.P, task, [&](int w, int lane) { score_task(p, w, lane); });
@@ -568,15 +619,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) tgn_step_kernel(const __grid_c
     }
 }
 
-int pick_tm(int64_t M, int N, int ctas) {
-    int best = 4;
+int pick_mi(int64_t M, int N, int teams) {
+    int best = 1;
     double cost = 1e30;
-    for (int tm : {1, 2, 4}) {
-        const int64_t tiles = ((M + 16 * tm - 1) / (16 * tm)) * ((N + 63) / 64);
-        const double c = (double)((tiles + ctas - 1) / ctas) * (tm + 0.35);   // waves x (work + fixed cost per tile)
+    for (int mi : {1, 2}) {
+        const int64_t tiles = ((M + 32 * mi - 1) / (32 * mi)) * ((N + 63) / 64);
+        const double c = (double)((tiles + teams - 1) / teams) * (mi + 1.0);   // waves x (A + W bytes per tile)
         if (c < cost) {
             cost = c;
-            best = tm;
+            best = mi;
         }
     }
     return best;
@@ -591,29 +642,36 @@ extern "C" int dyg_tgn_step(const dyg_tgn_step_t* ph, dyg_stream_t stream) {
     const P& p = *ph;
     DYG_CHECK_ARG(p.B > 0 && p.R > 0 && p.k > 0, "dyg_tgn_step: empty batch");
     DYG_CHECK_ARG(p.H == 2 && (p.G == 1 || p.G == 3), "dyg_tgn_step: H must be 2, G 1 (RNN) or 3 (GRU)");
-    DYG_CHECK_ARG(p.F % 4 == 0 && p.E % 4 == 0 && p.T % 4 == 0 && p.ld_node % 4 == 0 && p.ld_edge % 4 == 0 && p.ld_wqk % 4 == 0,
-                  "dyg_tgn_step: widths and leading dimensions must be multiples of 4");
-    DYG_CHECK_ARG(p.F + p.E <= 384 && p.T <= 128 && p.F + p.T <= 512, "dyg_tgn_step: feature widths out of range");
+    const int Dk = p.F + p.E + p.T, Dq = p.F + p.T, MD = 2 * p.F + p.T + p.E, Fp = (p.F + 7) & ~7;
+    DYG_CHECK_ARG(p.F % 4 == 0 && p.E % 4 == 0 && p.T % 4 == 0 && p.ld_node % 4 == 0 && p.ld_edge % 4 == 0 && Dq % 8 == 0 && MD % 8 == 0 &&
+                      (p.H * Dk) % 8 == 0,
+                  "dyg_tgn_step: F, E, T must be multiples of 4 and F + T, 2F + T + E, H (F + E + T) multiples of 8");
+    DYG_CHECK_ARG(p.F + p.E <= 384 && p.T <= 128 && Dq <= 512, "dyg_tgn_step: feature widths out of range");
     DYG_CHECK_ARG(p.he && p.indptr && p.src && p.dst && p.t && p.eid && p.roots && p.cand && p.node_raw && p.edge_raw && p.memory &&
                       p.last_update && p.mem_view && p.lu_view && p.pending && p.winner && p.msg_store && p.msg_time && p.flag && p.barrier,
                   "dyg_tgn_step: null state pointer");
-    DYG_CHECK_ARG(p.nbr_ids && p.nbr_eids && p.nbr_t && p.feat && p.qk && p.s && p.o && p.y && p.h1 && p.emb && p.msg && p.hnew,
-                  "dyg_tgn_step: null scratch pointer");
-    DYG_CHECK_ARG(!p.p1_w || (p.p1_b && p.p2_w && p.p2_b && p.pair_a && p.pair_b && p.ph && p.prob && p.P > 0), "dyg_tgn_step: incomplete link predictor");
+    DYG_CHECK_ARG(p.nbr_ids && p.nbr_eids && p.nbr_t && p.feat && p.qk && p.o && p.msg && p.hnew && p.emb, "dyg_tgn_step: null scratch pointer");
+    const dyg_planes_t* pls[] = {&p.wqk, &p.wvr, &p.m1, &p.m2, &p.w_ih, &p.w_hh, &p.feat_pl, &p.msg_pl, &p.s_pl, &p.y_pl, &p.h1_pl};
+    const int64_t need[] = {Fp, p.H * Dk, Dq + Fp, Fp, MD, Fp, Fp, MD, p.H * Dk, Dq, Fp};
+    for (int i = 0; i < 11; ++i)
+        DYG_CHECK_ARG(pls[i]->hi && pls[i]->mid && pls[i]->ld >= need[i] && pls[i]->ld % 8 == 0 && aligned16(pls[i]->hi) && aligned16(pls[i]->mid),
+                      "dyg_tgn_step: operand planes %d missing, misaligned or narrower than %lld columns", i, (long long)need[i]);
+    if (p.p1.hi)
+        DYG_CHECK_ARG(p.p1.mid && p.p1.ld >= 2 * Fp && p.p1.ld % 8 == 0 && p.p1_b && p.p2_w && p.p2_b && p.pair_a && p.pair_b && p.ph && p.prob && p.P > 0,
+                      "dyg_tgn_step: incomplete link predictor");
     const int ctas = dyg_num_sms();
     const int teams = ctas * TEAMS;
-    const int Dk = p.F + p.E + p.T, Dq = p.F + p.T;
     Plan plan;
-    plan.tm_qk = pick_tm(p.R, p.H * Dk, teams);
-    plan.tm_o = pick_tm(p.R, Dq, teams);
-    plan.tm_m1 = pick_tm(p.R, p.F, teams);
-    plan.tm_m2 = pick_tm(p.R, p.F, teams);
-    plan.tm_p1 = pick_tm(p.P > 0 ? p.P : 1, p.F, teams);
-    constexpr int smem_bytes = TEAMS * TEAM_SMEM_FLOATS * 4;
-    {   // per device and cheap: set on every call (one process may drive several devices)
-        cudaFuncSetAttribute(tgn_step_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        cudaFuncSetAttribute(tgn_step_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    }
+    plan.mi_qk = pick_mi(p.R, p.H * Dk, teams);
+    plan.mi_o = pick_mi(p.R, Dq, teams);
+    plan.mi_m1 = pick_mi(p.R, p.F, teams);
+    plan.mi_m2 = pick_mi(p.R, p.F, teams);
+    plan.mi_p1 = pick_mi(p.P > 0 ? p.P : 1, p.F, teams);
+    constexpr int smem_bytes = TEAMS * TEAM_SMEM_BYTES;
+    static_assert(smem_bytes <= 227 * 1024, "two tile teams must fit one SM");
+    static_assert(mt::Tile<64, 48>::SMEM_BYTES <= TEAM_SMEM_BYTES, "cell tile fits the team buffer");
+    cudaFuncSetAttribute(tgn_step_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);   // per device, cheap
+    cudaFuncSetAttribute(tgn_step_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     void* args[] = {(void*)&p, (void*)&plan};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ctas);

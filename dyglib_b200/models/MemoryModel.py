@@ -590,7 +590,56 @@ class MemoryModel(torch.nn.Module):
         return (self.fused_step and self.model_name == 'TGN' and self.num_layers == 1 and self.num_heads == 2 and B > 0 and
                 em.neighbor_sampler.sample_neighbor_strategy == 'recent' and self.node_feat_dim % 4 == 0 and self.edge_feat_dim % 4 == 0 and
                 self.time_feat_dim % 4 == 0 and self.node_feat_dim + self.edge_feat_dim <= 384 and self.time_feat_dim <= 128 and
+                (self.node_feat_dim + self.time_feat_dim) % 8 == 0 and self.message_dim % 8 == 0 and
+                (self.node_feat_dim + self.edge_feat_dim + self.time_feat_dim) % 4 == 0 and
                 self.node_raw_features.stride(0) % 4 == 0 and self.edge_raw_features.stride(0) % 4 == 0)
+
+    @staticmethod
+    def _pack_planes(weight, widths):
+        """BF16x3 operand planes (2, N, sum of padded widths) of ``weight[:, :sum(widths)]`` with every K segment zero-padded to a
+        multiple of 8 columns (dyg_tgn_step's weight layout)."""
+        w = weight.detach().float()
+        N = w.shape[0]
+        pads = [(x + 7) // 8 * 8 for x in widths]
+        packed = torch.zeros((N, sum(pads)), dtype=torch.float32, device=w.device)
+        src = dst = 0
+        for x, xp in zip(widths, pads):
+            packed[:, dst:dst + x] = w[:, src:src + x]
+            src += x
+            dst += xp
+        hi = packed.to(torch.bfloat16)
+        mid = (packed - hi.float()).to(torch.bfloat16)
+        return torch.stack([hi, mid]).contiguous()
+
+    def _step_weights(self, link_predictor):
+        """Weight-derived operands of dyg_tgn_step, rebuilt when a parameter changes."""
+        em = self.embedding_module
+        attn, merge, cell = em.temporal_conv_layers[0], em.merge_layers[0], self.memory_updater.memory_updater
+        params = [attn.query_projection.weight, attn.key_projection.weight, attn.value_projection.weight, attn.residual_fc.weight,
+                  merge.fc1.weight, merge.fc2.weight, cell.weight_ih, cell.weight_hh, self.time_encoder.w.weight, self.time_encoder.w.bias]
+        if link_predictor is not None:
+            params += [link_predictor.fc1.weight, link_predictor.fc1.bias, merge.fc2.bias]
+        key = (ops.WEIGHTS_EPOCH,) + tuple((q.data_ptr(), q._version) for q in params)
+        ent = getattr(self, '_step_w', None)
+        if ent is None or ent[0] != key:
+            F_, T_ = self.node_feat_dim, self.time_feat_dim
+            Dq = F_ + T_
+            dev = self.node_raw_features.device
+            t0 = zero_time_features(self.time_encoder, dev)
+            wqk, wvr = attn.folded()
+            w = dict(t0=t0, cq=query_constant(attn, self.time_encoder, t0),
+                     wqk=self._pack_planes(wqk, [F_]), wvr=self._pack_planes(wvr, [wvr.shape[1]]),
+                     m1=self._pack_planes(merge.fc1.weight, [Dq, F_]), m2=self._pack_planes(merge.fc2.weight, [F_]),
+                     w_ih=self._pack_planes(cell.weight_ih, [self.message_dim]), w_hh=self._pack_planes(cell.weight_hh, [F_]))
+            if link_predictor is not None:
+                # fc1([emb_a | emb_b]) with emb = W2 h + b2 folded onto h (float64 once per weight version, like MultiHeadAttention.folded)
+                wp, bp = link_predictor.fc1.weight.detach().double(), link_predictor.fc1.bias.detach().double()
+                w2, b2 = merge.fc2.weight.detach().double(), merge.fc2.bias.detach().double()
+                wa, wb = wp[:, :F_], wp[:, F_:2 * F_]
+                w['p1'] = self._pack_planes(torch.cat([wa @ w2, wb @ w2], dim=1).float(), [F_, F_])
+                w['p1_b'] = (bp + wa @ b2 + wb @ b2).float().contiguous()
+            ent = self._step_w = (key, w, params)
+        return ent[1]
 
     def _fused_step(self, roots, src, dst, tq, eid, k, link_predictor=None, pairs=None):
         """Embeddings of ``roots`` (root r at time tq[r % B]) on the look-ahead view, then the memory update of the positive batch
@@ -603,18 +652,21 @@ class MemoryModel(torch.nn.Module):
         cell = self.memory_updater.memory_updater
         F_, E_, T_ = self.node_feat_dim, self.edge_feat_dim, self.time_feat_dim
         H = self.num_heads
-        Dk, Dq, MD = F_ + E_ + T_, F_ + T_, self.message_dim
+        Dk, Dq, MD, Fp = F_ + E_ + T_, F_ + T_, self.message_dim, (F_ + 7) // 8 * 8
         B, R = src.numel(), roots.numel()
         P_ = 2 * B if link_predictor is not None else 0
         key = (R, B, P_, int(k), str(dev))
         sc = self._step_scratch.get(key)
         if sc is None:
             f32 = dict(dtype=torch.float32, device=dev)
+
+            def pl(rows, cols):       # operand planes written by the kernel; the padding columns stay zero
+                return torch.zeros((2, rows, cols), dtype=torch.bfloat16, device=dev)
             sc = dict(nbr_ids=torch.empty((R, k), dtype=torch.int64, device=dev), nbr_eids=torch.empty((R, k), dtype=torch.int64, device=dev),
                       nbr_t=torch.empty((R, k), **f32), feat=torch.empty((R, F_), **f32), qk=torch.empty((R, H * Dk), **f32),
-                      s=torch.empty((R, H * Dk), **f32), o=torch.empty((R, Dq), **f32), y=torch.empty((R, Dq), **f32),
-                      h1=torch.empty((R, F_), **f32), msg=torch.empty((2 * B, MD), **f32), hnew=torch.empty((2 * B, F_), **f32),
-                      ph=torch.empty((max(P_, 1), F_), **f32), barrier=torch.zeros(2, dtype=torch.int32, device=dev))
+                      o=torch.empty((R, Dq), **f32), msg=torch.empty((2 * B, MD), **f32), hnew=torch.empty((2 * B, F_), **f32),
+                      ph=torch.empty((max(P_, 1), F_), **f32), barrier=torch.zeros(2, dtype=torch.int32, device=dev),
+                      feat_pl=pl(R, Fp), msg_pl=pl(2 * B, MD), s_pl=pl(R, H * Dk), y_pl=pl(R, Dq), h1_pl=pl(R, Fp))
             if P_:
                 ar = torch.arange(B, dtype=torch.int64, device=dev)
                 sc['pair_a'] = torch.cat([ar, ar])                       # pos pairs (src, dst) then neg pairs (src, neg)
@@ -625,9 +677,7 @@ class MemoryModel(torch.nn.Module):
         emb = torch.empty((R, F_), dtype=torch.float32, device=dev)
         prob = torch.empty(max(P_, 1), dtype=torch.float32, device=dev)
         cand = torch.cat([src, dst])
-        t0 = zero_time_features(self.time_encoder, dev)
-        wqk, wvr = attn.folded()
-        cq = query_constant(attn, self.time_encoder, t0)
+        wts = self._step_weights(link_predictor)
         w, b = self.time_encoder.wb()
         p = _native.TgnStep()
         keep = []
@@ -635,6 +685,10 @@ class MemoryModel(torch.nn.Module):
         def ptr(x):
             keep.append(x)
             return _p(x).value if x is not None else None
+
+        def planes(field, x):
+            keep.append(x)
+            field.hi, field.mid, field.ld = x[0].data_ptr(), x[1].data_ptr(), x.shape[2]
         p.he, p.indptr, p.num_nodes = ptr(sampler.halfedges), ptr(sampler.indptr), sampler.num_nodes
         p.src, p.dst, p.t, p.eid, p.cand, p.roots = ptr(src), ptr(dst), ptr(tq), ptr(eid), ptr(cand), ptr(roots)
         p.B, p.R, p.k, p.H, p.G, p.check_time = B, R, int(k), H, self.memory_updater.gates, int(self.check_time_order)
@@ -644,21 +698,23 @@ class MemoryModel(torch.nn.Module):
         p.memory, p.last_update = ptr(bank.node_memories.data), ptr(bank.node_last_updated_times.data)
         p.mem_view, p.lu_view, p.pending, p.winner = ptr(st['mem_view']), ptr(st['lu_view']), ptr(st['pending']), ptr(st['winner'])
         p.msg_store, p.msg_time, p.flag = ptr(st['msg_store']), ptr(st['msg_time']), ptr(st['flag'])
-        p.time_w, p.time_b, p.t0 = ptr(w), ptr(b), ptr(t0)
-        p.wqk, p.ld_wqk, p.cq = ptr(wqk), wqk.stride(0), ptr(cq)
-        p.wvr, p.rbias = ptr(wvr), ptr(attn.residual_fc.bias.detach())
+        p.time_w, p.time_b, p.t0 = ptr(w), ptr(b), ptr(wts['t0'])
+        for name in ('wqk', 'wvr', 'm1', 'm2', 'w_ih', 'w_hh'):
+            planes(getattr(p, name), wts[name])
+        p.cq, p.rbias = ptr(wts['cq']), ptr(attn.residual_fc.bias.detach())
         p.ln_g, p.ln_b, p.ln_eps = ptr(attn.layer_norm.weight.detach()), ptr(attn.layer_norm.bias.detach()), float(attn.layer_norm.eps)
-        p.m1_w, p.m1_b = ptr(merge.fc1.weight.detach()), ptr(merge.fc1.bias.detach())
-        p.m2_w, p.m2_b = ptr(merge.fc2.weight.detach()), ptr(merge.fc2.bias.detach())
-        p.w_ih, p.b_ih = ptr(cell.weight_ih.detach()), ptr(cell.bias_ih.detach())
-        p.w_hh, p.b_hh = ptr(cell.weight_hh.detach()), ptr(cell.bias_hh.detach())
+        p.m1_b, p.m2_b = ptr(merge.fc1.bias.detach()), ptr(merge.fc2.bias.detach())
+        p.b_ih, p.b_hh = ptr(cell.bias_ih.detach()), ptr(cell.bias_hh.detach())
         if P_:
             lp = link_predictor
-            p.p1_w, p.p1_b = ptr(lp.fc1.weight.detach()), ptr(lp.fc1.bias.detach())
+            planes(p.p1, wts['p1'])
+            p.p1_b = ptr(wts['p1_b'])
             p.p2_w, p.p2_b = ptr(lp.fc2.weight.detach().reshape(-1)), ptr(lp.fc2.bias.detach())
             p.pair_a, p.pair_b, p.P = ptr(sc['pair_a']), ptr(sc['pair_b']), P_
-        for name in ('nbr_ids', 'nbr_eids', 'nbr_t', 'feat', 'qk', 's', 'o', 'y', 'h1', 'msg', 'hnew', 'ph', 'barrier'):
+        for name in ('nbr_ids', 'nbr_eids', 'nbr_t', 'feat', 'qk', 'o', 'msg', 'hnew', 'ph', 'barrier'):
             setattr(p, name, ptr(sc[name]))
+        for name in ('feat_pl', 'msg_pl', 's_pl', 'y_pl', 'h1_pl'):
+            planes(getattr(p, name), sc[name])
         p.emb, p.prob = ptr(emb), ptr(prob)
         if getattr(self, 'phase_ns', None) is not None:      # profiling hook: per-phase globaltimer stamps (scripts/tgn_phases.py)
             p.phase_ns = ptr(self.phase_ns)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 3
+#define DYG_ABI_VERSION 4
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -331,8 +331,14 @@ int dyg_tgn_check_time(const int64_t* node_ids, int64_t n, const float* last_upd
  * election, raw-message build, recurrent cell, commit into the look-ahead view / message store.  Semantics are those of the
  * separate entry points above (dyg_sample_recent, dyg_gather_rows, dyg_linear, dyg_temporal_attend, dyg_layernorm,
  * dyg_tgn_check_time / persist / select_last / build_messages, dyg_gru_update_fwd, dyg_tgn_cell_commit) run in that order.
- * Root r is embedded at time t[r % B]; cand[c] = c < B ? src[c] : dst[c - B].  All widths / leading dimensions % 4 == 0,
- * F + E <= 384, T <= 128, H = 2.  `barrier`: 2 uint32, zeroed once by the caller and left zero by every launch. */
+ * Root r is embedded at time t[r % B]; cand[c] = c < B ? src[c] : dst[c - B].  F, E, T % 4 == 0, (F + T) % 8 == 0, (F + E + T) % 4 == 0,
+ * (2F + T + E) % 8 == 0, F + E <= 384, T <= 128, H = 2.  Dense contractions run as BF16x3 on mma.sync tiles (csrc/mma_tile.cuh).  `barrier`: 2 uint32, zeroed once by the caller and left zero by every launch. */
+/* BF16x3 operand planes of a (rows, ld) matrix: x = hi + mid, bf16 each; ld % 8 == 0, both 16-byte aligned, padding columns zero */
+typedef struct {
+    const void* hi;
+    const void* mid;
+    int64_t ld;
+} dyg_planes_t;
 typedef struct {
     const dyg_halfedge_t* he; const int64_t* indptr; int64_t num_nodes;              /* device CSR */
     const int64_t* src; const int64_t* dst; const double* t; const int64_t* eid;      /* the positive batch (B events) */
@@ -343,16 +349,18 @@ typedef struct {
     float* memory; float* last_update; float* mem_view; float* lu_view; uint8_t* pending; int32_t* winner;
     float* msg_store; double* msg_time; int32_t* flag;
     const float* time_w; const float* time_b; const float* t0;                        /* TimeEncoder w, b and cos(b) */
-    const float* wqk; int32_t ld_wqk; const float* cq;                                /* folded query weights (H*Dk, >= F) and constant part (H*Dk) */
-    const float* wvr; const float* rbias;                                             /* folded value / residual_fc weights (Dq, H*Dk), bias (Dq) */
-    const float* ln_g; const float* ln_b; float ln_eps;
-    const float* m1_w; const float* m1_b; const float* m2_w; const float* m2_b;       /* MergeLayer (F, Dq + F), (F, F) */
-    const float* w_ih; const float* b_ih; const float* w_hh; const float* b_hh;       /* recurrent cell (G*F, 2F+T+E), (G*F, F) */
-    const float* p1_w; const float* p1_b; const float* p2_w; const float* p2_b;       /* link predictor MergeLayer or NULL */
+    /* dense weights as operand planes, every K segment padded with zero columns to a multiple of 8 (Fp = roundup(F, 8)):
+     * wqk (H*Dk, Fp) folded query weights; wvr (Dq, H*Dk) folded value / residual_fc weights; m1 (F, Dq + Fp), m2 (F, Fp) MergeLayer;
+     * w_ih (G*F, 2F+T+E), w_hh (G*F, Fp) recurrent cell; p1 (F, 2 Fp) = [Wp1[:, :F] W2 | Wp1[:, F:] W2], the link predictor's fc1 folded
+     * onto the MergeLayer's hidden activation (hi NULL: no predictor), p1_b = its bias + Wp1[:, :F] b2 + Wp1[:, F:] b2 */
+    dyg_planes_t wqk, wvr, m1, m2, w_ih, w_hh, p1;
+    const float* cq; const float* rbias; const float* ln_g; const float* ln_b; float ln_eps;
+    const float* m1_b; const float* m2_b; const float* b_ih; const float* b_hh;
+    const float* p1_b; const float* p2_w; const float* p2_b;                          /* predictor fc1 bias, fc2 weight (F) and bias */
     const int64_t* pair_a; const int64_t* pair_b; int32_t P;                          /* prob[i] = predictor(emb[pair_a[i]], emb[pair_b[i]]) */
     int64_t* nbr_ids; int64_t* nbr_eids; float* nbr_t;                                /* scratch (R, k) */
-    float* feat; float* qk; float* s; float* o; float* y; float* h1;                  /* scratch (R, F), (R, H*Dk) x2, (R, Dq) x2, (R, F) */
-    float* msg; float* hnew; float* ph;                                               /* scratch (2B, 2F+T+E), (2B, F), (P, F) */
+    float* feat; float* qk; float* o; float* msg; float* hnew; float* ph;             /* scratch fp32 (R,F), (R,H*Dk), (R,Dq), (2B,MD), (2B,F), (P,F) */
+    dyg_planes_t feat_pl, msg_pl, s_pl, y_pl, h1_pl;                                  /* scratch planes (R,Fp), (2B,MD), (R,H*Dk), (R,Dq), (R,Fp); padding zeroed by the caller */
     float* emb; float* prob;                                                          /* outputs (R, F), (P) */
     uint32_t* barrier;
     unsigned long long* phase_ns;   /* NULL, or 16 slots: globaltimer at the start, after every phase and at the end (profiling) */

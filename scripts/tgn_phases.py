@@ -31,7 +31,7 @@ with torch.no_grad():
             rows.append(st.copy())
 r = np.array(rows, dtype=np.float64)
 names = ['P0 search+feat | persist+elect', 'P1 qk GEMM | messages', 'P2 cell tiles | attention', 'P3 o GEMM | commit', 'P4 LayerNorm',
-         'P5 merge fc1', 'P6 merge fc2', 'P7 predictor fc1', 'P8 scores']
+         'P5 merge fc1', 'P6 merge fc2 | folded predictor fc1', '(P7 fused into P6)', 'P8 scores']
 ends = [1, 2, 3, 4, 5, 6, 7, 8, 15]
 prev = r[:, 0]
 print(f'batches {len(rows)}  L2 flush between steps: {len(sys.argv) > 2}')
@@ -40,3 +40,5 @@ for n, e in zip(names, ends):
     print(f'{n:34s} {d.mean():7.2f} us  (min {d.min():6.2f}, max {d.max():6.2f})')
     prev = r[:, e]
 print(f'{"total":34s} {((r[:, 15] - r[:, 0]) / 1e3).mean():7.2f} us')
+print('P3 tile 0 of team 0: start +%.2f us after the P2 barrier, K loop %.2f us, epilogue %.2f us, then %.2f us until the P3 barrier opens' % (
+    ((r[:, 9] - r[:, 3]) / 1e3).mean(), ((r[:, 10] - r[:, 9]) / 1e3).mean(), ((r[:, 11] - r[:, 10]) / 1e3).mean(), ((r[:, 4] - r[:, 11]) / 1e3).mean()))

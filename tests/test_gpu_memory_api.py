@@ -89,19 +89,20 @@ def test_sub_api_flow_equals_fused_call():
             ud, md = b.compute_new_node_raw_messages(dst, src, None, t, eid)
             bank.store_node_raw_messages(us, ms)
             bank.store_node_raw_messages(ud, md)
+    # a: one-launch step (BF16x3 mma tiles), b: fused fp32 cell through the sub-API -- the same state within the dense-layer tolerance
     for x, y in ((a.memory_bank.node_memories.data, b.memory_bank.node_memories.data),
                  (a.memory_bank.node_last_updated_times.data, b.memory_bank.node_last_updated_times.data)):
-        np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-3, atol=5e-5)
     ra, rb = a.memory_bank.node_raw_messages.to_dict(), b.memory_bank.node_raw_messages.to_dict()
     assert sorted(ra) == sorted(rb)
     for v in ra:
         assert ra[v][-1][1] == rb[v][-1][1]
-        np.testing.assert_allclose(ra[v][-1][0].cpu().numpy(), rb[v][-1][0].cpu().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ra[v][-1][0].cpu().numpy(), rb[v][-1][0].cpu().numpy(), rtol=1e-3, atol=5e-5)
     # and both continue identically
     nxt = list(batches(g, 240, 2, 30))
     for x, y in zip(_run(a, nxt), _run(b, nxt)):
         for p, q in zip(x, y):
-            np.testing.assert_allclose(p, q, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(p, q, rtol=1e-3, atol=5e-5)
 
 
 def test_memory_updater_compat_calls_match_torch_cells():
@@ -173,8 +174,8 @@ def test_load_state_dict_resyncs_the_view():
     b.load_state_dict(sd)
     b.memory_bank.node_raw_messages = raw
     got = _run(b, bs[3:4])[0]
-    for x, y in zip(got, want):
-        np.testing.assert_allclose(x, y, rtol=1e-5, atol=1e-6)
+    for x, y in zip(got, want):       # b's view was rebuilt by the fp32 cell, a's was maintained by the BF16x3 step
+        np.testing.assert_allclose(x, y, rtol=1e-3, atol=5e-5)
 
 
 def test_message_list_mutations_write_through():

@@ -168,12 +168,12 @@ def test_memory_model_fused_pos_neg_call_equals_two_calls(name):
             c, d = m1.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, 10)
             fa, fb, fc, fd = m2.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10)
             for x, y in zip((a, b, c, d), (fa, fb, fc, fd)):
-                if name == 'TGN':    # one-launch step (dyg_tgn_step) vs kernel-per-step negative call: fp32 summation order differs
-                    close(x, y, f'{name} {bi}', rtol=1e-4, atol=1e-5)
+                if name == 'TGN':    # one-launch step (dyg_tgn_step, BF16x3 mma tiles) vs kernel-per-step negative call (fp32 FFMA at B = 40)
+                    close(x, y, f'{name} {bi}', rtol=1e-3, atol=5e-5)
                 else:
                     assert torch.equal(x, y), (name, bi)
     if name == 'TGN':
-        close(mem_fn(m1)[0], mem_fn(m2)[0], rtol=1e-4, atol=1e-5)
+        close(mem_fn(m1)[0], mem_fn(m2)[0], rtol=1e-3, atol=5e-5)
     else:
         assert torch.equal(mem_fn(m1)[0], mem_fn(m2)[0])
     assert torch.equal(mem_fn(m1)[1], mem_fn(m2)[1])
@@ -200,22 +200,22 @@ def test_tgn_one_launch_step_equals_kernel_per_step_path(B, k):
             for x, y in zip(f, u):
                 close(x, y, f'batch {bi}', rtol=1e-3, atol=5e-5)     # fp32 FFMA tiles vs BF16x3 tcgen05 GEMMs at B >= 128
     m1.assert_time_order()
-    close(mem_fn(m1)[0], mem_fn(m2)[0], rtol=1e-4, atol=1e-5)
+    close(mem_fn(m1)[0], mem_fn(m2)[0], rtol=1e-3, atol=5e-5)
     assert torch.equal(mem_fn(m1)[1], mem_fn(m2)[1])
     s1, s2 = m1.memory_bank._ensure(), m2.memory_bank._ensure()
     assert torch.equal(s1['pending'], s2['pending']) and torch.equal(s1['msg_time'], s2['msg_time']) and torch.equal(s1['lu_view'], s2['lu_view'])
     assert int(s1['winner'].max().item()) == -1                                  # the election table is left clean
     assert all(int(sc['barrier'].abs().sum().item()) == 0 for sc in m1._step_scratch.values())   # and the grid barrier re-armed
     pend = s1['pending'].bool()
-    close(s1['msg_store'][pend], s2['msg_store'][pend], rtol=1e-4, atol=1e-5)
-    close(s1['mem_view'], s2['mem_view'], rtol=1e-4, atol=1e-5)
+    close(s1['msg_store'][pend], s2['msg_store'][pend], rtol=1e-3, atol=5e-5)
+    close(s1['mem_view'], s2['mem_view'], rtol=1e-3, atol=5e-5)
     # the positive call alone also runs as one launch
     src, dst, t, eid, neg = next(batches(g, 25 * B, 1, B))
     with torch.no_grad():
         a = m1.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, k)
         b = m2.compute_src_dst_node_temporal_embeddings(src, dst, t, eid, True, k)
     for x, y in zip(a, b):
-        close(x, y, rtol=1e-4, atol=1e-5)
+        close(x, y, rtol=1e-3, atol=5e-5)
 
 
 def test_tgn_same_node_src_and_dst_in_batch():
