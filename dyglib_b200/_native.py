@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lock = threading.Lock()
 _lib = None
@@ -147,6 +147,7 @@ SIGNATURES = {
                                 c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p],
     'dyg_seq_attention': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_seq_attention_tc': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
+    'dyg_seq_attention_fold': [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
     'dyg_mean_tokens': [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_tgn_persist': [c_p, c_l, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     'dyg_tgn_select_last': [c_p, c_p, c_l, c_p, c_p],

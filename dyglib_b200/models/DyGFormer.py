@@ -23,6 +23,9 @@ import os
 
 # LayerNorm + feed-forward as one kernel (dyg_ln_ffn_bf16x3); DYG_FUSED_FFN=0 selects the three-kernel path
 FUSED_FFN = os.environ.get('DYG_FUSED_FFN', '1') != '0'
+# attention sub-block as [q | k | v'] projection + dyg_seq_attention_fold (tcgen05); DYG_FUSED_ATTN=0 selects the
+# QKV GEMM + mma.sync attention + out-projection GEMM path
+FUSED_ATTN = os.environ.get('DYG_FUSED_ATTN', '1') != '0'
 
 
 class NeighborCooccurrenceEncoder(nn.Module):
@@ -91,6 +94,8 @@ class TransformerEncoder(nn.Module):
         self.norm_layers = nn.ModuleList([nn.LayerNorm(attention_dim), nn.LayerNorm(attention_dim)])
         self.attention_dim = attention_dim
         self.num_heads = num_heads
+        self._fold_key = None
+        self._fold = None
 
     def forward(self, inputs: torch.Tensor):
         """``TransformerEncoder.forward`` (``models/DyGFormer.py:442-461``): pre-norm block, no padding mask."""
@@ -103,13 +108,20 @@ class TransformerEncoder(nn.Module):
         l0, l1 = self.linear_layers
         # every dense contraction runs on tcgen05 from BF16x3 operand planes (ops.gemm); the residual stream stays fp32
         y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
-        qkv = ops.gemm(y, mha.in_proj_weight, mha.in_proj_bias.detach())
         hd = D // self.num_heads
-        if S <= 128 and hd <= 128 and hd % 2 == 0:
-            a = ops.seq_attention_tc(qkv, B, S, self.num_heads, hd, want='split')
+        if FUSED_ATTN and ops.attn_fold_fusable(S, D, self.num_heads):
+            # [q | k | v'] projection with the out-projection folded into v', then the tcgen05 attention kernel adds the
+            # residual: two launches for LayerNorm..residual instead of four, no attention-output round trip
+            wcat, bcat, bout = self._folded()
+            pl = ops.gemm(y, wcat, bcat, want='split')
+            x1 = ops.seq_attention_fold(pl, B, S, self.num_heads, D, x, bout)
         else:
-            a = ops.split_bf16(ops.seq_attention(qkv, B, S, self.num_heads, hd))
-        x1 = ops.gemm(a, mha.out_proj.weight, mha.out_proj.bias.detach(), residual=x)
+            qkv = ops.gemm(y, mha.in_proj_weight, mha.in_proj_bias.detach())
+            if S <= 128 and hd <= 128 and hd % 2 == 0:
+                a = ops.seq_attention_tc(qkv, B, S, self.num_heads, hd, want='split')
+            else:
+                a = ops.split_bf16(ops.seq_attention(qkv, B, S, self.num_heads, hd))
+            x1 = ops.gemm(a, mha.out_proj.weight, mha.out_proj.bias.detach(), residual=x)
         if FUSED_FFN and ops.ffn_fusable(D, l0.weight.shape[0]):
             # LayerNorm + FFN in one kernel: the normalised rows and the 4D hidden activation stay on the SM
             out = ops.ln_ffn(x1, n1.weight.detach(), n1.bias.detach(), n1.eps, l0.weight, l0.bias.detach(), l1.weight, l1.bias.detach())
@@ -119,6 +131,16 @@ class TransformerEncoder(nn.Module):
             out = ops.gemm(h, l1.weight, l1.bias.detach(), residual=x1)
         return out.reshape(B, S, D)
 
+
+    def _folded(self):
+        """(Split of W_cat, b_cat, b_out) of ops.attn_fold_weights, rebuilt when a parameter of the attention changes."""
+        mha = self.multi_head_attention
+        ps = (mha.in_proj_weight, mha.in_proj_bias, mha.out_proj.weight, mha.out_proj.bias)
+        key = (ops.WEIGHTS_EPOCH,) + tuple((q.data_ptr(), q._version) for q in ps)
+        if key != self._fold_key:
+            W, b, bo = ops.attn_fold_weights(ps[0], ps[1], ps[2], ps[3], self.num_heads)
+            self._fold, self._fold_key = (ops.split_bf16(W), b, bo), key
+        return self._fold
 
     def _forward_train(self, inputs):
         """Training mode: the same block with autograd.  Dense layers run forward on the tcgen05 GEMM through

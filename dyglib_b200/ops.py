@@ -540,6 +540,60 @@ def seq_attention_tc(qkv, B, S, H, hd, want='split'):
     return out if want == 'f32' else sp if want == 'split' else (out, sp)
 
 
+def attn_fold_layout(D, H):
+    """Column layout of the projection planes dyg_seq_attention_fold reads: (q_col0, k_col0, v_col0, hdk, total columns)."""
+    hd = D // H
+    hdk = (hd + 7) // 8 * 8
+    k0 = (H * hd + 7) // 8 * 8
+    v0 = k0 + H * hdk
+    return 0, k0, v0, hdk, v0 + H * D
+
+
+def attn_fold_fusable(S, D, H):
+    hd = D // H
+    return S <= 64 and D % H == 0 and hd % 4 == 0 and hd <= 112 and D % 8 == 0 and D <= 208
+
+
+def attn_fold_weights(in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bias, H):
+    """(W_cat (N, D) fp32, b_cat (N,), b_out (D,)) of the folded attention block: rows [q * log2(e)/sqrt(hd) | k | W_o,h W_v,h],
+    computed in float64.  softmax rows sum to one, so W_o,h b_v,h rides inside v' and b_o is added once at the end."""
+    D = in_proj_weight.shape[1]
+    hd = D // H
+    q0, k0, v0, hdk, N = attn_fold_layout(D, H)
+    w = in_proj_weight.detach().double()
+    b = in_proj_bias.detach().double()
+    wo = out_proj_weight.detach().double()
+    W = torch.zeros((N, D), dtype=torch.float64, device=w.device)
+    bb = torch.zeros(N, dtype=torch.float64, device=w.device)
+    c = 1.4426950408889634 / (hd ** 0.5)
+    W[q0:q0 + D] = w[:D] * c
+    bb[q0:q0 + D] = b[:D] * c
+    for h in range(H):
+        sl = slice(h * hd, (h + 1) * hd)
+        W[k0 + h * hdk:k0 + h * hdk + hd] = w[D:2 * D][sl]
+        bb[k0 + h * hdk:k0 + h * hdk + hd] = b[D:2 * D][sl]
+        W[v0 + h * D:v0 + (h + 1) * D] = wo[:, sl] @ w[2 * D:][sl]
+        bb[v0 + h * D:v0 + (h + 1) * D] = wo[:, sl] @ b[2 * D:][sl]
+    return W.float().contiguous(), bb.float().contiguous(), out_proj_bias.detach().float().contiguous()
+
+
+def seq_attention_fold(planes, B, S, H, D, x, bias, out=None):
+    """x + bias + sum_h softmax(q_h k_h^T) v'_h on tcgen05 (dyg_seq_attention_fold); ``planes``: Split (B*S, attn_fold_layout(D, H)[4])
+    written by the projection GEMM with attn_fold_weights."""
+    q0, k0, v0, hdk, N = attn_fold_layout(D, H)
+    hd = D // H
+    if planes.cols != N or planes.rows != B * S:
+        raise ValueError(f'seq_attention_fold: planes are {planes.rows} x {planes.cols}, expected {B * S} x {N}')
+    if out is None:
+        out = torch.empty((B * S, D), device=x.device, dtype=torch.float32)
+    with _Timed('seq_attention_fold_kernel', 2.0 * B * H * S * S * (hd + D), 4.0 * B * S * (N + 2 * D)):
+        _native.check(_lib().dyg_seq_attention_fold(_p(planes.hi), _p(planes.mid), int(planes.ld), q0, k0, v0, int(B), int(S), int(H),
+                                                    int(hd), int(D), _p(x), int(x.stride(0)), _p(bias), _p(out), int(out.stride(0)),
+                                                    _stream()))
+    _count()
+    return out
+
+
 def mean_tokens(x, B, S, D, tok0, cnt, out=None):
     if out is None:
         out = torch.empty((B, D), device=x.device, dtype=torch.float32)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 4
+#define DYG_ABI_VERSION 5
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -277,6 +277,15 @@ int dyg_seq_attention(const float* qkv, int ld_qkv, int64_t B, int S, int H, int
  * (~1e-5 relative); writes fp32 out (B*S, ldo) and / or the bf16 hi | mid planes (B*S, ldos) that feed dyg_gemm_bf16x3. */
 int dyg_seq_attention_tc(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, float* out, int ldo,
                          void* out_hi, void* out_mid, int ldos, dyg_stream_t stream);
+/* The whole self-attention sub-block of the TransformerEncoder (models/DyGFormer.py:442-455: multi_head_attention + residual)
+ * on tcgen05, with the output projection folded into the value projection:
+ *   out = x + bias + sum_h softmax(q_h k_h^T) v'_h,   v'_h = (W_o[:, h] W_v[h]) LN(x) + W_o[:, h] b_v[h]   (D wide per head)
+ * planes_hi / planes_mid: bf16 hi | mid planes (B*S, ldp) written by the projection GEMM, one row per token laid out as
+ * [q_0..q_{H-1} (hd each) at q_col0 | k_0..k_{H-1} (hd rounded up to 8 each) at k_col0 | v'_0..v'_{H-1} (D each) at v_col0];
+ * q pre-scaled by log2(e) / sqrt(hd) (the kernel uses exp2).  S <= 64, hd <= 112 (multiple of 4), D <= 208 (multiple of 8). */
+int dyg_seq_attention_fold(const void* planes_hi, const void* planes_mid, int ldp, int q_col0, int k_col0, int v_col0,
+                           int64_t B, int S, int H, int hd, int D, const float* x, int ldx, const float* bias, float* out,
+                           int ldo, dyg_stream_t stream);
 /* out[b,:] = mean over tokens [tok0, tok0+cnt) of x[b,:,:] (models/DyGFormer.py:185-187). */
 int dyg_mean_tokens(const float* x, int64_t B, int S, int D, int tok0, int cnt, float* out, int ldo, dyg_stream_t stream);
 
