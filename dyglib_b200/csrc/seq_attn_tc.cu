@@ -7,15 +7,16 @@
 // lets the bias through).  q is pre-scaled by log2(e) / sqrt(hd) in the projection weights; the kernel uses exp2.
 //
 // Inputs are BF16x3 operand planes (hi | mid) written by the projection GEMM's epilogue, one row per token:
-//   [ q_0 .. q_{H-1} (hd each) | k_0 .. k_{H-1} (hdk each, hdk = hd rounded up to 8) | v'_0 .. v'_{H-1} (D each) ]
+//   [ q_0 .. q_{H-1} | k_0 .. k_{H-1} (hdk each, hdk = hd rounded up to 8, zero padded) | v'_0 .. v'_{H-1} (D each) ]
 //
 // One CTA per SM (persistent), a tile = 128 rows = 128 / SP sequences in slots of SP = 32 or 64 rows (S <= SP valid):
 //   warp 0     TMA producer: K_h (K-major SWIZZLE_64B blocks) and V'_h (the same boxes read as an MN-major operand) through
 //              3-D tensor maps (column, token in sequence, sequence): rows past S are zero-filled, never read from HBM
 //   warp 1     TMEM allocation + MMA issue (cta_group::1, M = 128): S = Q K^T with A = Q from TMEM (BF16x3: three MMAs per
 //              k16 step), O' += P V'_h with A = P from TMEM and B = V' MN-major; O' accumulates over the heads
-//   warps 2-5  thread = tile row: Q row global -> registers -> TMEM, softmax of the row's slot window (exp2, masked),
-//              P as bf16 hi | mid written in place over S, final epilogue O' + x + b_o -> x1
+//   warps 2-5  thread = tile row: softmax of the row's slot window (exp2, masked), P as bf16 hi | mid written in place over S
+//   warps 6-9  thread = tile row: Q row global -> registers -> TMEM one step ahead, final epilogue O' + x + b_o -> x1 (it
+//              overlaps the next tile's Q K^T and softmax)
 // Keys of the other slots get P = 0, so one M=128 x K=128 product serves both sequences of a tile.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -36,7 +37,7 @@ constexpr int SA_VCH = 7;                         // 32-feature chunks of a V' p
 constexpr int SA_BLK = SA_ROWS * 64;              // one 32-column block of 128 rows: 8 KB
 constexpr int SA_K_PLANE = SA_KBLK * SA_BLK;      // 32 KB
 constexpr int SA_V_PLANE = SA_VCH * SA_BLK;       // 56 KB
-constexpr int SA_THREADS = 192;
+constexpr int SA_THREADS = 320;                   // TMA, MMA, 4 softmax warps, 4 IO warps
 constexpr uint32_t SA_O_COL = 0;                  // O' accumulator, 208 columns
 constexpr uint32_t SA_S_COL = 256;                // scores (128 fp32 columns), then P_hi [0,64) | P_mid [64,128) in place
 constexpr uint32_t SA_Q_COL = 384;                // Q_hi [0,56) | Q_mid [56,112)
@@ -88,6 +89,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
         "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 16 columns without the wait (several loads in flight, one wait)
@@ -225,67 +230,20 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
                 if (h == a.H - 1) umma_commit_e(o_full);
             }
         }
-    } else {
-        // ------------------------------------------------------------------ softmax / epilogue warps: thread = tile row
+    } else if (warp < 6) {
+        // ------------------------------------------------------------------ softmax warps: thread = tile row
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int slot = r / a.SP, i = r - slot * a.SP;
         const int win = slot * a.SP;                            // first key column of this row's window (warp-uniform)
-        const bool v8ok = ((a.ldx & 7) == 0) && ((a.ldo & 7) == 0) && (((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 31u) == 0);
-
-        // Q row of step n (tile it, head h) -> registers: hd bf16 per plane, 8-byte loads (hd % 4 == 0), zero past hd
-        uint32_t qh[56], qm[56];
-        auto load_q = [&](int64_t n) {
-            const int64_t it = n / a.H;
-            const int h = (int)(n - it * a.H);
-            const int64_t seq = (blockIdx.x + it * gridDim.x) * a.NS + slot;
-            const bool ok = i < a.S && seq < a.B;
-            const int64_t row = seq * a.S + i;
-            const uint2* ph = reinterpret_cast<const uint2*>(a.q_hi + (ok ? row : 0) * a.ldp + a.q_col0 + h * a.hd);
-            const uint2* pm = reinterpret_cast<const uint2*>(a.q_mid + (ok ? row : 0) * a.ldp + a.q_col0 + h * a.hd);
-#pragma unroll
-            for (int j = 0; j < 28; ++j) {
-                uint2 vh = make_uint2(0u, 0u), vm = vh;
-                if (ok && 4 * j < a.hd) {
-                    vh = __ldg(ph + j);
-                    vm = __ldg(pm + j);
-                }
-                qh[2 * j] = vh.x; qh[2 * j + 1] = vh.y;
-                qm[2 * j] = vm.x; qm[2 * j + 1] = vm.y;
-            }
-        };
-        auto store_q = [&]() {
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                tmem_st8(lane_addr + SA_Q_COL + 8 * j, qh + 8 * j);
-                tmem_st8(lane_addr + SA_Q_COL + 56 + 8 * j, qm + 8 * j);
-            }
-            tmem_st_wait();
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(q_full);
-        };
-        if (steps > 0) {
-            load_q(0);
-            store_q();
-        }
         int64_t n = 0;
         for (int64_t it = 0; it < my_tiles; ++it) {
             const int64_t seq = (blockIdx.x + it * gridDim.x) * a.NS + slot;
             const bool rowok = i < a.S && seq < a.B;
-            const int64_t row = seq * a.S + i;
-            if (rowok) {
-                const char* xp = reinterpret_cast<const char*>(a.x + row * a.ldx);
-                for (int b = 0; b < a.D * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + b));
-            }
             for (int h = 0; h < a.H; ++h, ++n) {
-                const bool more = n + 1 < steps;
-                if (more) load_q(n + 1);                         // in flight while the scores of this step are computed
                 mbar_wait(s_full, (uint32_t)(n & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (more) store_q();                             // Q K^T of this step has retired: the Q columns are free
-                // ---- softmax over the SP-wide window of this row's slot
                 uint32_t sv[64];
                 const uint32_t sa = lane_addr + SA_S_COL + (uint32_t)win;
                 tmem_ld16_nowait(sa, sv);
@@ -307,26 +265,28 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
                     sv[j] = __float_as_uint(p);
                 }
                 const float inv = rowok ? 1.f / sum : 0.f;
-                // ---- P = p / sum as bf16 hi | mid over all 128 key columns (zero outside the window): 2 keys per 32-bit column
-                uint32_t ph[32], pm[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) split_pack(__uint_as_float(sv[2 * j]) * inv, __uint_as_float(sv[2 * j + 1]) * inv, ph[j], pm[j]);
-                const uint32_t zero[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                // P = p / sum as bf16 hi | mid over all 128 key columns (zero outside the window): 2 keys per 32-bit column,
+                // 16 columns (32 keys) at a time
                 const uint32_t pa = lane_addr + SA_S_COL;
                 const int wc = win >> 1;                         // first column of the window inside a plane
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {                    // 16-column pieces of a 64-column plane
                     const int rel = 16 * c - wc;                 // warp-uniform
-                    const bool in = rel >= 0 && rel < (a.SP >> 1);
-                    if (in && rel == 0) {
+                    if (rel == 0 || (rel == 16 && a.SP == 64)) {
+                        uint32_t ph[16], pm[16];
+                        if (rel == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) split_pack(__uint_as_float(sv[2 * j]) * inv, __uint_as_float(sv[2 * j + 1]) * inv, ph[j], pm[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                split_pack(__uint_as_float(sv[32 + 2 * j]) * inv, __uint_as_float(sv[33 + 2 * j]) * inv, ph[j], pm[j]);
+                        }
                         tmem_st16(pa + 16 * c, ph);
                         tmem_st16(pa + 64 + 16 * c, pm);
-                    } else if (in) {
-                        tmem_st16(pa + 16 * c, ph + 16);
-                        tmem_st16(pa + 64 + 16 * c, pm + 16);
                     } else {
-                        tmem_st16(pa + 16 * c, zero);
-                        tmem_st16(pa + 64 + 16 * c, zero);
+                        tmem_st16_zero(pa + 16 * c);
+                        tmem_st16_zero(pa + 64 + 16 * c);
                     }
                 }
                 tmem_st_wait();
@@ -334,44 +294,113 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
             }
-            // ---- final epilogue of the tile: x1 = O' + x + b_o
+        }
+    } else {
+        // ------------------------------------------------------------------ IO warps: Q rows -> TMEM, final epilogue of every tile
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const int slot = r / a.SP, i = r - slot * a.SP;
+        // Q row of step n (tile it, head h) -> registers: hdk bf16 per plane (zero padded by the projection), 16-byte loads
+        auto load_q = [&](int64_t n, uint32_t (&qh)[56], uint32_t (&qm)[56]) {
+            const int64_t it = n / a.H;
+            const int h = (int)(n - it * a.H);
+            const int64_t seq = (blockIdx.x + it * gridDim.x) * a.NS + slot;
+            const bool ok = i < a.S && seq < a.B;
+            const int64_t row = ok ? seq * a.S + i : 0;
+            const uint4* ph = reinterpret_cast<const uint4*>(a.q_hi + row * a.ldp + a.q_col0 + h * a.hdk);
+            const uint4* pm = reinterpret_cast<const uint4*>(a.q_mid + row * a.ldp + a.q_col0 + h * a.hdk);
+#pragma unroll
+            for (int j = 0; j < 14; ++j) {
+                uint4 vh = make_uint4(0u, 0u, 0u, 0u), vm = vh;
+                if (ok && 8 * j < a.hdk) {
+                    vh = __ldg(ph + j);
+                    vm = __ldg(pm + j);
+                }
+                qh[4 * j] = vh.x; qh[4 * j + 1] = vh.y; qh[4 * j + 2] = vh.z; qh[4 * j + 3] = vh.w;
+                qm[4 * j] = vm.x; qm[4 * j + 1] = vm.y; qm[4 * j + 2] = vm.z; qm[4 * j + 3] = vm.w;
+            }
+        };
+        auto store_q = [&](const uint32_t (&qh)[56], const uint32_t (&qm)[56]) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                tmem_st8(lane_addr + SA_Q_COL + 8 * j, qh + 8 * j);
+                tmem_st8(lane_addr + SA_Q_COL + 56 + 8 * j, qm + 8 * j);
+            }
+            tmem_st_wait();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_full);
+        };
+        if (steps > 0) {
+            uint32_t qh[56], qm[56];
+            load_q(0, qh, qm);
+            store_q(qh, qm);
+        }
+        int64_t n = 0;
+        for (int64_t it = 0; it < my_tiles; ++it) {
+            const int64_t seq = (blockIdx.x + it * gridDim.x) * a.NS + slot;
+            const bool rowok = i < a.S && seq < a.B;
+            const int64_t row = rowok ? seq * a.S + i : 0;
+            const float* xr = a.x + row * a.ldx;
+            float* orow = a.out + row * a.ldo;
+            if (rowok) {
+                for (int b = 0; b < a.D * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(xr) + b));
+            }
+            for (int h = 0; h < a.H; ++h, ++n) {
+                uint32_t qh[56], qm[56];                         // scoped to the step: dead during the epilogue
+                load_q(n + 1 < steps ? n + 1 : n, qh, qm);       // in flight while the scores of this step are computed
+                mbar_wait(s_full, (uint32_t)(n & 1));            // Q K^T of this step has retired: the Q columns are free
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (n + 1 < steps) store_q(qh, qm);
+            }
+            // ---- final epilogue of the tile: x1 = O' + x + b_o in 16-column chunks (D % 8 == 0: the last one may be 8 wide);
+            // the residual chunks are requested two ahead of their use
+            float xa[16], xb[16], xc[16];
+#define SA_LOAD_X(COL, XV)                                          \
+    do {                                                             \
+        _Pragma("unroll") for (int j = 0; j < 16; ++j) XV[j] = 0.f;  \
+        if (rowok && (COL) < a.D) {                                  \
+            ld_v8(xr + (COL), XV);                                   \
+            if ((COL) + 8 < a.D) ld_v8(xr + (COL) + 8, XV + 8);      \
+        }                                                            \
+    } while (0)
+#define SA_EMIT(COL, XV)                                                                              \
+    do {                                                                                               \
+        if ((COL) < a.D) {                                                                             \
+            const bool wide = (COL) + 8 < a.D;                                                         \
+            float bv[16];                                                                              \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                            \
+                const float4 t = (j < 2 || wide) ? __ldg(reinterpret_cast<const float4*>(a.bias + (COL)) + j) \
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);                    \
+                bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;        \
+            }                                                                                          \
+            uint32_t rr[16];                                                                           \
+            tmem_ld16(lane_addr + SA_O_COL + (uint32_t)(COL), rr);                                     \
+            if (rowok) {                                                                               \
+                uint32_t o[16];                                                                        \
+                _Pragma("unroll") for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(rr[j]) + XV[j] + bv[j]); \
+                st_v8(orow + (COL), o);                                                                \
+                if (wide) st_v8(orow + (COL) + 8, o + 8);                                              \
+            }                                                                                          \
+            __syncwarp();                                                                              \
+        }                                                                                              \
+    } while (0)
+            SA_LOAD_X(0, xa);
+            SA_LOAD_X(16, xb);
             mbar_wait(o_full, (uint32_t)(it & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float* xr = a.x + (rowok ? row : 0) * a.ldx;
-            float* orow = a.out + (rowok ? row : 0) * a.ldo;
-            for (int col = 0; col < a.D; col += 16) {
-                uint32_t rr[16];
-                float xv[16];
-                const int valid = min(16, a.D - col);
-                if (rowok) {
-                    if (v8ok && valid == 16) {
-                        ld_v8(xr + col, xv);
-                        ld_v8(xr + col + 8, xv + 8);
-                    } else if (v8ok && valid == 8) {
-                        ld_v8(xr + col, xv);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) xv[j] = j < valid ? xr[col + j] : 0.f;
-                    }
-                }
-                tmem_ld16(lane_addr + SA_O_COL + (uint32_t)col, rr);
-                if (rowok) {
-                    uint32_t o[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(rr[j]) + xv[j] + (j < valid ? __ldg(a.bias + col + j) : 0.f));
-                    if (v8ok && valid == 16) {
-                        st_v8(orow + col, o);
-                        st_v8(orow + col + 8, o + 8);
-                    } else if (v8ok && valid == 8) {
-                        st_v8(orow + col, o);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (j < valid) orow[col + j] = __uint_as_float(o[j]);
-                    }
-                }
-                __syncwarp();
+#pragma unroll 1
+            for (int col = 0; col < a.D; col += 48) {
+                SA_LOAD_X(col + 32, xc);
+                SA_EMIT(col, xa);
+                SA_LOAD_X(col + 48, xa);
+                SA_EMIT(col + 16, xb);
+                SA_LOAD_X(col + 64, xb);
+                SA_EMIT(col + 32, xc);
             }
+#undef SA_LOAD_X
+#undef SA_EMIT
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
@@ -433,11 +462,13 @@ extern "C" int dyg_seq_attention_fold(const void* planes_hi, const void* planes_
     const int cols = v_col0 + H * D;
     DYG_CHECK_ARG((ldp % 8) == 0 && ldp >= cols && aligned16(planes_hi) && aligned16(planes_mid),
                   "dyg_seq_attention_fold: planes must be 16-byte aligned with ldp %% 8 == 0 and ldp >= %d", cols);
-    DYG_CHECK_ARG((q_col0 % 4) == 0 && (k_col0 % 8) == 0 && (v_col0 % 8) == 0 && q_col0 >= 0 && k_col0 >= q_col0 + H * hd &&
+    DYG_CHECK_ARG((q_col0 % 8) == 0 && (k_col0 % 8) == 0 && (v_col0 % 8) == 0 && q_col0 >= 0 && k_col0 >= q_col0 + H * hdk &&
                       v_col0 >= k_col0 + H * hdk,
                   "dyg_seq_attention_fold: segment offsets q=%d k=%d v=%d do not fit [q | k | v'] with 8-column alignment", q_col0, k_col0, v_col0);
     DYG_CHECK_ARG(B * (int64_t)S < ((int64_t)1 << 31), "dyg_seq_attention_fold: too many tokens");
-    DYG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0, "dyg_seq_attention_fold: misaligned x / out");
+    DYG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 31u) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0 && (ldx % 8) == 0 && (ldo % 8) == 0 &&
+                      aligned16(bias),
+                  "dyg_seq_attention_fold: x / out must be 32-byte aligned with leading dimensions that are multiples of 8, bias 16-byte aligned");
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.q_hi = reinterpret_cast<const __nv_bfloat16*>(planes_hi);

@@ -544,7 +544,7 @@ def attn_fold_layout(D, H):
     """Column layout of the projection planes dyg_seq_attention_fold reads: (q_col0, k_col0, v_col0, hdk, total columns)."""
     hd = D // H
     hdk = (hd + 7) // 8 * 8
-    k0 = (H * hd + 7) // 8 * 8
+    k0 = H * hdk
     v0 = k0 + H * hdk
     return 0, k0, v0, hdk, v0 + H * D
 
@@ -566,10 +566,10 @@ def attn_fold_weights(in_proj_weight, in_proj_bias, out_proj_weight, out_proj_bi
     W = torch.zeros((N, D), dtype=torch.float64, device=w.device)
     bb = torch.zeros(N, dtype=torch.float64, device=w.device)
     c = 1.4426950408889634 / (hd ** 0.5)
-    W[q0:q0 + D] = w[:D] * c
-    bb[q0:q0 + D] = b[:D] * c
     for h in range(H):
         sl = slice(h * hd, (h + 1) * hd)
+        W[q0 + h * hdk:q0 + h * hdk + hd] = w[:D][sl] * c
+        bb[q0 + h * hdk:q0 + h * hdk + hd] = b[:D][sl] * c
         W[k0 + h * hdk:k0 + h * hdk + hd] = w[D:2 * D][sl]
         bb[k0 + h * hdk:k0 + h * hdk + hd] = b[D:2 * D][sl]
         W[v0 + h * D:v0 + (h + 1) * D] = wo[:, sl] @ w[2 * D:][sl]

@@ -281,7 +281,7 @@ int dyg_seq_attention_tc(const float* qkv, int ld_qkv, int64_t B, int S, int H, 
  * on tcgen05, with the output projection folded into the value projection:
  *   out = x + bias + sum_h softmax(q_h k_h^T) v'_h,   v'_h = (W_o[:, h] W_v[h]) LN(x) + W_o[:, h] b_v[h]   (D wide per head)
  * planes_hi / planes_mid: bf16 hi | mid planes (B*S, ldp) written by the projection GEMM, one row per token laid out as
- * [q_0..q_{H-1} (hd each) at q_col0 | k_0..k_{H-1} (hd rounded up to 8 each) at k_col0 | v'_0..v'_{H-1} (D each) at v_col0];
+ * [q_0..q_{H-1} at q_col0 | k_0..k_{H-1} at k_col0 (hd rounded up to 8 columns each, zero padded) | v'_0..v'_{H-1} (D each) at v_col0];
  * q pre-scaled by log2(e) / sqrt(hd) (the kernel uses exp2).  S <= 64, hd <= 112 (multiple of 4), D <= 208 (multiple of 8). */
 int dyg_seq_attention_fold(const void* planes_hi, const void* planes_mid, int ldp, int q_col0, int k_col0, int v_col0,
                            int64_t B, int S, int H, int hd, int D, const float* x, int ldx, const float* bias, float* out,
