@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _lock = threading.Lock()
 _lib = None
@@ -148,6 +148,7 @@ SIGNATURES = {
     'dyg_seq_attention': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_seq_attention_tc': [c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
     'dyg_seq_attention_fold': [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
+    'dyg_attn_block': [c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_l, c_p],
     'dyg_mean_tokens': [c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p],
     'dyg_tgn_persist': [c_p, c_l, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     'dyg_tgn_select_last': [c_p, c_p, c_l, c_p, c_p],
@@ -186,6 +187,8 @@ def load():
         lib.dyg_csr_fence_entries.restype = c_l
         lib.dyg_csr_fence_entries.argtypes = [c_l]
         lib.dyg_ln_ffn_workspace_bytes.argtypes = []
+        lib.dyg_attn_block_workspace_bytes.restype = c_l
+        lib.dyg_attn_block_workspace_bytes.argtypes = [c_i]
         lib.dyg_tgn_step_sizeof.restype = c_l
         lib.dyg_tgn_step_sizeof.argtypes = []
         for name, args in SIGNATURES.items():

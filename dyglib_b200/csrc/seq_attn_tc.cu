@@ -62,66 +62,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// D[tmem] (+)= A[tmem] B[smem]: the A operand (bf16 pairs, one 32-bit column per two k) is read from tensor memory
-__device__ __forceinline__ void umma_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
-    asm volatile(
-        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]),
-        "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
-    const uint32_t z = 0u;
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// 16 columns without the wait (several loads in flight, one wait)
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// MN-major SWIZZLE_64B descriptor: 32 elements (64 bytes) contiguous along N per row, rows = k; 8-row groups SBO = 512 B
-// apart, 32-element chunks along N LBO = 8 KB apart (one 128-row block per chunk)
-__device__ __forceinline__ uint64_t make_desc_mn_sw64(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(SA_BLK >> 4) << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
-    return d;
-}
-
 __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const __grid_constant__ CUtensorMap map_hi,
                                                                            const __grid_constant__ CUtensorMap map_mid,
                                                                            const AttnArgs a) {
@@ -197,7 +137,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
         const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SA_ROWS >> 3) << 17) | ((uint32_t)(SA_ROWS >> 4) << 24);
         const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(SA_NV >> 3) << 17) | ((uint32_t)(SA_ROWS >> 4) << 24);
         const uint64_t kd_h = make_desc_sw64(smem_u32(k_buf)), kd_m = make_desc_sw64(smem_u32(k_buf + SA_K_PLANE));
-        const uint64_t vd_h = make_desc_mn_sw64(smem_u32(v_buf)), vd_m = make_desc_mn_sw64(smem_u32(v_buf + SA_V_PLANE));
+        const uint64_t vd_h = make_desc_mn_sw64(smem_u32(v_buf), SA_BLK), vd_m = make_desc_mn_sw64(smem_u32(v_buf + SA_V_PLANE), SA_BLK);
         const uint32_t tq = tmem_base + SA_Q_COL, ts = tmem_base + SA_S_COL, to = tmem_base + SA_O_COL;
         int64_t n = 0;
         for (int64_t it = 0; it < my_tiles; ++it) {

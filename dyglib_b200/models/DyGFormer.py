@@ -23,9 +23,9 @@ import os
 
 # LayerNorm + feed-forward as one kernel (dyg_ln_ffn_bf16x3); DYG_FUSED_FFN=0 selects the three-kernel path
 FUSED_FFN = os.environ.get('DYG_FUSED_FFN', '1') != '0'
-# attention sub-block as [q | k | v'] projection + dyg_seq_attention_fold (tcgen05); DYG_FUSED_ATTN=0 selects the
-# QKV GEMM + mma.sync attention + out-projection GEMM path
-FUSED_ATTN = os.environ.get('DYG_FUSED_ATTN', '1') != '0'
+# attention sub-block: 2 = one kernel (dyg_attn_block), 1 = LayerNorm planes + [q | k | v'] projection GEMM +
+# dyg_seq_attention_fold, 0 = QKV GEMM + mma.sync attention + out-projection GEMM
+FUSED_ATTN = int(os.environ.get('DYG_FUSED_ATTN', '2'))
 
 
 class NeighborCooccurrenceEncoder(nn.Module):
@@ -107,15 +107,20 @@ class TransformerEncoder(nn.Module):
         n0, n1 = self.norm_layers
         l0, l1 = self.linear_layers
         # every dense contraction runs on tcgen05 from BF16x3 operand planes (ops.gemm); the residual stream stays fp32
-        y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
         hd = D // self.num_heads
-        if FUSED_ATTN and ops.attn_fold_fusable(S, D, self.num_heads):
-            # [q | k | v'] projection with the out-projection folded into v', then the tcgen05 attention kernel adds the
-            # residual: two launches for LayerNorm..residual instead of four, no attention-output round trip
+        if FUSED_ATTN == 2 and ops.attn_fold_fusable(S, D, self.num_heads):
+            # LayerNorm + [q | k | v'] projection (out-projection folded into v') + attention + residual in ONE kernel: the
+            # projected rows never reach HBM
+            wcat, bcat, bout = self._folded()
+            x1 = ops.attn_block(x, n0.weight.detach(), n0.bias.detach(), n0.eps, wcat, bcat, bout, B, S, self.num_heads, D)
+        elif FUSED_ATTN and ops.attn_fold_fusable(S, D, self.num_heads):
+            # the same as three launches: LayerNorm planes, projection GEMM, tcgen05 attention + residual
+            y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
             wcat, bcat, bout = self._folded()
             pl = ops.gemm(y, wcat, bcat, want='split')
             x1 = ops.seq_attention_fold(pl, B, S, self.num_heads, D, x, bout)
         else:
+            y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
             qkv = ops.gemm(y, mha.in_proj_weight, mha.in_proj_bias.detach())
             if S <= 128 and hd <= 128 and hd % 2 == 0:
                 a = ops.seq_attention_tc(qkv, B, S, self.num_heads, hd, want='split')

@@ -594,6 +594,32 @@ def seq_attention_fold(planes, B, S, H, D, x, bias, out=None):
     return out
 
 
+_attn_ws = {}
+
+
+def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
+    """x + bout + sum_h softmax(q_h k_h^T) v'_h with [q | k | v'] = wcat LayerNorm(x) + bcat, one kernel (dyg_attn_block):
+    LayerNorm, projection, attention and residual; the projected rows live in an L2-resident scratch.  ``wcat``: Split of
+    attn_fold_weights(...)[0]."""
+    q0, k0, v0, hdk, N = attn_fold_layout(D, H)
+    if wcat.rows != N or wcat.cols != D or x.shape != (B * S, D):
+        raise ValueError(f'attn_block: weight {wcat.rows} x {wcat.cols} / x {tuple(x.shape)} do not match B={B} S={S} D={D} H={H}')
+    if out is None:
+        out = torch.empty_like(x)
+    key = (str(x.device), N)
+    if key not in _attn_ws:
+        _attn_ws[key] = torch.empty(int(_lib().dyg_attn_block_workspace_bytes(int(N))) + 1024, dtype=torch.uint8, device=x.device)
+    ws = _attn_ws[key]
+    off = (-ws.data_ptr()) % 1024
+    hd = D // H
+    with _Timed('attn_block_kernel', 2.0 * B * S * N * D + 2.0 * B * H * S * S * (hd + D), 8.0 * B * S * D):
+        _native.check(_lib().dyg_attn_block(_p(x), int(x.stride(0)), _p(gamma), _p(beta), float(eps), _p(wcat.hi), _p(wcat.mid), int(wcat.ld),
+                                            _p(bcat), int(N), q0, k0, v0, _p(bout), int(B), int(S), int(H), int(hd), int(D), _p(out),
+                                            int(out.stride(0)), ctypes.c_void_p(ws.data_ptr() + off), int(ws.numel() - off), _stream()))
+    _count()
+    return out
+
+
 def mean_tokens(x, B, S, D, tok0, cnt, out=None):
     if out is None:
         out = torch.empty((B, D), device=x.device, dtype=torch.float32)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 5
+#define DYG_ABI_VERSION 6
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -286,6 +286,15 @@ int dyg_seq_attention_tc(const float* qkv, int ld_qkv, int64_t B, int S, int H, 
 int dyg_seq_attention_fold(const void* planes_hi, const void* planes_mid, int ldp, int q_col0, int k_col0, int v_col0,
                            int64_t B, int S, int H, int hd, int D, const float* x, int ldx, const float* bias, float* out,
                            int ldo, dyg_stream_t stream);
+/* The same sub-block INCLUDING its LayerNorm and the [q | k | v'] projection, one kernel (models/DyGFormer.py:442-455):
+ *   out = x + bout + sum_h softmax(q_h k_h^T) v'_h,   [q | k | v'] = W LayerNorm(x; gamma, beta, eps) + bcat
+ * W_hi / W_mid: bf16 planes of the (N, D) projection weight in the column layout of dyg_seq_attention_fold (N = v_col0 + H*D).
+ * The projected rows stay in a per-CTA scratch inside `workspace` (dyg_attn_block_workspace_bytes(N) bytes, 1024-byte aligned,
+ * L2 resident); HBM traffic is x in and out out. */
+int64_t dyg_attn_block_workspace_bytes(int N);
+int dyg_attn_block(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W_hi, const void* W_mid,
+                   int ldw, const float* bcat, int N, int q_col0, int k_col0, int v_col0, const float* bout, int64_t B, int S,
+                   int H, int hd, int D, float* out, int ldo, void* workspace, int64_t workspace_bytes, dyg_stream_t stream);
 /* out[b,:] = mean over tokens [tok0, tok0+cnt) of x[b,:,:] (models/DyGFormer.py:185-187). */
 int dyg_mean_tokens(const float* x, int64_t B, int S, int D, int tok0, int cnt, float* out, int ldo, dyg_stream_t stream);
 

@@ -45,6 +45,11 @@ def test_seq_attention_fold_vs_float64(B, S, D, H):
     err = float((got.double().cpu() - want).abs().max())
     scale = float(want.abs().max())
     assert err < 3e-5 * max(scale, 1.0), (err, scale)
+    # the one-kernel form (LayerNorm + projection + attention + residual, dyg_attn_block)
+    got2 = ops.attn_block(x, ln.weight.detach(), ln.bias.detach(), ln.eps, ops.split_bf16(W), b, bo, B, S, H, D)
+    torch.cuda.synchronize()
+    err2 = float((got2.double().cpu() - want).abs().max())
+    assert err2 < 3e-5 * max(scale, 1.0), (err2, scale)
 
 
 def test_seq_attention_fold_rejects_unsupported():
