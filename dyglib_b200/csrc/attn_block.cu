@@ -13,7 +13,13 @@
 //            memory phase A no longer needs, Q and P as TMEM A operands, O' accumulated over the heads, + x + b_o -> x1
 //
 // so HBM sees x once in and x1 once out.  Warps: 0 TMA producer, 1 MMA issuer, 2-9 epilogue of phase A; in phase B warps 2-5
-// run the softmax and warps 6-9 move Q rows into TMEM, normalise the NEXT tile's rows and drain O'.
+// normalise the NEXT tile's rows and run the softmax, warps 6-9 move Q rows into TMEM and drain O'.
+//
+// Measured on B200 (profiles/README.md, round 2): parity-green, but 2.7 - 3.6 ms per DyGFormer launch against 2.13 ms for the
+// three-launch form (layernorm_split + projection GEMM + dyg_seq_attention_fold).  The phases of a tile cannot overlap (phase
+// B's K | V' alias phase A's operands: BF16x3 planes leave no room for both), every CTA streams the whole W_cat (731 KB) per
+// tile, and the scratch round trip moves the HBM traffic to L2, whose bandwidth is about the same: ~2.1 MB of L2 traffic per
+// tile.  It is kept as the DYG_FUSED_ATTN=2 path; the default is the three-launch form.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
@@ -143,8 +149,20 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const __grid_
             uint32_t ph = 0;
             int64_t n = 0;
             const int row0 = (int)blockIdx.x * AB_ROWS;
+            // contiguous rows of every sequence of a tile -> L2 (one bulk prefetch per sequence)
+            auto prefetch_x = [&](int64_t tile) {
+                if (tile >= a.tiles) return;
+                for (int sl = 0; sl < a.NS; ++sl) {
+                    const int64_t seq = tile * a.NS + sl;
+                    if (seq >= a.B) break;
+                    const char* p = reinterpret_cast<const char*>(a.x + seq * a.S * a.ldx);
+                    const uint32_t bytes = (uint32_t)(a.S * a.ldx * 4) & ~15u;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+                }
+            };
             for (int64_t it = 0; it < my_tiles; ++it) {
                 // ---- phase A: the image of this tile, then the W_cat stages
+                prefetch_x(blockIdx.x + (it + 1) * gridDim.x);                // the next tile's rows: LayerNorm reads them during this tile's phase B
                 mbar_wait(img_ready, (uint32_t)(it & 1));
                 if (it > 0) mbar_wait(o_full, (uint32_t)((it - 1) & 1));     // every MMA of the previous phase B retired: smem is free
                 mbar_expect_tx(a_full, (uint32_t)AB_A_BYTES);
@@ -164,8 +182,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const __grid_
                         }
                     }
                 }
-                // ---- phase B: K_h / V'_h of this tile from the scratch
                 mbar_wait(planes_ready, (uint32_t)(it & 1));
+                prefetch_x(blockIdx.x + it * gridDim.x);                      // this tile's rows again, for the residual of the final epilogue
                 for (int h = 0; h < a.H; ++h, ++n) {
                     const uint32_t par = (uint32_t)(n & 1);
                     mbar_wait(k_empty, par ^ 1u);
@@ -280,23 +298,23 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const __grid_
         const __nv_bfloat16* my_qh = eg.Chi + (size_t)r * a.ldp + a.q_col0;
         const __nv_bfloat16* my_qm = eg.Cmid + (size_t)r * a.ldp + a.q_col0;
 
-        // LayerNorm of the rows of tile `tile` owned by this IO warp (32 rows, lane = 8 columns) -> operand image in global memory
+        // LayerNorm of the rows of tile `tile` owned by this softmax warp (32 rows, lane = 8 columns) -> operand image in global memory
         const int c0 = 8 * lane;
         const bool own = c0 < a.D;
-        float gm8[8], bt8[8];
-        if (io) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                gm8[j] = own ? __ldg(a.gamma + c0 + j) : 0.f;
-                bt8[j] = own ? __ldg(a.beta + c0 + j) : 0.f;
-            }
-        }
         auto ln_image = [&](int64_t tile) {
-            constexpr int RB = 4;
+            constexpr int RB = 8;
             const int kb = lane >> 2;
             const uint32_t chunk = (uint32_t)(lane & 3);
             const int rbase = quarter * 32;
             for (int i0 = 0; i0 < 32; i0 += RB) {
+                // gamma / beta are re-read per batch (L1 / L2 hits) instead of living in registers across the whole tile loop:
+                // with 223 KB of shared memory the L1 is too small to absorb spills
+                float gm8[8], bt8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    gm8[j] = own ? __ldg(a.gamma + c0 + j) : 0.f;
+                    bt8[j] = own ? __ldg(a.beta + c0 + j) : 0.f;
+                }
                 float4 v[RB][2];
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const __grid_
         };
 
         // the zero fill of the image (all threads, before the barrier above) precedes the first LayerNorm
-        if (io && my_tiles > 0) ln_image((int64_t)blockIdx.x);
+        if (!io && my_tiles > 0) ln_image((int64_t)blockIdx.x);
         const int chunk0 = (warp - 2) >> 2;
         uint32_t ecnt0 = 0, ecnt1 = 0;
         int64_t n = 0;
@@ -402,6 +420,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const __grid_
             const int64_t seq = tile * a.NS + slot;
             const bool rowok = i < a.S && seq < a.B;
             if (!io) {
+                if (it + 1 < my_tiles) ln_image(tile + gridDim.x);   // the next tile's operand, while Q / K of this one are on their way
                 for (int h = 0; h < a.H; ++h, ++n) {
                     mbar_wait(s_full, (uint32_t)(n & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -465,7 +484,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_block_kernel(const __grid_
                     mbar_wait(s_full, (uint32_t)(n & 1));            // Q K^T of this head has retired: the Q columns are free
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (h + 1 < a.H) store_q(qh, qm);
-                    if (h == 0 && it + 1 < my_tiles) ln_image(tile + gridDim.x);   // the next tile's operand, while this one attends
                 }
                 // ---- final epilogue of the tile: x1 = O' + x + b_o
                 const int64_t row = rowok ? seq * a.S + i : 0;

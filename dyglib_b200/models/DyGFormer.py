@@ -23,9 +23,10 @@ import os
 
 # LayerNorm + feed-forward as one kernel (dyg_ln_ffn_bf16x3); DYG_FUSED_FFN=0 selects the three-kernel path
 FUSED_FFN = os.environ.get('DYG_FUSED_FFN', '1') != '0'
-# attention sub-block: 2 = one kernel (dyg_attn_block), 1 = LayerNorm planes + [q | k | v'] projection GEMM +
-# dyg_seq_attention_fold, 0 = QKV GEMM + mma.sync attention + out-projection GEMM
-FUSED_ATTN = int(os.environ.get('DYG_FUSED_ATTN', '2'))
+# attention sub-block: 1 (default) = LayerNorm planes + [q | k | v'] projection GEMM + dyg_seq_attention_fold (tcgen05),
+# 2 = one kernel (dyg_attn_block; parity-green but measured slower: L2-bound scratch round trip),
+# 0 = QKV GEMM + mma.sync attention + out-projection GEMM
+FUSED_ATTN = int(os.environ.get('DYG_FUSED_ATTN', '1'))
 
 
 class NeighborCooccurrenceEncoder(nn.Module):
