@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _lock = threading.Lock()
 _lib = None
@@ -134,6 +134,7 @@ SIGNATURES = {
     'dyg_linear_tc': [ctypes.POINTER(Seg), c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_i, c_i, c_i, c_p],
     'dyg_gemm_bf16x3': [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_p],
     'dyg_ln_ffn_bf16x3': [c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_p, c_l, c_p],
+    'dyg_ln_gemm_bf16x3': [c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_i, c_i, c_p, c_l, c_p],
     'dyg_split_bf16': [c_p, c_i, c_l, c_i, c_p, c_p, c_i, c_p],
     'dyg_layernorm_split': [c_p, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_p],
     'dyg_patch_project_stages': [c_i, c_i, c_i, c_i, c_i, c_p],

@@ -275,6 +275,112 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
 }
 
 
+// ------------------------------------------------------------------ LayerNorm warps shared by the fused kernels
+// The normalised rows of the NEXT tile are produced while the current tile computes: each of the four LN warps normalises
+// 32 rows of its CTA's 128 (statistics and values from one read of x) and stores them as BF16x3 planes into the CTA's image
+// of the A operand in global memory (L2 resident, already in the SWIZZLE_64B shared-memory layout).  When the MMA warp
+// releases A, ONE bulk copy moves the 112 KB image into shared memory at engine speed; only that copy is exposed.
+// Rows are handled eight at a time with the warp reductions of the eight rows interleaved step by step (a reduction is a
+// chain of five dependent shuffles; one row after the other took ~25 us per tile with one LN warp per scheduler).
+constexpr int LN_WARPS = 4;
+constexpr int LN_KB = 7;                  // k blocks of the image (K <= 224)
+struct LnSrc {
+    const float* x;
+    const float* gamma;
+    const float* beta;
+    int64_t M, m_super;
+    int ldx, D;
+    float eps;
+};
+__device__ __forceinline__ void ln_warps_loop(const LnSrc& f, int64_t pair, int64_t npairs, uint32_t rank, bool copier, int quarter, int lane,
+                                              unsigned char* a_img, unsigned char* a_res, uint64_t* a_free, uint64_t* a_copy, uint64_t* a_full) {
+    constexpr int RB = 8;                                               // rows per batch (16 float4 loads in flight per lane)
+    constexpr int a_stage = 2 * G_A_PLANE;
+    const int r0 = quarter * 32;                                        // this warp's 32 rows of the CTA's 128
+    // lane l owns columns [8l, 8l+8) of a row: two 16-byte loads, and one 16-byte bf16 chunk per plane on the way out
+    const int c0 = 8 * lane;
+    const bool own = c0 < f.D;                                          // D % 8 == 0
+    const int kb = lane >> 2;
+    const uint32_t chunk = (uint32_t)(lane & 3);
+    float gm8[8], bt8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        gm8[j] = own ? __ldg(f.gamma + c0 + j) : 0.f;
+        bt8[j] = own ? __ldg(f.beta + c0 + j) : 0.f;
+    }
+    const float invD = 1.f / (float)f.D;
+    int it = 0;
+    for (int64_t ms = pair; ms < f.m_super; ms += npairs, ++it) {
+        const int64_t m0 = ms * 2 * G_BM + (int64_t)rank * G_BM;
+        for (int i0 = 0; i0 < 32; i0 += RB) {
+            float4 v[RB][2];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int64_t m = m0 + r0 + i0 + i;
+                if (own && m < f.M) {
+                    const float4* xp = reinterpret_cast<const float4*>(f.x + m * f.ldx + c0);
+                    v[i][0] = xp[0];
+                    v[i][1] = xp[1];
+                } else {
+                    v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[i][1] = v[i][0];
+                }
+            }
+            float s[RB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) s[i] = ((v[i][0].x + v[i][0].y) + (v[i][0].z + v[i][0].w)) + ((v[i][1].x + v[i][1].y) + (v[i][1].z + v[i][1].w));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < RB; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+            }
+            float mean[RB], q[RB];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                mean[i] = s[i] * invD;
+                const float d0 = v[i][0].x - mean[i], d1 = v[i][0].y - mean[i], d2 = v[i][0].z - mean[i], d3 = v[i][0].w - mean[i];
+                const float d4 = v[i][1].x - mean[i], d5 = v[i][1].y - mean[i], d6 = v[i][1].z - mean[i], d7 = v[i][1].w - mean[i];
+                q[i] = own ? ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7)) : 0.f;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < RB; ++i) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+            }
+            if (own) {
+#pragma unroll
+                for (int i = 0; i < RB; ++i) {
+                    const float rstd = rsqrtf(q[i] * invD + f.eps);
+                    const float xs[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        split_pack((xs[2 * j] - mean[i]) * rstd * gm8[2 * j] + bt8[2 * j],
+                                   (xs[2 * j + 1] - mean[i]) * rstd * gm8[2 * j + 1] + bt8[2 * j + 1], h[j], l[j]);
+                    const int r = r0 + i0 + i;
+                    unsigned char* p = a_img + kb * a_stage + (uint32_t)((r >> 3) * 512 + (r & 7) * 64) + ((chunk ^ (uint32_t)((r >> 1) & 3)) << 4);
+                    *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(p + G_A_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");               // generic global writes -> visible to the bulk copy engine
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LN_WARPS) : "memory");   // all four LN warps finished the image
+        if (copier) {
+            mbar_wait(a_free, (uint32_t)((it & 1) ^ 1));                 // last MMA reading A of the previous tile retired
+            if (lane == 0) {
+                mbar_expect_tx(a_copy, (uint32_t)(LN_KB * a_stage));
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(a_res)),
+                             "l"(a_img), "r"((uint32_t)(LN_KB * a_stage)), "r"(smem_u32(a_copy))
+                             : "memory");
+            }
+            mbar_wait(a_copy, (uint32_t)(it & 1));
+            if (lane == 0) mbar_arrive_leader(a_full);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LN_WARPS) : "memory");   // the image may be overwritten for the next tile
+    }
+}
+
 // ====================================================================================================================
 // dyg_ln_ffn_bf16x3: out = x + W2 gelu(W1 LayerNorm(x) + b1) + b2 — the feed-forward half of DyGFormer's transformer block
 // (models/DyGFormer.py:456-461) as ONE kernel: the 4D-wide hidden activation never leaves the SM.
@@ -617,85 +723,181 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
         }
     } else {
         // ------------------------------------------------------------------ LN warps: LayerNorm -> resident A operand
-        // The normalised rows of the NEXT tile are produced while the current tile computes: each warp normalises its 32
-        // rows (statistics and values from one read of x) and stores them as BF16x3 planes into this CTA's image of the
-        // A operand in global memory (L2 resident, already in the SWIZZLE_64B shared-memory layout).  When the MMA warp
-        // releases A, ONE bulk copy moves the 112 KB image into shared memory at engine speed; only that copy is exposed.
-        const int quarter = warp & 3;
-        const int r0 = quarter * 32;                                        // this warp's 32 rows of the CTA's 128
-        constexpr int RB = 8;                                               // rows per batch (16 float4 loads in flight per lane)
-        // lane l owns columns [8l, 8l+8) of a row: two 16-byte loads, and one 16-byte bf16 chunk per plane on the way out
-        const int c0 = 8 * lane;
-        const bool own = c0 < f.D;                                          // D % 8 == 0
-        const int kb = lane >> 2;
-        const uint32_t chunk = (uint32_t)(lane & 3);
-        float gm8[8], bt8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            gm8[j] = own ? __ldg(f.gamma + c0 + j) : 0.f;
-            bt8[j] = own ? __ldg(f.beta + c0 + j) : 0.f;
+        LnSrc ls;
+        ls.x = f.x; ls.gamma = f.gamma; ls.beta = f.beta; ls.M = f.M; ls.m_super = f.m_super; ls.ldx = f.ldx; ls.D = f.D; ls.eps = f.eps;
+        ln_warps_loop(ls, pair, npairs, rank, warp == 2 + F_EPI_WARPS, warp & 3, lane, a_img, a_res, a_free, a_copy, a_full);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)G_TMEM_COLS) : "memory");
+    }
+}
+
+// ====================================================================================================================
+// dyg_ln_gemm_bf16x3: C = act(LayerNorm(x) W^T + bias) — the [q | k | v'] projection of DyGFormer's attention sub-block
+// (models/DyGFormer.py:447-454) with its LayerNorm fused in: gemm_bf16x3_kernel's resident schedule (CTA pairs, the A super
+// tile stays in shared memory across the n tiles, W streamed through the TMA ring, two accumulators in TMEM), but the A
+// operand comes from the LN warps (ln_warps_loop) instead of a planes round trip through HBM.
+constexpr int LG_THREADS = 64 + 32 * (G_EPI_WARPS + LN_WARPS);
+
+struct LnGemmArgs {
+    GemmArgs g;
+    LnSrc ln;
+    unsigned char* scratch;   // gridDim.x images of the A operand (LN_KB * 16 KB each), L2 resident
+};
+
+__global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_wh,
+                                                                       const __grid_constant__ CUtensorMap map_wm, const LnGemmArgs p) {
+    extern __shared__ __align__(1024) unsigned char lg_smem[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lg_smem) + 1023) & ~(uintptr_t)1023);
+    const GemmArgs& g = p.g;
+    const int nkb = (g.K + G_BK - 1) / G_BK;
+    const int w_plane = (g.NT / 2) * 64;
+    const int a_stage = 2 * G_A_PLANE;
+    const int stage_bytes = 2 * w_plane;
+    unsigned char* a_res = base;                               // LN_KB slots of [A_hi | A_mid]
+    unsigned char* ring = base + (size_t)LN_KB * a_stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * stage_bytes);
+    uint64_t* full_bar = bars;                                 // [stages]   leader
+    uint64_t* empty_bar = bars + G_MAX_STAGES;                 // [stages]   both
+    uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES;             // [2]        both
+    uint64_t* tempty_bar = bars + 2 * G_MAX_STAGES + 2;        // [2]        leader
+    uint64_t* a_full = bars + 2 * G_MAX_STAGES + 4;            //            leader: LN(x) of the tile is in both CTAs' shared memory
+    uint64_t* a_free = bars + 2 * G_MAX_STAGES + 5;            //            both:   last MMA of the tile retired
+    uint64_t* a_copy = bars + 2 * G_MAX_STAGES + 6;            //            local:  bulk copy of the image landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 7);
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    // zero this CTA's image of the A operand once: the K padding columns (D .. 32 nkb) are never written again
+    unsigned char* a_img = p.scratch + (size_t)blockIdx.x * (LN_KB * a_stage);
+    for (int i = tid; i < LN_KB * a_stage / 16; i += LG_THREADS) reinterpret_cast<uint4*>(a_img)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int s = 0; s < g.stages; ++s) {
+            mbar_init(full_bar + s, 1);
+            mbar_init(empty_bar + s, 1);
         }
-        int it = 0;
-        for (int64_t ms = pair; ms < f.m_super; ms += npairs, ++it) {
-            const int64_t m0 = ms * 2 * G_BM + (int64_t)rank * G_BM;
-            for (int i0 = 0; i0 < 32; i0 += RB) {
-                float4 v[RB][2];
-#pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                    const int64_t m = m0 + r0 + i0 + i;
-                    if (own && m < f.M) {
-                        const float4* xp = reinterpret_cast<const float4*>(f.x + m * f.ldx + c0);
-                        v[i][0] = xp[0];
-                        v[i][1] = xp[1];
-                    } else {
-                        v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        v[i][1] = v[i][0];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < RB; ++i) {
-                    const float xs[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) sum += xs[j];
-                    const float mean = warp_sum(sum) / (float)f.D;
-                    float sq = 0.f;
-                    if (own) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float d = xs[j] - mean;
-                            sq += d * d;
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar + b, 1);
+            mbar_init(tempty_bar + b, 2 * G_EPI_WARPS);
+        }
+        mbar_init(a_full, 2);
+        mbar_init(a_free, 1);
+        mbar_init(a_copy, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wm)) : "memory");
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");            // the zero fill above must be visible to the bulk copy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer: W k blocks of every n tile
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t ms = pair; ms < g.m_super; ms += npairs) {
+                for (int nt = 0; nt < g.n_tiles; ++nt) {
+                    const int n0 = nt * g.NS + (int)rank * (g.NT / 2);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(empty_bar + s, ph ^ 1u);
+                        if (leader) mbar_expect_tx(full_bar + s, 2u * (uint32_t)stage_bytes);
+                        unsigned char* st = ring + (size_t)s * stage_bytes;
+                        tma_load_2d_pair(&map_wh, full_bar + s, st, kb * G_BK, n0);
+                        tma_load_2d_pair(&map_wm, full_bar + s, st + w_plane, kb * G_BK, n0);
+                        if (++s == g.stages) {
+                            s = 0;
+                            ph ^= 1u;
                         }
                     }
-                    const float rstd = rsqrtf(warp_sum(sq) / (float)f.D + f.eps);
-                    if (own) {
-                        uint32_t h[4], l[4];
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, elected issue)
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((uint32_t)((2 * G_BM) >> 4) << 24);
+            const uint64_t ad_h = make_desc_sw64(smem_u32(a_res)), ad_m = ad_h + (uint64_t)(G_A_PLANE >> 4);
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0, tile = 0;
+            for (int64_t ms = pair; ms < g.m_super; ms += npairs, ++tile) {
+                mbar_wait(a_full, (uint32_t)(tile & 1));                         // LN(x) of this super tile is in shared memory (both CTAs)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int nt = 0; nt < g.n_tiles; ++nt, ++it) {
+                    const int buf = it & 1;
+                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(tempty_bar + buf, bph ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * G_BUF_COLS);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(full_bar + s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        unsigned char* st = ring + (size_t)s * stage_bytes;
+                        const uint64_t wd_h = make_desc_sw64(smem_u32(st)), wd_m = wd_h + (uint64_t)(w_plane >> 4);
+                        const uint64_t ao = (uint64_t)((kb * a_stage) >> 4);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            split_pack((xs[2 * j] - mean) * rstd * gm8[2 * j] + bt8[2 * j],
-                                       (xs[2 * j + 1] - mean) * rstd * gm8[2 * j + 1] + bt8[2 * j + 1], h[j], l[j]);
-                        const int r = r0 + i0 + i;
-                        unsigned char* p = a_img + kb * a_stage + (uint32_t)((r >> 3) * 512 + (r & 7) * 64) + ((chunk ^ (uint32_t)((r >> 1) & 3)) << 4);
-                        *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(p + G_A_PLANE) = make_uint4(l[0], l[1], l[2], l[3]);
+                        for (int kk = 0; kk < G_BK / 16; ++kk) {
+                            if (kb * G_BK + kk * 16 < g.K) {
+                                const uint64_t o = (uint64_t)(kk * 2);
+                                umma_bf16_pair_e(tacc, ad_h + ao + o, wd_h + o, idesc, (kb | kk) != 0);
+                                umma_bf16_pair_e(tacc, ad_h + ao + o, wd_m + o, idesc, 1);
+                                umma_bf16_pair_e(tacc, ad_m + ao + o, wd_h + o, idesc, 1);
+                            }
+                        }
+                        umma_commit_pair_e(empty_bar + s);
+                        if (kb == nkb - 1) {
+                            if (nt == g.n_tiles - 1) umma_commit_pair_e(a_free);     // A may be overwritten once these MMAs retire
+                            umma_commit_pair_e(tfull_bar + buf);
+                        }
+                        if (++s == g.stages) {
+                            s = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
             }
-            asm volatile("fence.proxy.async;" ::: "memory");               // generic global writes -> visible to the bulk copy engine
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * F_LN_WARPS) : "memory");   // all four LN warps finished the image
-            if (warp == 2 + F_EPI_WARPS) {
-                mbar_wait(a_free, (uint32_t)((it & 1) ^ 1));                 // last GEMM1 of the previous tile retired
-                if (lane == 0) {
-                    mbar_expect_tx(a_copy, (uint32_t)(F_KB1 * a_stage));
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(a_res)),
-                                 "l"(a_img), "r"((uint32_t)(F_KB1 * a_stage)), "r"(smem_u32(a_copy))
-                                 : "memory");
-                }
-                mbar_wait(a_copy, (uint32_t)(it & 1));
-                if (lane == 0) mbar_arrive_leader(a_full);
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * F_LN_WARPS) : "memory");   // the image may be overwritten for the next tile
         }
+    } else if (warp < 2 + G_EPI_WARPS) {
+        // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int chunk0 = (warp - 2) >> 2;
+        int it = 0;
+        for (int64_t ms = pair; ms < g.m_super; ms += npairs) {
+            const int64_t m = ms * 2 * G_BM + (int64_t)rank * G_BM + row;
+            for (int nt = 0; nt < g.n_tiles; ++nt, ++it) {
+                const int buf = it & 1;
+                const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                const int n0 = nt * g.NS;
+                const int ncols = min(g.NS, g.N - n0);
+                mbar_wait(tfull_bar + buf, bph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
+                epilogue_tile(g, taddr, m, n0, ncols, chunk0, G_EPI_WARPS / 4);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ LN warps: LayerNorm -> resident A operand
+        ln_warps_loop(p.ln, pair, npairs, rank, warp == 2 + G_EPI_WARPS, warp & 3, lane, a_img, a_res, a_free, a_copy, a_full);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();
@@ -1022,6 +1224,80 @@ extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, co
     cudaError_t le = cudaLaunchKernelEx(&cfg, ln_ffn_bf16x3_kernel, m1h, m1m, m2h, m2m, f);
     if (le != cudaSuccess) {
         dyg_set_error("dyg_ln_ffn_bf16x3: launch failed: %s", cudaGetErrorString(le));
+        return 1;
+    }
+    return 0;
+}
+
+extern "C" int dyg_ln_gemm_bf16x3(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W_hi,
+                                  const void* W_mid, int ldw, const float* bias, float* C, int ldc, void* C_hi, void* C_mid, int ldcs,
+                                  int64_t M, int N, int D, int act, void* workspace, int64_t workspace_bytes, dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && N > 0 && D > 0, "dyg_ln_gemm_bf16x3: bad sizes");
+    DYG_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= dyg_ln_ffn_workspace_bytes(),
+                  "dyg_ln_gemm_bf16x3: workspace of %lld bytes (16-byte aligned) required", (long long)dyg_ln_ffn_workspace_bytes());
+    DYG_CHECK_ARG(D <= 224 && (D % 8) == 0, "dyg_ln_gemm_bf16x3: width %d unsupported (multiple of 8, <= 224)", D);
+    DYG_CHECK_ARG(act >= DYG_ACT_NONE && act <= DYG_ACT_SIGMOID, "dyg_ln_gemm_bf16x3: unknown activation %d", act);
+    DYG_CHECK_ARG(M < ((int64_t)1 << 31) - 2 * G_BM, "dyg_ln_gemm_bf16x3: M too large");
+    if (M == 0) return 0;
+    DYG_CHECK_ARG(x && gamma && beta && W_hi && W_mid, "dyg_ln_gemm_bf16x3: NULL pointer");
+    DYG_CHECK_ARG((ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 3u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(beta) & 3u) == 0,
+                  "dyg_ln_gemm_bf16x3: x must be 16-byte aligned with ldx %% 4 == 0");
+    DYG_CHECK_ARG((ldw % 8) == 0 && ldw >= D && aligned16(W_hi) && aligned16(W_mid),
+                  "dyg_ln_gemm_bf16x3: weight planes must be 16-byte aligned with ldw a multiple of 8");
+    DYG_CHECK_ARG(C || (C_hi && C_mid), "dyg_ln_gemm_bf16x3: no output given");
+    DYG_CHECK_ARG((C_hi == nullptr) == (C_mid == nullptr), "dyg_ln_gemm_bf16x3: C_hi and C_mid go together");
+    DYG_CHECK_ARG(!C_hi || (ldcs % 2) == 0, "dyg_ln_gemm_bf16x3: ldcs must be even");
+    LnGemmArgs p;
+    memset(&p, 0, sizeof(p));
+    GemmArgs& g = p.g;
+    g.bias = bias; g.C = C; g.ldc = ldc;
+    g.Chi = reinterpret_cast<__nv_bfloat16*>(C_hi); g.Cmid = reinterpret_cast<__nv_bfloat16*>(C_mid); g.ldcs = ldcs;
+    g.M = M; g.N = N; g.K = D; g.act = act;
+    g.m_tiles = (M + G_BM - 1) / G_BM;
+    g.m_super = (M + 2 * G_BM - 1) / (2 * G_BM);
+    g.n_tiles = (N + 207) / 208;
+    g.NS = ((N + g.n_tiles - 1) / g.n_tiles + 15) / 16 * 16;
+    g.NT = g.NS;
+    g.resident = 1;
+    const int stage_bytes = 2 * (g.NT / 2) * 64;
+    const int fixed = LN_KB * 2 * G_A_PLANE + 1024 + 512;
+    g.stages = (227 * 1024 - fixed) / stage_bytes;
+    if (g.stages > G_MAX_STAGES) g.stages = G_MAX_STAGES;
+    DYG_CHECK_ARG(g.stages >= 2, "dyg_ln_gemm_bf16x3: tile does not fit shared memory");
+    p.ln.x = x; p.ln.gamma = gamma; p.ln.beta = beta; p.ln.M = M; p.ln.m_super = g.m_super; p.ln.ldx = ldx; p.ln.D = D; p.ln.eps = eps;
+    p.scratch = reinterpret_cast<unsigned char*>(workspace);
+    const size_t smem = (size_t)g.stages * stage_bytes + fixed;
+    CUtensorMap mwh, mwm;
+    if (!dyg_tensor_map_bf16(W_hi, (uint64_t)N, (uint64_t)D, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwh)) return 1;
+    if (!dyg_tensor_map_bf16(W_mid, (uint64_t)N, (uint64_t)D, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwm)) return 1;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(ln_gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            dyg_set_error("dyg_ln_gemm_bf16x3: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+            return 1;
+        }
+        configured = smem;
+    }
+    const int max_pairs = dyg_num_sms() / 2;
+    const int pairs = (int)(g.m_super < max_pairs ? g.m_super : max_pairs);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(LG_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, ln_gemm_bf16x3_kernel, mwh, mwm, p);
+    if (le != cudaSuccess) {
+        dyg_set_error("dyg_ln_gemm_bf16x3: launch failed: %s", cudaGetErrorString(le));
         return 1;
     }
     return 0;

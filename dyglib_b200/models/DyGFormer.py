@@ -23,10 +23,12 @@ import os
 
 # LayerNorm + feed-forward as one kernel (dyg_ln_ffn_bf16x3); DYG_FUSED_FFN=0 selects the three-kernel path
 FUSED_FFN = os.environ.get('DYG_FUSED_FFN', '1') != '0'
-# attention sub-block: 1 (default) = LayerNorm planes + [q | k | v'] projection GEMM + dyg_seq_attention_fold (tcgen05),
+# attention sub-block: 1 (default) = LayerNorm + [q | k | v'] projection GEMM, then dyg_seq_attention_fold (tcgen05),
 # 2 = one kernel (dyg_attn_block; parity-green but measured slower: L2-bound scratch round trip),
 # 0 = QKV GEMM + mma.sync attention + out-projection GEMM
 FUSED_ATTN = int(os.environ.get('DYG_FUSED_ATTN', '1'))
+# LayerNorm inside the projection GEMM (dyg_ln_gemm_bf16x3); DYG_FUSED_LN=0 runs layernorm_split + dyg_gemm_bf16x3
+FUSED_LN = os.environ.get('DYG_FUSED_LN', '1') != '0'
 
 
 class NeighborCooccurrenceEncoder(nn.Module):
@@ -115,10 +117,13 @@ class TransformerEncoder(nn.Module):
             wcat, bcat, bout = self._folded()
             x1 = ops.attn_block(x, n0.weight.detach(), n0.bias.detach(), n0.eps, wcat, bcat, bout, B, S, self.num_heads, D)
         elif FUSED_ATTN and ops.attn_fold_fusable(S, D, self.num_heads):
-            # the same as three launches: LayerNorm planes, projection GEMM, tcgen05 attention + residual
-            y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)
+            # two launches: LayerNorm + [q | k | v'] projection (out-projection folded into v'), then the tcgen05 attention
+            # kernel, which also adds the residual
             wcat, bcat, bout = self._folded()
-            pl = ops.gemm(y, wcat, bcat, want='split')
+            if FUSED_LN and ops.ln_gemm_fusable(D):
+                pl = ops.ln_gemm(x, n0.weight.detach(), n0.bias.detach(), n0.eps, wcat, bcat, want='split')
+            else:
+                pl = ops.gemm(ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps), wcat, bcat, want='split')
             x1 = ops.seq_attention_fold(pl, B, S, self.num_heads, D, x, bout)
         else:
             y = ops.layernorm_split(x, n0.weight.detach(), n0.bias.detach(), eps=n0.eps)

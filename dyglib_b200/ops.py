@@ -414,6 +414,32 @@ def ln_ffn(x, gamma, beta, eps, w1, b1, w2, b2, out=None):
     return out
 
 
+def ln_gemm(x, gamma, beta, eps, weight, bias=None, act=ACT_NONE, want='split'):
+    """act(LayerNorm(x) @ weight.T + bias) in one kernel (dyg_ln_gemm_bf16x3): the normalised rows never reach HBM.
+    ``weight``: fp32 (N, D) parameter or Split; ``want`` as in ``gemm``."""
+    w = weight if isinstance(weight, Split) else split_weight(weight)
+    M, D = x.shape
+    N = w.rows
+    if w.cols != D:
+        raise ValueError(f'ln_gemm: x has {D} columns, W has {w.cols}')
+    dev = x.device
+    out = torch.empty((M, N), dtype=torch.float32, device=dev) if want in ('f32', 'both') else None
+    sp = empty_split(M, N, dev) if want in ('split', 'both') else None
+    ws = _ffn_workspace(dev)
+    with _Timed('ln_gemm_bf16x3_kernel', 2.0 * M * N * D, 4.0 * (M * D + N * D + M * N) * (2 if want == 'both' else 1)):
+        _native.check(_lib().dyg_ln_gemm_bf16x3(
+            _p(x), int(x.stride(0)), _p(gamma), _p(beta), float(eps), _p(w.hi), _p(w.mid), int(w.ld), _p(bias),
+            _p(out), int(out.stride(0)) if out is not None else 0, _p(sp.hi) if sp is not None else None,
+            _p(sp.mid) if sp is not None else None, int(sp.ld) if sp is not None else 0, int(M), int(N), int(D), int(act),
+            _p(ws), int(ws.numel()), _stream()))
+    _count()
+    return out if want == 'f32' else sp if want == 'split' else (out, sp)
+
+
+def ln_gemm_fusable(D):
+    return D % 8 == 0 and D <= 224
+
+
 def layernorm_split(x, gamma, beta, eps=1e-5, out=None, y=None):
     """LayerNorm(x) as a Split (and optionally also as fp32 ``y``)."""
     M, D = x.shape

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 6
+#define DYG_ABI_VERSION 7
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -175,6 +175,12 @@ int dyg_linear_tc(const dyg_seg_t* segs_host, int nseg, const void* W_hi, const 
 int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, const void* W_hi, const void* W_mid, int ldw,
                     const float* bias, const float* residual, int ldr, float* C, int ldc, void* C_hi, void* C_mid,
                     int ldcs, int64_t M, int N, int K, int act, dyg_stream_t stream);
+/* C = act(LayerNorm(x; gamma, beta, eps) W^T + bias): dyg_gemm_bf16x3 with the LayerNorm of models/DyGFormer.py:447 fused in
+ * (the normalised rows go straight into the resident A operand; no planes round trip).  x (M, D) fp32, D <= 224 and a multiple
+ * of 8; outputs as in dyg_gemm_bf16x3; workspace as for dyg_ln_ffn_bf16x3 (dyg_ln_ffn_workspace_bytes()). */
+int dyg_ln_gemm_bf16x3(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W_hi,
+                       const void* W_mid, int ldw, const float* bias, float* C, int ldc, void* C_hi, void* C_mid, int ldcs,
+                       int64_t M, int N, int D, int act, void* workspace, int64_t workspace_bytes, dyg_stream_t stream);
 /* Feed-forward half of the transformer block fused into one kernel (models/DyGFormer.py:456-461):
  *   out = x + W2 gelu(W1 LayerNorm(x) + b1) + b2   (LayerNorm with gamma / beta / eps, exact-erf GELU).
  * x, out: (M, ld) fp32.  W1_hi | W1_mid: (Dff, ldw1) operand planes of linear_layers.0.weight (Dff x D);

@@ -202,3 +202,22 @@ def test_gemm_rejects_bad_arguments():
         ops.ln_ffn(torch.randn(4, 50, device='cuda'), torch.ones(50, device='cuda'), torch.zeros(50, device='cuda'), 1e-5,
                    torch.randn(64, 50, device='cuda'), torch.zeros(64, device='cuda'), torch.randn(50, 64, device='cuda'),
                    torch.zeros(50, device='cuda'))                # D % 8 != 0
+
+
+@pytest.mark.parametrize('M,N,D', [(1, 8, 8), (129, 50, 176), (1000, 816, 200), (40000, 816, 200), (777, 600, 200), (513, 224, 224),
+                                   (148 * 128 * 2 + 5, 208, 72)])
+def test_ln_gemm_vs_float64(M, N, D):
+    """dyg_ln_gemm_bf16x3: LayerNorm fused into the projection GEMM, against float64 LayerNorm + matmul."""
+    g = torch.Generator(device='cuda').manual_seed(M + 3 * N + 7 * D)
+    x = torch.randn(M, D, device='cuda', generator=g) * 2.0 + 0.3
+    w = torch.randn(N, D, device='cuda', generator=g) / np.sqrt(D)
+    b = torch.randn(N, device='cuda', generator=g)
+    gamma = torch.randn(D, device='cuda', generator=g) * 0.2 + 1.0
+    beta = torch.randn(D, device='cuda', generator=g) * 0.2
+    y = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+    want = y @ w.double().t() + b.double()
+    got, gs = ops.ln_gemm(x, gamma, beta, 1e-5, w, b, want='both')
+    assert rel_err(got, want) < 3e-5, rel_err(got, want)
+    assert rel_err(gs.float(), want) < 5e-5
+    gs = ops.ln_gemm(x, gamma, beta, 1e-5, w, b, act=ops.ACT_GELU, want='split')
+    assert rel_err(gs.float(), torch.nn.functional.gelu(want)) < 5e-5
