@@ -28,18 +28,21 @@ struct GemmArgs {
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == DYG_ACT_RELU) return fmaxf(v, 0.f);
     if (act == DYG_ACT_GELU) {
-        // exact-erf GELU (F.gelu default, models/DyGFormer.py:458) with erf from Abramowitz-Stegun 7.1.26
-        // (|error| <= 1.5e-7, below the BF16x3 noise of the contraction feeding it): branch-free, two MUFU + 9 FP32 ops
-        // instead of erff's divergent ~25 (measured: FFN1 epilogue 426 -> 334 us at M = 204,800)
-        const float z = v * 0.70710678118654752440f, az = fabsf(z);
-        float t;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.f)));
-        float p = fmaf(t, 1.061405429f, -1.453152027f);
-        p = fmaf(t, p, 1.421413741f);
-        p = fmaf(t, p, -0.284496736f);
-        p = fmaf(t, p, 0.254829592f);
-        const float e = 1.f - p * t * __expf(-az * az);
-        return 0.5f * v * (1.f + copysignf(e, z));
+        // exact-erf GELU (F.gelu default, models/DyGFormer.py:458) as max(v, 0) - 0.5 |v| erfc(|v| / sqrt 2) with
+        // erfc(z) = 2^(-z Q(z)), Q a degree-6 minimax fit on [0, 6] (|erfc error| <= 1.2e-7 in fp32 arithmetic; GELU within
+        // 4e-7 absolute, below the BF16x3 noise of the contraction feeding it): branch-free, ONE MUFU + 11 FP32 instructions.
+        // (erff: ~25 divergent instructions; the Abramowitz-Stegun 7.1.26 form used before: two MUFU + 15.  The fused FFN's
+        // epilogue warps are bound by the MUFU / conversion pipe, profiles/README.md.)
+        const float az = fminf(fabsf(v) * 0.70710678118654752440f, 6.0f);
+        float q = fmaf(-1.0021893831435591e-4f, az, 4.6156023745425045e-4f);
+        q = fmaf(q, az, 2.302266424521804e-3f);
+        q = fmaf(q, az, -2.9452543705701828e-2f);
+        q = fmaf(q, az, 1.4896368980407715e-1f);
+        q = fmaf(q, az, 9.183286428451538e-1f);
+        q = fmaf(q, az, 1.6279137134552002f);
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-az * q));
+        return fmaf(-0.5f * fabsf(v), e, fmaxf(v, 0.f));
     }
     if (act == DYG_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
     return v;
