@@ -426,9 +426,11 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(
                 ei.y = r.eid;
                 tf.y = (float)r.t;
             }
-            *reinterpret_cast<longlong2*>(out_nbr + base + j) = nb;
-            *reinterpret_cast<longlong2*>(out_eid + base + j) = ei;
-            *reinterpret_cast<float2*>(out_t + base + j) = tf;
+            // streaming stores: the rows are written once and not read by this kernel; keeping them out of the way leaves L2
+            // to the fence levels and the row pointers
+            __stcs(reinterpret_cast<longlong2*>(out_nbr + base + j), nb);
+            __stcs(reinterpret_cast<longlong2*>(out_eid + base + j), ei);
+            __stcs(reinterpret_cast<float2*>(out_t + base + j), tf);
         }
     } else {
         for (int j = lane; j < k; j += LANES) {
