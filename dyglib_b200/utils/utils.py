@@ -48,9 +48,7 @@ class NeighborSampler:
         (``utils/utils.py:73-110``); position 0 is the empty list of the padding node.
         """
         ops.require_cuda()
-        if sample_neighbor_strategy not in ('uniform', 'recent', 'time_interval_aware'):
-            # the reference raises at query time (utils/utils.py:211); failing at construction is stricter
-            self._bad_strategy = True
+        # an unknown strategy raises ValueError at query time, like the reference (utils/utils.py:211)
         self.sample_neighbor_strategy = sample_neighbor_strategy
         self.seed = seed
         self.device = torch.device(device)
