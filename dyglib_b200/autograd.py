@@ -2,8 +2,9 @@
 
 The reference trains by differentiating its eager PyTorch modules (``train_link_prediction.py:255-257``).  Here the forward
 passes stay on the fused kernels; the backward of the neighbour gather / temporal attention is its own kernel
-(``dyg_temporal_attend_bwd``), the backward of the dense layers are plain fp32 library GEMMs (``dX = dY W``,
-``dW = dY^T X``), and LayerNorm / dropout / ReLU masks are elementwise torch ops on (n, 272)-sized tensors.
+(``dyg_temporal_attend_bwd``), the backward of a dense layer is ``dX = dY W`` on the tcgen05 GEMM plus ``dW = dY^T X`` / ``db`` on
+``dyg_gemm_dw``; DyGFormer's transformer block differentiates through ``dyg_layernorm_bwd``, ``dyg_gelu_bwd`` and
+``dyg_seq_attention_train_bwd`` (csrc/train.cu).  Dropout masks, ReLU masks and residual adds are elementwise torch ops.
 There is still no CPU path: every function below needs CUDA tensors.
 """
 from __future__ import annotations
@@ -38,10 +39,27 @@ class _Linear(torch.autograd.Function):
         elif ctx.act != ops.ACT_NONE:
             raise NotImplementedError('backward of this activation')
         w = weight.detach()
-        gx = gy @ w                                               # (M, K)
-        x = xs[0] if len(xs) == 1 else torch.cat(xs, dim=1)
-        gw = gy.t() @ x if ctx.needs_input_grad[0] else None
-        gb = gy.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[1]) else None
+        gy = gy.float()
+        need_x = any(ctx.needs_input_grad[3 + i] for i in range(len(xs)))
+        gx = None
+        if need_x:
+            # dX = dY W on the tcgen05 GEMM: A = planes of dY, "weight" = W^T (K, N)
+            gx = ops.gemm(ops.split_bf16(gy), ops.split_bf16(w.t().contiguous().float()))
+        gw = gb = None
+        want_b = ctx.has_bias and ctx.needs_input_grad[1]
+        if ctx.needs_input_grad[0] or want_b:
+            # dW = dY^T X (and db = column sums of dY) split over the rows (dyg_gemm_dw); one call per concatenated segment
+            gw = torch.zeros((w.shape[0], sum(ctx.widths)), dtype=torch.float32, device=gy.device)
+            gb = torch.zeros(w.shape[0], dtype=torch.float32, device=gy.device) if want_b else None
+            off = 0
+            for i, x in enumerate(xs):
+                ops.gemm_dw(gy, x, dw=gw[:, off:off + ctx.widths[i]], db=gb if i == 0 else None)
+                off += ctx.widths[i]
+            if not ctx.needs_input_grad[0]:
+                gw = None
+        if gx is None:
+            gxs = (None,) * len(xs)
+            return (gw, gb, None) + gxs
         gxs = torch.split(gx, ctx.widths, dim=1) if len(xs) > 1 else (gx,)
         gxs = tuple(g if ctx.needs_input_grad[3 + i] else None for i, g in enumerate(gxs))
         return (gw, gb, None) + gxs
@@ -122,3 +140,76 @@ class _TimeEncode(torch.autograd.Function):
 def time_encode(dt, w, b):
     """Differentiable time encoding of ``dt`` (any shape) -> (*dt.shape, T); ``w``: (T, 1) weight, ``b``: (T,) bias."""
     return _TimeEncode.apply(dt, w, b)
+
+
+class _LayerNorm(torch.autograd.Function):
+    """``nn.LayerNorm`` over the last dimension of a (M, D) matrix: forward ``dyg_layernorm``, backward ``dyg_layernorm_bwd``."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        xc = x.detach().float().contiguous()
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        ctx.save_for_backward(xc, g)
+        ctx.eps = eps
+        return ops.layernorm(xc, g, b, eps=eps)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, g = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(xc, g, ctx.eps, gy.float().contiguous())
+        return dx, dg, db, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    """Differentiable LayerNorm of a (M, D) matrix on the library's own kernels."""
+    return _LayerNorm.apply(x, gamma, beta, eps)
+
+
+class _Gelu(torch.autograd.Function):
+    """``dropout(F.gelu(v))`` (exact erf, ``models/DyGFormer.py:458``): the dropout multipliers ride inside the kernels."""
+
+    @staticmethod
+    def forward(ctx, v, p):
+        vc = v.detach().float().contiguous()
+        mask = None
+        if p > 0.0:
+            mask = (torch.rand(vc.shape, device=vc.device) >= p).float() / (1.0 - p)
+        ctx.save_for_backward(vc, mask)
+        return ops.gelu_fwd(vc, mask, want='f32')
+
+    @staticmethod
+    def backward(ctx, gh):
+        vc, mask = ctx.saved_tensors
+        return ops.gelu_bwd(vc, mask, gh.float().contiguous()), None
+
+
+def gelu(v, dropout=0.0):
+    """Differentiable ``dropout(gelu(v))`` of a (M, N) matrix."""
+    return _Gelu.apply(v, dropout)
+
+
+class _SeqAttention(torch.autograd.Function):
+    """The attention core of ``nn.MultiheadAttention`` (``models/DyGFormer.py:454``) on packed (B*S, 3*H*hd) projections, with
+    attention dropout: forward ``dyg_seq_attention_train_fwd`` (keeps the softmax), backward ``dyg_seq_attention_train_bwd``."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, S, H, hd, p):
+        q = qkv.detach().float().contiguous()
+        mask = None
+        if p > 0.0:
+            mask = (torch.rand((B, H, S, S), device=q.device) >= p).float() / (1.0 - p)
+        out, probs = ops.seq_attention_train_fwd(q, B, S, H, hd, mask)
+        ctx.save_for_backward(q, mask, probs)
+        ctx.dims = (B, S, H, hd)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        q, mask, probs = ctx.saved_tensors
+        B, S, H, hd = ctx.dims
+        return ops.seq_attention_train_bwd(q, B, S, H, hd, mask, probs, go.float().contiguous()), None, None, None, None, None
+
+
+def seq_attention(qkv, B, S, H, hd, dropout=0.0):
+    """Differentiable softmax(q k^T / sqrt(hd)) v per (sequence, head); ``qkv``: (B*S, 3*H*hd) packed [q | k | v]."""
+    return _SeqAttention.apply(qkv, B, S, H, hd, dropout)

@@ -154,10 +154,33 @@ class TransformerEncoder(nn.Module):
         return self._fold
 
     def _forward_train(self, inputs):
-        """Training mode: the same block with autograd.  Dense layers run forward on the tcgen05 GEMM through
-        ``autograd.linear`` (backward: fp32 library GEMMs); LayerNorm, GELU, dropout and the 64-token softmax(QK^T)V core (5 % of
-        the block's flops) are library ops here.  Dropout sits where the reference has it: attention probabilities
-        (``nn.MultiheadAttention(dropout=...)``), the attention output, the hidden activation and the FFN output."""
+        """Training mode: the same block under autograd, on the library's kernels both ways (``dyglib_b200/autograd.py``): dense
+        layers forward on the GEMM kernels, backward ``dX`` on the tcgen05 GEMM and ``dW`` / ``db`` on ``dyg_gemm_dw``; LayerNorm,
+        GELU and the softmax(QK^T)V core with their own backward kernels (``csrc/train.cu``).  Dropout sits where the reference has it:
+        attention probabilities (``nn.MultiheadAttention(dropout=...)``), the attention output, the hidden activation and the FFN
+        output; the dropout masks of the two residual branches and the residual adds are elementwise library ops."""
+        from .. import autograd as ag
+        import torch.nn.functional as F
+        B, S, D = inputs.shape
+        H = self.num_heads
+        hd = D // H
+        mha = self.multi_head_attention
+        n0, n1 = self.norm_layers
+        l0, l1 = self.linear_layers
+        p = self.dropout.p
+        x = inputs.reshape(B * S, D)
+        if S > 64 or hd > 128:
+            return self._forward_train_library(inputs)
+        y = ag.layer_norm(x, n0.weight, n0.bias, n0.eps)
+        qkv = ag.linear(y, mha.in_proj_weight, mha.in_proj_bias)                        # (B*S, 3D) packed [q | k | v]
+        a = ag.seq_attention(qkv, B, S, H, hd, mha.dropout)
+        x1 = x + F.dropout(ag.linear(a, mha.out_proj.weight, mha.out_proj.bias), p, True)
+        h = ag.gelu(ag.linear(ag.layer_norm(x1, n1.weight, n1.bias, n1.eps), l0.weight, l0.bias), p)
+        out = x1 + F.dropout(ag.linear(h, l1.weight, l1.bias), p, True)
+        return out.reshape(B, S, D)
+
+    def _forward_train_library(self, inputs):
+        """Sequences longer than 64 tokens (outside the training kernels' range): LayerNorm / GELU / softmax as library ops."""
         from .. import autograd as ag
         import torch.nn.functional as F
         B, S, D = inputs.shape
@@ -371,12 +394,12 @@ class DyGFormer(nn.Module):
         enc = self.neighbor_co_occurrence_encoder.neighbor_co_occurrence_encode_layer
         max_count = int(max(cs[0].max().item(), cs[1].max().item(), cd[0].max().item(), cd[1].max().item()))
         counts = torch.arange(max_count + 1, dtype=torch.float32, device=tq.device).reshape(-1, 1)
-        lut = enc[2](torch.relu(enc[0](counts)))                                          # (max_count + 1, C), models/DyGFormer.py:409-411
+        lut = ag.linear(ag.linear(counts, enc[0].weight, enc[0].bias, act=ops.ACT_RELU), enc[2].weight, enc[2].bias)   # (max_count + 1, C), models/DyGFormer.py:409-411
         toks = []
         for pn, pe, pt, cnt in ((s_pn, s_pe, s_pt, cs), (d_pn, d_pe, d_pt, cd)):
             Lp = pn.shape[1]
-            nodef = self.node_raw_features[pn]
-            edgef = self.edge_raw_features[pe]
+            nodef = ops.gather_rows(self.node_raw_features, pn.reshape(-1)).reshape(B, Lp, -1)      # constant tables: no gradient
+            edgef = ops.gather_rows(self.edge_raw_features, pe.reshape(-1)).reshape(B, Lp, -1)
             dt = (tq.reshape(B, 1) - pt.double()).float()
             te = ag.time_encode(dt, self.time_encoder.w.weight, self.time_encoder.w.bias) * (pn != 0).unsqueeze(-1)
             co = lut[cnt[0]] + lut[cnt[1]]

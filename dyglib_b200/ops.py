@@ -646,6 +646,72 @@ def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
     return out
 
 
+# ------------------------------------------------------------------ training path (backward kernels, csrc/train.cu)
+def gemm_dw(g, x, dw=None, db=None, want_bias=False):
+    """(dW (N, K), db (N) or None) of y = x W^T + b from g = dL/dy (M, N): dW = g^T x accumulated into ``dw`` (dyg_gemm_dw)."""
+    M, N = g.shape
+    K = x.shape[1]
+    if dw is None:
+        dw = torch.zeros((N, K), dtype=torch.float32, device=g.device)
+    if want_bias and db is None:
+        db = torch.zeros(N, dtype=torch.float32, device=g.device)
+    _native.check(_lib().dyg_gemm_dw(_p(g), int(g.stride(0)), _p(x), int(x.stride(0)), int(M), int(N), int(K), _p(dw), int(dw.stride(0)),
+                                     _p(db), _stream()))
+    _count()
+    return dw, db
+
+
+def layernorm_bwd(x, gamma, eps, dy):
+    """(dx, dgamma, dbeta) of LayerNorm(x) * gamma + beta (dyg_layernorm_bwd)."""
+    M, D = x.shape
+    dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
+    dg = torch.zeros(D, dtype=torch.float32, device=x.device)
+    dbt = torch.zeros(D, dtype=torch.float32, device=x.device)
+    _native.check(_lib().dyg_layernorm_bwd(_p(x), int(x.stride(0)), _p(gamma), float(eps), _p(dy), int(dy.stride(0)), _p(dx), int(dx.stride(0)),
+                                           _p(dg), _p(dbt), int(M), int(D), _stream()))
+    _count()
+    return dx, dg, dbt
+
+
+def gelu_fwd(v, mask=None, want='f32'):
+    """gelu(v) * mask as fp32 ('f32'), operand planes ('split') or both."""
+    M, N = v.shape
+    h = torch.empty((M, N), dtype=torch.float32, device=v.device) if want in ('f32', 'both') else None
+    sp = empty_split(M, N, v.device) if want in ('split', 'both') else None
+    _native.check(_lib().dyg_gelu_fwd(_p(v), int(v.stride(0)), _p(mask), int(mask.stride(0)) if mask is not None else 0, _p(h),
+                                      int(h.stride(0)) if h is not None else 0, _p(sp.hi) if sp is not None else None,
+                                      _p(sp.mid) if sp is not None else None, int(sp.ld) if sp is not None else 0, int(M), int(N), _stream()))
+    _count()
+    return h if want == 'f32' else sp if want == 'split' else (h, sp)
+
+
+def gelu_bwd(v, mask, dh):
+    M, N = v.shape
+    dv = torch.empty((M, N), dtype=torch.float32, device=v.device)
+    _native.check(_lib().dyg_gelu_bwd(_p(v), int(v.stride(0)), _p(mask), int(mask.stride(0)) if mask is not None else 0, _p(dh),
+                                      int(dh.stride(0)), _p(dv), int(dv.stride(0)), int(M), int(N), _stream()))
+    _count()
+    return dv
+
+
+def seq_attention_train_fwd(qkv, B, S, H, hd, prob_mask=None):
+    """(out (B*S, H*hd), probs (B, H, S, S)) with the softmax kept for the backward pass (dyg_seq_attention_train_fwd)."""
+    out = torch.empty((B * S, H * hd), dtype=torch.float32, device=qkv.device)
+    probs = torch.empty((B, H, S, S), dtype=torch.float32, device=qkv.device)
+    _native.check(_lib().dyg_seq_attention_train_fwd(_p(qkv), int(qkv.stride(0)), int(B), int(S), int(H), int(hd), _p(prob_mask), _p(probs),
+                                                     _p(out), int(out.stride(0)), _stream()))
+    _count()
+    return out, probs
+
+
+def seq_attention_train_bwd(qkv, B, S, H, hd, prob_mask, probs, dout):
+    dqkv = torch.empty((B * S, 3 * H * hd), dtype=torch.float32, device=qkv.device)
+    _native.check(_lib().dyg_seq_attention_train_bwd(_p(qkv), int(qkv.stride(0)), int(B), int(S), int(H), int(hd), _p(prob_mask), _p(probs),
+                                                     _p(dout), int(dout.stride(0)), _p(dqkv), int(dqkv.stride(0)), _stream()))
+    _count()
+    return dqkv
+
+
 def mean_tokens(x, B, S, D, tok0, cnt, out=None):
     if out is None:
         out = torch.empty((B, D), device=x.device, dtype=torch.float32)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 7
+#define DYG_ABI_VERSION 8
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -301,6 +301,29 @@ int64_t dyg_attn_block_workspace_bytes(int N);
 int dyg_attn_block(const float* x, int ldx, const float* gamma, const float* beta, float eps, const void* W_hi, const void* W_mid,
                    int ldw, const float* bcat, int N, int q_col0, int k_col0, int v_col0, const float* bout, int64_t B, int S,
                    int H, int hd, int D, float* out, int ldo, void* workspace, int64_t workspace_bytes, dyg_stream_t stream);
+/* ---- backward kernels of DyGFormer's training path (dyg_patch_project_bwd / dyg_tfm_block_bwd;
+ * train_link_prediction.py:230-257 differentiates models/DyGFormer.py:148-192, 442-461).  The forward of a training step runs on
+ * the GEMMs above; its backward is composed of dX = dY W on dyg_gemm_bf16x3 and the fp32 kernels below (dyglib_b200/autograd.py). ---- */
+/* dW[n, k] += sum_m G[m, n] X[m, k], db[n] += sum_m G[m, n] (db may be NULL): weight / bias gradient of y = x W^T + b, split over the rows
+ * with atomic accumulation (zero dW / db first).  For the patch projections X is the gathered patch matrix of a channel. */
+int dyg_gemm_dw(const float* G, int ldg, const float* X, int ldx, int64_t M, int N, int K, float* dW, int ldw, float* db,
+                dyg_stream_t stream);
+/* y = LayerNorm(x) gamma + beta: dx (M, D) written, dgamma / dbeta (D) accumulated (zero them first; may be NULL). */
+int dyg_layernorm_bwd(const float* x, int ldx, const float* gamma, float eps, const float* dy, int lddy, float* dx, int lddx,
+                      float* dgamma, float* dbeta, int64_t M, int D, dyg_stream_t stream);
+/* h = gelu(v) * mask (exact erf; mask = dropout multipliers or NULL) as fp32 and / or bf16 hi | mid planes; dv = dh * mask * gelu'(v). */
+int dyg_gelu_fwd(const float* v, int ldv, const float* mask, int ldm, float* h, int ldh, void* h_hi, void* h_mid, int lds,
+                 int64_t M, int N, dyg_stream_t stream);
+int dyg_gelu_bwd(const float* v, int ldv, const float* mask, int ldm, const float* dh, int lddh, float* dv, int lddv, int64_t M,
+                 int N, dyg_stream_t stream);
+/* softmax(q k^T / sqrt(hd)) v per (sequence, head) with the probabilities kept for the backward pass: probs (B, H, S, S) holds the
+ * softmax, prob_mask (same shape, may be NULL) the dropout multipliers applied before the product with v (nn.MultiheadAttention's
+ * attention dropout).  S <= 64, hd <= 128.  _bwd writes dqkv (B*S, 3*H*hd) from dout (B*S, H*hd). */
+int dyg_seq_attention_train_fwd(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, const float* prob_mask, float* probs,
+                                float* out, int ldo, dyg_stream_t stream);
+int dyg_seq_attention_train_bwd(const float* qkv, int ld_qkv, int64_t B, int S, int H, int hd, const float* prob_mask,
+                                const float* probs, const float* dout, int lddo, float* dqkv, int lddq, dyg_stream_t stream);
+
 /* out[b,:] = mean over tokens [tok0, tok0+cnt) of x[b,:,:] (models/DyGFormer.py:185-187). */
 int dyg_mean_tokens(const float* x, int64_t B, int S, int D, int tok0, int cnt, float* out, int ldo, dyg_stream_t stream);
 
