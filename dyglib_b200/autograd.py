@@ -43,14 +43,16 @@ class _Linear(torch.autograd.Function):
         need_x = any(ctx.needs_input_grad[3 + i] for i in range(len(xs)))
         gx = None
         if need_x:
-            # dX = dY W on the tcgen05 GEMM: A = planes of dY, "weight" = W^T (K, N)
-            gx = ops.gemm(ops.split_bf16(gy), ops.split_bf16(w.t().contiguous().float()))
+            # dX = dY W: the tcgen05 GEMM on planes of dY and W^T for large layers, one fp32 launch for small ones
+            gx = ops.gemm_dx(gy, w.float())
         gw = gb = None
         want_b = ctx.has_bias and ctx.needs_input_grad[1]
         if ctx.needs_input_grad[0] or want_b:
             # dW = dY^T X (and db = column sums of dY) split over the rows (dyg_gemm_dw); one call per concatenated segment
-            gw = torch.zeros((w.shape[0], sum(ctx.widths)), dtype=torch.float32, device=gy.device)
-            gb = torch.zeros(w.shape[0], dtype=torch.float32, device=gy.device) if want_b else None
+            Kt = sum(ctx.widths)
+            buf = torch.zeros(w.shape[0] * (Kt + 1), dtype=torch.float32, device=gy.device)      # dW | db: one memset
+            gw = buf[:w.shape[0] * Kt].view(w.shape[0], Kt)
+            gb = buf[w.shape[0] * Kt:] if want_b else None
             off = 0
             for i, x in enumerate(xs):
                 ops.gemm_dw(gy, x, dw=gw[:, off:off + ctx.widths[i]], db=gb if i == 0 else None)

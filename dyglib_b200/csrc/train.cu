@@ -1,7 +1,9 @@
 // Backward kernels of DyGFormer's training path (train_link_prediction.py:230-257 differentiates the reference's eager
 // modules; SURVEY.md 8(b): dyg_patch_project_bwd / dyg_tfm_block_bwd).  The forward of a training step runs on the same
 // tcgen05 GEMMs as evaluation; what autograd needs on top is here, in fp32:
-//   dyg_gemm_dw            dW += G^T X, db += column sums of G        (weight / bias gradient of every dense layer; split over the rows)
+//   dyg_gemm_dw            dW += G^T X, db += column sums of G        (weight / bias gradient of small dense layers; split over the rows;
+//                          large layers: dyg_gemm_bf16x3 on planes of G^T and X^T)
+//   dyg_gemm_dx            dX = G W for small layers in one launch (large ones: dyg_gemm_bf16x3 on planes of G and W^T)
 //   dyg_layernorm_bwd      dx, dgamma, dbeta of y = LayerNorm(x) gamma + beta                 (models/DyGFormer.py:447, 456)
 //   dyg_gelu_fwd / _bwd    h = gelu(v) * mask -> operand planes, dv = dh * mask * gelu'(v)     (models/DyGFormer.py:458)
 //   dyg_seq_attention_train_fwd / _bwd   softmax(q k^T / sqrt(hd)) (with dropout multipliers) v and its gradient (:454)
@@ -64,6 +66,52 @@ __global__ void __launch_bounds__(256) gemm_dw_kernel(const float* __restrict__ 
         for (int b = 0; b < 4; ++b)
             if (n0 + tn + a < N && k0 + tk + b < K) atomicAdd(dW + (int64_t)(n0 + tn + a) * ldw + k0 + tk + b, acc[a][b]);
     if (db && blockIdx.y == 0 && tid < DW_T && n0 + tid < N) atomicAdd(db + n0 + tid, bsum);
+}
+
+// ------------------------------------------------------------------ dX = G W  (M x K) for small layers (one launch, no operand planes)
+__global__ void __launch_bounds__(256) gemm_dx_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W, int ldw, int64_t M,
+                                                      int N, int K, float* __restrict__ dX, int lddx) {
+    __shared__ float sg[DW_T][DW_MC + 1];                        // [m][n]
+    __shared__ float sw[DW_MC][DW_T + 1];                        // [n][k]
+    const int64_t m0 = (int64_t)blockIdx.x * DW_T;
+    const int k0 = blockIdx.y * DW_T;
+    const int tid = threadIdx.x;
+    const int tm = (tid >> 4) * 4, tk = (tid & 15) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int n0 = 0; n0 < N; n0 += DW_MC) {
+        for (int i = tid; i < DW_T * DW_MC; i += 256) {
+            const int r = i / DW_MC, c = i - r * DW_MC;
+            sg[r][c] = (m0 + r < M && n0 + c < N) ? G[(m0 + r) * ldg + n0 + c] : 0.f;
+        }
+        for (int i = tid; i < DW_MC * DW_T; i += 256) {
+            const int r = i / DW_T, c = i - r * DW_T;
+            sw[r][c] = (n0 + r < N && k0 + c < K) ? W[(int64_t)(n0 + r) * ldw + k0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int n = 0; n < DW_MC; ++n) {
+            float g[4], w[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                g[a] = sg[tm + a][n];
+                w[a] = sw[n][tk + a];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], w[b], acc[a][b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (m0 + tm + a < M && k0 + tk + b < K) dX[(m0 + tm + a) * lddx + k0 + tk + b] = acc[a][b];
 }
 
 // ------------------------------------------------------------------ LayerNorm backward: one warp per row, rows strided over the grid
@@ -303,6 +351,18 @@ extern "C" int dyg_gemm_dw(const float* G, int ldg, const float* X, int ldx, int
     splits = (M + rows - 1) / rows;
     gemm_dw_kernel<<<dim3((unsigned)gn, (unsigned)gk, (unsigned)splits), 256, 0, as_stream(stream)>>>(G, ldg, X, ldx, M, N, K, dW, ldw, db, rows);
     DYG_LAUNCH_CHECK("dyg_gemm_dw");
+    return 0;
+}
+
+extern "C" int dyg_gemm_dx(const float* G, int ldg, const float* W, int ldw, int64_t M, int N, int K, float* dX, int lddx,
+                           dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldg >= N && ldw >= K && lddx >= K, "dyg_gemm_dx: bad sizes");
+    if (M == 0) return 0;
+    DYG_CHECK_ARG(G && W && dX, "dyg_gemm_dx: NULL pointer");
+    const int64_t gm = (M + DW_T - 1) / DW_T;
+    DYG_CHECK_ARG(gm < ((int64_t)1 << 31), "dyg_gemm_dx: M too large");
+    gemm_dx_kernel<<<dim3((unsigned)gm, (unsigned)((K + DW_T - 1) / DW_T)), 256, 0, as_stream(stream)>>>(G, ldg, W, ldw, M, N, K, dX, lddx);
+    DYG_LAUNCH_CHECK("dyg_gemm_dx");
     return 0;
 }
 

@@ -647,18 +647,52 @@ def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
 
 
 # ------------------------------------------------------------------ training path (backward kernels, csrc/train.cu)
+# input gradients of dense layers above this many flops go to the tcgen05 GEMM (three more launches: split, transpose, split)
+GEMM_DX_TC_FLOPS = float(os.environ.get('DYG_GEMM_DX_TC_FLOPS', '2e8'))
+# weight gradients above this many flops: planes of g^T and x^T through the tcgen05 GEMM (four more launches)
+GEMM_DW_TC_FLOPS = float(os.environ.get('DYG_GEMM_DW_TC_FLOPS', '1.2e10'))
+
+
 def gemm_dw(g, x, dw=None, db=None, want_bias=False):
-    """(dW (N, K), db (N) or None) of y = x W^T + b from g = dL/dy (M, N): dW = g^T x accumulated into ``dw`` (dyg_gemm_dw)."""
+    """(dW (N, K), db (N) or None) of y = x W^T + b from g = dL/dy (M, N): dW = g^T x ACCUMULATED into ``dw`` (zeroed when created
+    here).  Small layers: one split-over-rows fp32 launch (dyg_gemm_dw).  Large layers: the tcgen05 GEMM on planes of g^T and
+    x^T (contraction over the rows), bias gradient from dyg_gemm_dw against a column of ones."""
     M, N = g.shape
     K = x.shape[1]
-    if dw is None:
+    fresh = dw is None
+    if fresh:
         dw = torch.zeros((N, K), dtype=torch.float32, device=g.device)
     if want_bias and db is None:
         db = torch.zeros(N, dtype=torch.float32, device=g.device)
+    if 2.0 * M * N * K >= GEMM_DW_TC_FLOPS:
+        part = gemm(split_bf16(g.t().contiguous()), split_bf16(x.t().contiguous().float()))
+        if fresh:
+            dw = part
+        else:
+            dw += part
+        if db is not None:
+            ones = torch.ones((M, 1), dtype=torch.float32, device=g.device)
+            scratch = torch.zeros((N, 1), dtype=torch.float32, device=g.device)
+            _native.check(_lib().dyg_gemm_dw(_p(g), int(g.stride(0)), _p(ones), 1, int(M), int(N), 1, _p(scratch), 1, _p(db), _stream()))
+            _count()
+        return dw, db
     _native.check(_lib().dyg_gemm_dw(_p(g), int(g.stride(0)), _p(x), int(x.stride(0)), int(M), int(N), int(K), _p(dw), int(dw.stride(0)),
                                      _p(db), _stream()))
     _count()
     return dw, db
+
+
+def gemm_dx(g, w):
+    """dX = g @ w for y = x W^T: one fp32 launch for small layers (dyg_gemm_dx), the tcgen05 GEMM on planes of g and W^T otherwise."""
+    M, N = g.shape
+    K = w.shape[1]
+    if 2.0 * M * N * K >= GEMM_DX_TC_FLOPS:
+        return gemm(split_bf16(g), split_bf16(w.t().contiguous().float()))
+    dx = torch.empty((M, K), dtype=torch.float32, device=g.device)
+    _native.check(_lib().dyg_gemm_dx(_p(g), int(g.stride(0)), _p(w), int(w.stride(0)), int(M), int(N), int(K), _p(dx), int(dx.stride(0)),
+                                     _stream()))
+    _count()
+    return dx
 
 
 def layernorm_bwd(x, gamma, eps, dy):

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 8
+#define DYG_ABI_VERSION 9
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -308,6 +308,9 @@ int dyg_attn_block(const float* x, int ldx, const float* gamma, const float* bet
  * with atomic accumulation (zero dW / db first).  For the patch projections X is the gathered patch matrix of a channel. */
 int dyg_gemm_dw(const float* G, int ldg, const float* X, int ldx, int64_t M, int N, int K, float* dW, int ldw, float* db,
                 dyg_stream_t stream);
+/* dX[m, k] = sum_n G[m, n] W[n, k]: input gradient of y = x W^T + b for small layers, one fp32 launch (large layers use
+ * dyg_gemm_bf16x3 on the planes of G and W^T). */
+int dyg_gemm_dx(const float* G, int ldg, const float* W, int ldw, int64_t M, int N, int K, float* dX, int lddx, dyg_stream_t stream);
 /* y = LayerNorm(x) gamma + beta: dx (M, D) written, dgamma / dbeta (D) accumulated (zero them first; may be NULL). */
 int dyg_layernorm_bwd(const float* x, int ldx, const float* gamma, float eps, const float* dy, int lddy, float* dx, int lddx,
                       float* dgamma, float* dbeta, int64_t M, int D, dyg_stream_t stream);

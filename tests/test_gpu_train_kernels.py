@@ -21,6 +21,14 @@ def test_gemm_dw_vs_float64(M, N, K):
     dw, db = ops.gemm_dw(G, X, want_bias=True)
     assert rel(dw, G.double().t() @ X.double()) < 2e-5
     assert rel(db, G.double().sum(0)) < 2e-5
+    if M >= 1000:
+        # the tcgen05 route for very large layers (planes of G^T and X^T): BF16x3 over a contraction of M terms
+        old, ops.GEMM_DW_TC_FLOPS = ops.GEMM_DW_TC_FLOPS, 0.0
+        try:
+            dw2, db2 = ops.gemm_dw(G, X, want_bias=True)
+        finally:
+            ops.GEMM_DW_TC_FLOPS = old
+        assert rel(dw2, G.double().t() @ X.double()) < 3e-4 and rel(db2, G.double().sum(0)) < 2e-5
     # accumulation into a column window of a wider gradient (concatenated inputs of one layer)
     wide = torch.zeros(N, K + 7, device='cuda')
     ops.gemm_dw(G, X, dw=wide[:, 3:3 + K])
@@ -92,3 +100,11 @@ def test_linear_backward_runs_on_own_kernels():
     torch.relu(xd @ wd.t() + bd).backward(gy.double())
     assert rel(torch.cat([x1.grad, x2.grad], 1), xd.grad) < 5e-5
     assert rel(w.grad, wd.grad) < 5e-5 and rel(b.grad, bd.grad) < 5e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 1, 1), (37, 5, 9), (700, 272, 444), (25600, 800, 200)])
+def test_gemm_dx_small_and_tcgen05_paths(M, N, K):
+    g = torch.Generator(device='cuda').manual_seed(M + N + K)
+    G = torch.randn(M, N, device='cuda', generator=g)
+    W = torch.randn(N, K, device='cuda', generator=g)
+    assert rel(ops.gemm_dx(G, W), G.double() @ W.double()) < 3e-5
