@@ -204,6 +204,40 @@ class NeighborSampler:
         ints = rec[:, 1].copy().view(np.int32).reshape(-1, 2)
         return ints[:, 0].astype(np.int64), ints[:, 1].astype(np.int64), t
 
+    def _host_lists(self):
+        """Per-node host views of the device CSR (one D2H copy, cached): the reference's list attributes, built lazily."""
+        if getattr(self, '_host_cache', None) is None:
+            n = self.num_half_edges
+            indptr = self.indptr.cpu().numpy()
+            nbr, eid, t = self._host_records(0, n) if n else (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64))
+            cut = indptr[1:-1]
+            cache = {'ids': np.split(nbr, cut), 'eids': np.split(eid, cut), 'times': np.split(t, cut)}
+            if self.sample_neighbor_strategy == 'time_interval_aware':
+                prob = self._prob_host if self._prob_host is not None else self.tia_prob[:n].cpu().numpy()
+                cache['prob'] = np.split(prob, cut)
+            self._host_cache = cache
+        return self._host_cache
+
+    @property
+    def nodes_neighbor_ids(self):
+        """``self.nodes_neighbor_ids`` of the reference (``utils/utils.py:85-103``): list over nodes of time-sorted neighbour ids."""
+        return self._host_lists()['ids']
+
+    @property
+    def nodes_edge_ids(self):
+        return self._host_lists()['eids']
+
+    @property
+    def nodes_neighbor_times(self):
+        return self._host_lists()['times']
+
+    @property
+    def nodes_neighbor_sampled_probabilities(self):
+        """``utils/utils.py:88-110``: only for ``time_interval_aware`` (AttributeError otherwise, as in the reference)."""
+        if self.sample_neighbor_strategy != 'time_interval_aware':
+            raise AttributeError("'NeighborSampler' object has no attribute 'nodes_neighbor_sampled_probabilities'")
+        return self._host_lists()['prob']
+
     def find_neighbors_before(self, node_id: int, interact_time: float, return_sampled_probabilities: bool = False):
         """``find_neighbors_before`` (``utils/utils.py:130-147``); host views of one node's prefix."""
         a, b = self._node_slice(int(node_id))

@@ -106,6 +106,20 @@ def test_adj_list_constructor_matches():
     nb, ei, tt, _ = c.find_neighbors_before(int(nodes[100]), float(times[100]))
     a, i = o.count_before(nodes[100], times[100])
     assert np.array_equal(nb, o.nbr[a:a + i]) and np.array_equal(ei, o.eid[a:a + i]) and np.array_equal(tt, o.t[a:a + i])
+    # the reference's list attributes (utils/utils.py:85-110) as lazy host views of the device CSR
+    assert len(c.nodes_neighbor_ids) == len(adj) and len(c.nodes_neighbor_ids[0]) == 0
+    vq = int(g.src_node_ids[7])
+    for v in (1, vq, g.num_nodes - 1):
+        ref = sorted(adj[v], key=lambda x: x[2])
+        assert np.array_equal(c.nodes_neighbor_ids[v], np.array([x[0] for x in ref], dtype=np.int64))
+        assert np.array_equal(c.nodes_edge_ids[v], np.array([x[1] for x in ref], dtype=np.int64))
+        assert np.array_equal(c.nodes_neighbor_times[v], np.array([x[2] for x in ref], dtype=np.float64))
+    with pytest.raises(AttributeError):
+        c.nodes_neighbor_sampled_probabilities
+    ct = NeighborSampler(adj, 'time_interval_aware', time_scaling_factor=1e-5, seed=0)
+    tv = np.array([x[2] for x in sorted(adj[vq], key=lambda x: x[2])])
+    e = np.exp(1e-5 * (tv - tv.max()))
+    assert np.allclose(ct.nodes_neighbor_sampled_probabilities[vq], e / np.cumsum(e), rtol=1e-12)
 
 
 @pytest.mark.parametrize('strategy', ['uniform', 'time_interval_aware'])
