@@ -252,6 +252,26 @@ def test_dygformer_full_size_batch_vs_oracle():
                 close(x, y)
 
 
+@pytest.mark.parametrize('attn,ln', [(0, True), (1, False), (1, True), (2, True)])
+def test_dygformer_attention_paths_agree_with_oracle(monkeypatch, attn, ln):
+    """Every implementation of the attention half of the block (mma.sync path, LayerNorm planes + GEMM + tcgen05 attention, LayerNorm
+    fused into the GEMM, the one-kernel form) against the oracle on batches with full and short padded lengths."""
+    import dyglib_b200.models.DyGFormer as mod
+    monkeypatch.setattr(mod, 'FUSED_ATTN', attn)
+    monkeypatch.setattr(mod, 'FUSED_LN', ln)
+    _, _, dygformer, _ = cuda_factories()
+    _, _, odyg, _ = oracle_factories()
+    g = small_graph(seed=21, E=6000, nu=150, ni=40)
+    m, o = dygformer(g, 2, 32, 2), odyg(g, 2, 32, 2)
+    with torch.no_grad():
+        for start, n in ((40, 30), (4000, 120)):
+            src, dst, t, _, _ = next(batches(g, start, 1, n))
+            a = m.compute_src_dst_node_temporal_embeddings(src, dst, t)
+            b = o.compute_src_dst_node_temporal_embeddings(src, dst, t)
+            for x, y in zip(a, b):
+                close(x, y)
+
+
 def test_dygformer_grouped_equals_per_batch():
     """batch_size= groups keep the reference's per-batch padding unit: identical to one call per batch."""
     _, _, dygformer, _ = cuda_factories()
