@@ -387,8 +387,9 @@ _ffn_ws = {}
 
 
 def _ffn_workspace(device):
-    """Per-device scratch of dyg_ln_ffn_bf16x3 (one A-operand image per CTA, stays in L2)."""
-    key = str(device)
+    """Per-device, per-stream scratch of dyg_ln_ffn_bf16x3 / dyg_ln_gemm_bf16x3 (one A-operand image per CTA, stays in L2)."""
+    # one scratch per (device, stream): two forwards on different streams of a device must not share the operand images
+    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream))
     if key not in _ffn_ws:
         _ffn_ws[key] = torch.empty(int(_lib().dyg_ln_ffn_workspace_bytes()), dtype=torch.uint8, device=device)
     return _ffn_ws[key]
@@ -632,7 +633,7 @@ def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
         raise ValueError(f'attn_block: weight {wcat.rows} x {wcat.cols} / x {tuple(x.shape)} do not match B={B} S={S} D={D} H={H}')
     if out is None:
         out = torch.empty_like(x)
-    key = (str(x.device), N)
+    key = (str(x.device), int(torch.cuda.current_stream(x.device).cuda_stream), N)
     if key not in _attn_ws:
         _attn_ws[key] = torch.empty(int(_lib().dyg_attn_block_workspace_bytes(int(N))) + 1024, dtype=torch.uint8, device=x.device)
     ws = _attn_ws[key]

@@ -342,6 +342,16 @@ class NeighborSampler:
                 p = torch.softmax(torch.from_numpy(self._prob_host[a:a + c]).float(), dim=0).numpy()
                 sel_h[q] = rs.choice(a=c, size=k, p=p)
         sel.copy_(torch.from_numpy(sel_h), non_blocking=False)
+        # The reference re-sorts a query's draws with ndarray.argsort() on their float32 times (utils/utils.py:196), an UNSTABLE sort:
+        # distinct records whose times round to the same float32 come out in numpy's order, not in draw order.  Parity mode replays
+        # that call on the host (times of the drawn records come back from the device) and hands the kernel positions that are
+        # already in the reference's order; its own stable rank sort is then the identity.
+        if len(nz):
+            a0 = self.indptr[ids].reshape(n, 1)
+            t32 = self.halfedges[:, 0][(a0 + sel).clamp_(max=max(self.num_half_edges - 1, 0))].float().cpu().numpy()
+            order = np.argsort(t32[nz], axis=1)
+            sel_h[nz] = np.take_along_axis(sel_h[nz], order, axis=1)
+            sel.copy_(torch.from_numpy(sel_h), non_blocking=False)
         return sel
 
     def get_all_first_hop_neighbors_device(self, node_ids, node_interact_times, max_input_sequence_length: int,

@@ -141,6 +141,23 @@ def test_random_strategies_replay_stream_across_calls(strategy):
             assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize('strategy', ['uniform', 'time_interval_aware'])
+def test_replay_mode_reproduces_numpy_tie_order(strategy):
+    """Timestamps above 2^24: distinct records round to the same float32 time, and the reference's unstable argsort
+    (utils/utils.py:196) decides their order.  Replay mode must come out in that order, not in draw order."""
+    g = small_graph(seed=77, E=6000, nu=30, ni=12)
+    g.node_interact_times = g.node_interact_times + 3.0e8        # float32 spacing 32: neighbouring events collide
+    c, o = _pair(g, strategy, seed=3, tsf=1e-6)
+    rng = np.random.default_rng(4)
+    nodes, times = make_queries(g, 400, rng)
+    a = c.get_historical_neighbors(nodes, times, 20)
+    b = o.get_historical_neighbors(nodes, times, 20)
+    ties = sum(len(np.unique(r)) < len(r) for r in b[2])
+    assert ties > 100                                             # the case is exercised
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 def test_tia_device_table_mismatch_rate():
     """Device prefix-CDF draw fed with the replayed random_sample stream: indices equal the reference's unless a
     uniform lands within float32-softmax rounding of a CDF boundary (expected rate <~ 1e-6 per draw)."""
