@@ -33,35 +33,37 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         weight, y, *xs = ctx.saved_tensors
-        gy = gy.contiguous()
-        if ctx.act == ops.ACT_RELU:
-            gy = gy * (y > 0)
-        elif ctx.act != ops.ACT_NONE:
+        gy = gy.contiguous().float()
+        if ctx.act not in (ops.ACT_RELU, ops.ACT_NONE):
             raise NotImplementedError('backward of this activation')
-        w = weight.detach()
-        gy = gy.float()
+        w = weight.detach().float()
         need_x = any(ctx.needs_input_grad[3 + i] for i in range(len(xs)))
-        gx = None
-        if need_x:
-            # dX = dY W: the tcgen05 GEMM on planes of dY and W^T for large layers, one fp32 launch for small ones
-            gx = ops.gemm_dx(gy, w.float())
-        gw = gb = None
+        need_w = ctx.needs_input_grad[0]
         want_b = ctx.has_bias and ctx.needs_input_grad[1]
-        if ctx.needs_input_grad[0] or want_b:
-            # dW = dY^T X (and db = column sums of dY) split over the rows (dyg_gemm_dw); one call per concatenated segment
-            Kt = sum(ctx.widths)
-            buf = torch.zeros(w.shape[0] * (Kt + 1), dtype=torch.float32, device=gy.device)      # dW | db: one memset
-            gw = buf[:w.shape[0] * Kt].view(w.shape[0], Kt)
-            gb = buf[w.shape[0] * Kt:] if want_b else None
-            off = 0
-            for i, x in enumerate(xs):
-                ops.gemm_dw(gy, x, dw=gw[:, off:off + ctx.widths[i]], db=gb if i == 0 else None)
-                off += ctx.widths[i]
-            if not ctx.needs_input_grad[0]:
-                gw = None
+        Kt = sum(ctx.widths)
+        if 2.0 * gy.shape[0] * gy.shape[1] * Kt < ops.LINEAR_BWD_FUSED_FLOPS and w.stride(1) == 1:
+            # small layer: dX, dW, db and the ReLU mask in one launch per input segment
+            gx, gw, gb = ops.linear_bwd(gy, y if ctx.act == ops.ACT_RELU else None, xs, ctx.widths, w, need_x, need_w, want_b)
+        else:
+            if ctx.act == ops.ACT_RELU:
+                gy = gy * (y > 0)
+            gx = gw = gb = None
+            if need_x:
+                # dX = dY W: the tcgen05 GEMM on planes of dY and W^T for large layers, one fp32 launch for small ones
+                gx = ops.gemm_dx(gy, w)
+            if need_w or want_b:
+                # dW = dY^T X (and db = column sums of dY) split over the rows (dyg_gemm_dw); one call per concatenated segment
+                buf = torch.zeros(w.shape[0] * (Kt + 1), dtype=torch.float32, device=gy.device)      # dW | db: one memset
+                gw = buf[:w.shape[0] * Kt].view(w.shape[0], Kt)
+                gb = buf[w.shape[0] * Kt:] if want_b else None
+                off = 0
+                for i, x in enumerate(xs):
+                    ops.gemm_dw(gy, x, dw=gw[:, off:off + ctx.widths[i]], db=gb if i == 0 else None)
+                    off += ctx.widths[i]
+                if not need_w:
+                    gw = None
         if gx is None:
-            gxs = (None,) * len(xs)
-            return (gw, gb, None) + gxs
+            return (gw, gb, None) + (None,) * len(xs)
         gxs = torch.split(gx, ctx.widths, dim=1) if len(xs) > 1 else (gx,)
         gxs = tuple(g if ctx.needs_input_grad[3 + i] else None for i, g in enumerate(gxs))
         return (gw, gb, None) + gxs

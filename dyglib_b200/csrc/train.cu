@@ -3,6 +3,7 @@
 // tcgen05 GEMMs as evaluation; what autograd needs on top is here, in fp32:
 //   dyg_gemm_dw            dW += G^T X, db += column sums of G        (weight / bias gradient of small dense layers; split over the rows;
 //                          large layers: dyg_gemm_bf16x3 on planes of G^T and X^T)
+//   dyg_linear_bwd         dX, dW, db of a small layer in ONE launch, ReLU mask applied on the way in
 //   dyg_gemm_dx            dX = G W for small layers in one launch (large ones: dyg_gemm_bf16x3 on planes of G and W^T)
 //   dyg_layernorm_bwd      dx, dgamma, dbeta of y = LayerNorm(x) gamma + beta                 (models/DyGFormer.py:447, 456)
 //   dyg_gelu_fwd / _bwd    h = gelu(v) * mask -> operand planes, dv = dh * mask * gelu'(v)     (models/DyGFormer.py:458)
@@ -112,6 +113,104 @@ __global__ void __launch_bounds__(256) gemm_dx_kernel(const float* __restrict__ 
 #pragma unroll
         for (int b = 0; b < 4; ++b)
             if (m0 + tm + a < M && k0 + tk + b < K) dX[(m0 + tm + a) * lddx + k0 + tk + b] = acc[a][b];
+}
+
+// ------------------------------------------------------------------ dX and dW (+ db) of a small dense layer in ONE launch
+// Blocks [0, dx_tiles) compute 64 x 64 tiles of dX = G W, the others 64 x 64 tiles of dW += G^T X over a slice of the rows (and db).
+// With `Y` the gradient is masked on the way in (ReLU layers: G * (Y > 0)), so the mask needs no launch of its own.
+__device__ __forceinline__ float lb_g(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy, int64_t m, int n) {
+    const float g = G[m * ldg + n];
+    return (Y && !(Y[m * ldy + n] > 0.f)) ? 0.f : g;
+}
+__global__ void __launch_bounds__(256) linear_bwd_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
+                                                         const float* __restrict__ X, int ldx, const float* __restrict__ W, int ldw, int64_t M,
+                                                         int N, int K, float* __restrict__ dX, int lddx, float* __restrict__ dW, int lddw,
+                                                         float* __restrict__ db, int dx_tiles, int dx_ktiles, int dw_ktiles, int dw_tiles,
+                                                         int64_t rows_per_cta) {
+    __shared__ float sa[DW_T][DW_MC + 1];
+    __shared__ float sb[DW_MC][DW_T + 1];
+    const int tid = threadIdx.x;
+    const int ta = (tid >> 4) * 4, tb = (tid & 15) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    if ((int)blockIdx.x < dx_tiles) {
+        // ---- dX tile (m0, k0): contraction over n
+        const int64_t m0 = (int64_t)(blockIdx.x / dx_ktiles) * DW_T;
+        const int k0 = (blockIdx.x % dx_ktiles) * DW_T;
+        for (int n0 = 0; n0 < N; n0 += DW_MC) {
+            for (int i = tid; i < DW_T * DW_MC; i += 256) {
+                const int r = i / DW_MC, c = i - r * DW_MC;
+                sa[r][c] = (m0 + r < M && n0 + c < N) ? lb_g(G, ldg, Y, ldy, m0 + r, n0 + c) : 0.f;
+            }
+            for (int i = tid; i < DW_MC * DW_T; i += 256) {
+                const int r = i / DW_T, c = i - r * DW_T;
+                sb[r][c] = (n0 + r < N && k0 + c < K) ? W[(int64_t)(n0 + r) * ldw + k0 + c] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int n = 0; n < DW_MC; ++n) {
+                float g[4], w[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    g[a] = sa[ta + a][n];
+                    w[a] = sb[n][tb + a];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], w[b], acc[a][b]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (m0 + ta + a < M && k0 + tb + b < K) dX[(m0 + ta + a) * lddx + k0 + tb + b] = acc[a][b];
+    } else {
+        // ---- dW tile (n0, k0) over rows [m_begin, m_end): contraction over m; sa holds G^T chunks as [n][m]
+        const int t = (int)blockIdx.x - dx_tiles;
+        const int tile = t % dw_tiles, split = t / dw_tiles;
+        const int n0 = (tile / dw_ktiles) * DW_T, k0 = (tile % dw_ktiles) * DW_T;
+        const int64_t m_begin = split * rows_per_cta, m_end = min(M, m_begin + rows_per_cta);
+        float bsum = 0.f;
+        for (int64_t m0 = m_begin; m0 < m_end; m0 += DW_MC) {
+            for (int i = tid; i < DW_MC * DW_T; i += 256) {
+                const int r = i / DW_T, c = i - r * DW_T;         // r: row m of the chunk, c: n / k of the tile
+                const int64_t m = m0 + r;
+                sa[c][r] = (m < m_end && n0 + c < N) ? lb_g(G, ldg, Y, ldy, m, n0 + c) : 0.f;
+                sb[r][c] = (m < m_end && k0 + c < K) ? X[m * ldx + k0 + c] : 0.f;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int r = 0; r < DW_MC; ++r) {
+                float g[4], x[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    g[a] = sa[ta + a][r];
+                    x[a] = sb[r][tb + a];
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], x[b], acc[a][b]);
+            }
+            if (db && k0 == 0 && tid < DW_T) {
+#pragma unroll 8
+                for (int r = 0; r < DW_MC; ++r) bsum += sa[tid][r];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (n0 + ta + a < N && k0 + tb + b < K) atomicAdd(dW + (int64_t)(n0 + ta + a) * lddw + k0 + tb + b, acc[a][b]);
+        if (db && k0 == 0 && tid < DW_T && n0 + tid < N) atomicAdd(db + n0 + tid, bsum);
+    }
 }
 
 // ------------------------------------------------------------------ LayerNorm backward: one warp per row, rows strided over the grid
@@ -363,6 +462,36 @@ extern "C" int dyg_gemm_dx(const float* G, int ldg, const float* W, int ldw, int
     DYG_CHECK_ARG(gm < ((int64_t)1 << 31), "dyg_gemm_dx: M too large");
     gemm_dx_kernel<<<dim3((unsigned)gm, (unsigned)((K + DW_T - 1) / DW_T)), 256, 0, as_stream(stream)>>>(G, ldg, W, ldw, M, N, K, dX, lddx);
     DYG_LAUNCH_CHECK("dyg_gemm_dx");
+    return 0;
+}
+
+extern "C" int dyg_linear_bwd(const float* G, int ldg, const float* Y, int ldy, const float* X, int ldx, const float* W, int ldw, int64_t M,
+                              int N, int K, float* dX, int lddx, float* dW, int lddw, float* db, dyg_stream_t stream) {
+    DYG_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldg >= N, "dyg_linear_bwd: bad sizes");
+    if (M == 0) return 0;
+    DYG_CHECK_ARG(G && (dX || dW), "dyg_linear_bwd: nothing to compute");
+    DYG_CHECK_ARG(!dX || (W && ldw >= K && lddx >= K), "dyg_linear_bwd: dX needs W (N, K)");
+    DYG_CHECK_ARG(!dW || (X && ldx >= K && lddw >= K), "dyg_linear_bwd: dW needs X (M, K)");
+    DYG_CHECK_ARG(!db || dW, "dyg_linear_bwd: db is computed with dW");
+    const int kt = (K + DW_T - 1) / DW_T;
+    const int64_t dx_tiles64 = dX ? ((M + DW_T - 1) / DW_T) * kt : 0;
+    DYG_CHECK_ARG(dx_tiles64 < ((int64_t)1 << 30), "dyg_linear_bwd: M too large");
+    const int dw_tiles = dW ? ((N + DW_T - 1) / DW_T) * kt : 0;
+    int64_t splits = 0, rows = 0;
+    if (dW) {
+        splits = (4 * (int64_t)dyg_num_sms() + dw_tiles - 1) / dw_tiles;
+        const int64_t max_splits = (M + 4 * DW_MC - 1) / (4 * DW_MC);
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+        rows = (M + splits - 1) / splits;
+        rows = (rows + DW_MC - 1) / DW_MC * DW_MC;
+        splits = (M + rows - 1) / rows;
+    }
+    const int64_t grid = dx_tiles64 + dw_tiles * splits;
+    DYG_CHECK_ARG(grid < ((int64_t)1 << 31), "dyg_linear_bwd: grid too large");
+    linear_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(G, ldg, Y, ldy, X, ldx, W, ldw, M, N, K, dX, lddx, dW, lddw, db, (int)dx_tiles64,
+                                                                    kt, kt, dw_tiles > 0 ? dw_tiles : 1, rows);
+    DYG_LAUNCH_CHECK("dyg_linear_bwd");
     return 0;
 }
 

@@ -650,6 +650,8 @@ def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
 # ------------------------------------------------------------------ training path (backward kernels, csrc/train.cu)
 # input gradients of dense layers above this many flops go to the tcgen05 GEMM (three more launches: split, transpose, split)
 GEMM_DX_TC_FLOPS = float(os.environ.get('DYG_GEMM_DX_TC_FLOPS', '2e8'))
+# dense layers below this many flops (2 M N K) take the one-launch backward (dyg_linear_bwd)
+LINEAR_BWD_FUSED_FLOPS = float(os.environ.get('DYG_LINEAR_BWD_FUSED_FLOPS', '2e8'))
 # weight gradients above this many flops: planes of g^T and x^T through the tcgen05 GEMM (four more launches)
 GEMM_DW_TC_FLOPS = float(os.environ.get('DYG_GEMM_DW_TC_FLOPS', '1.2e10'))
 
@@ -681,6 +683,32 @@ def gemm_dw(g, x, dw=None, db=None, want_bias=False):
                                      _p(db), _stream()))
     _count()
     return dw, db
+
+
+def linear_bwd(g, y_mask, xs, widths, w, need_x=True, need_w=True, need_b=False):
+    """Backward of a small dense layer y = act(cat(xs) W^T + b) in one launch per input segment (dyg_linear_bwd):
+    (dX (M, sum widths) or None, dW (N, sum widths) or None, db (N) or None); ``y_mask``: the ReLU output (masks g) or None."""
+    M, N = g.shape
+    Kt = sum(widths)
+    dev = g.device
+    dx = torch.empty((M, Kt), dtype=torch.float32, device=dev) if need_x else None
+    dw = db = None
+    if need_w or need_b:
+        buf = torch.zeros(N * (Kt + 1), dtype=torch.float32, device=dev)                       # dW | db: one memset
+        dw = buf[:N * Kt].view(N, Kt)
+        db = buf[N * Kt:] if need_b else None
+    off = 0
+    for i, x in enumerate(xs):
+        K = widths[i]
+        _native.check(_lib().dyg_linear_bwd(
+            _p(g), int(g.stride(0)), _p(y_mask), int(y_mask.stride(0)) if y_mask is not None else 0,
+            _p(x) if dw is not None else None, int(x.stride(0)) if dw is not None else 0,
+            ctypes.c_void_p(w.data_ptr() + 4 * off) if need_x else None, int(w.stride(0)), int(M), int(N), int(K),
+            ctypes.c_void_p(dx.data_ptr() + 4 * off) if need_x else None, Kt,
+            ctypes.c_void_p(dw.data_ptr() + 4 * off) if dw is not None else None, Kt, _p(db) if (db is not None and i == 0) else None, _stream()))
+        _count()
+        off += K
+    return dx, (dw if need_w else None), db
 
 
 def gemm_dx(g, w):

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 9
+#define DYG_ABI_VERSION 10
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -311,6 +311,10 @@ int dyg_gemm_dw(const float* G, int ldg, const float* X, int ldx, int64_t M, int
 /* dX[m, k] = sum_n G[m, n] W[n, k]: input gradient of y = x W^T + b for small layers, one fp32 launch (large layers use
  * dyg_gemm_bf16x3 on the planes of G and W^T). */
 int dyg_gemm_dx(const float* G, int ldg, const float* W, int ldw, int64_t M, int N, int K, float* dX, int lddx, dyg_stream_t stream);
+/* dyg_gemm_dx and dyg_gemm_dw (+ db) of one small layer in ONE launch (either output may be NULL); Y (M, N), when given, is the layer's
+ * ReLU output and masks the gradient on the way in (G * (Y > 0)).  dW / db are accumulated (zero them first). */
+int dyg_linear_bwd(const float* G, int ldg, const float* Y, int ldy, const float* X, int ldx, const float* W, int ldw, int64_t M,
+                   int N, int K, float* dX, int lddx, float* dW, int lddw, float* db, dyg_stream_t stream);
 /* y = LayerNorm(x) gamma + beta: dx (M, D) written, dgamma / dbeta (D) accumulated (zero them first; may be NULL). */
 int dyg_layernorm_bwd(const float* x, int ldx, const float* gamma, float eps, const float* dy, int lddy, float* dx, int lddx,
                       float* dgamma, float* dbeta, int64_t M, int D, dyg_stream_t stream);

@@ -108,3 +108,21 @@ def test_gemm_dx_small_and_tcgen05_paths(M, N, K):
     G = torch.randn(M, N, device='cuda', generator=g)
     W = torch.randn(N, K, device='cuda', generator=g)
     assert rel(ops.gemm_dx(G, W), G.double() @ W.double()) < 3e-5
+
+
+@pytest.mark.parametrize('M,N,K1,K2,relu', [(1, 1, 1, 0, False), (500, 64, 172, 100, True), (803, 172, 172, 272, False), (77, 1, 172, 0, True)])
+def test_linear_bwd_one_launch(M, N, K1, K2, relu):
+    """dyg_linear_bwd: dX, dW, db of a small layer (with concatenated inputs and the ReLU mask) against float64."""
+    g = torch.Generator(device='cuda').manual_seed(M + N + K1)
+    widths = [K1] + ([K2] if K2 else [])
+    xs = [torch.randn(M, k, device='cuda', generator=g) for k in widths]
+    w = torch.randn(N, sum(widths), device='cuda', generator=g)
+    gy = torch.randn(M, N, device='cuda', generator=g)
+    y = torch.randn(M, N, device='cuda', generator=g) if relu else None
+    dx, dw, db = ops.linear_bwd(gy, y, xs, widths, w, True, True, True)
+    gm = (gy * (y > 0)).double() if relu else gy.double()
+    assert rel(dx, gm @ w.double()) < 2e-5
+    assert rel(dw, gm.t() @ torch.cat(xs, 1).double()) < 2e-5
+    assert rel(db, gm.sum(0)) < 2e-5
+    dx2, dw2, db2 = ops.linear_bwd(gy, y, xs, widths, w, True, False, False)
+    assert dw2 is None and db2 is None and rel(dx2, gm @ w.double()) < 2e-5
