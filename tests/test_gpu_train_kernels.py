@@ -19,7 +19,8 @@ def test_gemm_dw_vs_float64(M, N, K):
     G = torch.randn(M, N, device='cuda', generator=g)
     X = torch.randn(M, K, device='cuda', generator=g)
     dw, db = ops.gemm_dw(G, X, want_bias=True)
-    assert rel(dw, G.double().t() @ X.double()) < 2e-5
+    tol = 2e-5 if M < 512 else 2e-4        # from 512 rows on: BF16x3 on mma.sync (dropped terms ~2^-16 per product over M products)
+    assert rel(dw, G.double().t() @ X.double()) < tol
     assert rel(db, G.double().sum(0)) < 2e-5
     if M >= 1000:
         # the tcgen05 route for very large layers (planes of G^T and X^T): BF16x3 over a contraction of M terms
@@ -32,7 +33,7 @@ def test_gemm_dw_vs_float64(M, N, K):
     # accumulation into a column window of a wider gradient (concatenated inputs of one layer)
     wide = torch.zeros(N, K + 7, device='cuda')
     ops.gemm_dw(G, X, dw=wide[:, 3:3 + K])
-    assert rel(wide[:, 3:3 + K], G.double().t() @ X.double()) < 2e-5 and float(wide[:, :3].abs().max()) == 0.0
+    assert rel(wide[:, 3:3 + K], G.double().t() @ X.double()) < tol and float(wide[:, :3].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize('M,D', [(1, 8), (77, 200), (5000, 172), (333, 272), (64, 512)])
