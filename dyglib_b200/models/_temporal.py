@@ -92,7 +92,6 @@ def temporal_conv_train(attn, merge, time_encoder, conv, root_feat, node_tab, nb
                            t_query=tq, t_nbr=nbr_t.reshape(-1).contiguous(), zero_row0=zero_row0, dropout=p)
     o = ag.linear(s, wvr, attn.residual_fc.bias)
     o = torch.nn.functional.dropout(o, p, attn.training)
-    y = torch.nn.functional.layer_norm(o + query_in, (attn.query_dim,), attn.layer_norm.weight, attn.layer_norm.bias,
-                                       attn.layer_norm.eps)
+    y = ag.layer_norm(o + query_in, attn.layer_norm.weight, attn.layer_norm.bias, attn.layer_norm.eps)
     h = ag.linear([y, root_feat], merge.fc1.weight, merge.fc1.bias, act=ops.ACT_RELU)
     return ag.linear(h, merge.fc2.weight, merge.fc2.bias)
