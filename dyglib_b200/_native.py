@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _lock = threading.Lock()
 _lib = None
@@ -151,7 +151,7 @@ SIGNATURES = {
     'dyg_seq_attention_fold': [c_p, c_p, c_i, c_i, c_i, c_i, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p],
     'dyg_attn_block': [c_p, c_i, c_p, c_p, c_f, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p, c_l, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_l, c_p],
     'dyg_gemm_dw': [c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_p],
-    'dyg_gemm_dx': [c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p],
+    'dyg_gemm_dx': [c_p, c_i, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p],
     'dyg_linear_bwd': [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_l, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p],
     'dyg_layernorm_bwd': [c_p, c_i, c_p, c_f, c_p, c_i, c_p, c_i, c_p, c_p, c_l, c_i, c_p],
     'dyg_gelu_fwd': [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_l, c_i, c_p],

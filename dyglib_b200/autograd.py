@@ -45,12 +45,13 @@ class _Linear(torch.autograd.Function):
             # small layer: dX, dW, db and the ReLU mask in one launch per input segment
             gx, gw, gb = ops.linear_bwd(gy, y if ctx.act == ops.ACT_RELU else None, xs, ctx.widths, w, need_x, need_w, want_b)
         else:
-            if ctx.act == ops.ACT_RELU:
-                gy = gy * (y > 0)
             gx = gw = gb = None
+            relu = ctx.act == ops.ACT_RELU
             if need_x:
-                # dX = dY W: the tcgen05 GEMM on planes of dY and W^T for large layers, one fp32 launch for small ones
-                gx = ops.gemm_dx(gy, w)
+                # dX = (dY * mask) W: one BF16x3 mma.sync launch; the tcgen05 GEMM on planes of dY and W^T for very large layers
+                gx = ops.gemm_dx(gy, w, y if relu else None)
+            if relu and (need_w or want_b):
+                gy = gy * (y > 0)
             if need_w or want_b:
                 # dW = dY^T X (and db = column sums of dY) split over the rows (dyg_gemm_dw); one call per concatenated segment
                 buf = torch.zeros(w.shape[0] * (Kt + 1), dtype=torch.float32, device=gy.device)      # dW | db: one memset

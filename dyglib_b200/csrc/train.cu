@@ -4,7 +4,8 @@
 //   dyg_gemm_dw            dW += G^T X, db += column sums of G        (weight / bias gradient of a dense layer, split over the rows: FFMA tiles for
 //                          short contractions, BF16x3 mma.sync with ldmatrix.trans operands from 512 rows on)
 //   dyg_linear_bwd         dX, dW, db of a small layer in ONE launch, ReLU mask applied on the way in
-//   dyg_gemm_dx            dX = G W for small layers in one launch (large ones: dyg_gemm_bf16x3 on planes of G and W^T)
+//   dyg_gemm_dx            dX = (G * mask) W in one launch: BF16x3 mma.sync, W read with ldmatrix.trans (very large layers:
+//                          dyg_gemm_bf16x3 on planes of G and W^T)
 //   dyg_layernorm_bwd      dx, dgamma, dbeta of y = LayerNorm(x) gamma + beta                 (models/DyGFormer.py:447, 456)
 //   dyg_gelu_fwd / _bwd    h = gelu(v) * mask -> operand planes, dv = dh * mask * gelu'(v)     (models/DyGFormer.py:458)
 //   dyg_seq_attention_train_fwd / _bwd   softmax(q k^T / sqrt(hd)) (with dropout multipliers) v and its gradient (:454)
@@ -200,50 +201,109 @@ __global__ void __launch_bounds__(128) gemm_dw_mma_kernel(const float* __restric
     }
 }
 
-// ------------------------------------------------------------------ dX = G W  (M x K) for small layers (one launch, no operand planes)
-__global__ void __launch_bounds__(256) gemm_dx_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ W, int ldw, int64_t M,
-                                                      int N, int K, float* __restrict__ dX, int lddx) {
-    __shared__ float sg[DW_T][DW_MC + 1];                        // [m][n]
-    __shared__ float sw[DW_MC][DW_T + 1];                        // [n][k]
-    const int64_t m0 = (int64_t)blockIdx.x * DW_T;
-    const int k0 = blockIdx.y * DW_T;
-    const int tid = threadIdx.x;
-    const int tm = (tid >> 4) * 4, tk = (tid & 15) * 4;
-    float acc[4][4];
+// ------------------------------------------------------------------ dX on the warp-level tensor cores (mid-size layers, one launch)
+// dX[m, k] = sum_n G[m, n] W[n, k] as BF16x3 mma.sync: G rows are the A operand as they lie in memory (plain ldmatrix), W (N, K) is read
+// with ldmatrix.trans (its row index is the contraction).  fp32 operands are split into bf16 hi | mid on the way into shared memory,
+// so no operand planes and no transposed copy of W are needed; with `Y` the gradient is masked on the way in (ReLU layers).
+constexpr int DXM_P = DM_MC + 8;                         // pitch of the G tile: 40 bf16 = 80 B
+__device__ __forceinline__ void ldsm_x4_n(uint32_t (&r)[4], const __nv_bfloat16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__global__ void __launch_bounds__(128) gemm_dx_mma_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
+                                                          const float* __restrict__ W, int ldw, int64_t M, int N, int K,
+                                                          float* __restrict__ dX, int lddx) {
+    __shared__ __align__(16) __nv_bfloat16 sg[2][DM_T][DXM_P];    // [plane][m][n chunk]
+    __shared__ __align__(16) __nv_bfloat16 sw[2][DM_MC][DM_P];    // [plane][n chunk][k]
+    const int64_t m0 = (int64_t)blockIdx.x * DM_T;
+    const int k0 = blockIdx.y * DM_T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = (warp >> 1) * 32, wk = (warp & 1) * 32;
+    const int gc = (tid & 7) * 4, gr = tid >> 3;                  // G tile: columns 4 (t % 8) .. + 3 of rows t / 8 + 16 i
+    const int wc = (tid & 15) * 4, wr = tid >> 4;                 // W chunk: columns 4 (t % 16) .. + 3 of rows t / 16 + 8 i
+    float acc[2][4][4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    for (int n0 = 0; n0 < N; n0 += DW_MC) {
-        for (int i = tid; i < DW_T * DW_MC; i += 256) {
-            const int r = i / DW_MC, c = i - r * DW_MC;
-            sg[r][c] = (m0 + r < M && n0 + c < N) ? G[(m0 + r) * ldg + n0 + c] : 0.f;
-        }
-        for (int i = tid; i < DW_MC * DW_T; i += 256) {
-            const int r = i / DW_T, c = i - r * DW_T;
-            sw[r][c] = (n0 + r < N && k0 + c < K) ? W[(int64_t)(n0 + r) * ldw + k0 + c] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int n = 0; n < DW_MC; ++n) {
-            float g[4], w[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                g[a] = sg[tm + a][n];
-                w[a] = sw[n][tk + a];
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(g[a], w[b], acc[a][b]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b)
-            if (m0 + tm + a < M && k0 + tk + b < K) dX[(m0 + tm + a) * lddx + k0 + tk + b] = acc[a][b];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    float gv[4][4], wv[4][4];
+    auto fetch = [&](int n0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t m = m0 + gr + 16 * i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + gc + j;
+                float g = 0.f;
+                if (m < M && n < N) {
+                    g = G[m * ldg + n];
+                    if (Y && !(Y[m * ldy + n] > 0.f)) g = 0.f;
+                }
+                gv[i][j] = g;
+                const int nn = n0 + wr + 8 * i, kk = k0 + wc + j;
+                wv[i][j] = (nn < N && kk < K) ? W[(int64_t)nn * ldw + kk] : 0.f;
+            }
+        }
+    };
+    fetch(0);
+    for (int n0 = 0; n0 < N; n0 += DM_MC) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t h0, l0, h1, l1;
+            split_pack(gv[i][0], gv[i][1], h0, l0);
+            split_pack(gv[i][2], gv[i][3], h1, l1);
+            *reinterpret_cast<uint2*>(&sg[0][gr + 16 * i][gc]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(&sg[1][gr + 16 * i][gc]) = make_uint2(l0, l1);
+            split_pack(wv[i][0], wv[i][1], h0, l0);
+            split_pack(wv[i][2], wv[i][3], h1, l1);
+            *reinterpret_cast<uint2*>(&sw[0][wr + 8 * i][wc]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(&sw[1][wr + 8 * i][wc]) = make_uint2(l0, l1);
+        }
+        __syncthreads();
+        if (n0 + DM_MC < N) fetch(n0 + DM_MC);
+#pragma unroll
+        for (int ks = 0; ks < DM_MC / 16; ++ks) {
+            const int nr = ks * 16;
+            uint32_t ah[2][4], am[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+                // A block (16 m x 16 n): lanes 0-15 rows m at n, lanes 16-31 the same rows at n + 8
+                const int row = wm + mi * 16 + (lane & 15), col = nr + (lane >> 4) * 8;
+                ldsm_x4_n(ah[mi], &sg[0][row][col]);
+                ldsm_x4_n(am[mi], &sg[1][row][col]);
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ni += 2) {
+                const int row = nr + (lane & 7) + ((lane >> 3) & 1) * 8, col = wk + ni * 8 + (lane >> 4) * 8;
+                uint32_t bh[4], bm[4];
+                ldsm_x4_t(bh, &sw[0][row][col]);
+                ldsm_x4_t(bm, &sw[1][row][col]);
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi) {
+                    mma_bf16(acc[mi][ni], ah[mi], bh[0], bh[1]);
+                    mma_bf16(acc[mi][ni], ah[mi], bm[0], bm[1]);
+                    mma_bf16(acc[mi][ni], am[mi], bh[0], bh[1]);
+                    mma_bf16(acc[mi][ni + 1], ah[mi], bh[2], bh[3]);
+                    mma_bf16(acc[mi][ni + 1], ah[mi], bm[2], bm[3]);
+                    mma_bf16(acc[mi][ni + 1], am[mi], bh[2], bh[3]);
+                }
+            }
+        }
+    }
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t m = m0 + wm + mi * 16 + g + (c >> 1) * 8;
+                const int k = k0 + wk + ni * 8 + 2 * t + (c & 1);
+                if (m < M && k < K) dX[m * lddx + k] = acc[mi][ni][c];
+            }
 }
 
 // ------------------------------------------------------------------ dX and dW (+ db) of a small dense layer in ONE launch
@@ -599,14 +659,14 @@ extern "C" int dyg_gemm_dw(const float* G, int ldg, const float* X, int ldx, int
     return 0;
 }
 
-extern "C" int dyg_gemm_dx(const float* G, int ldg, const float* W, int ldw, int64_t M, int N, int K, float* dX, int lddx,
-                           dyg_stream_t stream) {
+extern "C" int dyg_gemm_dx(const float* G, int ldg, const float* Y, int ldy, const float* W, int ldw, int64_t M, int N, int K, float* dX,
+                           int lddx, dyg_stream_t stream) {
     DYG_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldg >= N && ldw >= K && lddx >= K, "dyg_gemm_dx: bad sizes");
     if (M == 0) return 0;
     DYG_CHECK_ARG(G && W && dX, "dyg_gemm_dx: NULL pointer");
-    const int64_t gm = (M + DW_T - 1) / DW_T;
+    const int64_t gm = (M + DM_T - 1) / DM_T;
     DYG_CHECK_ARG(gm < ((int64_t)1 << 31), "dyg_gemm_dx: M too large");
-    gemm_dx_kernel<<<dim3((unsigned)gm, (unsigned)((K + DW_T - 1) / DW_T)), 256, 0, as_stream(stream)>>>(G, ldg, W, ldw, M, N, K, dX, lddx);
+    gemm_dx_mma_kernel<<<dim3((unsigned)gm, (unsigned)((K + DM_T - 1) / DM_T)), 128, 0, as_stream(stream)>>>(G, ldg, Y, ldy, W, ldw, M, N, K, dX, lddx);
     DYG_LAUNCH_CHECK("dyg_gemm_dx");
     return 0;
 }

@@ -648,8 +648,9 @@ def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
 
 
 # ------------------------------------------------------------------ training path (backward kernels, csrc/train.cu)
-# input gradients of dense layers above this many flops go to the tcgen05 GEMM (three more launches: split, transpose, split)
-GEMM_DX_TC_FLOPS = float(os.environ.get('DYG_GEMM_DX_TC_FLOPS', '2e8'))
+# input gradients of dense layers above this many flops go to the tcgen05 GEMM (three more launches: split, transpose, split);
+# below it one BF16x3 mma.sync launch (dyg_gemm_dx)
+GEMM_DX_TC_FLOPS = float(os.environ.get('DYG_GEMM_DX_TC_FLOPS', '3e9'))
 # dense layers below this many flops (2 M N K) take the one-launch backward (dyg_linear_bwd)
 LINEAR_BWD_FUSED_FLOPS = float(os.environ.get('DYG_LINEAR_BWD_FUSED_FLOPS', '2e8'))
 # weight gradients above this many flops: planes of g^T and x^T through the tcgen05 GEMM (four more launches)
@@ -711,15 +712,18 @@ def linear_bwd(g, y_mask, xs, widths, w, need_x=True, need_w=True, need_b=False)
     return dx, (dw if need_w else None), db
 
 
-def gemm_dx(g, w):
-    """dX = g @ w for y = x W^T: one fp32 launch for small layers (dyg_gemm_dx), the tcgen05 GEMM on planes of g and W^T otherwise."""
+def gemm_dx(g, w, y_mask=None):
+    """dX = (g * (y_mask > 0)) @ w for y = act(x W^T): one BF16x3 mma.sync launch (dyg_gemm_dx); above GEMM_DX_TC_FLOPS the tcgen05
+    GEMM on planes of g and W^T."""
     M, N = g.shape
     K = w.shape[1]
     if 2.0 * M * N * K >= GEMM_DX_TC_FLOPS:
+        if y_mask is not None:
+            g = g * (y_mask > 0)
         return gemm(split_bf16(g), split_bf16(w.t().contiguous().float()))
     dx = torch.empty((M, K), dtype=torch.float32, device=g.device)
-    _native.check(_lib().dyg_gemm_dx(_p(g), int(g.stride(0)), _p(w), int(w.stride(0)), int(M), int(N), int(K), _p(dx), int(dx.stride(0)),
-                                     _stream()))
+    _native.check(_lib().dyg_gemm_dx(_p(g), int(g.stride(0)), _p(y_mask), int(y_mask.stride(0)) if y_mask is not None else 0, _p(w),
+                                     int(w.stride(0)), int(M), int(N), int(K), _p(dx), int(dx.stride(0)), _stream()))
     _count()
     return dx
 

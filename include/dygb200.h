@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 10
+#define DYG_ABI_VERSION 11
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -308,9 +308,11 @@ int dyg_attn_block(const float* x, int ldx, const float* gamma, const float* bet
  * with atomic accumulation (zero dW / db first).  For the patch projections X is the gathered patch matrix of a channel. */
 int dyg_gemm_dw(const float* G, int ldg, const float* X, int ldx, int64_t M, int N, int K, float* dW, int ldw, float* db,
                 dyg_stream_t stream);
-/* dX[m, k] = sum_n G[m, n] W[n, k]: input gradient of y = x W^T + b for small layers, one fp32 launch (large layers use
- * dyg_gemm_bf16x3 on the planes of G and W^T). */
-int dyg_gemm_dx(const float* G, int ldg, const float* W, int ldw, int64_t M, int N, int K, float* dX, int lddx, dyg_stream_t stream);
+/* dX[m, k] = sum_n G[m, n] W[n, k]: input gradient of y = act(x W^T + b) in one launch (BF16x3 on mma.sync; fp32 operands split on the
+ * way into shared memory, W read transposed by ldmatrix).  Y (M, N), when given, is the layer's ReLU output and masks G.  Very large
+ * layers use dyg_gemm_bf16x3 on the planes of G and W^T instead. */
+int dyg_gemm_dx(const float* G, int ldg, const float* Y, int ldy, const float* W, int ldw, int64_t M, int N, int K, float* dX, int lddx,
+                dyg_stream_t stream);
 /* dyg_gemm_dx and dyg_gemm_dw (+ db) of one small layer in ONE launch (either output may be NULL); Y (M, N), when given, is the layer's
  * ReLU output and masks the gradient on the way in (G * (Y > 0)).  dW / db are accumulated (zero them first). */
 int dyg_linear_bwd(const float* G, int ldg, const float* Y, int ldy, const float* X, int ldx, const float* W, int ldw, int64_t M,

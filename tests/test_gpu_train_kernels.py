@@ -109,6 +109,8 @@ def test_gemm_dx_small_and_tcgen05_paths(M, N, K):
     G = torch.randn(M, N, device='cuda', generator=g)
     W = torch.randn(N, K, device='cuda', generator=g)
     assert rel(ops.gemm_dx(G, W), G.double() @ W.double()) < 3e-5
+    Y = torch.randn(M, N, device='cuda', generator=g)
+    assert rel(ops.gemm_dx(G, W, Y), (G * (Y > 0)).double() @ W.double()) < 3e-5
 
 
 @pytest.mark.parametrize('M,N,K1,K2,relu', [(1, 1, 1, 0, False), (500, 64, 172, 100, True), (803, 172, 172, 272, False), (77, 1, 172, 0, True)])
