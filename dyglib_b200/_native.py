@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _lock = threading.Lock()
 _lib = None
@@ -113,6 +113,8 @@ class TgnStep(ctypes.Structure):
 # name -> argtypes, exactly the prototypes of include/dygb200.h (tests check the symbol list against the header)
 SIGNATURES = {
     'dyg_csr_degrees': [c_p, c_p, c_l, c_l, c_p, c_p],
+    'dyg_radix_digit_hist': [c_p, c_i, c_l, c_p, c_p],
+    'dyg_radix_sort_pass': [c_p, c_p, c_p, c_p, c_i, c_l, c_i, c_p, c_p, c_p],
     'dyg_csr_pack': [c_p, c_p, c_p, c_p, c_p, c_l, c_p, c_p],
     'dyg_csr_tia_tables': [c_p, c_p, c_l, c_d, c_p, c_p, c_p],
     'dyg_csr_tia_cum': [c_p, c_p, c_l, c_p, c_p],
@@ -198,6 +200,8 @@ def load():
         lib.dyg_ln_ffn_workspace_bytes.argtypes = []
         lib.dyg_attn_block_workspace_bytes.restype = c_l
         lib.dyg_attn_block_workspace_bytes.argtypes = [c_i]
+        lib.dyg_radix_sort_workspace_entries.restype = c_l
+        lib.dyg_radix_sort_workspace_entries.argtypes = [c_l]
         lib.dyg_tgn_step_sizeof.restype = c_l
         lib.dyg_tgn_step_sizeof.argtypes = []
         for name, args in SIGNATURES.items():

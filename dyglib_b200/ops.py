@@ -647,6 +647,47 @@ def attn_block(x, gamma, beta, eps, wcat, bcat, bout, B, S, H, D, out=None):
     return out
 
 
+# ------------------------------------------------------------------ stable radix sort (csrc/sort.cu): the CSR build's ordering
+def stable_argsort(keys):
+    """Positions that sort ``keys`` stably (LSD radix sort on the raw bit pattern, 8 bits per pass; passes whose digit is the same for
+    every key are skipped).  ``keys``: int32 / int64 CUDA tensor holding UNSIGNED-orderable bit patterns.  Returns int64 positions."""
+    n = keys.numel()
+    kb = keys.element_size()
+    if kb not in (4, 8):
+        raise TypeError('stable_argsort: 4- or 8-byte keys')
+    dev = keys.device
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=dev)
+    keys = keys.contiguous()
+    hist = torch.empty(kb * 256, dtype=torch.int64, device=dev)
+    _native.check(_lib().dyg_radix_digit_hist(_p(keys), kb, int(n), _p(hist), _stream()))
+    _count()
+    h = hist.cpu().reshape(kb, 256)
+    passes = [p for p in range(kb) if int(h[p].max()) < n]
+    if not passes:
+        return torch.arange(n, dtype=torch.int64, device=dev)
+    ws = torch.empty(int(_lib().dyg_radix_sort_workspace_entries(int(n))), dtype=torch.int32, device=dev)
+    ka, kbuf = keys, torch.empty_like(keys)
+    va, vb = None, torch.empty(n, dtype=torch.int32, device=dev)
+    spare = torch.empty(n, dtype=torch.int32, device=dev) if len(passes) > 1 else None
+    for p in passes:
+        _native.check(_lib().dyg_radix_sort_pass(_p(ka), _p(va), _p(kbuf), _p(vb), kb, int(n), int(p), _p(hist), _p(ws), _stream()))
+        _count(3)
+        if ka is keys:
+            ka, kbuf = kbuf, torch.empty_like(keys)
+        else:
+            ka, kbuf = kbuf, ka
+        va, vb = vb, (spare if va is None else va)
+    return va.to(torch.int64) & 0xFFFFFFFF
+
+
+def float64_sort_key(t):
+    """Bit pattern of float64 values whose UNSIGNED order equals the numeric order (sign bit flipped for non-negatives, all bits for
+    negatives); -0.0 sorts before +0.0, which a stable sort by value would keep in input order: callers must not mix them."""
+    b = t.contiguous().view(torch.int64)
+    return b ^ ((b >> 63) | torch.iinfo(torch.int64).min)
+
+
 # ------------------------------------------------------------------ training path (backward kernels, csrc/train.cu)
 # input gradients of dense layers above this many flops go to the tcgen05 GEMM (three more launches: split, transpose, split);
 # below it one BF16x3 mma.sync launch (dyg_gemm_dx)

@@ -126,15 +126,17 @@ class NeighborSampler:
         self.indptr = torch.zeros(self.num_nodes + 1, dtype=torch.int64, device=dev)
         torch.cumsum(deg, 0, out=self.indptr[1:])
         del deg
-        # ordering keys: stable by time, then stable by owner (radix sort from torch = plumbing)
+        # ordering: stable by time, then stable by owner — the package's own LSD radix sort (csrc/sort.cu, ops.stable_argsort)
         if n_half:
+            owner32 = owner_d.to(torch.int32)
             if tkey is None:
-                order = torch.sort(owner_d, stable=True).indices
+                order = ops.stable_argsort(owner32)
             else:
-                o1 = torch.sort(tkey, stable=True).indices
-                o2 = torch.sort(owner_d[o1], stable=True).indices
+                o1 = ops.stable_argsort(ops.float64_sort_key(tkey + 0.0))      # + 0.0: -0.0 -> +0.0, equal under the reference's comparison
+                o2 = ops.stable_argsort(owner32[o1])
                 order = o1[o2]
                 del o1, o2
+            del owner32
             if events is None:
                 order = order * 2
         del owner_d, tkey

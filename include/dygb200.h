@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 11
+#define DYG_ABI_VERSION 12
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -43,6 +43,15 @@ int dyg_abi_version(void);
 /* deg[v] += number of half-edges owned by v.  deg must be zeroed by the caller (num_nodes entries). */
 int dyg_csr_degrees(const int64_t* src, const int64_t* dst, int64_t num_events, int64_t num_nodes,
                     int64_t* deg, dyg_stream_t stream);
+/* Stable LSD radix sort of (key, value) pairs for the CSR build (utils/utils.py:96-103: sorted(..., key=time) is stable; the build
+ * sorts half-edges stably by time, then stably by owner).  Keys are 4- or 8-byte unsigned bit patterns, values uint32 positions.
+ * dyg_radix_digit_hist: hist[p * 256 + d] = number of keys whose byte p equals d (the caller skips passes whose digit is constant).
+ * dyg_radix_sort_pass: one 8-bit pass from (keys_in, vals_in) to (keys_out, vals_out); vals_in == NULL means vals = 0..n-1;
+ * workspace: dyg_radix_sort_workspace_entries(n) uint32.  No atomics decide an output position: the result is deterministic. */
+int dyg_radix_digit_hist(const void* keys, int key_bytes, int64_t n, unsigned long long* hist, dyg_stream_t stream);
+int64_t dyg_radix_sort_workspace_entries(int64_t n);
+int dyg_radix_sort_pass(const void* keys_in, const uint32_t* vals_in, void* keys_out, uint32_t* vals_out, int key_bytes, int64_t n,
+                        int pass, const unsigned long long* hist, uint32_t* workspace, dyg_stream_t stream);
 /* order[i] = index of the i-th half-edge in CSR order; half-edge h = 2*e + side (side 0: owner src[e],
  * neighbour dst[e]; side 1: owner dst[e], neighbour src[e]).  Packs the 16-byte records. */
 int dyg_csr_pack(const int64_t* order, const int64_t* src, const int64_t* dst, const int64_t* eid,

@@ -422,3 +422,18 @@ def test_philox_mode_follows_the_reference_sampling_law(strategy):
         we = wrong * obs.sum() if not small.any() else None
         if we is not None:
             assert stats.chisquare(obs, we)[1] < 1e-6
+
+
+@pytest.mark.parametrize('n,bits', [(1, 3), (31, 2), (4096, 8), (4097, 9), (100_003, 5), (1_000_003, 20), (300_000, 31)])
+def test_own_stable_radix_sort_matches_torch_stable_sort(n, bits):
+    """csrc/sort.cu (the CSR build's ordering): positions equal torch.sort(stable=True) on heavily tied keys, 4- and 8-byte keys,
+    and float64 times through the order-preserving bit pattern."""
+    import torch
+    from dyglib_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(n + bits)
+    k32 = torch.randint(0, 2 ** bits, (n,), device='cuda', generator=g, dtype=torch.int64).to(torch.int32)
+    assert torch.equal(ops.stable_argsort(k32), torch.sort(k32.to(torch.int64), stable=True).indices)
+    k64 = torch.randint(0, 2 ** 62, (n,), device='cuda', generator=g, dtype=torch.int64) >> (62 - min(bits + 30, 62))
+    assert torch.equal(ops.stable_argsort(k64), torch.sort(k64, stable=True).indices)
+    t = (torch.randint(0, 2 ** bits, (n,), device='cuda', generator=g).double() - 2 ** (bits - 1)) * 0.37
+    assert torch.equal(ops.stable_argsort(ops.float64_sort_key(t + 0.0)), torch.sort(t, stable=True).indices)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_python_signatures_cover_header():
     declared = set(declared_symbols()) - {'dyg_last_error', 'dyg_abi_version', 'dyg_ln_ffn_workspace_bytes', 'dyg_csr_fence_entries', 'dyg_tgn_step_sizeof',
-                                         'dyg_attn_block_workspace_bytes'}   # non-int returns
+                                         'dyg_attn_block_workspace_bytes', 'dyg_radix_sort_workspace_entries'}   # non-int returns
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
 
 
