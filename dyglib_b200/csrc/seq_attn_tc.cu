@@ -15,8 +15,8 @@
 //   warp 1     TMEM allocation + MMA issue (cta_group::1, M = 128): S = Q K^T with A = Q from TMEM (BF16x3: three MMAs per
 //              k16 step), O' += P V'_h with A = P from TMEM and B = V' MN-major; O' accumulates over the heads
 //   warps 2-5  thread = tile row: softmax of the row's slot window (exp2, masked), P as bf16 hi | mid written in place over S
-//   warps 6-9  thread = tile row: Q row global -> registers -> TMEM one step ahead, final epilogue O' + x + b_o -> x1 (it
-//              overlaps the next tile's Q K^T and softmax)
+//   warps 6-9  thread = tile row: Q row global -> registers -> TMEM one step ahead
+//   both groups share the final epilogue O' + x + b_o -> x1 (even / odd 16-column chunks, the whole residual row requested up front)
 // Keys of the other slots get P = 0, so one M=128 x K=128 product serves both sequences of a tile.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -62,6 +62,52 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Final epilogue of a tile, shared by the softmax and the IO warp of a TMEM lane quarter (16-column chunks `first`, `first + 2`, ...):
+// x1 = O' + x + b_o.  ALL residual chunks of the row are requested before the accumulator is awaited (up to 7 x 16 registers): with
+// two chunks in flight the epilogue was one HBM round trip per pair of chunks, 13 us per tile on the critical path of the single O'
+// buffer (globaltimer stamps, profiles/README.md).
+__device__ __forceinline__ void sa_tile_epilogue(const AttnArgs& a, uint32_t lane_addr, bool rowok, const float* xr, float* orow, int first,
+                                                 uint64_t* o_full, uint32_t parity) {
+    constexpr int MAXC = (SA_NV / 16 + 1) / 2;                  // chunks per warp
+    float xv[MAXC][16];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int col = 16 * (first + 2 * c);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xv[c][j] = 0.f;
+        if (rowok && col < a.D) {
+            ld_v8(xr + col, xv[c]);
+            if (col + 8 < a.D) ld_v8(xr + col + 8, xv[c] + 8);
+        }
+    }
+    mbar_wait(o_full, parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        const int col = 16 * (first + 2 * c);
+        if (col < a.D) {                                         // warp-uniform
+            const bool wide = col + 8 < a.D;
+            float bv[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = (j < 2 || wide) ? __ldg(reinterpret_cast<const float4*>(a.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+            }
+            uint32_t rr[16];
+            tmem_ld16(lane_addr + SA_O_COL + (uint32_t)col, rr);
+            if (rowok) {
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(rr[j]) + xv[c][j] + bv[j]);
+                st_v8(orow + col, o);
+                if (wide) st_v8(orow + col + 8, o + 8);
+            }
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const __grid_constant__ CUtensorMap map_hi,
                                                                            const __grid_constant__ CUtensorMap map_mid,
                                                                            const AttnArgs a) {
@@ -85,7 +131,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
         mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-        mbar_init(q_full, 4); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_empty, 4);
+        mbar_init(q_full, 4); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -234,6 +280,12 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
             }
+            {
+                const int64_t row = rowok ? seq * a.S + i : 0;
+                sa_tile_epilogue(a, lane_addr, rowok, a.x + row * a.ldx, a.out + row * a.ldo, 0, o_full, (uint32_t)(it & 1));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(o_empty);
+            }
         }
     } else {
         // ------------------------------------------------------------------ IO warps: Q rows -> TMEM, final epilogue of every tile
@@ -294,53 +346,8 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (n + 1 < steps) store_q(qh, qm);
             }
-            // ---- final epilogue of the tile: x1 = O' + x + b_o in 16-column chunks (D % 8 == 0: the last one may be 8 wide);
-            // the residual chunks are requested two ahead of their use
-            float xa[16], xb[16], xc[16];
-#define SA_LOAD_X(COL, XV)                                          \
-    do {                                                             \
-        _Pragma("unroll") for (int j = 0; j < 16; ++j) XV[j] = 0.f;  \
-        if (rowok && (COL) < a.D) {                                  \
-            ld_v8(xr + (COL), XV);                                   \
-            if ((COL) + 8 < a.D) ld_v8(xr + (COL) + 8, XV + 8);      \
-        }                                                            \
-    } while (0)
-#define SA_EMIT(COL, XV)                                                                              \
-    do {                                                                                               \
-        if ((COL) < a.D) {                                                                             \
-            const bool wide = (COL) + 8 < a.D;                                                         \
-            float bv[16];                                                                              \
-            _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                            \
-                const float4 t = (j < 2 || wide) ? __ldg(reinterpret_cast<const float4*>(a.bias + (COL)) + j) \
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);                    \
-                bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;        \
-            }                                                                                          \
-            uint32_t rr[16];                                                                           \
-            tmem_ld16(lane_addr + SA_O_COL + (uint32_t)(COL), rr);                                     \
-            if (rowok) {                                                                               \
-                uint32_t o[16];                                                                        \
-                _Pragma("unroll") for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(rr[j]) + XV[j] + bv[j]); \
-                st_v8(orow + (COL), o);                                                                \
-                if (wide) st_v8(orow + (COL) + 8, o + 8);                                              \
-            }                                                                                          \
-            __syncwarp();                                                                              \
-        }                                                                                              \
-    } while (0)
-            SA_LOAD_X(0, xa);
-            SA_LOAD_X(16, xb);
-            mbar_wait(o_full, (uint32_t)(it & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int col = 0; col < a.D; col += 48) {
-                SA_LOAD_X(col + 32, xc);
-                SA_EMIT(col, xa);
-                SA_LOAD_X(col + 48, xa);
-                SA_EMIT(col + 16, xb);
-                SA_LOAD_X(col + 64, xb);
-                SA_EMIT(col + 32, xc);
-            }
-#undef SA_LOAD_X
-#undef SA_EMIT
+            // ---- final epilogue of the tile (the odd chunks; the softmax warp of this lane quarter takes the even ones)
+            sa_tile_epilogue(a, lane_addr, rowok, xr, orow, 1, o_full, (uint32_t)(it & 1));
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
