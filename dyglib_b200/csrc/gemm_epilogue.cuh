@@ -173,4 +173,109 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
     }
 }
 
+// planes-only output (bias, no residual / activation / fp32 copy, every chunk whole): eligible for the TMA-store epilogue below
+__host__ __device__ __forceinline__ bool planes_fast_path(const GemmArgs& g) {
+    return g.Chi && !g.C && !g.residual && g.bias && g.act == DYG_ACT_NONE && (g.N & 15) == 0 && ((g.ldcs & 15) == 0) &&
+           (((reinterpret_cast<uintptr_t>(g.Chi) | reinterpret_cast<uintptr_t>(g.Cmid)) & 31u) == 0) &&
+           ((reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0);
+}
+__device__ __forceinline__ void pin16(uint32_t (&r)[16]) {
+    // orders every use of r after the tcgen05.wait::ld that precedes this statement
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+// one 16-column chunk of a row -> hi | mid planes with two 256-bit stores
+__device__ __forceinline__ void planes_chunk(const GemmArgs& g, const uint32_t (&r)[16], const float4 (&bq)[4], int64_t m, int n, bool rowok) {
+    if (!rowok) return;
+    uint32_t hi[8], mid[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        split_pack(__uint_as_float(r[4 * j]) + bq[j].x, __uint_as_float(r[4 * j + 1]) + bq[j].y, hi[2 * j], mid[2 * j]);
+        split_pack(__uint_as_float(r[4 * j + 2]) + bq[j].z, __uint_as_float(r[4 * j + 3]) + bq[j].w, hi[2 * j + 1], mid[2 * j + 1]);
+    }
+    st_v8(g.Chi + m * g.ldcs + n, hi);
+    st_v8(g.Cmid + m * g.ldcs + n, mid);
+}
+// Planes epilogue through shared memory + TMA stores.  A row-strided st.global costs the LSU one wavefront per 32-byte sector
+// (32 per 256-bit store instruction): globaltimer stamps put the plane stores of ln_gemm at a third of its epilogue time, and
+// the LN warps' own loads / stores queue behind them.  Here a warp converts a unit of 32 columns (two TMEM chunks) of its 32
+// rows, writes the hi | mid images (64-byte rows, SWIZZLE_64B: conflict-free 16-byte stores) into its 4 KB staging slot and
+// one lane hands two 32 x 32 boxes to the TMA engine, which also clips the rows past M.  A trailing 16-column unit of the
+// tile goes out with direct stores.  `stage` must be 1 KB aligned; the slot is reused once the previous boxes have been read.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, const uint32_t* r) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+template <typename Done>
+__device__ __forceinline__ void epilogue_planes_tma_tile(const GemmArgs& g, const float* bias_s, const CUtensorMap* map_h, const CUtensorMap* map_m,
+                                                         unsigned char* stage, uint32_t taddr, int lane, int64_t m, int n0, int ncols, int unit0,
+                                                         int step, Done tmem_done) {
+    const bool rowok = m < g.M;
+    const int m_first = (int)(m - lane);
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+    const uint32_t row_h = smem_u32(stage) + (uint32_t)lane * 64u, row_m = row_h + 2048u;
+    const uint32_t bias_a = smem_u32(bias_s);
+    int col = 32 * unit0;
+    if (col >= ncols) {
+        tmem_done();
+        return;
+    }
+    while (col < ncols) {
+        const int next = col + 32 * step;
+        const bool two = col + 32 <= ncols;
+        uint32_t ra[16], rb[16];
+        float4 ba[4], bb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ba[j] = lds_f4(bias_a + (uint32_t)(n0 + col) * 4u + 16u * j);
+        tmem_ld16_nowait(taddr + (uint32_t)col, ra);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = lds_f4(bias_a + (uint32_t)(n0 + col + 16) * 4u + 16u * j);
+            tmem_ld16_nowait(taddr + (uint32_t)(col + 16), rb);
+        }
+        tmem_ld_wait();
+        pin16(ra);
+        if (next >= ncols) tmem_done();
+        if (!two) {
+            planes_chunk(g, ra, ba, m, n0 + col, rowok);
+            break;
+        }
+        pin16(rb);
+        uint32_t hi[16], mid[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            split_pack(__uint_as_float(ra[4 * j]) + ba[j].x, __uint_as_float(ra[4 * j + 1]) + ba[j].y, hi[2 * j], mid[2 * j]);
+            split_pack(__uint_as_float(ra[4 * j + 2]) + ba[j].z, __uint_as_float(ra[4 * j + 3]) + ba[j].w, hi[2 * j + 1], mid[2 * j + 1]);
+            split_pack(__uint_as_float(rb[4 * j]) + bb[j].x, __uint_as_float(rb[4 * j + 1]) + bb[j].y, hi[8 + 2 * j], mid[8 + 2 * j]);
+            split_pack(__uint_as_float(rb[4 * j + 2]) + bb[j].z, __uint_as_float(rb[4 * j + 3]) + bb[j].w, hi[8 + 2 * j + 1], mid[8 + 2 * j + 1]);
+        }
+        // the boxes of the previous unit must have left the staging slot
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t off = ((uint32_t)u ^ sw) << 4;
+            sts_v4(row_h + off, hi + 4 * u);
+            sts_v4(row_m + off, mid + 4 * u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && m_first < g.M) {
+            tma_store_2d(map_h, stage, n0 + col, m_first);
+            tma_store_2d(map_m, stage + 2048, n0 + col, m_first);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        col = next;
+    }
+}
+
 }  // namespace

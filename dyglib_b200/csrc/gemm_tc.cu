@@ -745,10 +745,15 @@ struct LnGemmArgs {
     GemmArgs g;
     LnSrc ln;
     unsigned char* scratch;   // gridDim.x images of the A operand (LN_KB * 16 KB each), L2 resident
+    int tma_out;              // planes leave through shared memory + TMA stores (epilogue_planes_tma_tile)
 };
+constexpr int LG_EPI_SLOT = 4096;
+__host__ __device__ inline int lg_bias_bytes(int N) { return (N * 4 + 255) / 256 * 256; }
 
 __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_wh,
-                                                                       const __grid_constant__ CUtensorMap map_wm, const LnGemmArgs p) {
+                                                                       const __grid_constant__ CUtensorMap map_wm,
+                                                                       const __grid_constant__ CUtensorMap map_ch,
+                                                                       const __grid_constant__ CUtensorMap map_cm, const LnGemmArgs p) {
     extern __shared__ __align__(1024) unsigned char lg_smem[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(lg_smem) + 1023) & ~(uintptr_t)1023);
     const GemmArgs& g = p.g;
@@ -757,7 +762,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __g
     const int a_stage = 2 * G_A_PLANE;
     const int stage_bytes = 2 * w_plane;
     unsigned char* a_res = base;                               // LN_KB slots of [A_hi | A_mid]
-    unsigned char* ring = base + (size_t)LN_KB * a_stage;
+    unsigned char* epi_stage = base + (size_t)LN_KB * a_stage;  // one 4 KB slot per epilogue warp (planes on their way to the TMA store)
+    unsigned char* ring = epi_stage + (p.tma_out ? G_EPI_WARPS * LG_EPI_SLOT : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * stage_bytes);
     uint64_t* full_bar = bars;                                 // [stages]   leader
     uint64_t* empty_bar = bars + G_MAX_STAGES;                 // [stages]   both
@@ -767,6 +773,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __g
     uint64_t* a_free = bars + 2 * G_MAX_STAGES + 5;            //            both:   last MMA of the tile retired
     uint64_t* a_copy = bars + 2 * G_MAX_STAGES + 6;            //            local:  bulk copy of the image landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 7);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * G_MAX_STAGES + 8);   // the bias (tma_out): read per chunk by every epilogue warp
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -777,6 +784,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __g
     // zero this CTA's image of the A operand once: the K padding columns (D .. 32 nkb) are never written again
     unsigned char* a_img = p.scratch + (size_t)blockIdx.x * (LN_KB * a_stage);
     for (int i = tid; i < LN_KB * a_stage / 16; i += LG_THREADS) reinterpret_cast<uint4*>(a_img)[i] = make_uint4(0, 0, 0, 0);
+    if (p.tma_out)
+        for (int i = tid; i < g.N; i += LG_THREADS) bias_s[i] = g.bias[i];
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(full_bar + s, 1);
@@ -799,6 +808,10 @@ __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __g
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wh)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wm)) : "memory");
+        if (p.tma_out) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ch)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_cm)) : "memory");
+        }
     }
     asm volatile("fence.proxy.async;" ::: "memory");            // the zero fill above must be visible to the bulk copy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -889,12 +902,22 @@ __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __g
                 mbar_wait(tfull_bar + buf, bph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
-                epilogue_tile(g, taddr, m, n0, ncols, chunk0, G_EPI_WARPS / 4);
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
+                if (p.tma_out) {
+                    epilogue_planes_tma_tile(g, bias_s, &map_ch, &map_cm, epi_stage + (warp - 2) * LG_EPI_SLOT, taddr, lane, m, n0, ncols, chunk0,
+                                             G_EPI_WARPS / 4, [&]() {
+                                                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                                                 __syncwarp();
+                                                 if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
+                                             });
+                } else {
+                    epilogue_tile(g, taddr, m, n0, ncols, chunk0, G_EPI_WARPS / 4);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
+                }
             }
         }
+        if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         // ------------------------------------------------------------------ LN warps: LayerNorm -> resident A operand
         ln_warps_loop(p.ln, pair, npairs, rank, warp == 2 + G_EPI_WARPS, warp & 3, lane, a_img, a_res, a_free, a_copy, a_full);
@@ -1261,7 +1284,8 @@ extern "C" int dyg_ln_gemm_bf16x3(const float* x, int ldx, const float* gamma, c
     g.NT = g.NS;
     g.resident = 1;
     const int stage_bytes = 2 * (g.NT / 2) * 64;
-    const int fixed = LN_KB * 2 * G_A_PLANE + 1024 + 512;
+    p.tma_out = planes_fast_path(g);
+    const int fixed = LN_KB * 2 * G_A_PLANE + (p.tma_out ? G_EPI_WARPS * LG_EPI_SLOT + lg_bias_bytes(N) : 0) + 1024 + 512;
     g.stages = (227 * 1024 - fixed) / stage_bytes;
     if (g.stages > G_MAX_STAGES) g.stages = G_MAX_STAGES;
     DYG_CHECK_ARG(g.stages >= 2, "dyg_ln_gemm_bf16x3: tile does not fit shared memory");
@@ -1271,6 +1295,11 @@ extern "C" int dyg_ln_gemm_bf16x3(const float* x, int ldx, const float* gamma, c
     CUtensorMap mwh, mwm;
     if (!dyg_tensor_map_bf16(W_hi, (uint64_t)N, (uint64_t)D, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwh)) return 1;
     if (!dyg_tensor_map_bf16(W_mid, (uint64_t)N, (uint64_t)D, (uint64_t)ldw, (uint32_t)(g.NT / 2), &mwm)) return 1;
+    CUtensorMap mch = mwh, mcm = mwm;
+    if (p.tma_out) {
+        if (!dyg_tensor_map_bf16(C_hi, (uint64_t)M, (uint64_t)N, (uint64_t)ldcs, 32u, &mch)) return 1;
+        if (!dyg_tensor_map_bf16(C_mid, (uint64_t)M, (uint64_t)N, (uint64_t)ldcs, 32u, &mcm)) return 1;
+    }
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(ln_gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1295,7 +1324,7 @@ extern "C" int dyg_ln_gemm_bf16x3(const float* x, int ldx, const float* gamma, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, ln_gemm_bf16x3_kernel, mwh, mwm, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, ln_gemm_bf16x3_kernel, mwh, mwm, mch, mcm, p);
     if (le != cudaSuccess) {
         dyg_set_error("dyg_ln_gemm_bf16x3: launch failed: %s", cudaGetErrorString(le));
         return 1;
