@@ -390,7 +390,11 @@ class TGNWL(Workload):
         # the reference loop's negative call then positive call (train_link_prediction.py:236-247) in one embedding pass
         # ... and the link predictor of train_link_prediction.py:243-244 inside the same launch (dyg_tgn_step)
         out = self.model.compute_pos_neg_temporal_embeddings(src, dst, neg, t, eid, 10, link_predictor=self.pred)
-        return torch.cat([out[4], out[5]]).reshape(-1, 1)
+        pos, neg_ = out[4], out[5]
+        base = pos._base
+        if base is not None and base is neg_._base and base.numel() == pos.numel() + neg_.numel() and pos.data_ptr() == base.data_ptr():
+            return base.reshape(-1, 1)          # the fused step wrote [pos | neg] into one buffer: no concatenation kernel
+        return torch.cat([pos, neg_]).reshape(-1, 1)
 
     def oracle(self):
         from oracle.sampler import OracleSampler

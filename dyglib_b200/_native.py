@@ -19,7 +19,7 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', 
               '-Xcompiler', '-fPIC']
 
 # DYG_ABI_VERSION of include/dygb200.h these SIGNATURES were written against (bumped with every prototype change)
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _lock = threading.Lock()
 _lib = None
@@ -95,7 +95,7 @@ class Planes(ctypes.Structure):
 class TgnStep(ctypes.Structure):
     """dyg_tgn_step_t (include/dygb200.h), field for field."""
     _fields_ = ([('he', c_p), ('indptr', c_p), ('num_nodes', ctypes.c_int64), ('src', c_p), ('dst', c_p), ('t', c_p), ('eid', c_p),
-                 ('cand', c_p), ('roots', c_p)] +
+                 ('neg', c_p), ('roots', c_p)] +
                 [(n, ctypes.c_int32) for n in ('B', 'R', 'k', 'H', 'G', 'check_time')] +
                 [('node_raw', c_p), ('ld_node', ctypes.c_int32), ('edge_raw', c_p), ('ld_edge', ctypes.c_int32),
                  ('F', ctypes.c_int32), ('E', ctypes.c_int32), ('T', ctypes.c_int32)] +

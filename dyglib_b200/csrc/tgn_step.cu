@@ -94,8 +94,15 @@ __device__ __forceinline__ int64_t warp_lower_bound(const dyg_halfedge_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ warp tasks
+// roots == NULL: the batch's own node lists are the roots ([src | neg | dst], or [src | dst] without negatives) -- no host-side concatenation
+__device__ __forceinline__ int64_t root_id(const P& p, int r) {
+    if (p.roots) return p.roots[r];
+    if (r < p.B) return p.src[r];
+    if (p.neg) return r < 2 * p.B ? p.neg[r - p.B] : p.dst[r - 2 * p.B];
+    return p.dst[r - p.B];
+}
 __device__ __forceinline__ void root_task(const P& p, int r, int lane) {
-    const int64_t v = p.roots[r];
+    const int64_t v = root_id(p, r);
     const double tq = p.t[r % p.B];
     int64_t a = 0, deg = 0;
     if (v >= 0 && v < p.num_nodes) {
@@ -467,7 +474,7 @@ __device__ __forceinline__ void cell_tile(const P& p, int tile, mt::bf16* smem, 
     for (int half = 0; half < 2; ++half) {
         const int64_t m = m0 + wm * 16 + gq + 8 * half;
         if (m >= Pn) continue;
-        const int64_t v = p.cand[m];
+        const int64_t v = cand_node(p, (int)m);
         if (__ldcg(p.winner + v) != (int32_t)m) continue;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -642,12 +649,13 @@ extern "C" int dyg_tgn_step(const dyg_tgn_step_t* ph, dyg_stream_t stream) {
     const P& p = *ph;
     DYG_CHECK_ARG(p.B > 0 && p.R > 0 && p.k > 0, "dyg_tgn_step: empty batch");
     DYG_CHECK_ARG(p.H == 2 && (p.G == 1 || p.G == 3), "dyg_tgn_step: H must be 2, G 1 (RNN) or 3 (GRU)");
+    DYG_CHECK_ARG(p.roots || p.R == (p.neg ? 3 : 2) * p.B, "dyg_tgn_step: without a root list R must be 3 B ([src | neg | dst]) or 2 B ([src | dst])");
     const int Dk = p.F + p.E + p.T, Dq = p.F + p.T, MD = 2 * p.F + p.T + p.E, Fp = (p.F + 7) & ~7;
     DYG_CHECK_ARG(p.F % 4 == 0 && p.E % 4 == 0 && p.T % 4 == 0 && p.ld_node % 4 == 0 && p.ld_edge % 4 == 0 && Dq % 8 == 0 && MD % 8 == 0 &&
                       (p.H * Dk) % 8 == 0,
                   "dyg_tgn_step: F, E, T must be multiples of 4 and F + T, 2F + T + E, H (F + E + T) multiples of 8");
     DYG_CHECK_ARG(p.F + p.E <= 384 && p.T <= 128 && Dq <= 512, "dyg_tgn_step: feature widths out of range");
-    DYG_CHECK_ARG(p.he && p.indptr && p.src && p.dst && p.t && p.eid && p.roots && p.cand && p.node_raw && p.edge_raw && p.memory &&
+    DYG_CHECK_ARG(p.he && p.indptr && p.src && p.dst && p.t && p.eid && p.node_raw && p.edge_raw && p.memory &&
                       p.last_update && p.mem_view && p.lu_view && p.pending && p.winner && p.msg_store && p.msg_time && p.flag && p.barrier,
                   "dyg_tgn_step: null state pointer");
     DYG_CHECK_ARG(p.nbr_ids && p.nbr_eids && p.nbr_t && p.feat && p.qk && p.o && p.msg && p.hnew && p.emb, "dyg_tgn_step: null scratch pointer");

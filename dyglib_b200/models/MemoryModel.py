@@ -536,7 +536,7 @@ class MemoryModel(torch.nn.Module):
         B = src.numel()
         if edges_are_positive and self._fused_step_ok(B):
             assert edge_ids is not None
-            emb, _ = self._fused_step(torch.cat([src, dst]), src, dst, tq, _as_dev(edge_ids, torch.int64, dev), num_neighbors)
+            emb, _ = self._fused_step(None, src, dst, tq, _as_dev(edge_ids, torch.int64, dev), num_neighbors)
             return emb[:B], emb[B:]
         emb, ret = self._embed_eval([src, dst], tq, num_neighbors)
         if edges_are_positive:
@@ -576,7 +576,7 @@ class MemoryModel(torch.nn.Module):
         assert edge_ids is not None
         if self._fused_step_ok(B):
             # the src embedding of the negative pair equals that of the positive pair (same memory state, same times): 3 B roots
-            emb, prob = self._fused_step(torch.cat([src, neg, dst]), src, dst, tq, _as_dev(edge_ids, torch.int64, dev), num_neighbors,
+            emb, prob = self._fused_step(neg, src, dst, tq, _as_dev(edge_ids, torch.int64, dev), num_neighbors,
                                          link_predictor=link_predictor, pairs='pos_neg')
             out = (emb[:B], emb[B:2 * B], emb[:B], emb[2 * B:])
             return out if link_predictor is None else out + (prob[:B], prob[B:])
@@ -641,9 +641,10 @@ class MemoryModel(torch.nn.Module):
             ent = self._step_w = (key, w, params)
         return ent[1]
 
-    def _fused_step(self, roots, src, dst, tq, eid, k, link_predictor=None, pairs=None):
-        """Embeddings of ``roots`` (root r at time tq[r % B]) on the look-ahead view, then the memory update of the positive batch
-        (src, dst, tq, eid), then optionally the link probabilities -- one cooperative launch (csrc/tgn_step.cu)."""
+    def _fused_step(self, neg, src, dst, tq, eid, k, link_predictor=None, pairs=None):
+        """Embeddings of the roots ``[src | neg | dst]`` (``[src | dst]`` when ``neg`` is None; root r at time tq[r % B]) on the
+        look-ahead view, then the memory update of the positive batch (src, dst, tq, eid), then optionally the link probabilities
+        -- one cooperative launch (csrc/tgn_step.cu), which reads the three id lists where they lie."""
         lib = _native.load()
         dev = self.node_raw_features.device
         bank, em, sampler = self.memory_bank, self.embedding_module, self.embedding_module.neighbor_sampler
@@ -653,7 +654,8 @@ class MemoryModel(torch.nn.Module):
         F_, E_, T_ = self.node_feat_dim, self.edge_feat_dim, self.time_feat_dim
         H = self.num_heads
         Dk, Dq, MD, Fp = F_ + E_ + T_, F_ + T_, self.message_dim, (F_ + 7) // 8 * 8
-        B, R = src.numel(), roots.numel()
+        B = src.numel()
+        R = (3 if neg is not None else 2) * B
         P_ = 2 * B if link_predictor is not None else 0
         key = (R, B, P_, int(k), str(dev))
         sc = self._step_scratch.get(key)
@@ -676,7 +678,6 @@ class MemoryModel(torch.nn.Module):
             self._step_scratch[key] = sc
         emb = torch.empty((R, F_), dtype=torch.float32, device=dev)
         prob = torch.empty(max(P_, 1), dtype=torch.float32, device=dev)
-        cand = torch.cat([src, dst])
         wts = self._step_weights(link_predictor)
         w, b = self.time_encoder.wb()
         p = _native.TgnStep()
@@ -690,7 +691,7 @@ class MemoryModel(torch.nn.Module):
             keep.append(x)
             field.hi, field.mid, field.ld = x[0].data_ptr(), x[1].data_ptr(), x.shape[2]
         p.he, p.indptr, p.num_nodes = ptr(sampler.halfedges), ptr(sampler.indptr), sampler.num_nodes
-        p.src, p.dst, p.t, p.eid, p.cand, p.roots = ptr(src), ptr(dst), ptr(tq), ptr(eid), ptr(cand), ptr(roots)
+        p.src, p.dst, p.t, p.eid, p.neg, p.roots = ptr(src), ptr(dst), ptr(tq), ptr(eid), ptr(neg), None
         p.B, p.R, p.k, p.H, p.G, p.check_time = B, R, int(k), H, self.memory_updater.gates, int(self.check_time_order)
         p.node_raw, p.ld_node = ptr(self.node_raw_features), self.node_raw_features.stride(0)
         p.edge_raw, p.ld_edge = ptr(self.edge_raw_features), self.edge_raw_features.stride(0)

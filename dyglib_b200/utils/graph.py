@@ -45,8 +45,22 @@ class GraphedStep:
         # capture records, it does not run: the state is still what after_warmup left
 
     def __call__(self, *inputs):
-        for dst, src in zip(self.static_in, inputs):
-            dst.copy_(src, non_blocking=True)
+        if all(x.is_cuda for x in inputs):
+            # device-resident inputs: one multi-tensor copy kernel per dtype instead of one launch per tensor (a 200-event memory
+            # step is ~80 us of kernel time; five 3-us copy launches in front of it were visible in the step time)
+            by_dtype = {}
+            for dst, src in zip(self.static_in, inputs):
+                by_dtype.setdefault((dst.dtype, src.dtype), ([], []))
+                by_dtype[(dst.dtype, src.dtype)][0].append(dst)
+                by_dtype[(dst.dtype, src.dtype)][1].append(src)
+            for dsts, srcs in by_dtype.values():
+                if len(dsts) > 1:
+                    torch._foreach_copy_(dsts, srcs, non_blocking=True)
+                else:
+                    dsts[0].copy_(srcs[0], non_blocking=True)
+        else:
+            for dst, src in zip(self.static_in, inputs):
+                dst.copy_(src, non_blocking=True)
         self.graph.replay()
         if self.grad:
             ops.bump_weights_epoch()   # the replay moved the parameters without bumping their version counters

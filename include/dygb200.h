@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DYG_ABI_VERSION 12
+#define DYG_ABI_VERSION 13
 
 typedef void* dyg_stream_t; /* cudaStream_t */
 
@@ -396,7 +396,7 @@ int dyg_tgn_check_time(const int64_t* node_ids, int64_t n, const float* last_upd
  * election, raw-message build, recurrent cell, commit into the look-ahead view / message store.  Semantics are those of the
  * separate entry points above (dyg_sample_recent, dyg_gather_rows, dyg_linear, dyg_temporal_attend, dyg_layernorm,
  * dyg_tgn_check_time / persist / select_last / build_messages, dyg_gru_update_fwd, dyg_tgn_cell_commit) run in that order.
- * Root r is embedded at time t[r % B]; cand[c] = c < B ? src[c] : dst[c - B].  F, E, T % 4 == 0, (F + T) % 8 == 0, (F + E + T) % 4 == 0,
+ * Root r is embedded at time t[r % B]; candidate c is the src (c < B) or dst (c >= B) role of event c % B.  F, E, T % 4 == 0, (F + T) % 8 == 0, (F + E + T) % 4 == 0,
  * (2F + T + E) % 8 == 0, F + E <= 384, T <= 128, H = 2.  Dense contractions run as BF16x3 on mma.sync tiles (csrc/mma_tile.cuh).  `barrier`: 2 uint32, zeroed once by the caller and left zero by every launch. */
 /* BF16x3 operand planes of a (rows, ld) matrix: x = hi + mid, bf16 each; ld % 8 == 0, both 16-byte aligned, padding columns zero */
 typedef struct {
@@ -407,8 +407,8 @@ typedef struct {
 typedef struct {
     const dyg_halfedge_t* he; const int64_t* indptr; int64_t num_nodes;              /* device CSR */
     const int64_t* src; const int64_t* dst; const double* t; const int64_t* eid;      /* the positive batch (B events) */
-    const int64_t* cand;                                                              /* (2B) = [src | dst] */
-    const int64_t* roots;                                                             /* (R) node ids to embed */
+    const int64_t* neg;                                                               /* (B) negative destinations, or NULL */
+    const int64_t* roots;                                                             /* (R) node ids to embed; NULL: [src | neg | dst] (R = 3B) or, without neg, [src | dst] (R = 2B) */
     int32_t B, R, k, H, G, check_time;
     const float* node_raw; int32_t ld_node; const float* edge_raw; int32_t ld_edge; int32_t F, E, T;
     float* memory; float* last_update; float* mem_view; float* lu_view; uint8_t* pending; int32_t* winner;
