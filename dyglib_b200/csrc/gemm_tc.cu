@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) ln_gemm_bf16x3_kernel(const __g
     uint64_t* a_copy = bars + 2 * G_MAX_STAGES + 6;            //            local:  bulk copy of the image landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 7);
     float* bias_s = reinterpret_cast<float*>(bars + 2 * G_MAX_STAGES + 8);   // the bias (tma_out): read per chunk by every epilogue warp
+    static_assert(((2 * G_MAX_STAGES + 8) * 8) % 16 == 0 && (2 * G_MAX_STAGES + 8) * 8 <= 512, "barrier block layout: bias_s is read with 16-byte loads");
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
