@@ -1,7 +1,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dyglib_b200 import ops
-M = 204800
+M = int(os.environ.get("FFN_M", 204800))
 x = torch.randn(M, 200, device='cuda'); gm = torch.ones(200, device='cuda'); bt = torch.zeros(200, device='cuda')
 w1 = torch.randn(800, 200, device='cuda') / 14; b1 = torch.randn(800, device='cuda'); w2 = torch.randn(200, 800, device='cuda') / 28; b2 = torch.randn(200, device='cuda')
 out = torch.empty_like(x)
