@@ -391,11 +391,15 @@ __device__ __forceinline__ void ln_warps_loop(const LnSrc& f, int64_t pair, int6
 //              as the MMA warp releases A; the same warps run the final epilogue (+ b2 + x -> global)
 //   per macro chunk of 128 hidden columns (7 for 800, the last one ragged):
 //     GEMM1    acc1[mc&1] (TMEM, 128 cols) = LN(x) W1[mc]^T     (M=256, N=128, K=200: 13 k16 steps x 3 MMAs; W1 streamed
-//              per 32-wide k block through a 3-stage TMA ring)
+//              per 32-wide k block through the weight ring)
 //     per 32-column sub chunk:
 //       EPI1   8 warps (the two warps of a TMEM lane quarter take sub chunks round-robin): tcgen05.ld -> + b1 -> GELU ->
 //              bf16 hi|mid -> h[.] in shared memory as the next A operand (3 buffers)
-//       GEMM2  acc2 (TMEM, 208 cols) += h[.] W2[:, sub]^T        (M=256, N=208, K=32: 2 x 3 MMAs; W2 through a 3-stage ring)
+//       GEMM2  acc2 (TMEM, 208 cols) += h[.] W2[:, sub]^T        (M=256, N=208, K=32: 2 x 3 MMAs; W2 through the weight ring)
+//   Weight ring: W1 k blocks (hi | mid, 8 KB) and the two planes of a W2 sub chunk (6.5 KB each) share ONE ring of eight 8 KB
+//   slots, filled by the producer in the order the MMA warp consumes them.  With a 3-slot ring per weight the MMA-issuing thread
+//   spent 15 % of the kernel waiting for W1 (a GEMM1 burst needs 7 k blocks, a slot turns around in ~2,000 cycles of TMA
+//   latency against 384 cycles of MMAs) and 4 % for W2; the shared ring lets a burst take all the capacity: 1.56 -> 1.45 ms.
 //   GEMM1 of macro chunk mc+1 is issued before the GEMM2s of mc, so the tensor pipe works while the GELU of mc runs.
 // MMAs are sized so that each one is worth its issue cost (a first version with N=32 GEMM1s was bound by the issuing
 // thread).  Barriers consumed by the leader's MMA warp live in the leader CTA (remote arrivals from the peer), barriers
@@ -405,7 +409,8 @@ constexpr int F_MC = 128;                 // hidden columns per macro chunk (N o
 constexpr int F_KB1 = 7;                  // k blocks of GEMM1 (K <= 224)
 constexpr int F_W1_PLANE = (F_MC / 2) * 64;
 constexpr int F_W1_STAGE = 2 * F_W1_PLANE;   // one k block of this CTA's half of a macro chunk, hi | mid
-constexpr int F_S1 = 3, F_S2 = 3, F_HB = 3;
+constexpr int F_HB = 3;
+constexpr int F_MAX_WS = 8;                // W1 k blocks and W2 sub chunks share ONE ring of equal slots, filled in the order the MMA warp consumes them
 constexpr int F_EPI_WARPS = 8, F_LN_WARPS = 4;    // EPI warps per TMEM lane quarter: F_EPI_WARPS / 4, taking sub chunks round-robin
 constexpr int F_THREADS = 64 + 32 * (F_EPI_WARPS + F_LN_WARPS);
 constexpr int F_ACC1_COL = 256;           // acc2 at TMEM columns [0, 208), acc1 buffers at 256 and 384
@@ -425,6 +430,7 @@ struct FfnArgs {
     int NT2;               // MMA N of GEMM2 (D rounded up to 16)
     float eps;
     unsigned char* scratch;   // gridDim.x images of the A operand (F_KB1 * 16 KB each), L2 resident
+    int wstages;              // slots of the shared W1 / W2 ring
 };
 
 __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __grid_constant__ CUtensorMap map_w1h,
@@ -435,26 +441,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ffn_smem) + 1023) & ~(uintptr_t)1023);
     const int a_stage = 2 * G_A_PLANE;                         // one k block of A (or one h buffer): hi | mid
     const int w2_plane = (f.NT2 / 2) * 64;
-    const int w2_stage = 2 * w2_plane;
     unsigned char* a_res = base;                               // [F_KB1] k blocks of LN(x)
     unsigned char* h_buf = a_res + F_KB1 * a_stage;            // [F_HB] hidden sub chunks
-    unsigned char* w1_ring = h_buf + F_HB * a_stage;           // [F_S1]
-    unsigned char* w2_ring = w1_ring + F_S1 * F_W1_STAGE;      // [F_S2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w2_ring + F_S2 * w2_stage);
-    uint64_t* w1_full = bars;              // [3] leader
-    uint64_t* w1_empty = bars + 3;         // [3] both
-    uint64_t* w2_full = bars + 6;          // [3] leader
-    uint64_t* w2_empty = bars + 9;         // [3] both
-    uint64_t* h_full = bars + 12;          // [3] leader: h[b] written by both CTAs' EPI1 warps
-    uint64_t* h_empty = bars + 15;         // [3] both:   GEMM2 finished reading h[b]
-    uint64_t* acc1_full = bars + 18;       // [2] both
-    uint64_t* acc1_empty = bars + 20;      // [2] leader: both CTAs' EPI1 warps drained acc1[b]
-    uint64_t* a_full = bars + 22;          //     leader: LN(x) of the tile written by both CTAs
-    uint64_t* a_free = bars + 23;          //     both:   last GEMM1 of the tile retired
-    uint64_t* acc2_full = bars + 24;       //     both
-    uint64_t* acc2_empty = bars + 25;      //     leader: final epilogue (EPI warps of both CTAs) drained acc2
-    uint64_t* a_copy = bars + 26;          //     local:  bulk copy of the normalised tile into A landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+    constexpr int w_slot = F_W1_STAGE;                         // 8 KB: a W1 k block (hi | mid) or ONE plane of a W2 sub chunk (<= 6.5 KB)
+    unsigned char* w_ring = h_buf + F_HB * a_stage;            // [f.wstages] slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + (size_t)f.wstages * w_slot);
+    uint64_t* w_full = bars;               // [8] leader
+    uint64_t* w_empty = bars + 8;          // [8] both
+    uint64_t* h_full = bars + 16;          // [3] leader: h[b] written by both CTAs' EPI1 warps
+    uint64_t* h_empty = bars + 19;         // [3] both:   GEMM2 finished reading h[b]
+    uint64_t* acc1_full = bars + 22;       // [2] both
+    uint64_t* acc1_empty = bars + 24;      // [2] leader: both CTAs' EPI1 warps drained acc1[b]
+    uint64_t* a_full = bars + 26;          //     leader: LN(x) of the tile written by both CTAs
+    uint64_t* a_free = bars + 27;          //     both:   last GEMM1 of the tile retired
+    uint64_t* acc2_full = bars + 28;       //     both
+    uint64_t* acc2_empty = bars + 29;      //     leader: final epilogue (EPI warps of both CTAs) drained acc2
+    uint64_t* a_copy = bars + 30;          //     local:  bulk copy of the normalised tile into A landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
@@ -468,9 +471,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
     unsigned char* a_img = f.scratch + (size_t)blockIdx.x * (F_KB1 * a_stage);
     for (int i = tid; i < F_KB1 * a_stage / 16; i += F_THREADS) reinterpret_cast<uint4*>(a_img)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
+        for (int s = 0; s < F_MAX_WS; ++s) {
+            mbar_init(w_full + s, 1);
+            mbar_init(w_empty + s, 1);
+        }
         for (int s = 0; s < 3; ++s) {
-            mbar_init(w1_full + s, 1); mbar_init(w1_empty + s, 1);
-            mbar_init(w2_full + s, 1); mbar_init(w2_empty + s, 1);
             mbar_init(h_full + s, 8); mbar_init(h_empty + s, 1);                 // one EPI warp per lane quarter and CTA writes a sub chunk
         }
         for (int s = 0; s < 2; ++s) {
@@ -504,18 +509,18 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer: W1 k blocks and W2 sub chunks
         if (lane == 0) {
-            int s1 = 0, s2 = 0;
-            uint32_t p1 = 0, p2 = 0;
+            int ws = 0;
+            uint32_t wp = 0;
             auto load_w1 = [&](int mc) {
                 const int nmc = min(F_MC, f.Dff - mc * F_MC);
                 const int row = mc * F_MC + (int)rank * (nmc / 2);
                 for (int kb = 0; kb < nkb1; ++kb) {
-                    mbar_wait(w1_empty + s1, p1 ^ 1u);
-                    if (leader) mbar_expect_tx(w1_full + s1, 2u * F_W1_STAGE);
-                    unsigned char* d1 = w1_ring + s1 * F_W1_STAGE;
-                    tma_load_2d_pair(&map_w1h, w1_full + s1, d1, kb * G_BK, row);
-                    tma_load_2d_pair(&map_w1m, w1_full + s1, d1 + F_W1_PLANE, kb * G_BK, row);
-                    if (++s1 == F_S1) { s1 = 0; p1 ^= 1u; }
+                    mbar_wait(w_empty + ws, wp ^ 1u);
+                    if (leader) mbar_expect_tx(w_full + ws, 2u * F_W1_STAGE);
+                    unsigned char* d1 = w_ring + (size_t)ws * w_slot;
+                    tma_load_2d_pair(&map_w1h, w_full + ws, d1, kb * G_BK, row);
+                    tma_load_2d_pair(&map_w1m, w_full + ws, d1 + F_W1_PLANE, kb * G_BK, row);
+                    if (++ws == f.wstages) { ws = 0; wp ^= 1u; }
                 }
             };
             for (int64_t ms = pair; ms < f.m_super; ms += npairs) {
@@ -524,13 +529,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                     if (mc + 1 < nmacro) load_w1(mc + 1);                  // same order as the MMA warp consumes them
                     const int nsub = min(F_MC, f.Dff - mc * F_MC) / F_SUB;
                     for (int sub = 0; sub < nsub; ++sub) {
-                        mbar_wait(w2_empty + s2, p2 ^ 1u);
-                        if (leader) mbar_expect_tx(w2_full + s2, 2u * (uint32_t)w2_stage);
-                        unsigned char* d2 = w2_ring + s2 * w2_stage;
                         const int row2 = (int)rank * (f.NT2 / 2);
-                        tma_load_2d_pair(&map_w2h, w2_full + s2, d2, mc * F_MC + sub * F_SUB, row2);
-                        tma_load_2d_pair(&map_w2m, w2_full + s2, d2 + w2_plane, mc * F_MC + sub * F_SUB, row2);
-                        if (++s2 == F_S2) { s2 = 0; p2 ^= 1u; }
+#pragma unroll
+                        for (int pl = 0; pl < 2; ++pl) {                   // hi plane, then mid plane: one slot each
+                            mbar_wait(w_empty + ws, wp ^ 1u);
+                            if (leader) mbar_expect_tx(w_full + ws, 2u * (uint32_t)w2_plane);
+                            tma_load_2d_pair(pl ? &map_w2m : &map_w2h, w_full + ws, w_ring + (size_t)ws * w_slot, mc * F_MC + sub * F_SUB, row2);
+                            if (++ws == f.wstages) { ws = 0; wp ^= 1u; }
+                        }
                     }
                 }
             }
@@ -540,8 +546,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
         if (leader) {
             const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(f.NT2 >> 3) << 17) | ((uint32_t)((2 * G_BM) >> 4) << 24);
             const uint64_t ad_h = make_desc_sw64(smem_u32(a_res)), ad_m = ad_h + (uint64_t)(G_A_PLANE >> 4);
-            int s1 = 0, s2 = 0;
-            uint32_t p1 = 0, p2 = 0;
+            int ws = 0;
+            uint32_t wp = 0;
             int64_t gm = 0;      // global macro chunk counter: acc1 buffer gm & 1
             int64_t gs = 0;      // global sub chunk counter:   h buffer gs % F_HB
             int it = 0;
@@ -553,9 +559,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(F_ACC1_COL + F_MC * pb);
                 for (int kb = 0; kb < nkb1; ++kb) {
-                    mbar_wait(w1_full + s1, p1);
+                    mbar_wait(w_full + ws, wp);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t wd_h = make_desc_sw64(smem_u32(w1_ring + s1 * F_W1_STAGE)), wd_m = wd_h + (uint64_t)(F_W1_PLANE >> 4);
+                    const uint64_t wd_h = make_desc_sw64(smem_u32(w_ring + (size_t)ws * w_slot)), wd_m = wd_h + (uint64_t)(F_W1_PLANE >> 4);
                     const uint64_t ao = (uint64_t)((kb * a_stage) >> 4);
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk) {
@@ -566,8 +572,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                             umma_bf16_pair_e(tacc, ad_m + ao + o, wd_h + o, idesc1, 1);
                         }
                     }
-                    umma_commit_pair_e(w1_empty + s1);
-                    if (++s1 == F_S1) { s1 = 0; p1 ^= 1u; }
+                    umma_commit_pair_e(w_empty + ws);
+                    if (++ws == f.wstages) { ws = 0; wp ^= 1u; }
                 }
                 umma_commit_pair_e(acc1_full + pb);
             };
@@ -586,10 +592,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                         const int hb = (int)(gs % F_HB);
                         if (mc == 0 && sub == 0) mbar_wait(acc2_empty, (uint32_t)((it & 1) ^ 1));   // previous tile's final epilogue done
                         mbar_wait(h_full + hb, (uint32_t)((gs / F_HB) & 1));          // GELU(sub chunk) is in h[hb] in both CTAs
-                        mbar_wait(w2_full + s2, p2);
+                        const int ws_h = ws;
+                        mbar_wait(w_full + ws, wp);
+                        if (++ws == f.wstages) { ws = 0; wp ^= 1u; }
+                        const int ws_m = ws;
+                        mbar_wait(w_full + ws, wp);
+                        if (++ws == f.wstages) { ws = 0; wp ^= 1u; }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t hd_h = make_desc_sw64(smem_u32(h_buf + hb * a_stage)), hd_m = hd_h + (uint64_t)(G_A_PLANE >> 4);
-                        const uint64_t vd_h = make_desc_sw64(smem_u32(w2_ring + s2 * w2_stage)), vd_m = vd_h + (uint64_t)(w2_plane >> 4);
+                        const uint64_t vd_h = make_desc_sw64(smem_u32(w_ring + (size_t)ws_h * w_slot)), vd_m = make_desc_sw64(smem_u32(w_ring + (size_t)ws_m * w_slot));
 #pragma unroll
                         for (int kk = 0; kk < F_SUB / 16; ++kk) {
                             const uint64_t o = (uint64_t)(kk * 2);                    // 32 bytes >> 4
@@ -597,10 +608,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                             umma_bf16_pair_e(tmem_base, hd_h + o, vd_m + o, idesc2, 1);
                             umma_bf16_pair_e(tmem_base, hd_m + o, vd_h + o, idesc2, 1);
                         }
-                        umma_commit_pair_e(w2_empty + s2);
+                        umma_commit_pair_e(w_empty + ws_h);
+                        umma_commit_pair_e(w_empty + ws_m);
                         umma_commit_pair_e(h_empty + hb);
                         if (mc == nmacro - 1 && sub == nsub - 1) umma_commit_pair_e(acc2_full);
-                        if (++s2 == F_S2) { s2 = 0; p2 ^= 1u; }
                     }
                 }
             }
@@ -1220,7 +1231,12 @@ extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, co
     if (!dyg_tensor_map_bf16(W1_mid, (uint64_t)Dff, (uint64_t)D, (uint64_t)ldw1, F_MC / 2, &m1m)) return 1;
     if (!dyg_tensor_map_bf16(W2_hi, (uint64_t)D, (uint64_t)Dff, (uint64_t)ldw2, (uint32_t)(f.NT2 / 2), &m2h)) return 1;
     if (!dyg_tensor_map_bf16(W2_mid, (uint64_t)D, (uint64_t)Dff, (uint64_t)ldw2, (uint32_t)(f.NT2 / 2), &m2m)) return 1;
-    const size_t smem = (size_t)(F_KB1 + F_HB) * 2 * G_A_PLANE + (size_t)F_S1 * F_W1_STAGE + (size_t)F_S2 * 2 * (f.NT2 / 2) * 64 + 1024 + 512;
+    const int w_slot = F_W1_STAGE;
+    const size_t fixed = (size_t)(F_KB1 + F_HB) * 2 * G_A_PLANE + 1024 + 512;
+    f.wstages = (int)((227 * 1024 - fixed) / w_slot);
+    if (f.wstages > F_MAX_WS) f.wstages = F_MAX_WS;
+    DYG_CHECK_ARG(f.wstages >= 3, "dyg_ln_ffn_bf16x3: weight ring does not fit shared memory");
+    const size_t smem = fixed + (size_t)f.wstages * w_slot;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(ln_ffn_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
