@@ -458,6 +458,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
     uint64_t* acc2_empty = bars + 29;      //     leader: final epilogue (EPI warps of both CTAs) drained acc2
     uint64_t* a_copy = bars + 30;          //     local:  bulk copy of the normalised tile into A landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+    // b1 | b2 (b2 zero-padded to NT2): the epilogue warps read them per chunk, and the L1 (~30 KB next to 220 KB of shared memory) is
+    // swept by the LN warps' row loads, so __ldg of the biases kept missing to L2 on the critical path of both epilogues
+    float* b1_s = reinterpret_cast<float*>(bars + 32);
+    float* b2_s = b1_s + f.Dff;
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
@@ -470,6 +474,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
     // zero this CTA's image of the A operand once: the K padding columns (D .. 32*nkb1) are never written again
     unsigned char* a_img = f.scratch + (size_t)blockIdx.x * (F_KB1 * a_stage);
     for (int i = tid; i < F_KB1 * a_stage / 16; i += F_THREADS) reinterpret_cast<uint4*>(a_img)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < f.Dff; i += F_THREADS) b1_s[i] = f.b1[i];
+    for (int i = tid; i < f.NT2; i += F_THREADS) b2_s[i] = i < f.D ? f.b2[i] : 0.f;
     if (tid == 0) {
         for (int s = 0; s < F_MAX_WS; ++s) {
             mbar_init(w_full + s, 1);
@@ -644,11 +650,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                     const int hb = (int)(gs % F_HB);
                     uint32_t rr[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(F_ACC1_COL + F_MC * pb + sub * F_SUB), rr);
-                    const float* bp = f.b1 + mc * F_MC + sub * F_SUB;
+                    const float* bp = b1_s + mc * F_MC + sub * F_SUB;
                     uint32_t hi[16], mid[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float2 b2v = __ldg(reinterpret_cast<const float2*>(bp + 2 * j));
+                        const float2 b2v = *reinterpret_cast<const float2*>(bp + 2 * j);
                         const float v0 = act_apply(__uint_as_float(rr[2 * j]) + b2v.x, DYG_ACT_GELU);
                         const float v1 = act_apply(__uint_as_float(rr[2 * j + 1]) + b2v.y, DYG_ACT_GELU);
                         split_pack(v0, v1, hi[j], mid[j]);
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ln_ffn_bf16x3_kernel(const __gri
                             uint32_t o[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                o[j] = __float_as_uint(__uint_as_float(rr[j]) + rv[j] + ((col + j < f.D) ? __ldg(f.b2 + col + j) : 0.f));
+                                o[j] = __float_as_uint(__uint_as_float(rr[j]) + rv[j] + b2_s[col + j]);
                             float* dst = f.out + m * f.ldo + col;
                             st_v8(dst, o);
                             if (col + 8 < f.D) st_v8(dst + 8, o + 8);
@@ -1232,7 +1238,7 @@ extern "C" int dyg_ln_ffn_bf16x3(const float* x, int ldx, const float* gamma, co
     if (!dyg_tensor_map_bf16(W2_hi, (uint64_t)D, (uint64_t)Dff, (uint64_t)ldw2, (uint32_t)(f.NT2 / 2), &m2h)) return 1;
     if (!dyg_tensor_map_bf16(W2_mid, (uint64_t)D, (uint64_t)Dff, (uint64_t)ldw2, (uint32_t)(f.NT2 / 2), &m2m)) return 1;
     const int w_slot = F_W1_STAGE;
-    const size_t fixed = (size_t)(F_KB1 + F_HB) * 2 * G_A_PLANE + 1024 + 512;
+    const size_t fixed = (size_t)(F_KB1 + F_HB) * 2 * G_A_PLANE + 1024 + 512 + (size_t)(Dff + f.NT2) * 4;
     f.wstages = (int)((227 * 1024 - fixed) / w_slot);
     if (f.wstages > F_MAX_WS) f.wstages = F_MAX_WS;
     DYG_CHECK_ARG(f.wstages >= 3, "dyg_ln_ffn_bf16x3: weight ring does not fit shared memory");
