@@ -116,3 +116,28 @@ def test_graph_replayed_training_then_eval_sees_the_new_weights(tmp_path):
         want = fresh.compute_node_temporal_embeddings(src, t, 2, 20)
     assert not torch.allclose(before, after, atol=1e-4)
     assert torch.equal(after, want)
+
+
+def test_graphed_step_input_paths_agree():
+    """GraphedStep copies its inputs into one captured device slab: device tensors (one multi-tensor copy per dtype), pinned host
+    tensors (packed into a pinned slab ring, ONE H2D copy) and pageable host tensors (per-tensor copies) must replay the same step,
+    also when the ring of pinned slabs wraps around while earlier copies are still in flight."""
+    from dyglib_b200.utils.graph import GraphedStep
+    g = torch.Generator().manual_seed(0)
+    n = 257
+    mk = lambda: (torch.randint(0, 1000, (n,), generator=g), torch.randint(0, 1000, (n,), generator=g),   # noqa: E731
+                  torch.rand(n, generator=g, dtype=torch.float64), torch.randint(0, 1000, (5, 3), generator=g))
+    w = torch.arange(n, device='cuda', dtype=torch.float64)
+
+    def step(a, b, t, c):
+        return (a.double() * 3.0 + b.double()) * t + w + c.double().sum()
+    first = tuple(x.cuda() for x in mk())
+    graphed = GraphedStep(step, first, warmup=1)
+    assert torch.equal(graphed(*first), step(*first))
+    for i in range(20):                     # more calls than ring slots
+        host = mk()
+        want = step(*[x.cuda() for x in host])
+        got_pinned = graphed(*[x.pin_memory() for x in host]).clone()
+        got_pageable = graphed(*host).clone()
+        got_device = graphed(*[x.cuda() for x in host]).clone()
+        assert torch.equal(got_pinned, want) and torch.equal(got_pageable, want) and torch.equal(got_device, want), i
