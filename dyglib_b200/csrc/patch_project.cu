@@ -251,33 +251,64 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
         // 32 wavefronts whatever its width; globaltimer stamps put this epilogue at 21 of the 88 us of a tile)
         const bool v4 = a.C == 50 && ((a.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.X) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(a.bias) & 15u) == 0);
         if (v4) {
-            const int pc = warp >> 2;                                            // channels 2 pc, 2 pc + 1 -> output columns [100 pc, 100 pc + 100)
-            float4* dst4 = reinterpret_cast<float4*>(a.X + orow * a.ldx + pc * 100);
-            const float4* b4 = reinterpret_cast<const float4*>(a.bias + pc * 100);
+            // Output floats o = 0 .. 99 of this warp's row segment: o < 50 is channel 2 pc (TMEM columns 0 .. 49 of its accumulator), o >= 50
+            // channel 2 pc + 1.  The segment starts at column 100 pc of a 32-byte aligned row: pc = 0 stores twelve 256-bit groups and
+            // one 128-bit tail, pc = 1 one 128-bit head (columns 100 .. 103) and twelve 256-bit groups from column 104.
+            const int pc = warp >> 2;
+            float* dst = a.X + orow * a.ldx + pc * 100;
+            const float* bp = a.bias + pc * 100;
             const uint32_t t0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(2 * pc * PP_NT);
-            auto put = [&](int g, float x0, float x1, float x2, float x3) {
-                const float4 b = __ldg(b4 + g);
-                if (eok) dst4[g] = make_float4(x0 + b.x, x1 + b.y, x2 + b.z, x3 + b.w);
+            auto put8 = [&](int o, const uint32_t* x) {                      // x[0..7] -> output floats o .. o + 7 (o % 4 == 0)
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + o)), b1 = __ldg(reinterpret_cast<const float4*>(bp + o + 4));
+                uint32_t y[8];
+                y[0] = __float_as_uint(__uint_as_float(x[0]) + b0.x); y[1] = __float_as_uint(__uint_as_float(x[1]) + b0.y);
+                y[2] = __float_as_uint(__uint_as_float(x[2]) + b0.z); y[3] = __float_as_uint(__uint_as_float(x[3]) + b0.w);
+                y[4] = __float_as_uint(__uint_as_float(x[4]) + b1.x); y[5] = __float_as_uint(__uint_as_float(x[5]) + b1.y);
+                y[6] = __float_as_uint(__uint_as_float(x[6]) + b1.z); y[7] = __float_as_uint(__uint_as_float(x[7]) + b1.w);
+                if (eok) st_v8(dst + o, y);
             };
+            auto put4 = [&](int o, const uint32_t* x) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bp + o));
+                if (eok)
+                    *reinterpret_cast<float4*>(dst + o) = make_float4(__uint_as_float(x[0]) + b.x, __uint_as_float(x[1]) + b.y,
+                                                                       __uint_as_float(x[2]) + b.z, __uint_as_float(x[3]) + b.w);
+            };
+            uint32_t w[48];                                                      // channel A columns 0 .. 47
+            tmem_ld16(t0, *reinterpret_cast<uint32_t(*)[16]>(w));
+            tmem_ld16(t0 + 16u, *reinterpret_cast<uint32_t(*)[16]>(w + 16));
+            tmem_ld16(t0 + 32u, *reinterpret_cast<uint32_t(*)[16]>(w + 32));
+            uint32_t ta[16], u[40];
+            if (pc == 0) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {                                        // first channel, columns 0 .. 47
-                uint32_t rr[16];
-                tmem_ld16(t0 + 16u * k, rr);
+                for (int g = 0; g < 6; ++g) put8(8 * g, w + 8 * g);             // o = 0 .. 47
+                tmem_ld16(t0 + 48u, ta);                                         // A 48, 49
+                tmem_ld16(t0 + PP_NT, *reinterpret_cast<uint32_t(*)[16]>(u + 2));       // B 0 .. 31
+                tmem_ld16(t0 + PP_NT + 16u, *reinterpret_cast<uint32_t(*)[16]>(u + 18));
+                u[0] = ta[0]; u[1] = ta[1];                                      // u = {A48, A49, B0 .. B31}: o = 48 .. 81
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    put(4 * k + j, __uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
-            }
-            uint32_t ta[16], v[64];
-            tmem_ld16(t0 + 48u, ta);                                             // first channel, columns 48, 49
-            tmem_ld16(t0 + PP_NT, *reinterpret_cast<uint32_t(*)[16]>(v));        // second channel, columns 0 .. 63 (50 used)
-            tmem_ld16(t0 + PP_NT + 16u, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
-            tmem_ld16(t0 + PP_NT + 32u, *reinterpret_cast<uint32_t(*)[16]>(v + 32));
-            tmem_ld16(t0 + PP_NT + 48u, *reinterpret_cast<uint32_t(*)[16]>(v + 48));
-            put(12, __uint_as_float(ta[0]), __uint_as_float(ta[1]), __uint_as_float(v[0]), __uint_as_float(v[1]));
+                for (int g = 0; g < 4; ++g) put8(48 + 8 * g, u + 8 * g);        // o = 48 .. 79
+                u[0] = u[32]; u[1] = u[33];                                      // carry B30, B31
+                tmem_ld16(t0 + PP_NT + 32u, *reinterpret_cast<uint32_t(*)[16]>(u + 2));       // B 32 .. 63 (50 used)
+                tmem_ld16(t0 + PP_NT + 48u, *reinterpret_cast<uint32_t(*)[16]>(u + 18));
+                put8(80, u);                                                     // B30 .. B37
+                put8(88, u + 8);                                                 // B38 .. B45
+                put4(96, u + 16);                                                // B46 .. B49
+            } else {
+                put4(0, w);                                                      // columns 100 .. 103
 #pragma unroll
-            for (int g = 13; g < 25; ++g) {
-                const int c = 4 * (g - 13) + 2;
-                put(g, __uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+                for (int g = 0; g < 5; ++g) put8(4 + 8 * g, w + 4 + 8 * g);     // o = 4 .. 43
+                tmem_ld16(t0 + 48u, ta);
+                tmem_ld16(t0 + PP_NT, *reinterpret_cast<uint32_t(*)[16]>(u + 6));
+                tmem_ld16(t0 + PP_NT + 16u, *reinterpret_cast<uint32_t(*)[16]>(u + 22));
+                u[0] = w[44]; u[1] = w[45]; u[2] = w[46]; u[3] = w[47]; u[4] = ta[0]; u[5] = ta[1];   // u = {A44 .. A49, B0 .. B31}: o = 44 .. 81
+#pragma unroll
+                for (int g = 0; g < 4; ++g) put8(44 + 8 * g, u + 8 * g);        // o = 44 .. 75
+#pragma unroll
+                for (int q = 0; q < 6; ++q) u[q] = u[32 + q];                   // carry B26 .. B31
+                tmem_ld16(t0 + PP_NT + 32u, *reinterpret_cast<uint32_t(*)[16]>(u + 6));
+                tmem_ld16(t0 + PP_NT + 48u, *reinterpret_cast<uint32_t(*)[16]>(u + 22));
+#pragma unroll
+                for (int g = 0; g < 3; ++g) put8(76 + 8 * g, u + 8 * g);        // B26 .. B49
             }
             __syncwarp();
         } else
