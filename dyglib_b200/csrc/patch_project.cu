@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
     uint64_t* acc_bar = bars + 2 * PP_STAGES;     // accumulators complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * PP_STAGES + 1);
     StageInfo* stage_tab = reinterpret_cast<StageInfo*>(bars + 2 * PP_STAGES + 2);   // [nst]
+    // time-encoder weights / biases: read 32 times per thread and time stage; the gathers allocate in L1 (cp.async.ca) and evict them
+    float* tw_s = reinterpret_cast<float*>(stage_tab + a.base[5]);                    // [T] | [T]
+    float* tb_s = tw_s + a.T;
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
@@ -116,6 +119,10 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
     const int nst = a.base[5];
 
     for (int s = tid; s < nst; s += PP_THREADS) stage_tab[s] = decode_stage(a, s);
+    for (int c = tid; c < a.T; c += PP_THREADS) {
+        tw_s[c] = __ldg(a.tw + c);
+        tb_s[c] = __ldg(a.tb + c);
+    }
     if (tid == 0) {
         for (int s = 0; s < PP_STAGES; ++s) {
             mbar_init(full_bar + s, PP_PRODUCERS + 1);
@@ -221,8 +228,8 @@ __global__ void __launch_bounds__(PP_THREADS, 2) patch_project_kernel(const __gr
                         const int c = c0 + 2 * j;
                         float v0 = 0.f, v1 = 0.f;
                         if (!masked) {
-                            if (c < a.T) v0 = dyg_time_enc(dt, __ldg(a.tw + c), __ldg(a.tb + c));
-                            if (c + 1 < a.T) v1 = dyg_time_enc(dt, __ldg(a.tw + c + 1), __ldg(a.tb + c + 1));
+                            if (c < a.T) v0 = dyg_time_enc(dt, tw_s[c], tb_s[c]);
+                            if (c + 1 < a.T) v1 = dyg_time_enc(dt, tw_s[c + 1], tb_s[c + 1]);
                         }
                         split_pack(v0, v1, hi[j], mid[j]);
                     }
@@ -453,7 +460,7 @@ extern "C" int dyg_patch_project(const dyg_proj_side_t* sides_host, int nsides, 
     if (!dyg_tensor_map_bf16(W_hi, PP_NT, (uint64_t)nst * 32, (uint64_t)ldw, PP_NT, &mwh)) return 1;
     if (!dyg_tensor_map_bf16(W_mid, PP_NT, (uint64_t)nst * 32, (uint64_t)ldw, PP_NT, &mwm)) return 1;
     DYG_CHECK_ARG(nst <= PP_MAX_STAGES, "dyg_patch_project: %d stages exceed the stage table (%d)", nst, PP_MAX_STAGES);
-    const size_t smem = (size_t)PP_STAGES * PP_STAGE_BYTES + 1024 + 128 + (size_t)nst * sizeof(StageInfo);
+    const size_t smem = (size_t)PP_STAGES * PP_STAGE_BYTES + 1024 + 128 + (size_t)nst * sizeof(StageInfo) + (size_t)2 * T * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(patch_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
