@@ -66,8 +66,8 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 // x1 = O' + x + b_o.  ALL residual chunks of the row are requested before the accumulator is awaited (up to 7 x 16 registers): with
 // two chunks in flight the epilogue was one HBM round trip per pair of chunks, 13 us per tile on the critical path of the single O'
 // buffer (globaltimer stamps, profiles/README.md).
-__device__ __forceinline__ void sa_tile_epilogue(const AttnArgs& a, uint32_t lane_addr, bool rowok, const float* xr, float* orow, int first,
-                                                 uint64_t* o_full, uint32_t parity) {
+__device__ __forceinline__ void sa_tile_epilogue(const AttnArgs& a, const float* bias_s, uint32_t lane_addr, bool rowok, const float* xr, float* orow,
+                                                 int first, uint64_t* o_full, uint32_t parity) {
     constexpr int MAXC = (SA_NV / 16 + 1) / 2;                  // chunks per warp
     float xv[MAXC][16];
 #pragma unroll
@@ -90,7 +90,7 @@ __device__ __forceinline__ void sa_tile_epilogue(const AttnArgs& a, uint32_t lan
             float bv[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 t = (j < 2 || wide) ? __ldg(reinterpret_cast<const float4*>(a.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 t = reinterpret_cast<const float4*>(bias_s + col)[j];
                 bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
             }
             uint32_t rr[16];
@@ -126,9 +126,12 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
     uint64_t* o_full = bars + 7;    // O' of the tile complete
     uint64_t* o_empty = bars + 8;   // 4 warps: O' drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* bias_s = reinterpret_cast<float*>(bars + 10);   // (SA_NV) b_o, zero padded: the L1 is swept by the Q / residual rows, so
+                                                           // the epilogue's bias reads kept going to L2 on the critical path of the O' buffer
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    for (int c = tid; c < SA_NV; c += blockDim.x) bias_s[c] = c < a.D ? a.bias[c] : 0.f;
     if (tid == 0) {
         mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
         mbar_init(q_full, 4); mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_empty, 8);
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
             }
             {
                 const int64_t row = rowok ? seq * a.S + i : 0;
-                sa_tile_epilogue(a, lane_addr, rowok, a.x + row * a.ldx, a.out + row * a.ldo, 0, o_full, (uint32_t)(it & 1));
+                sa_tile_epilogue(a, bias_s, lane_addr, rowok, a.x + row * a.ldx, a.out + row * a.ldo, 0, o_full, (uint32_t)(it & 1));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_empty);
             }
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(SA_THREADS, 1) seq_attention_fold_kernel(const
                 if (n + 1 < steps) store_q(qh, qm);
             }
             // ---- final epilogue of the tile (the odd chunks; the softmax warp of this lane quarter takes the even ones)
-            sa_tile_epilogue(a, lane_addr, rowok, xr, orow, 1, o_full, (uint32_t)(it & 1));
+            sa_tile_epilogue(a, bias_s, lane_addr, rowok, xr, orow, 1, o_full, (uint32_t)(it & 1));
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
@@ -429,7 +432,7 @@ extern "C" int dyg_seq_attention_fold(const void* planes_hi, const void* planes_
     CUtensorMap mh, mm;
     if (!seq_tensor_map(planes_hi, (uint64_t)cols, (uint64_t)ldp, (uint64_t)S, (uint64_t)B, (uint32_t)a.SP, (uint32_t)a.NS, &mh)) return 1;
     if (!seq_tensor_map(planes_mid, (uint64_t)cols, (uint64_t)ldp, (uint64_t)S, (uint64_t)B, (uint32_t)a.SP, (uint32_t)a.NS, &mm)) return 1;
-    const size_t smem = (size_t)2 * SA_K_PLANE + 2 * SA_V_PLANE + 1024 + 256;
+    const size_t smem = (size_t)2 * SA_K_PLANE + 2 * SA_V_PLANE + 1024 + 256 + SA_NV * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(seq_attention_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
