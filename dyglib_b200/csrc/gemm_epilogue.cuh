@@ -67,7 +67,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
         const bool bias_q = g.bias && b_v4 && valid == 16;
         if (bias_q) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bq[j] = __ldg(reinterpret_cast<const float4*>(g.bias + n) + j);
+            for (int j = 0; j < 4; ++j) bq[j] = reinterpret_cast<const float4*>(g.bias + n)[j];   // generic loads: the bias may sit in shared memory
         }
         uint32_t r[16];
         tmem_ld16(taddr + (uint32_t)col, r);
@@ -84,7 +84,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __ldg(g.bias + n + j);
+                        for (int j = 0; j < 16; ++j) v[j] += g.bias[n + j];
                     }
                 }
                 if (g.residual) {
@@ -157,7 +157,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint32_t taddr,
                 for (int j = 0; j < 16; ++j) {
                     if (j >= valid) break;
                     float x = v[j];
-                    if (g.bias) x += __ldg(g.bias + n + j);
+                    if (g.bias) x += g.bias[n + j];
                     if (g.residual) x += g.residual[m * g.ldr + n + j];
                     x = act_apply(x, g.act);
                     if (g.C) g.C[m * g.ldc + n + j] = x;

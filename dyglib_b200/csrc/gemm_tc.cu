@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
     uint64_t* tfull_bar = bars + 2 * G_MAX_STAGES + 16;        // [2]        both:   accumulator buffer complete
     uint64_t* tempty_bar = bars + 2 * G_MAX_STAGES + 18;       // [2]        leader: accumulator buffer drained by both epilogues
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_MAX_STAGES + 20);
+    float* bias_s = reinterpret_cast<float*>(bars + 2 * G_MAX_STAGES + 22);   // the bias (when given): ~30 KB of L1 next to the ring cannot keep it
 
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform: role branches stay on the uniform path
@@ -124,6 +125,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
     const bool leader = rank == 0;
     const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
+    if (g.bias)
+        for (int c = tid; c < g.N; c += G_THREADS) bias_s[c] = g.bias[c];
     if (tid == 0) {
         for (int s = 0; s < g.stages; ++s) {
             mbar_init(full_bar + s, 1);
@@ -242,6 +245,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
         // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
         const int quarter = warp & 3;                                      // TMEM lane quarter this warp may read
         const int row = quarter * 32 + lane;
+        GemmArgs eg = g;
+        if (g.bias) eg.bias = bias_s;
         const int chunk0 = (warp - 2) >> 2;
         int it = 0;
         for (int64_t ms = pair; ms < g.m_super; ms += npairs) {
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16x3_kernel(const __grid_
                 mbar_wait(tfull_bar + buf, bph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * G_BUF_COLS);
-                epilogue_tile(g, taddr, m, n0, ncols, chunk0, G_EPI_WARPS / 4);
+                epilogue_tile(eg, taddr, m, n0, ncols, chunk0, G_EPI_WARPS / 4);
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(tempty_bar + buf);
@@ -1129,7 +1134,7 @@ extern "C" int dyg_gemm_bf16x3(const void* A_hi, const void* A_mid, int lda, con
     g.resident = (nkb <= 7 && g.n_tiles > 1) ? 1 : 0;
     const int w_stage = 2 * (g.NT / 2) * 64;
     const int stage_bytes = (g.resident ? 0 : 2 * G_A_PLANE) + w_stage;
-    const int fixed = (g.resident ? nkb * 2 * G_A_PLANE : 0) + 1024 + 512;
+    const int fixed = (g.resident ? nkb * 2 * G_A_PLANE : 0) + 1024 + 512 + (bias ? (N * 4 + 15) / 16 * 16 : 0);
     const int max_smem = 227 * 1024;
     g.stages = (max_smem - fixed) / stage_bytes;
     if (g.stages > G_MAX_STAGES) g.stages = G_MAX_STAGES;
